@@ -1,0 +1,81 @@
+"""Synthetic Gaussian-mixture workloads in the shape of the reference's own test program.
+
+Recipe follows tests/test_emgmm.f90:105-124 (testGMM): centres XC ~ sigmaC*N(0,I); a common
+spectrum w_i = sqrt(sigmaX*(1/i)/mean_j(1/j)) (:116-117); per component C12 = O*diag(w) with O a
+Haar-random orthogonal matrix (src/mlf_matrix.f90:149-180, Stewart 1980) and NX points
+x = c_k + C12*N(0,I) (:118-121); the points are then shuffled (:122-124).  The reference draws from
+an unseeded RANDOM_NUMBER stream, so only the distribution -- not the bits -- can be reproduced; our
+streams are seeded NumPy / torch generators.
+
+Layouts: X (N, d) C-contiguous == Fortran X(d,N); Mu (K, d); Cov (K, d, d); lambda (K,).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def spectrum(d: int, sigma_x: float) -> np.ndarray:
+    w = 1.0 / np.arange(1, d + 1, dtype=np.float64)
+    return np.sqrt(sigma_x * w / w.mean())
+
+
+def haar_orthogonal(rng: np.random.Generator, d: int) -> np.ndarray:
+    q, r = np.linalg.qr(rng.standard_normal((d, d)))
+    return q * np.sign(np.diag(r))
+
+
+def make_mixture(d: int, K: int, n_per_comp: int, sigma_c: float, sigma_x: float, seed: int, shuffle: bool = True):
+    """Host (NumPy) generator; returns dict(X, centres, C12, labels) with labels 1-based."""
+    rng = np.random.default_rng(seed)
+    XC = sigma_c * rng.standard_normal((K, d))
+    w = spectrum(d, sigma_x)
+    C12 = np.empty((K, d, d))
+    X = np.empty((K * n_per_comp, d))
+    lab = np.empty(K * n_per_comp, dtype=np.int32)
+    for k in range(K):
+        C12[k] = haar_orthogonal(rng, d) * w  # O*diag(w): column i scaled by w_i
+        X[k * n_per_comp:(k + 1) * n_per_comp] = XC[k] + rng.standard_normal((n_per_comp, d)) @ C12[k].T
+        lab[k * n_per_comp:(k + 1) * n_per_comp] = k + 1
+    if shuffle:
+        perm = rng.permutation(K * n_per_comp)
+        X, lab = X[perm], lab[perm]
+    return {"X": np.ascontiguousarray(X), "centres": XC, "C12": C12, "labels": lab}
+
+
+def injected_init(centres: np.ndarray, seed: int, jitter: float = 0.5):
+    """What stepF sets after its k-means call (src/unsupervised/mlf_emgmm.f90:140-145): Mu near the
+    clusters, Cov = I, lambda = 1/K.  The reference's k-means is RNG-driven, so tests inject this."""
+    rng = np.random.default_rng(seed + 7919)
+    K, d = centres.shape
+    Mu = centres + jitter * rng.standard_normal((K, d))
+    Cov = np.tile(np.eye(d), (K, 1, 1))
+    lam = np.full(K, 1.0 / K)
+    return Mu, Cov, lam
+
+
+def make_mixture_torch(d: int, K: int, N: int, sigma_c: float, sigma_x: float, seed: int, device, chunk: int = 1 << 22):
+    """Device generator for the large bench shapes (same distribution; component of point i is
+    drawn uniformly, which is what shuffling equal-sized blocks yields in the limit).
+    Returns (X [N,d] float64 on device, centres [K,d] numpy, C12 [K,d,d] numpy)."""
+    import torch
+
+    rng = np.random.default_rng(seed)
+    XC = sigma_c * rng.standard_normal((K, d))
+    w = spectrum(d, sigma_x)
+    C12 = np.stack([haar_orthogonal(rng, d) * w for _ in range(K)])
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    X = torch.empty((N, d), dtype=torch.float64, device=device)
+    tXC = torch.as_tensor(XC, device=device)
+    tC12T = torch.as_tensor(np.ascontiguousarray(C12.transpose(0, 2, 1)), device=device)
+    for s in range(0, N, chunk):
+        n = min(chunk, N - s)
+        comp = torch.randint(0, K, (n,), generator=g, device=device)
+        z = torch.randn((n, d), generator=g, dtype=torch.float64, device=device)
+        # x = c_k + C12_k z, batched by sorting into components would cost a sort; use bmm on gathered factors in slices
+        out = X[s:s + n]
+        step = 1 << 18
+        for t in range(0, n, step):
+            cc = comp[t:t + step]
+            out[t:t + step] = tXC[cc] + torch.bmm(z[t:t + step].unsqueeze(1), tC12T[cc]).squeeze(1)
+    return X, XC, C12
