@@ -1,0 +1,114 @@
+/*
+ * mlf_b200.h -- C-ABI of the B200-native drop-in for MlFortran's Gaussian-mixture EM path.
+ *
+ * The first block re-declares, with the *Fortran-true* signatures, the subset of the reference's C handle
+ * interface (include/mlf_cintf.h) that touches the EM path.  Where mlf_cintf.h and the Fortran bind(C)
+ * definitions disagree (mlf_getClass/mlf_getProba, mlf_evalGaussian/mlf_maxGaussian have swapped prototypes
+ * in the header, include/mlf_cintf.h:109-111,122-123), the Fortran definitions are the real ABI and are
+ * what is declared here.  Handles returned by this library are only valid with this library.
+ *
+ * Array layouts are the reference's (Fortran column-major):
+ *   X(d,N) -> X[i*d + a];  Mu(d,K) -> Mu[k*d + a];  Cov(d,d,K) -> Cov[k*d*d + b*d + a];  Proba(N,K) -> P[k*N + i].
+ */
+#ifndef MLF_B200_H
+#define MLF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLF_MAXRANK 15
+
+typedef void MLF_OBJ;
+
+/* include/mlf_cintf.h:42-45 */
+typedef enum { mlf_UNK = 0, mlf_BOOL = 1, mlf_INT = 2, mlf_INT64 = 3, mlf_SIZE = 4, mlf_FLOAT = 5, mlf_DOUBLE = 6, mlf_SIZEPARAM = 7, mlf_RAW = 8 } MLF_DATATYPE;
+typedef enum { mlf_DIRECT = 1, mlf_INDIRECT = 2, mlf_READONLY = 3, mlf_COPYONLY = 4, mlf_WRITEONLY = 5 } MLF_ACCESSTYPE;
+typedef enum { mlf_NAME = 1, mlf_DESC = 2, mlf_FIELDS = 3, mlf_FUNINFO } MLF_INFOTYPE;
+typedef enum { mlf_OK = 0, mlf_UNINIT = -1, mlf_FUNERROR = -2, mlf_WRONGTYPE = -3, mlf_WRONGRANK = -4, mlf_FILENOTFOUND = -5, mlf_FILEERROR = -6, mlf_OTHERERROR = -7 } MLF_ERRORTYPE;
+#define mlf_STEP_OK 0
+#define mlf_STEP_STOP 1 /* src/mlf_step_algo.f90:40 */
+
+typedef struct {
+  short dt;     /* MLF_DATATYPE */
+  short access; /* MLF_ACCESSTYPE */
+} MLF_DT;      /* include/mlf_cintf.h:47-50, src/mlf_intf.f90:66-69 */
+
+/* ---- reference interface (same names, argument meaning and error behaviour) ------------------------------- */
+
+int mlf_init(void);  /* src/mlf_intf.f90:439-443 (h5open_f) -- here: checks that a CUDA device exists */
+int mlf_quit(void);  /* src/mlf_intf.f90:445-449 */
+
+int mlf_dealloc(MLF_OBJ *obj);   /* src/mlf_intf.f90:257-278; -1 on NULL */
+int mlf_getnumrsc(MLF_OBJ *obj); /* src/mlf_intf.f90:323-331; 7 for an EM object, -1 on NULL/foreign */
+
+/* src/mlf_intf.f90:335-351 + src/mlf_rsc_array.f90:617-635,718-792.  id is 1-based:
+ * 1 iPar(int64[1]) 2 rPar(f64[2]) 3 iVar(int64[2]) 4 rVar(f64[3]) 5 Mu(f64 d x K) 6 Cov(f64 d x d x K) 7 lambda(f64 K).
+ * Fills rank and Fortran-order dims, dt = {mlf_DOUBLE|mlf_INT64, mlf_DIRECT}; returns a direct pointer into the
+ * object's host array when data == NULL, otherwise memcpy's into data and returns data.  NULL on error. */
+void *mlf_getrsc(MLF_OBJ *obj, int id, MLF_DT *dt, int *rank, int *dims, void *data);
+char *mlf_getinfo(MLF_OBJ *obj, int id, int type);      /* src/mlf_intf.f90:354-366; NUL-terminated, object-owned */
+int mlf_updatersc(MLF_OBJ *obj, int id, void *data);    /* src/mlf_intf.f90:369-382 */
+int mlf_pushState(MLF_OBJ *handler, MLF_OBJ *obj, int override_); /* src/mlf_intf.f90:384-396, src/mlf_hdf5.f90:671-737 */
+
+/* src/mlf_step_algo.f90:204-219: niter iterations; on a fresh object the first one is the initialiser
+ * (src/unsupervised/mlf_emgmm.f90:135-145).  Returns 0, mlf_STEP_STOP (1) when cpuTime>cpuMax or realTime>realMax,
+ * -1 on NULL/foreign handles, other negatives on errors.  *dt receives the wall time of the call (the reference
+ * never writes it: "dt0 = dt", src/mlf_step_algo.f90:195). */
+int mlf_step(MLF_OBJ *obj, double *dt, int64_t *niter);
+
+/* Model interface, Fortran-true argument order (src/mlf_models.f90:277-289,302-313,324-331): nX = dimension d,
+ * nIn = number of points.  Cl is 1-based (MAXLOC).  P is written as Proba(nIn, nCl): P[k*nIn + i]
+ * (the reference's c_getProba views it as [nCl,nIn], which is inconsistent with ExpStep). */
+int mlf_getClass(MLF_OBJ *obj, const double *X, int *Cl, int nX, int nIn);
+int mlf_getProba(MLF_OBJ *obj, const double *X, double *P, int nX, int nIn, int nCl);
+int mlf_getNumClasses(MLF_OBJ *obj);
+
+MLF_OBJ *mlf_hdf5_createFile(const char *fname, int trunk); /* src/mlf_hdf5.f90:168-188 */
+MLF_OBJ *mlf_hdf5_openFile(const char *fname, int rw);      /* src/mlf_hdf5.f90:205-225 */
+
+/* Single-component entry points (src/unsupervised/mlf_gaussian.f90:53-59,81-88). */
+int mlf_evalGaussian(int ND, int NX, const double *X, double *P, const double *mu, const double *C, double lambda, double *sumLL);
+double mlf_maxGaussian(int ND, int NX, const double *X, const double *Proba, double *mu, double *C);
+
+/* ---- extension the reference lacks: an EM constructor for C callers ------------------------------------------
+ * Modelled on mlf_kmeans_c (src/unsupervised/mlf_kmeans_naive.f90:99-116) and on mlf_getoptimobj's optional
+ * checkpoint handle (src/mlf_optim_intf.f90:51-88).  X is nY x nX (nX points of dimension nY), borrowed like the
+ * reference's `this%X => X` but copied once to HBM.  handler != NULL restores Mu/Cov/lambda (and K) from the
+ * checkpoint and marks the object initialised (src/unsupervised/mlf_emgmm.f90:90-110).  NULL on failure. */
+MLF_OBJ *mlf_emgmm_c(double *X, int nX, int nY, int nC, double minProba, MLF_OBJ *handler);
+
+/* ---- B200-specific extensions ----------------------------------------------------------------------------------- */
+#define MLF_B200_X_ON_DEVICE 1u /* X is a device pointer (kept alive by the caller) */
+
+/* As mlf_emgmm_c with 64-bit point count, device selection (-1 = current) and flags. */
+MLF_OBJ *mlf_b200_emgmm_create(const double *X, int64_t nX, int nY, int nC, double minProba, MLF_OBJ *handler, int device, unsigned flags);
+
+/* Sharded operation (one process per GPU): install an in-place sum all-reduce over `count` doubles at device
+ * pointer buf, enqueued on CUDA stream `stream`.  The object then treats its X as one shard of the global data. */
+typedef int (*mlf_b200_allreduce_fn)(void *ctx, double *buf, int64_t count, void *stream);
+int mlf_b200_set_allreduce(MLF_OBJ *obj, mlf_b200_allreduce_fn fn, void *ctx, int rank, int world);
+
+int mlf_b200_set_initialized(MLF_OBJ *obj, int initialized); /* the Fortran API exposes %initialized directly */
+int mlf_b200_get_initialized(MLF_OBJ *obj);
+int mlf_b200_refresh_x(MLF_OBJ *obj, const double *X);        /* re-copy X after the caller changed it */
+const char *mlf_b200_last_error(MLF_OBJ *obj);
+/* sumLL of each EM iteration of the most recent mlf_step call (at most n values); returns how many exist. */
+int64_t mlf_b200_sumll_trace(MLF_OBJ *obj, double *out, int64_t n);
+/* Responsibilities (ProbaC(N,K), P[k*N+i]) and labels of the resident shard, as of the last E-pass. */
+int mlf_b200_resident_proba(MLF_OBJ *obj, double *P);
+int mlf_b200_resident_labels(MLF_OBJ *obj, int *Cl);
+/* Profiling counters: out[0..5] = ms in refresh, E-pass, mid, M-pass, finalize, and iterations counted. */
+int mlf_b200_set_profile(MLF_OBJ *obj, int on);
+int mlf_b200_get_times(MLF_OBJ *obj, double out[6]);
+int64_t mlf_b200_launch_count(MLF_OBJ *obj);
+void *mlf_b200_stream(MLF_OBJ *obj);
+int64_t mlf_b200_global_points(MLF_OBJ *obj);
+const char *mlf_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLF_B200_H */

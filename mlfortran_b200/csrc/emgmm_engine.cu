@@ -1,0 +1,323 @@
+// EM-GMM device engine: see emgmm_engine.h.  Reference call sequence being replaced:
+// mlf_algo_emgmm_stepF -> ExpStep -> mlf_EvalGaussian / MaxStep -> mlf_MaxGaussian -> GECovMatrix
+// (src/unsupervised/mlf_emgmm.f90:125-207).
+#include "emgmm_engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace mlfb200 {
+
+#define CKE(call, what)                         \
+  do {                                          \
+    cudaError_t e__ = (call);                   \
+    if (e__ != cudaSuccess) return fail(what, e__); \
+  } while (0)
+
+int EmgmmEngine::fail(const char* what, cudaError_t e) {
+  err_ = std::string(what) + ": " + cudaGetErrorString(e);
+  fprintf(stderr, "mlfortran_b200: %s\n", err_.c_str());
+  return -7;  // mlf_OTHERERROR
+}
+
+EmgmmEngine::~EmgmmEngine() {
+  if (st_ || dGamma_ || dXown_) {
+    cudaSetDevice(device_);
+    if (st_) cudaStreamSynchronize(st_);
+  }
+  double* bufs[] = {dXown_, dGamma_, dMu_, dCov_, dLambda_, dMupad_, dThr_, dPack_, dScratch_, dSumLLk_, dSumLL_,
+                    dStatsA_, dStatsB_, dPartA_, dPartB_, dSc_, dMean_, dNglob_};
+  for (double* b : bufs)
+    if (b) cudaFree(b);
+  if (dInfo_) cudaFree(dInfo_);
+  if (dLabels_) cudaFree(dLabels_);
+  for (auto& e : ev_)
+    if (e) cudaEventDestroy(e);
+  if (own_stream_ && st_) cudaStreamDestroy(st_);
+}
+
+void EmgmmEngine::set_stream(cudaStream_t st) {
+  if (own_stream_ && st_) {
+    cudaStreamSynchronize(st_);
+    cudaStreamDestroy(st_);
+  }
+  st_ = st;
+  own_stream_ = false;
+}
+
+int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d, int K, int device) {
+  if (n_local < 0 || d < 1 || K < 1) { err_ = "invalid shape"; return -7; }
+  if (d > 32) { err_ = "d > 32 is not supported by this build (DMMA fragment-resident path covers d <= 32)"; return -7; }
+  int ndev = 0;
+  cudaError_t e0 = cudaGetDeviceCount(&ndev);
+  if (e0 != cudaSuccess || ndev == 0) {
+    err_ = "no CUDA device: mlfortran_b200 has no CPU fallback";
+    fprintf(stderr, "mlfortran_b200: %s\n", err_.c_str());
+    return -7;
+  }
+  device_ = device < 0 ? 0 : device;
+  CKE(cudaSetDevice(device_), "cudaSetDevice");
+  cudaDeviceProp prop;
+  CKE(cudaGetDeviceProperties(&prop, device_), "cudaGetDeviceProperties");
+  sms_ = prop.multiProcessorCount;
+  smem_limit_ = prop.sharedMemPerBlockOptin;
+  geom_ = make_geom(d, K);
+  if (estep_smem_bytes(geom_) > smem_limit_) {
+    err_ = "K*d^2 parameter pack + logit tile exceed shared memory for this (d,K)";
+    return -7;
+  }
+  n_ = n_local;
+  nglob_ = n_local;
+  ldg_ = ((n_ + 31) / 32) * 32;
+  if (ldg_ == 0) ldg_ = 32;
+  CKE(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking), "cudaStreamCreate");
+  own_stream_ = true;
+  for (auto& e : ev_) CKE(cudaEventCreate(&e), "cudaEventCreate");
+  const Geom& g = geom_;
+  const int KP = g.K8 * 8;
+  const int64_t etiles = (n_ + kEstepTilePts - 1) / kEstepTilePts;
+  egrid_ = (int)std::max<int64_t>(1, std::min<int64_t>(sms_, etiles));
+  mstep_grid(g, sms_, n_, &mgx_, &mgy_);
+  auto A = [&](double** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(double)); };
+  CKE(A(&dGamma_, (size_t)K * ldg_), "cudaMalloc gamma (N*K responsibilities)");
+  CKE(A(&dMu_, (size_t)K * d), "cudaMalloc");
+  CKE(A(&dCov_, (size_t)K * d * d), "cudaMalloc");
+  CKE(A(&dLambda_, K), "cudaMalloc");
+  CKE(A(&dMupad_, (size_t)K * 8 * g.DN), "cudaMalloc");
+  CKE(A(&dThr_, K), "cudaMalloc");
+  CKE(A(&dPack_, (size_t)KP * g.PS), "cudaMalloc");
+  CKE(A(&dScratch_, (size_t)K * 3 * d * d), "cudaMalloc");
+  CKE(A(&dSumLLk_, KP), "cudaMalloc");
+  CKE(A(&dStatsA_, (size_t)KP * g.DS), "cudaMalloc");
+  CKE(A(&dStatsB_, (size_t)K * g.MS), "cudaMalloc");
+  CKE(A(&dPartA_, (size_t)sms_ * KP * g.DS), "cudaMalloc");
+  CKE(A(&dPartB_, (size_t)sms_ * K * g.MS), "cudaMalloc");
+  CKE(A(&dSc_, (size_t)d * d), "cudaMalloc");
+  CKE(A(&dMean_, (size_t)8 * g.DN + 8), "cudaMalloc");
+  CKE(A(&dNglob_, 8), "cudaMalloc");
+  CKE(cudaMalloc((void**)&dInfo_, sizeof(int) * KP), "cudaMalloc");
+  CKE(cudaMemsetAsync(dGamma_, 0, (size_t)K * ldg_ * sizeof(double), st_), "memset gamma");
+  return refresh_x(X, x_on_device);
+}
+
+int EmgmmEngine::refresh_x(const double* X, bool x_on_device) {
+  CKE(cudaSetDevice(device_), "cudaSetDevice");
+  const size_t bytes = (size_t)n_ * geom_.d * sizeof(double);
+  if (x_on_device) {
+    dX_ = X;
+  } else {
+    if (!dXown_) CKE(cudaMalloc((void**)&dXown_, std::max<size_t>(bytes, 8)), "cudaMalloc X");
+    if (bytes) CKE(cudaMemcpyAsync(dXown_, X, bytes, cudaMemcpyHostToDevice, st_), "H2D X");
+    dX_ = dXown_;
+  }
+  moments_ready_ = false;
+  return 0;
+}
+
+int EmgmmEngine::allreduce(double* buf, int64_t count) {
+  if (!ar_) return 0;
+  const int r = ar_(ar_ctx_, buf, count, (void*)st_);
+  if (r != 0) { err_ = "all-reduce callback failed"; return -7; }
+  return 0;
+}
+
+// One-time global moments: N, mean m and centred scatter Sc = sum_i (x_i-m)(x_i-m)^T, used by the closed form of
+// sum_i maha_ik in k_refresh (sumLL, src/unsupervised/mlf_gaussian.f90:73-76).
+int EmgmmEngine::ensure_moments() {
+  if (moments_ready_) return 0;
+  const Geom& g = geom_;
+  const int d = g.d;
+  const int grid = std::max(1, std::min<int>(sms_, (int)((n_ + 255) / 256)));
+  CKE(launch_colsum(dX_, n_, d, dPartB_, grid, st_), "colsum");
+  CKE(launch_reduce_partials(dPartB_, grid, d, dMean_, st_), "reduce colsum");
+  launches_ += 2;
+  const double nl = (double)n_;
+  CKE(cudaMemcpyAsync(dMean_ + d, &nl, sizeof(double), cudaMemcpyHostToDevice, st_), "H2D n");
+  CKE(cudaStreamSynchronize(st_), "sync");
+  if (int r = allreduce(dMean_, d + 1)) return r;
+  std::vector<double> h(8 * g.DN + 8, 0.0);
+  CKE(cudaMemcpyAsync(h.data(), dMean_, (d + 1) * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H mean");
+  CKE(cudaStreamSynchronize(st_), "sync");
+  nglob_ = (int64_t)llround(h[d]);
+  const double ng = h[d];
+  for (int a = 0; a < d; ++a) h[a] /= ng;
+  for (size_t a = d; a < h.size(); ++a) h[a] = 0.0;
+  CKE(cudaMemcpyAsync(dMean_, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, st_), "H2D mean");
+  // centred scatter through the M-pass kernel with unit weights and a single "component" centred at m
+  Geom g1 = make_geom(d, 1);
+  int gx, gy;
+  mstep_grid(g1, sms_, n_, &gx, &gy);
+  const double zero = 0.0;
+  CKE(cudaMemcpyAsync(dThr_, &zero, sizeof(double), cudaMemcpyHostToDevice, st_), "H2D thr");
+  CKE(launch_mstep(g1, dX_, n_, nullptr, 0, dMean_, dThr_, dPartB_, gx, st_), "mstep(moments)");
+  CKE(launch_reduce_partials(dPartB_, gx, g1.MS, dStatsB_, st_), "reduce moments");
+  launches_ += 2;
+  if (int r = allreduce(dStatsB_, g1.MS)) return r;
+  std::vector<double> sb(g1.MS), sc((size_t)d * d);
+  CKE(cudaMemcpyAsync(sb.data(), dStatsB_, g1.MS * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H moments");
+  CKE(cudaStreamSynchronize(st_), "sync");
+  for (int a = 0; a < d; ++a)
+    for (int b = 0; b <= a; ++b) {
+      const int ab = a >> 3, bb = b >> 3;
+      const double v = sb[(size_t)(ab * (ab + 1) / 2 + bb) * 64 + (a & 7) * 8 + (b & 7)];
+      sc[(size_t)b * d + a] = v;
+      sc[(size_t)a * d + b] = v;
+    }
+  CKE(cudaMemcpyAsync(dSc_, sc.data(), sc.size() * sizeof(double), cudaMemcpyHostToDevice, st_), "H2D Sc");
+  CKE(cudaStreamSynchronize(st_), "sync");
+  moments_ready_ = true;
+  return 0;
+}
+
+int EmgmmEngine::upload_params(const double* Mu, const double* Cov, const double* lambda) {
+  CKE(cudaSetDevice(device_), "cudaSetDevice");
+  const int d = geom_.d, K = geom_.K;
+  CKE(cudaMemcpyAsync(dMu_, Mu, (size_t)K * d * sizeof(double), cudaMemcpyHostToDevice, st_), "H2D Mu");
+  CKE(cudaMemcpyAsync(dCov_, Cov, (size_t)K * d * d * sizeof(double), cudaMemcpyHostToDevice, st_), "H2D Cov");
+  CKE(cudaMemcpyAsync(dLambda_, lambda, (size_t)K * sizeof(double), cudaMemcpyHostToDevice, st_), "H2D lambda");
+  CKE(cudaStreamSynchronize(st_), "sync");  // host mirrors may be pageable and change after we return
+  return 0;
+}
+
+int EmgmmEngine::download_params(double* Mu, double* Cov, double* lambda) {
+  CKE(cudaSetDevice(device_), "cudaSetDevice");
+  const int d = geom_.d, K = geom_.K;
+  CKE(cudaMemcpyAsync(Mu, dMu_, (size_t)K * d * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H Mu");
+  CKE(cudaMemcpyAsync(Cov, dCov_, (size_t)K * d * d * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H Cov");
+  CKE(cudaMemcpyAsync(lambda, dLambda_, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H lambda");
+  CKE(cudaStreamSynchronize(st_), "sync");
+  return 0;
+}
+
+int EmgmmEngine::run_estep(const double* X, int64_t n, double* gamma, int64_t ldg, int32_t* labels, bool want_stats) {
+  const Geom& g = geom_;
+  const int64_t etiles = (n + kEstepTilePts - 1) / kEstepTilePts;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sms_, etiles));
+  CKE(launch_estep(g, X, n, dPack_, gamma, ldg, labels, dPartA_, grid, smem_limit_, st_), "estep");
+  ++launches_;
+  if (want_stats) {
+    CKE(launch_reduce_partials(dPartA_, grid, (int64_t)g.K8 * 8 * g.DS, dStatsA_, st_), "reduce statsA");
+    ++launches_;
+  }
+  return 0;
+}
+
+int EmgmmEngine::iterate(int64_t niter, double minProba, double* sumLL_last, double* sumLL_trace) {
+  if (niter <= 0) return 0;
+  CKE(cudaSetDevice(device_), "cudaSetDevice");
+  if (int r = ensure_moments()) return r;
+  const Geom& g = geom_;
+  if (trace_cap_ < niter) {
+    if (dSumLL_) cudaFree(dSumLL_);
+    trace_cap_ = std::max<int64_t>(niter, 64);
+    CKE(cudaMalloc((void**)&dSumLL_, trace_cap_ * sizeof(double)), "cudaMalloc trace");
+  }
+  const double minW = 1e-3 / (double)(float)nglob_;  // 1d-3/real(NX)  (src/unsupervised/mlf_gaussian.f90:50)
+  for (int64_t it = 0; it < niter; ++it) {
+    if (profile_) cudaEventRecord(ev_[0], st_);
+    CKE(launch_refresh(g, dMu_, dCov_, dLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_),
+        "refresh");
+    CKE(launch_sum_k(dSumLLk_, g.K, dSumLL_ + it, st_), "sum_k");
+    launches_ += 2;
+    if (profile_) cudaEventRecord(ev_[1], st_);
+    if (int r = run_estep(dX_, n_, dGamma_, ldg_, nullptr, true)) return r;
+    if (int r = allreduce(dStatsA_, (int64_t)g.K8 * 8 * g.DS)) return r;
+    if (profile_) cudaEventRecord(ev_[2], st_);
+    CKE(launch_mid(g, dStatsA_, minW, dMu_, dMupad_, dThr_, st_), "mid");
+    ++launches_;
+    if (profile_) cudaEventRecord(ev_[3], st_);
+    CKE(launch_mstep(g, dX_, n_, dGamma_, ldg_, dMupad_, dThr_, dPartB_, mgx_, st_), "mstep");
+    CKE(launch_reduce_partials(dPartB_, mgx_, (int64_t)g.K * g.MS, dStatsB_, st_), "reduce statsB");
+    launches_ += 2;
+    if (int r = allreduce(dStatsB_, (int64_t)g.K * g.MS)) return r;
+    if (profile_) cudaEventRecord(ev_[4], st_);
+    CKE(launch_finalize(g, dStatsA_, dStatsB_, minProba, dCov_, dLambda_, st_), "finalize");
+    ++launches_;
+    if (profile_) {
+      cudaEventRecord(ev_[5], st_);
+      CKE(cudaEventSynchronize(ev_[5]), "event sync");
+      float ms;
+      cudaEventElapsedTime(&ms, ev_[0], ev_[1]); times_.refresh += ms;
+      cudaEventElapsedTime(&ms, ev_[1], ev_[2]); times_.estep += ms;
+      cudaEventElapsedTime(&ms, ev_[2], ev_[3]); times_.mid += ms;
+      cudaEventElapsedTime(&ms, ev_[3], ev_[4]); times_.mstep += ms;
+      cudaEventElapsedTime(&ms, ev_[4], ev_[5]); times_.fin += ms;
+      times_.iters += 1;
+    }
+  }
+  std::vector<double> tr((size_t)niter);
+  CKE(cudaMemcpyAsync(tr.data(), dSumLL_, niter * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H sumLL");
+  CKE(cudaStreamSynchronize(st_), "sync");
+  if (sumLL_last) *sumLL_last = tr[(size_t)niter - 1];
+  if (sumLL_trace) std::memcpy(sumLL_trace, tr.data(), niter * sizeof(double));
+  return 0;
+}
+
+int EmgmmEngine::expectation(const double* Xq, bool on_device, int64_t nq, double* P_host, int32_t* labels_host) {
+  CKE(cudaSetDevice(device_), "cudaSetDevice");
+  if (nq <= 0) return 0;
+  if (int r = ensure_moments()) return r;
+  const Geom& g = geom_;
+  const int d = g.d, K = g.K;
+  CKE(launch_refresh(g, dMu_, dCov_, dLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_),
+      "refresh");
+  ++launches_;
+  const int64_t chunk = std::min<int64_t>(nq, (int64_t)1 << 20);
+  const int64_t ldq = ((chunk + 31) / 32) * 32;
+  double *dxq = nullptr, *dpq = nullptr;
+  int32_t* dlq = nullptr;
+  if (!on_device) CKE(cudaMalloc((void**)&dxq, (size_t)chunk * d * sizeof(double)), "cudaMalloc Xq");
+  CKE(cudaMalloc((void**)&dpq, (size_t)K * ldq * sizeof(double)), "cudaMalloc Pq");
+  if (labels_host) CKE(cudaMalloc((void**)&dlq, (size_t)chunk * sizeof(int32_t)), "cudaMalloc labels");
+  int rc = 0;
+  for (int64_t s = 0; s < nq && rc == 0; s += chunk) {
+    const int64_t n = std::min(chunk, nq - s);
+    const double* xs = Xq + (size_t)s * d;
+    if (!on_device) {
+      cudaError_t e = cudaMemcpyAsync(dxq, xs, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice, st_);
+      if (e != cudaSuccess) { rc = fail("H2D Xq", e); break; }
+      xs = dxq;
+    }
+    rc = run_estep(xs, n, dpq, ldq, dlq, false);
+    if (rc) break;
+    if (P_host) {
+      cudaError_t e = cudaMemcpy2DAsync(P_host + s, (size_t)nq * sizeof(double), dpq, (size_t)ldq * sizeof(double),
+                                        (size_t)n * sizeof(double), K, cudaMemcpyDeviceToHost, st_);
+      if (e != cudaSuccess) { rc = fail("D2H P", e); break; }
+    }
+    if (labels_host) {
+      cudaError_t e = cudaMemcpyAsync(labels_host + s, dlq, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st_);
+      if (e != cudaSuccess) { rc = fail("D2H labels", e); break; }
+    }
+    cudaError_t e = cudaStreamSynchronize(st_);
+    if (e != cudaSuccess) { rc = fail("sync", e); break; }
+  }
+  if (dxq) cudaFree(dxq);
+  cudaFree(dpq);
+  if (dlq) cudaFree(dlq);
+  return rc;
+}
+
+int EmgmmEngine::resident_labels(int32_t* labels_host) {
+  CKE(cudaSetDevice(device_), "cudaSetDevice");
+  if (n_ == 0) return 0;
+  if (int r = ensure_moments()) return r;
+  const Geom& g = geom_;
+  if (!dLabels_) CKE(cudaMalloc((void**)&dLabels_, (size_t)n_ * sizeof(int32_t)), "cudaMalloc labels");
+  CKE(launch_refresh(g, dMu_, dCov_, dLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_),
+      "refresh");
+  ++launches_;
+  if (int r = run_estep(dX_, n_, dGamma_, ldg_, dLabels_, false)) return r;
+  CKE(cudaMemcpyAsync(labels_host, dLabels_, (size_t)n_ * sizeof(int32_t), cudaMemcpyDeviceToHost, st_), "D2H labels");
+  CKE(cudaStreamSynchronize(st_), "sync");
+  return 0;
+}
+
+int EmgmmEngine::kmeans_init(int /*nkm*/, uint64_t /*seed*/) {
+  err_ = "k-means initialiser not built yet: inject Mu/Cov/lambda (mlf_updatersc + mlf_b200_emgmm_set_initialized)";
+  return -7;
+}
+
+}  // namespace mlfb200

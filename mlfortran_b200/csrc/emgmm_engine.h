@@ -1,0 +1,100 @@
+// Device engine of the EM-GMM step object: owns the HBM-resident shard of X, the responsibilities and the
+// per-iteration kernel sequence.  Host code (mlf_capi.cu) keeps the reference-visible host mirrors.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "emgmm_kernels.cuh"
+
+namespace mlfb200 {
+
+// In-place sum all-reduce of `count` doubles that live at device pointer `buf`, enqueued on `stream`.
+// Returns 0 on success.  Installed by the multi-GPU host layer (torch.distributed / NCCL); absent => 1 rank.
+typedef int (*allreduce_fn)(void* ctx, double* buf, int64_t count, void* stream);
+
+struct EngineTimes {  // CUDA-event milliseconds accumulated over iterate() calls (profiling counters)
+  double refresh = 0, estep = 0, mid = 0, mstep = 0, fin = 0;
+  int64_t iters = 0;
+};
+
+class EmgmmEngine {
+ public:
+  EmgmmEngine() = default;
+  ~EmgmmEngine();
+  EmgmmEngine(const EmgmmEngine&) = delete;
+  EmgmmEngine& operator=(const EmgmmEngine&) = delete;
+
+  // X: N_local x d, point-major (Fortran X(d,N)).  x_on_device: X is a device pointer that the caller keeps
+  // alive (borrowed, like the reference's `this%X => X`); otherwise it is copied host->device here.
+  int init(const double* X, bool x_on_device, int64_t n_local, int d, int K, int device);
+  void set_allreduce(allreduce_fn fn, void* ctx) { ar_ = fn; ar_ctx_ = ctx; moments_ready_ = false; }
+  void set_stream(cudaStream_t st);
+  int refresh_x(const double* X, bool x_on_device);
+
+  int upload_params(const double* Mu, const double* Cov, const double* lambda);
+  int download_params(double* Mu, double* Cov, double* lambda);
+
+  // niter EM iterations (ExpStep + MaxStep, src/unsupervised/mlf_emgmm.f90:147-149) on resident data.
+  // sumLL_last receives sumLL of the last iteration; sumLL_trace (optional, host, niter entries) all of them.
+  int iterate(int64_t niter, double minProba, double* sumLL_last, double* sumLL_trace);
+
+  // ExpStep on caller data with the current device parameters (getProba / getClass).  Xq host or device.
+  // P (optional) is written component-major P[k*nq + i] to host memory; labels (optional) 1-based.
+  int expectation(const double* Xq, bool on_device, int64_t nq, double* P_host, int32_t* labels_host);
+  // Labels / responsibilities of the resident shard from the most recent E-pass parameters.
+  int resident_labels(int32_t* labels_host);
+  const double* gamma_device() const { return dGamma_; }
+  int64_t gamma_ld() const { return ldg_; }
+
+  // k-means initialiser (src/unsupervised/mlf_emgmm.f90:135-145): seeding + nkm-1 Lloyd steps, Cov=I, lambda=1/K.
+  int kmeans_init(int nkm, uint64_t seed);
+
+  int64_t n_local() const { return n_; }
+  int64_t n_global() const { return nglob_; }
+  int d() const { return geom_.d; }
+  int K() const { return geom_.K; }
+  const Geom& geom() const { return geom_; }
+  cudaStream_t stream() const { return st_; }
+  const std::string& last_error() const { return err_; }
+  EngineTimes& times() { return times_; }
+  void set_profile(bool on) { profile_ = on; }
+  int64_t launches() const { return launches_; }
+
+ private:
+  int fail(const char* what, cudaError_t e);
+  int ensure_moments();
+  int run_estep(const double* X, int64_t n, double* gamma, int64_t ldg, int32_t* labels, bool want_stats);
+  int allreduce(double* buf, int64_t count);
+
+  Geom geom_{};
+  int device_ = 0, sms_ = 148;
+  size_t smem_limit_ = 0;
+  cudaStream_t st_ = nullptr;
+  bool own_stream_ = false;
+  int64_t n_ = 0, nglob_ = 0, ldg_ = 0;
+  const double* dX_ = nullptr;
+  double* dXown_ = nullptr;
+  double* dGamma_ = nullptr;
+  double *dMu_ = nullptr, *dCov_ = nullptr, *dLambda_ = nullptr;
+  double *dMupad_ = nullptr, *dThr_ = nullptr, *dPack_ = nullptr, *dScratch_ = nullptr, *dSumLLk_ = nullptr;
+  double *dSumLL_ = nullptr;   // trace buffer on device
+  int64_t trace_cap_ = 0;
+  double *dStatsA_ = nullptr, *dStatsB_ = nullptr, *dPartA_ = nullptr, *dPartB_ = nullptr;
+  double *dSc_ = nullptr, *dMean_ = nullptr, *dNglob_ = nullptr;
+  int* dInfo_ = nullptr;
+  int32_t* dLabels_ = nullptr;
+  int egrid_ = 0, mgx_ = 0, mgy_ = 0;
+  bool moments_ready_ = false;
+  allreduce_fn ar_ = nullptr;
+  void* ar_ctx_ = nullptr;
+  std::string err_;
+  EngineTimes times_;
+  bool profile_ = false;
+  int64_t launches_ = 0;
+  cudaEvent_t ev_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+}  // namespace mlfb200

@@ -1,0 +1,734 @@
+// Hand-written sm_100a kernels of the EM-GMM hot path (reference: src/unsupervised/mlf_emgmm.f90:174-207,
+// src/unsupervised/mlf_gaussian.f90:41-79, src/mlf_matrix.f90:99-147,229-300).
+//
+// All arithmetic is IEEE fp64.  The two N*K*d^2 contractions run on the fp64 tensor pipe
+// (mma.sync.aligned.m8n8k4.f64 -> SASS DMMA.8x8x4): on B200 DMMA and DFMA share one pipe, DMMA peaks at
+// 37.2 TFLOP/s vs 34.2 for register-resident DFMA and needs 8x fewer issue slots (profiles/fp64_peaks_r01.json).
+//
+//  k_refresh : per component: Jacobi eigendecomposition -> reference pseudo-inverse and (sign-quirked) lnDet
+//              -> Cholesky factor L of invC packed in DMMA B-fragment order; closed-form sum_i maha_ik.
+//  k_estep   : u = L^T (x - mu_k) as [8 points x 4 dims] x [4 dims x 8 coords] DMMA tiles, maha = |u|^2,
+//              log-sum-exp over k, responsibilities, and the pass-A statistics (sum g, sum g^2, sum g x).
+//  k_mstep   : thresholded centred scatter sum g (x-mu)(x-mu)^T as [8 x 4 points] x [4 points x 8] DMMA tiles,
+//              skipping 4-point groups in which no point passes the reference's W >= minW test.
+#include "emgmm_kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+
+namespace mlfb200 {
+
+// ---------------------------------------------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int blk_off(int mb) {  // fragment blocks before k-block mb: sum_{m<mb} (m/2+1)
+  int s = 0;
+  for (int m = 0; m < mb; ++m) s += m / 2 + 1;
+  return s;
+}
+
+Geom make_geom(int d, int K) {
+  Geom g{};
+  g.d = d;
+  g.K = K;
+  g.DM = (d + 3) / 4;
+  g.DN = (g.DM + 1) / 2;
+  g.NB = blk_off(g.DM);
+  g.PS = g.NB * 32 + 4 * g.DM + 4;
+  g.K8 = (K + 7) / 8;
+  g.K4 = 2 * g.K8;
+  const int Kt = ((g.K8 * 8 + 15) / 16) * 16;
+  g.S = Kt + 4;
+  g.DS = 8 * g.DN + 2;
+  g.MB = g.DN * (g.DN + 1) / 2;
+  g.MS = g.MB * 64 + 2;
+  return g;
+}
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// parameter refresh
+// ---------------------------------------------------------------------------------------------------------------
+__device__ double block_sum(double v, double* red) {
+  const int tid = threadIdx.x;
+  red[tid] = v;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (tid < s) red[tid] += red[tid + s];
+    __syncthreads();
+  }
+  const double r = red[0];
+  __syncthreads();
+  return r;
+}
+
+// One block (128 threads) per component.  Matrices are column-major M(a,b) = M[b*d + a] in global scratch.
+// Follows InverseSymMatrix(C, invC, lnDet, .TRUE.)  (src/mlf_matrix.f90:256-298) with a cyclic Jacobi
+// eigensolver in place of dsytrd/dorgtr/dsteqr (only invC and lnDet enter the result, not the eigenvectors).
+__global__ void __launch_bounds__(128) k_refresh(Geom g, const double* __restrict__ Mu, const double* __restrict__ Cov,
+                                                 const double* __restrict__ lambda, const double* __restrict__ Sc,
+                                                 const double* __restrict__ mean, double Nglob, double* __restrict__ scratch,
+                                                 double* __restrict__ pack, double* __restrict__ sumLLk,
+                                                 int* __restrict__ info) {
+  const int k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, d = g.d;
+  const int OFFMU = g.NB * 32, OFFC = OFFMU + 4 * g.DM;
+  double* pk = pack + (size_t)k * g.PS;
+  if (k >= g.K) {  // dummy component: contributes gamma = 0
+    for (int i = tid; i < g.PS; i += nt) pk[i] = 0.0;
+    __syncthreads();
+    if (tid == 0) pk[OFFC] = -INFINITY;
+    return;
+  }
+  double* A = scratch + (size_t)k * 3 * d * d;
+  double* V = A + (size_t)d * d;
+  double* W = V + (size_t)d * d;
+  const double* Ck = Cov + (size_t)k * d * d;
+  __shared__ double s_c[64], s_s[64], s_red[128], s_f[128];
+  __shared__ int s_p[64], s_q[64];
+  __shared__ int s_flag;
+
+  // dsytrd 'U' reads the upper triangle only (src/mlf_matrix.f90:269)
+  for (int i = tid; i < d * d; i += nt) {
+    const int a = i % d, b = i / d;
+    const int lo = a < b ? a : b, hi = a < b ? b : a;
+    A[i] = Ck[(size_t)hi * d + lo];
+    V[i] = (a == b) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+
+  const int ne = d + (d & 1);
+  int sweeps = 0;
+  for (; sweeps < 60 && d > 1; ++sweeps) {
+    double off = 0, dg = 0;
+    for (int i = tid; i < d * d; i += nt) {
+      const int a = i % d, b = i / d;
+      const double v = A[i];
+      if (a < b) off += v * v;
+      else if (a == b) dg += v * v;
+    }
+    off = block_sum(off, s_red);
+    dg = block_sum(dg, s_red);
+    if (!(off > 1e-31 * (dg + off))) break;  // also exits on NaN
+    for (int rnd = 0; rnd < ne - 1; ++rnd) {
+      for (int j = tid; j < ne / 2; j += nt) {  // round-robin tournament pairing
+        int a, b;
+        if (j == 0) { a = rnd; b = ne - 1; }
+        else { a = (rnd + j) % (ne - 1); b = (rnd - j + ne - 1) % (ne - 1); }
+        const int p = a < b ? a : b, q = a < b ? b : a;
+        double c = 1.0, s = 0.0;
+        if (q < d) {
+          const double apq = A[(size_t)q * d + p];
+          if (apq != 0.0) {
+            const double theta = (A[(size_t)q * d + q] - A[(size_t)p * d + p]) / (2.0 * apq);
+            const double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            c = 1.0 / sqrt(tt * tt + 1.0);
+            s = tt * c;
+          }
+        }
+        s_p[j] = p; s_q[j] = q; s_c[j] = c; s_s[j] = s;
+      }
+      __syncthreads();
+      for (int i = tid; i < (ne / 2) * d; i += nt) {  // A <- A J, V <- V J   (columns p,q)
+        const int j = i / d, r = i % d, p = s_p[j], q = s_q[j];
+        if (q >= d) continue;
+        const double c = s_c[j], s = s_s[j];
+        const double arp = A[(size_t)p * d + r], arq = A[(size_t)q * d + r];
+        A[(size_t)p * d + r] = c * arp - s * arq;
+        A[(size_t)q * d + r] = s * arp + c * arq;
+        const double vrp = V[(size_t)p * d + r], vrq = V[(size_t)q * d + r];
+        V[(size_t)p * d + r] = c * vrp - s * vrq;
+        V[(size_t)q * d + r] = s * vrp + c * vrq;
+      }
+      __syncthreads();
+      for (int i = tid; i < (ne / 2) * d; i += nt) {  // A <- J^T A   (rows p,q)
+        const int j = i / d, r = i % d, p = s_p[j], q = s_q[j];
+        if (q >= d) continue;
+        const double c = s_c[j], s = s_s[j];
+        const double apr = A[(size_t)r * d + p], aqr = A[(size_t)r * d + q];
+        A[(size_t)r * d + p] = c * apr - s * aqr;
+        A[(size_t)r * d + q] = s * apr + c * aqr;
+      }
+      __syncthreads();
+    }
+  }
+  if (tid == 0 && info) info[k] = (sweeps >= 60) ? 1 : 0;
+
+  // eigenvalues -> pseudo-inverse spectrum with penalty, lnDet  (src/mlf_matrix.f90:283-290)
+  double mx = -INFINITY;
+  for (int a = tid; a < d; a += nt) mx = fmax(mx, A[(size_t)a * d + a]);
+  s_red[tid] = mx;
+  __syncthreads();
+  for (int s = nt / 2; s > 0; s >>= 1) {
+    if (tid < s) s_red[tid] = fmax(s_red[tid], s_red[tid + s]);
+    __syncthreads();
+  }
+  mx = s_red[0];
+  __syncthreads();
+  const double valM = (double)10e-9f * mx;
+  const double penality = 1.0 / valM;
+  for (int a = tid; a < d; a += nt) {
+    const double ld = A[(size_t)a * d + a];
+    s_f[a] = (ld <= valM) ? penality : 1.0 / ld;
+  }
+  __syncthreads();
+  double lnDet;
+  {
+    double s = 0;
+    for (int a = 0; a < d; ++a) s += log(s_f[a]);  // every thread, same order: deterministic
+    lnDet = 0.5 * (d * log(2.0 * acos(-1.0)) + s);
+  }
+  // invC = (V diag f) V^T  -> W
+  for (int i = tid; i < d * d; i += nt) {
+    const int a = i % d, b = i / d;
+    double acc = 0;
+    for (int e = 0; e < d; ++e) acc += V[(size_t)e * d + a] * s_f[e] * V[(size_t)e * d + b];
+    W[i] = acc;
+  }
+  __syncthreads();
+  // in-place Cholesky W = L L^T (lower), right-looking
+  for (int j = 0; j < d; ++j) {
+    if (tid == 0) W[(size_t)j * d + j] = sqrt(W[(size_t)j * d + j]);
+    __syncthreads();
+    const double ljj = W[(size_t)j * d + j];
+    for (int i = j + 1 + tid; i < d; i += nt) W[(size_t)j * d + i] /= ljj;
+    __syncthreads();
+    const int rem = d - j - 1;
+    for (int i = tid; i < rem * rem; i += nt) {
+      const int a = j + 1 + i % rem, b = j + 1 + i / rem;
+      if (a >= b) W[(size_t)b * d + a] -= W[(size_t)j * d + a] * W[(size_t)j * d + b];
+    }
+    __syncthreads();
+  }
+  // pack: B fragments of u = L^T z, block (mb, nb): lane l holds L[4mb + l%4][8nb + l/4]
+  for (int i = tid; i < g.NB * 32; i += nt) {
+    const int blk = i >> 5, l = i & 31;
+    int mb = 0;
+    while (blk_off(mb + 1) <= blk) ++mb;
+    const int nb = blk - blk_off(mb);
+    const int m = 4 * mb + (l & 3), n = 8 * nb + (l >> 2);
+    pk[i] = (m < d && n < d && m >= n) ? W[(size_t)n * d + m] : 0.0;
+  }
+  const double* muk = Mu + (size_t)k * d;
+  for (int a = tid; a < 4 * g.DM + 4; a += nt) pk[OFFMU + a] = (a < d) ? muk[a] : 0.0;
+  __syncthreads();
+  const double ck = log(lambda[k]) - lnDet;
+  if (tid == 0) pk[OFFC] = ck;
+
+  // closed form of sum_i (x_i-mu)^T invC (x_i-mu) = tr(L^T Sc L) + N |L^T (m - mu)|^2   (Sc = centred scatter)
+  double part = 0;
+  for (int n = tid; n < d; n += nt) {
+    double y = 0, q = 0;
+    for (int a = n; a < d; ++a) {
+      const double lan = W[(size_t)n * d + a];
+      y += lan * (mean[a] - muk[a]);
+      double tsum = 0;
+      for (int b = n; b < d; ++b) tsum += Sc[(size_t)b * d + a] * W[(size_t)n * d + b];
+      q += lan * tsum;
+    }
+    part += q + Nglob * y * y;
+  }
+  part = block_sum(part, s_red);
+  // sumLL_k = N (log lambda_k - lnDet_k) + sum_i (-1/2 maha_ik)   (src/unsupervised/mlf_gaussian.f90:73-76)
+  if (tid == 0) sumLLk[k] = Nglob * ck - 0.5 * part;
+}
+
+cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, const double* lambda, const double* Sc,
+                           const double* mean, double Nglob, double* scratch, double* pack, double* sumLLk, int* info,
+                           cudaStream_t st) {
+  k_refresh<<<g.K8 * 8, 128, 0, st>>>(g, Mu, Cov, lambda, Sc, mean, Nglob, scratch, pack, sumLLk, info);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// E-pass
+// ---------------------------------------------------------------------------------------------------------------
+template <int DM, int CBMAX>
+__global__ void __launch_bounds__(kEstepThreads, 1)
+k_estep(const double* __restrict__ X, int64_t N, int d, int K, int K8, int S, const double* __restrict__ pack,
+        double* __restrict__ gamma, int64_t ldg, int32_t* __restrict__ labels, double* __restrict__ partial) {
+  constexpr int DN = (DM + 1) / 2;
+  constexpr int NB = blk_off(DM);
+  constexpr int PS = NB * 32 + 4 * DM + 4;
+  constexpr int OFFMU = NB * 32, OFFC = OFFMU + 4 * DM;
+  constexpr int DS = 8 * DN + 2;
+  extern __shared__ __align__(16) double smem[];
+  const int KP = K8 * 8, K4 = 2 * K8;
+  double* sp = smem;                       // [KP][PS] parameter pack
+  double* tile = smem + (size_t)KP * PS;   // [128][S] logits -> exp -> responsibilities
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+
+  for (int i = tid; i < KP * PS; i += kEstepThreads) sp[i] = pack[i];
+  __syncthreads();
+
+  double acc[CBMAX][DN][2];
+  double sg[CBMAX], sg2[CBMAX];
+#pragma unroll
+  for (int c = 0; c < CBMAX; ++c) {
+    sg[c] = 0; sg2[c] = 0;
+#pragma unroll
+    for (int b = 0; b < DN; ++b) { acc[c][b][0] = 0; acc[c][b][1] = 0; }
+  }
+
+  const int64_t ntiles = (N + kEstepTilePts - 1) / kEstepTilePts;
+  for (int64_t bt = blockIdx.x; bt < ntiles; bt += gridDim.x) {
+    const int64_t p0 = bt * kEstepTilePts + warp * 16;
+    // ---- phase 1: logits of 16 points x all components -------------------------------------------------------
+    double xf[2][DM];
+#pragma unroll
+    for (int grp = 0; grp < 2; ++grp) {
+      const int64_t p = p0 + 8 * grp + g;
+#pragma unroll
+      for (int mb = 0; mb < DM; ++mb) {
+        const int a = 4 * mb + t;
+        xf[grp][mb] = (p < N && a < d) ? X[p * d + a] : 0.0;
+      }
+    }
+    double* row[2] = {tile + (size_t)(warp * 16 + g) * S, tile + (size_t)(warp * 16 + 8 + g) * S};
+    double rmax[2] = {-INFINITY, -INFINITY};
+    int rarg[2] = {0, 0};
+    for (int k4 = 0; k4 < K4; ++k4) {
+      double part[2][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double* pk = sp + (size_t)(4 * k4 + j) * PS;
+        double Lf[NB], mu[DM];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) Lf[b] = pk[b * 32 + lane];
+#pragma unroll
+        for (int mb = 0; mb < DM; ++mb) mu[mb] = pk[OFFMU + 4 * mb + t];
+#pragma unroll
+        for (int grp = 0; grp < 2; ++grp) {
+          double c[DN][2];
+#pragma unroll
+          for (int nb = 0; nb < DN; ++nb) { c[nb][0] = 0; c[nb][1] = 0; }
+#pragma unroll
+          for (int mb = 0; mb < DM; ++mb) {
+            const double z = xf[grp][mb] - mu[mb];
+#pragma unroll
+            for (int nb = 0; nb <= mb / 2; ++nb) dmma884(c[nb], z, Lf[blk_off(mb) + nb]);
+          }
+          double s = c[0][0] * c[0][0];
+          s = fma(c[0][1], c[0][1], s);
+#pragma unroll
+          for (int nb = 1; nb < DN; ++nb) { s = fma(c[nb][0], c[nb][0], s); s = fma(c[nb][1], c[nb][1], s); }
+          part[grp][j] = s;
+        }
+      }
+      const double ck = sp[(size_t)(4 * k4 + t) * PS + OFFC];
+#pragma unroll
+      for (int grp = 0; grp < 2; ++grp) {
+        // transposed reduction over the 4 lanes of a row: lane t ends with the full |u|^2 of component 4*k4+t
+        const bool hi2 = (t & 2) != 0, hi1 = (t & 1) != 0;
+        const double send0 = hi2 ? part[grp][0] : part[grp][2];
+        const double send1 = hi2 ? part[grp][1] : part[grp][3];
+        const double keep0 = hi2 ? part[grp][2] : part[grp][0];
+        const double keep1 = hi2 ? part[grp][3] : part[grp][1];
+        const double a0 = keep0 + shfl_xor_d(send0, 2);
+        const double a1 = keep1 + shfl_xor_d(send1, 2);
+        const double maha = (hi1 ? a1 : a0) + shfl_xor_d(hi1 ? a0 : a1, 1);
+        const double logit = fma(-0.5, maha, ck);  // log lambda_k - lnDet_k - maha/2
+        row[grp][4 * k4 + t] = logit;
+        if (logit > rmax[grp]) { rmax[grp] = logit; rarg[grp] = 4 * k4 + t; }
+      }
+    }
+    // ---- phase 2: log-sum-exp over k, responsibilities ---------------------------------------------------------
+#pragma unroll
+    for (int grp = 0; grp < 2; ++grp) {
+      const int64_t p = p0 + 8 * grp + g;
+      const bool valid = p < N;
+      double m = rmax[grp];
+      int am = rarg[grp];
+#pragma unroll
+      for (int sh = 1; sh <= 2; sh <<= 1) {
+        const double om = shfl_xor_d(m, sh);
+        const int oa = __shfl_xor_sync(0xffffffffu, am, sh);
+        if (om > m || (om == m && oa < am)) { m = om; am = oa; }
+      }
+      double sum = 0;
+      for (int k4 = 0; k4 < K4; ++k4) {
+        const double e = exp(row[grp][4 * k4 + t] - m);
+        row[grp][4 * k4 + t] = e;
+        sum += e;
+      }
+      sum += shfl_xor_d(sum, 1);
+      sum += shfl_xor_d(sum, 2);
+      const double inv = valid ? 1.0 / sum : 0.0;
+      for (int k4 = 0; k4 < K4; ++k4) {
+        const int k = 4 * k4 + t;
+        const double gk = row[grp][k] * inv;
+        row[grp][k] = gk;
+        if (valid && k < K) gamma[(size_t)k * ldg + p] = gk;
+      }
+      if (labels != nullptr && valid && t == 0) labels[p] = am + 1;  // MAXLOC: first maximum, 1-based
+    }
+    __syncthreads();
+    // ---- phase 3: pass-A statistics of this block tile; warp w owns component blocks w, w+8, ... ---------------
+#pragma unroll
+    for (int ci = 0; ci < CBMAX; ++ci) {
+      const int cb = warp + 8 * ci;
+      if (cb < K8) {
+        const int64_t q0 = bt * kEstepTilePts;
+#pragma unroll 4
+        for (int pb = 0; pb < kEstepTilePts / 4; ++pb) {
+          const double a = tile[(size_t)(4 * pb + t) * S + 8 * cb + g];
+          sg[ci] += a;
+          sg2[ci] = fma(a, a, sg2[ci]);
+          const int64_t p = q0 + 4 * pb + t;
+#pragma unroll
+          for (int db = 0; db < DN; ++db) {
+            const int dim = 8 * db + g;
+            const double b = (p < N && dim < d) ? X[p * d + dim] : 0.0;
+            dmma884(acc[ci][db], a, b);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- per-block partial statistics [KP][DS]: [sum g, sum g^2, sum g x] ------------------------------------------
+  double* out = partial + (size_t)blockIdx.x * KP * DS;
+#pragma unroll
+  for (int ci = 0; ci < CBMAX; ++ci) {
+    const int cb = warp + 8 * ci;
+    if (cb < K8) {
+      double a = sg[ci], b = sg2[ci];
+      a += shfl_xor_d(a, 1); a += shfl_xor_d(a, 2);
+      b += shfl_xor_d(b, 1); b += shfl_xor_d(b, 2);
+      double* o = out + (size_t)(8 * cb + g) * DS;
+      if (t == 0) { o[0] = a; o[1] = b; }
+#pragma unroll
+      for (int db = 0; db < DN; ++db) {
+        o[2 + 8 * db + 2 * t] = acc[ci][db][0];
+        o[2 + 8 * db + 2 * t + 1] = acc[ci][db][1];
+      }
+    }
+  }
+}
+
+size_t estep_smem_bytes(const Geom& g) {
+  return ((size_t)g.K8 * 8 * g.PS + (size_t)kEstepTilePts * g.S) * sizeof(double);
+}
+int estep_cbmax(const Geom& g) { return g.K8 <= 8 ? 1 : (g.K8 <= 16 ? 2 : (g.K8 <= 32 ? 4 : 8)); }
+
+template <int DM, int CBMAX>
+static cudaError_t launch_estep_t(const Geom& g, const double* X, int64_t N, const double* pack, double* gamma, int64_t ldg,
+                                  int32_t* labels, double* partial, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(k_estep<DM, CBMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_estep<DM, CBMAX><<<grid, kEstepThreads, smem, st>>>(X, N, g.d, g.K, g.K8, g.S, pack, gamma, ldg, labels, partial);
+  return cudaGetLastError();
+}
+
+template <int DM>
+static cudaError_t launch_estep_dm(const Geom& g, const double* X, int64_t N, const double* pack, double* gamma, int64_t ldg,
+                                   int32_t* labels, double* partial, int grid, size_t smem, cudaStream_t st) {
+  switch (estep_cbmax(g)) {
+    case 1: return launch_estep_t<DM, 1>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
+    case 2: return launch_estep_t<DM, 2>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
+    case 4: return launch_estep_t<DM, 4>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
+    default: return launch_estep_t<DM, 8>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
+  }
+}
+
+cudaError_t launch_estep(const Geom& g, const double* X, int64_t N, const double* pack, double* gamma, int64_t ldg,
+                         int32_t* labels, double* partial, int grid, size_t smem_limit, cudaStream_t st) {
+  const size_t smem = estep_smem_bytes(g);
+  if (smem > smem_limit || g.K8 > 64) return cudaErrorInvalidConfiguration;
+  switch (g.DM) {
+    case 1: return launch_estep_dm<1>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
+    case 2: return launch_estep_dm<2>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
+    case 3: return launch_estep_dm<3>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
+    case 4: return launch_estep_dm<4>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
+    case 5: return launch_estep_dm<5>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
+    case 6: return launch_estep_dm<6>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
+    case 7: return launch_estep_dm<7>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
+    case 8: return launch_estep_dm<8>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
+    default: return cudaErrorInvalidConfiguration;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// reductions / small per-component kernels
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_reduce_partials(const double* __restrict__ partial, int nblocks, int64_t n, double* __restrict__ out) {
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double s = 0;
+  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * n + j];  // fixed order: run-to-run deterministic
+  out[j] = s;
+}
+cudaError_t launch_reduce_partials(const double* partial, int nblocks, int64_t n, double* out, cudaStream_t st) {
+  k_reduce_partials<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(partial, nblocks, n, out);
+  return cudaGetLastError();
+}
+
+// mlf_MaxGaussian / GECovMatrix prologue: W = P/s, Mu = A.W, minW  (src/unsupervised/mlf_gaussian.f90:47-50,
+// src/mlf_matrix.f90:132).  "W(i) < minW -> CYCLE" becomes gamma < minW*s.
+__global__ void k_mid(Geom g, const double* __restrict__ statsA, double minW, double* __restrict__ Mu,
+                      double* __restrict__ mupad, double* __restrict__ thr) {
+  const int k = blockIdx.x;
+  const double* sa = statsA + (size_t)k * g.DS;
+  const double s = sa[0];
+  for (int a = threadIdx.x; a < 8 * g.DN; a += blockDim.x) {
+    const double m = (a < g.d) ? sa[2 + a] / s : 0.0;
+    mupad[(size_t)k * 8 * g.DN + a] = m;
+    if (a < g.d) Mu[(size_t)k * g.d + a] = m;
+  }
+  if (threadIdx.x == 0) thr[k] = minW * s;
+}
+cudaError_t launch_mid(const Geom& g, const double* statsA, double minW, double* Mu, double* mupad, double* thr,
+                       cudaStream_t st) {
+  k_mid<<<g.K, 32, 0, st>>>(g, statsA, minW, Mu, mupad, thr);
+  return cudaGetLastError();
+}
+
+// GECovMatrix epilogue + MaxStep tail (src/mlf_matrix.f90:119,137,145-146; src/unsupervised/mlf_emgmm.f90:184-187).
+__global__ void k_finalize(Geom g, const double* __restrict__ statsA, const double* __restrict__ statsB, double minProba,
+                           double* __restrict__ Cov, double* __restrict__ lambda) {
+  const int d = g.d;
+  for (int k = blockIdx.x; k < g.K; k += gridDim.x) {
+    const double s = statsA[(size_t)k * g.DS];
+    const double* sb = statsB + (size_t)k * g.MS;
+    const double sw2 = sb[g.MB * 64] / (s * s);
+    const double ms = 1.0 / (1.0 - sw2);
+    const double scale = ms * ms / s;
+    double* Ck = Cov + (size_t)k * d * d;
+    for (int i = threadIdx.x; i < d * d; i += blockDim.x) {
+      const int a = i % d, b = i / d;
+      if (a < b) continue;  // lower triangle a >= b, mirrored (SymmetrizeMatrix, src/mlf_matrix.f90:56-63)
+      const int ab = a >> 3, bb = b >> 3;
+      const double v = scale * sb[(ab * (ab + 1) / 2 + bb) * 64 + (a & 7) * 8 + (b & 7)];
+      Ck[(size_t)b * d + a] = v;
+      Ck[(size_t)a * d + b] = v;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double mx = -INFINITY;
+    for (int k = 0; k < g.K; ++k) mx = fmax(mx, statsA[(size_t)k * g.DS]);
+    double sum = 0;
+    for (int k = 0; k < g.K; ++k) {
+      double l = statsA[(size_t)k * g.DS];
+      if (minProba > 0 && !(l >= minProba * mx)) l = minProba * mx;
+      lambda[k] = l;
+      sum += l;
+    }
+    for (int k = 0; k < g.K; ++k) lambda[k] /= sum;
+  }
+}
+cudaError_t launch_finalize(const Geom& g, const double* statsA, const double* statsB, double minProba, double* Cov,
+                            double* lambda, cudaStream_t st) {
+  k_finalize<<<g.K < 148 ? g.K : 148, 128, 0, st>>>(g, statsA, statsB, minProba, Cov, lambda);
+  return cudaGetLastError();
+}
+
+__global__ void k_sum_k(const double* __restrict__ v, int K, double* __restrict__ out) {
+  double s = 0;
+  for (int k = 0; k < K; ++k) s += v[k];
+  *out = s;
+}
+cudaError_t launch_sum_k(const double* v, int K, double* out, cudaStream_t st) {
+  k_sum_k<<<1, 1, 0, st>>>(v, K, out);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) k_colsum(const double* __restrict__ X, int64_t N, int d, double* __restrict__ partial) {
+  __shared__ double red[256];
+  const int tid = threadIdx.x;
+  const int lanes = 256 / d;  // point lanes per block (d <= 128)
+  const int a = tid % d, pl = tid / d;
+  double s = 0;
+  if (pl < lanes)
+    for (int64_t p = (int64_t)blockIdx.x * lanes + pl; p < N; p += (int64_t)gridDim.x * lanes) s += X[p * d + a];
+  red[tid] = (pl < lanes) ? s : 0.0;
+  __syncthreads();
+  if (tid < d) {
+    double r = 0;
+    for (int j = 0; j < lanes; ++j) r += red[j * d + tid];
+    partial[(size_t)blockIdx.x * d + tid] = r;
+  }
+}
+cudaError_t launch_colsum(const double* X, int64_t N, int d, double* partial, int grid, cudaStream_t st) {
+  k_colsum<<<grid, 256, 0, st>>>(X, N, d, partial);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// M-pass
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMstepWarps = 16;
+constexpr int kMstepBatch = 8;  // gamma strips in flight per warp
+
+template <int DN, int CPW>
+__global__ void __launch_bounds__(kMstepWarps * 32, 1)
+k_mstep(const double* __restrict__ X, int64_t N, int d, int K, const double* __restrict__ gamma, int64_t ldg,
+        const double* __restrict__ mupad, const double* __restrict__ thr, double* __restrict__ partial, int MS) {
+  constexpr int MB = DN * (DN + 1) / 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int cbase = (blockIdx.y * kMstepWarps + warp) * CPW;
+  double acc[CPW][MB][2];
+  double sg2[CPW], muf[CPW][DN], th[CPW];
+#pragma unroll
+  for (int c = 0; c < CPW; ++c) {
+    const int k = cbase + c;
+    sg2[c] = 0;
+    th[c] = (k < K) ? thr[k] : INFINITY;
+#pragma unroll
+    for (int b = 0; b < MB; ++b) { acc[c][b][0] = 0; acc[c][b][1] = 0; }
+#pragma unroll
+    for (int ab = 0; ab < DN; ++ab) muf[c][ab] = (k < K) ? mupad[(size_t)k * 8 * DN + 8 * ab + g] : 0.0;
+  }
+  const int64_t ntiles = (N + kMstepTilePts - 1) / kMstepTilePts;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t ibeg = tile * kMstepTilePts;
+    const int64_t iend = (ibeg + kMstepTilePts < N) ? ibeg + kMstepTilePts : N;
+#pragma unroll
+    for (int c = 0; c < CPW; ++c) {
+      const int k = cbase + c;
+      if (k >= K) continue;
+      const double* gk = gamma ? gamma + (size_t)k * ldg : nullptr;
+      for (int64_t i0 = ibeg; i0 < iend; i0 += 32 * kMstepBatch) {
+        double gv[kMstepBatch];
+#pragma unroll
+        for (int u = 0; u < kMstepBatch; ++u) {
+          const int64_t p = i0 + 32 * u + lane;
+          gv[u] = (p < iend) ? (gk ? gk[p] : 1.0) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kMstepBatch; ++u) {
+          const double gval = gv[u];
+          sg2[c] = fma(gval, gval, sg2[c]);  // SUM(W*W) runs over all points (src/mlf_matrix.f90:119)
+          const bool kept = !(gval < th[c]) && (i0 + 32 * u + lane < iend);  // "if(W(i)<minW0) CYCLE" (:135)
+          const unsigned mask = __ballot_sync(0xffffffffu, kept);
+          if (mask == 0) continue;
+          unsigned gm = mask | (mask >> 1);
+          gm |= gm >> 2;
+          gm &= 0x11111111u;  // bit 4q set <=> some point of 4-group q is kept
+          while (gm) {
+            const int q = (__ffs(gm) - 1) >> 2;
+            gm &= gm - 1;
+            const double wq = __shfl_sync(0xffffffffu, gval, 4 * q + t);
+            const double w = ((mask >> (4 * q + t)) & 1u) ? wq : 0.0;
+            const int64_t pp = i0 + 32 * u + 4 * q + t;
+            double z[DN], wz[DN];
+#pragma unroll
+            for (int ab = 0; ab < DN; ++ab) {
+              const int dim = 8 * ab + g;
+              const double xa = (pp < N && dim < d) ? X[pp * d + dim] : 0.0;
+              z[ab] = (dim < d) ? xa - muf[c][ab] : 0.0;
+              wz[ab] = w * z[ab];
+            }
+#pragma unroll
+            for (int ab = 0; ab < DN; ++ab)
+#pragma unroll
+              for (int bb = 0; bb <= ab; ++bb) dmma884(acc[c][ab * (ab + 1) / 2 + bb], wz[ab], z[bb]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CPW; ++c) {
+    const int k = cbase + c;
+    if (k >= K) continue;
+    double* o = partial + ((size_t)blockIdx.x * K + k) * MS;
+#pragma unroll
+    for (int b = 0; b < MB; ++b) {
+      o[b * 64 + g * 8 + 2 * t] = acc[c][b][0];
+      o[b * 64 + g * 8 + 2 * t + 1] = acc[c][b][1];
+    }
+    double s = sg2[c];
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) s += shfl_xor_d(s, sh);
+    if (lane == 0) { o[MB * 64] = s; o[MB * 64 + 1] = 0.0; }
+  }
+}
+
+int mstep_cpw(const Geom& g) {
+  const int cmax = g.DN == 1 ? 4 : (g.DN == 2 ? 4 : (g.DN == 3 ? 2 : 1));
+  int c = (g.K + kMstepWarps - 1) / kMstepWarps;
+  if (c > cmax) c = cmax;
+  if (c == 3) c = (cmax >= 4) ? 4 : 2;
+  return c < 1 ? 1 : c;
+}
+void mstep_grid(const Geom& g, int sms, int64_t N, int* gx, int* gy) {
+  const int cpw = mstep_cpw(g);
+  *gy = (g.K + kMstepWarps * cpw - 1) / (kMstepWarps * cpw);
+  const int64_t ntiles = (N + kMstepTilePts - 1) / kMstepTilePts;
+  int64_t x = ntiles < sms ? ntiles : sms;
+  *gx = (int)(x < 1 ? 1 : x);
+}
+
+template <int DN, int CPW>
+static cudaError_t launch_mstep_t(const Geom& g, const double* X, int64_t N, const double* gamma, int64_t ldg,
+                                  const double* mupad, const double* thr, double* partial, dim3 grid, cudaStream_t st) {
+  k_mstep<DN, CPW><<<grid, kMstepWarps * 32, 0, st>>>(X, N, g.d, g.K, gamma, ldg, mupad, thr, partial, g.MS);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mstep(const Geom& g, const double* X, int64_t N, const double* gamma, int64_t ldg, const double* mupad,
+                         const double* thr, double* partial, int gridx, cudaStream_t st) {
+  const int cpw = mstep_cpw(g);
+  const int gy = (g.K + kMstepWarps * cpw - 1) / (kMstepWarps * cpw);
+  const dim3 grid(gridx, gy);
+#define MLF_M(DNv, CPWv) \
+  if (g.DN == DNv && cpw == CPWv) return launch_mstep_t<DNv, CPWv>(g, X, N, gamma, ldg, mupad, thr, partial, grid, st);
+  MLF_M(1, 1) MLF_M(1, 2) MLF_M(1, 4)
+  MLF_M(2, 1) MLF_M(2, 2) MLF_M(2, 4)
+  MLF_M(3, 1) MLF_M(3, 2)
+  MLF_M(4, 1)
+#undef MLF_M
+  return cudaErrorInvalidConfiguration;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k-means Lloyd step (initialiser; src/unsupervised/mlf_kmeans.f90:151-165, mlf_kmeans_naive.f90:74-96)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_kmeans_assign(const double* __restrict__ X, int64_t N, int d, int K,
+                                                       const double* __restrict__ Mu, int32_t* __restrict__ cl,
+                                                       double* __restrict__ minDist, double* __restrict__ partial) {
+  extern __shared__ double sm[];
+  double* smu = sm;                     // [K][d]
+  double* ssum = sm + (size_t)K * d;    // [K][d+1]
+  for (int i = threadIdx.x; i < K * d; i += blockDim.x) smu[i] = Mu[i];
+  for (int i = threadIdx.x; i < K * (d + 1); i += blockDim.x) ssum[i] = 0.0;
+  __syncthreads();
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x) {
+    const double* x = X + p * d;
+    int best = 0;
+    double bd = INFINITY;
+    for (int k = 0; k < K; ++k) {
+      double s = 0;
+      for (int a = 0; a < d; ++a) { const double tdiff = x[a] - smu[(size_t)k * d + a]; s = fma(tdiff, tdiff, s); }
+      const double dist = sqrt(s);  // norm2
+      if (dist < bd) { bd = dist; best = k; }  // MINLOC: first minimum
+    }
+    if (cl) cl[p] = best + 1;
+    if (minDist) minDist[p] = bd;
+    if (partial) {
+      for (int a = 0; a < d; ++a) atomicAdd(&ssum[(size_t)best * (d + 1) + a], x[a]);
+      atomicAdd(&ssum[(size_t)best * (d + 1) + d], 1.0);
+    }
+  }
+  __syncthreads();
+  if (partial)
+    for (int i = threadIdx.x; i < K * (d + 1); i += blockDim.x) partial[(size_t)blockIdx.x * K * (d + 1) + i] = ssum[i];
+}
+cudaError_t launch_kmeans_assign(const double* X, int64_t N, int d, int K, const double* Mu, int32_t* cl, double* minDist,
+                                 double* partial, int grid, cudaStream_t st) {
+  const size_t smem = ((size_t)K * d + (size_t)K * (d + 1)) * sizeof(double);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_kmeans_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  k_kmeans_assign<<<grid, 256, smem, st>>>(X, N, d, K, Mu, cl, minDist, partial);
+  return cudaGetLastError();
+}
+
+}  // namespace mlfb200

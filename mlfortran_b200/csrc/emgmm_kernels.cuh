@@ -1,0 +1,74 @@
+// Device-side interface of the EM-GMM hot path (sm_100a).  See DESIGN.md for the data layout.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mlfb200 {
+
+// Geometry shared by host and device code.
+struct Geom {
+  int d;        // point dimension
+  int K;        // mixture components
+  int DM;       // ceil(d/4): k-blocks of the whitening GEMM
+  int DN;       // ceil(d/8): n-blocks
+  int NB;       // active (mb,nb) fragment blocks of the lower-triangular factor: sum_mb (mb/2+1)
+  int PS;       // doubles per component in the E-pass parameter pack (multiple of 4)
+  int K4;       // ceil(K/4)   (quads of components, dummy components have c=-inf)
+  int K8;       // ceil(K/8)
+  int S;        // row stride (doubles) of the per-block logit/responsibility tile, == 4 (mod 16)
+  int DS;       // doubles per component of the pass-A statistics: [sum g, sum g^2, sum g*x (8*DN)]
+  int MB;       // lower-triangular 8x8 blocks of the scatter matrix: DN*(DN+1)/2
+  int MS;       // doubles per component of the pass-B statistics: [MB*64 scatter blocks, sum g^2] padded
+};
+
+Geom make_geom(int d, int K);
+
+constexpr int kEstepThreads = 256;      // 8 warps per persistent block
+constexpr int kEstepTilePts = 128;      // 16 points per warp
+constexpr int kMstepThreads = 256;
+constexpr int kMstepTilePts = 2048;     // points per block tile of the M-pass sweep
+
+// Parameter refresh (reference InverseSymMatrix eigen branch + E-pass packing + closed-form sum of maha).
+//   scratch: K * 3*d*d doubles.  Sc (d*d, column-major) / mean (d) / Nglob describe the whole data set.
+cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, const double* lambda, const double* Sc,
+                           const double* mean, double Nglob, double* scratch, double* pack, double* sumLLk, int* info,
+                           cudaStream_t st);
+
+// E-pass: responsibilities (component-major gamma[k*ldg + i]), optional 1-based labels, and per-block
+// partial pass-A statistics partial[block][K8*8][DS].  Returns the grid size used through *grid_out.
+cudaError_t launch_estep(const Geom& g, const double* X, int64_t N, const double* pack, double* gamma, int64_t ldg,
+                         int32_t* labels, double* partial, int grid, size_t smem_limit, cudaStream_t st);
+size_t estep_smem_bytes(const Geom& g);
+int estep_cbmax(const Geom& g);
+
+// Fixed-order reduction over blocks: out[j] = sum_b partial[b*n + j].
+cudaError_t launch_reduce_partials(const double* partial, int nblocks, int64_t n, double* out, cudaStream_t st);
+
+// After pass A (and its all-reduce): s_k, mu_k = (sum g x)/s_k, thr_k = minW*s_k; writes Mu (K*d) and
+// mupad (K*8*DN, zero padded), thr (K).
+cudaError_t launch_mid(const Geom& g, const double* statsA, double minW, double* Mu, double* mupad, double* thr,
+                       cudaStream_t st);
+
+// M-pass: thresholded centred scatter sum_{g>=thr} g (x-mu)(x-mu)^T per component via DMMA, plus sum g^2.
+// partial[block][K][MS].  gamma may be nullptr (weight 1 for every point; used for the global moments).
+cudaError_t launch_mstep(const Geom& g, const double* X, int64_t N, const double* gamma, int64_t ldg, const double* mupad,
+                         const double* thr, double* partial, int grid, cudaStream_t st);
+int mstep_cpw(const Geom& g);
+void mstep_grid(const Geom& g, int sms, int64_t N, int* gx, int* gy);
+
+// After pass B (and its all-reduce): Cov_k = ms^2/s_k * S_k (lower triangle mirrored), lambda floor + normalise.
+cudaError_t launch_finalize(const Geom& g, const double* statsA, const double* statsB, double minProba, double* Cov,
+                            double* lambda, cudaStream_t st);
+
+// sum over points of x (per block partials [grid][d]) for the one-time global mean.
+cudaError_t launch_colsum(const double* X, int64_t N, int d, double* partial, int grid, cudaStream_t st);
+
+// sumLL = sum_k sumLLk[k] in k order (single thread; deterministic).
+cudaError_t launch_sum_k(const double* v, int K, double* out, cudaStream_t st);
+
+// k-means (initialiser): assignment + per-block centre sums.  Lloyd step of the reference
+// (src/unsupervised/mlf_kmeans.f90:151-165, mlf_kmeans_naive.f90:74-96).
+cudaError_t launch_kmeans_assign(const double* X, int64_t N, int d, int K, const double* Mu, int32_t* cl, double* minDist,
+                                 double* partial /*[grid][K][d+1]*/, int grid, cudaStream_t st);
+
+}  // namespace mlfb200

@@ -1,0 +1,491 @@
+// C-ABI of the drop-in (include/mlf_b200.h).  Host-side mirror of the reference's step-object runtime for the EM
+// path: resource slots (src/mlf_rsc_array.f90), step wrapper and timers (src/mlf_step_algo.f90:144-219), EM object
+// (src/unsupervised/mlf_emgmm.f90:76-153), model getters (src/mlf_models.f90:239-331), checkpoint
+// (src/mlf_hdf5.f90:671-737).  All compute is delegated to EmgmmEngine (CUDA); there is no CPU fallback.
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <ctime>
+#include <limits>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/mlf_b200.h"
+#include "emgmm_engine.h"
+#include "mlf_hdf5_min.h"
+
+using mlfb200::EmgmmEngine;
+
+namespace {
+
+constexpr uint64_t kMagic = 0x4d4c4642323030ull;  // "MLFB200"
+enum Kind { KIND_EMGMM = 1, KIND_HDF5 = 2 };
+
+struct Handle {
+  uint64_t magic = kMagic;
+  Kind kind;
+  explicit Handle(Kind k) : kind(k) {}
+  virtual ~Handle() { magic = 0; }
+};
+
+struct Slot {
+  std::string name, fields;  // NUL-terminated by std::string::c_str()
+  short dt = mlf_DOUBLE;
+  int rank = 1;
+  int dims[3] = {0, 0, 0};  // Fortran order
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  bool has_fields = false;
+};
+
+struct Hdf5Handle : Handle {
+  std::string path;
+  bool writable = true;
+  std::vector<mlfh5::Dataset> ds;
+  Hdf5Handle() : Handle(KIND_HDF5) {}
+  mlfh5::Dataset* find(const std::string& n) {
+    for (auto& d : ds)
+      if (d.name == n) return &d;
+    return nullptr;
+  }
+  int flush() { return writable ? mlfh5::write_file(path, ds) : 0; }
+};
+
+struct EmObject : Handle {
+  EmObject() : Handle(KIND_EMGMM) {}
+  // slot storage.  rPar holds [cpuMax, realMax, minProba] but is exposed with extent 2: the reference binds
+  // minProba to rPar(3) of a 2-element array (src/unsupervised/mlf_emgmm.f90:84,104; src/mlf_step_algo.f90:124),
+  // so it is neither in the slot's dims nor in the checkpoint.  Same observable layout here, minus the overrun.
+  int64_t iPar[1] = {0};
+  double rPar[3] = {0, 0, 0};
+  int64_t iVar[2] = {0, 0};
+  double rVar[3] = {0, 0, 0};
+  std::vector<double> Mu, Cov, lambda;
+  Slot slots[7];
+  int d = 0, K = 0;
+  int64_t N = 0;
+  bool initialized = false;
+  const double* X = nullptr;
+  bool x_on_device = false;
+  EmgmmEngine eng;
+  std::vector<double> trace;
+  std::string err;
+  int rank = 0, world = 1;
+  uint64_t seed = 0x9E3779B97F4A7C15ull;
+
+  int64_t& niter() { return iVar[0]; }
+  int64_t& niterMax() { return iPar[0]; }
+  double& cpuTime() { return rVar[0]; }
+  double& realTime() { return rVar[1]; }
+  double& sumLL() { return rVar[2]; }
+  double& cpuMax() { return rPar[0]; }
+  double& realMax() { return rPar[1]; }
+  double& minProba() { return rPar[2]; }
+
+  void build_slots() {
+    auto set = [&](int i, const char* nm, const char* fl, short dt, int rank, int d0, int d1, int d2, void* p, size_t b) {
+      Slot& s = slots[i];
+      s.name = nm; s.dt = dt; s.rank = rank; s.dims[0] = d0; s.dims[1] = d1; s.dims[2] = d2; s.ptr = p; s.bytes = b;
+      s.has_fields = fl != nullptr;
+      if (fl) s.fields = fl;
+    };
+    // names/fields: src/mlf_rsc_array.f90:507-510, src/mlf_step_algo.f90:127-141, src/unsupervised/mlf_emgmm.f90:90-104
+    set(0, "iPar", "niterMax", mlf_INT64, 1, 1, 0, 0, iPar, sizeof(int64_t));
+    set(1, "rPar", "cpuMax;realMax;minProba", mlf_DOUBLE, 1, 2, 0, 0, rPar, 2 * sizeof(double));
+    set(2, "iVar", "niter", mlf_INT64, 1, 2, 0, 0, iVar, 2 * sizeof(int64_t));
+    set(3, "rVar", "cpuTime;realTime;sumLL", mlf_DOUBLE, 1, 3, 0, 0, rVar, 3 * sizeof(double));
+    set(4, "Mu", nullptr, mlf_DOUBLE, 2, d, K, 0, Mu.data(), Mu.size() * sizeof(double));
+    set(5, "Cov", nullptr, mlf_DOUBLE, 3, d, d, K, Cov.data(), Cov.size() * sizeof(double));
+    set(6, "lambda", nullptr, mlf_DOUBLE, 1, K, 0, 0, lambda.data(), lambda.size() * sizeof(double));
+  }
+
+  // mlf_step_obj_reinit + mlf_algo_emgmm_reinit (src/mlf_step_algo.f90:144-153, src/unsupervised/mlf_emgmm.f90:115-122)
+  void reinit() {
+    niter() = 0;
+    niterMax() = std::numeric_limits<int64_t>::max();
+    cpuTime() = 0;
+    realTime() = 0;
+    realMax() = std::numeric_limits<double>::max();
+    cpuMax() = std::numeric_limits<double>::max();
+    std::fill(Mu.begin(), Mu.end(), 0.0);
+    std::fill(Cov.begin(), Cov.end(), 0.0);
+    initialized = false;
+  }
+};
+
+Handle* as_handle(MLF_OBJ* p) {
+  if (!p) return nullptr;
+  Handle* h = reinterpret_cast<Handle*>(p);
+  return h->magic == kMagic ? h : nullptr;
+}
+EmObject* as_em(MLF_OBJ* p) {
+  Handle* h = as_handle(p);
+  return (h && h->kind == KIND_EMGMM) ? static_cast<EmObject*>(h) : nullptr;
+}
+Hdf5Handle* as_h5(MLF_OBJ* p) {
+  Handle* h = as_handle(p);
+  return (h && h->kind == KIND_HDF5) ? static_cast<Hdf5Handle*>(h) : nullptr;
+}
+
+// mlf_algo_emgmm_stepF (src/unsupervised/mlf_emgmm.f90:125-153)
+int em_stepF(EmObject* o, int64_t niter) {
+  if (niter <= 0) return 0;
+  int64_t em_iters = niter;
+  if (!o->initialized) {
+    // first iteration of a fresh object: k-means (nkm = 16), Cov = I, lambda = 1/K  (:135-145)
+    int r = o->eng.kmeans_init(16, o->seed);
+    if (r < 0) { o->err = o->eng.last_error(); return r; }
+    r = o->eng.download_params(o->Mu.data(), o->Cov.data(), o->lambda.data());
+    if (r < 0) return r;
+    o->initialized = true;
+    em_iters = niter - 1;
+  } else {
+    // host mirrors are the source of truth between steps: callers hold direct pointers (mlf_getrsc) and may
+    // write them, and mlf_updatersc memcpy's into them
+    int r = o->eng.upload_params(o->Mu.data(), o->Cov.data(), o->lambda.data());
+    if (r < 0) { o->err = o->eng.last_error(); return r; }
+  }
+  if (em_iters > 0) {
+    o->trace.assign((size_t)em_iters, 0.0);
+    int r = o->eng.iterate(em_iters, o->minProba(), &o->sumLL(), o->trace.data());
+    if (r < 0) { o->err = o->eng.last_error(); return r; }
+    r = o->eng.download_params(o->Mu.data(), o->Cov.data(), o->lambda.data());
+    if (r < 0) { o->err = o->eng.last_error(); return r; }
+  } else {
+    o->trace.clear();
+  }
+  return 0;
+}
+
+bool restore_from(Hdf5Handle* h, EmObject* o, int d, int& K) {
+  // data_handler%getData for every slot (src/mlf_rsc_array.f90:336-338,366-368,396-398; src/mlf_hdf5.f90:303-410):
+  // Mu is read with fixed_dims=[T,F] so K comes from the file (src/unsupervised/mlf_emgmm.f90:90-101)
+  mlfh5::Dataset* mu = h->find("Mu");
+  mlfh5::Dataset* cov = h->find("Cov");
+  mlfh5::Dataset* lam = h->find("lambda");
+  if (!mu || !cov || !lam) return false;
+  if (mu->type != mlfh5::F64 || mu->dims.size() != 2 || (int)mu->dims[1] != d) return false;
+  K = (int)mu->dims[0];
+  if (cov->type != mlfh5::F64 || cov->dims.size() != 3 || (int)cov->dims[0] != K || (int)cov->dims[1] != d || (int)cov->dims[2] != d) return false;
+  if (lam->type != mlfh5::F64 || lam->dims.size() != 1 || (int)lam->dims[0] != K) return false;
+  o->Mu.assign((size_t)K * d, 0.0);
+  o->Cov.assign((size_t)K * d * d, 0.0);
+  o->lambda.assign((size_t)K, 0.0);
+  std::memcpy(o->Mu.data(), mu->data.data(), o->Mu.size() * 8);
+  std::memcpy(o->Cov.data(), cov->data.data(), o->Cov.size() * 8);
+  std::memcpy(o->lambda.data(), lam->data.data(), o->lambda.size() * 8);
+  auto rd = [&](const char* nm, mlfh5::DType t, void* dst, size_t n) {
+    mlfh5::Dataset* s = h->find(nm);
+    if (!s || s->type != t || s->dims.size() != 1 || s->dims[0] != n) return false;
+    std::memcpy(dst, s->data.data(), n * 8);
+    return true;
+  };
+  return rd("iPar", mlfh5::I64, o->iPar, 1) && rd("rPar", mlfh5::F64, o->rPar, 2) && rd("iVar", mlfh5::I64, o->iVar, 2) &&
+         rd("rVar", mlfh5::F64, o->rVar, 3);
+}
+
+MLF_OBJ* em_create(const double* X, int64_t nX, int nY, int nC, double minProba, MLF_OBJ* handler, int device, unsigned flags) {
+  if (!X && nX > 0) return nullptr;
+  if (nX < 0 || nY < 1) return nullptr;
+  std::unique_ptr<EmObject> o(new EmObject());
+  o->d = nY;
+  o->N = nX;
+  o->X = X;
+  o->x_on_device = (flags & MLF_B200_X_ON_DEVICE) != 0;
+  int K = nC;
+  Hdf5Handle* h5 = nullptr;
+  if (handler) {
+    h5 = as_h5(handler);
+    if (!h5) return nullptr;
+    if (!restore_from(h5, o.get(), nY, K)) {
+      fprintf(stderr, "emgmm: error creating Mu\n");  // CheckF message of src/unsupervised/mlf_emgmm.f90:92
+      return nullptr;
+    }
+  }
+  if (K < 1) return nullptr;
+  o->K = K;
+  if (!h5) {
+    o->Mu.assign((size_t)K * nY, 0.0);
+    o->Cov.assign((size_t)K * nY * nY, 0.0);
+    o->lambda.assign((size_t)K, 0.0);
+  }
+  o->build_slots();
+  int cur = 0;
+  if (device < 0) {
+    if (cudaGetDevice(&cur) != cudaSuccess) cur = 0;
+    device = cur;
+  }
+  if (o->eng.init(X, o->x_on_device, nX, nY, K, device) < 0) {
+    fprintf(stderr, "mlf_emgmm_c: %s\n", o->eng.last_error().c_str());
+    return nullptr;
+  }
+  if (h5) {
+    o->minProba() = minProba;  // not part of the checkpoint (see rPar note above)
+    o->initialized = true;     // src/unsupervised/mlf_emgmm.f90:106-107
+    if (o->eng.upload_params(o->Mu.data(), o->Cov.data(), o->lambda.data()) < 0) return nullptr;
+  } else {
+    o->reinit();  // :109
+    o->minProba() = minProba;  // InitOrDefault(this%minProba, 0d0, minProba) (:105)
+  }
+  return o.release();
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mlf_b200_version(void) { return "mlfortran_b200 0.1 (sm_100a, fp64 DMMA EM-GMM)"; }
+
+int mlf_init(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    fprintf(stderr, "mlf_init: no CUDA device visible; mlfortran_b200 has no CPU fallback\n");
+    return -1;
+  }
+  return 0;
+}
+int mlf_quit(void) { return 0; }
+
+int mlf_dealloc(MLF_OBJ* obj) {
+  Handle* h = as_handle(obj);
+  if (!h) return -1;
+  if (h->kind == KIND_HDF5) static_cast<Hdf5Handle*>(h)->flush();
+  delete h;
+  return 0;
+}
+
+int mlf_getnumrsc(MLF_OBJ* obj) {
+  EmObject* o = as_em(obj);
+  return o ? 7 : -1;
+}
+
+void* mlf_getrsc(MLF_OBJ* obj, int id, MLF_DT* dt, int* rank, int* dims, void* data) {
+  EmObject* o = as_em(obj);
+  if (!o || id < 1 || id > 7) return nullptr;
+  const Slot& s = o->slots[id - 1];
+  if (rank) *rank = s.rank;
+  if (dims)
+    for (int i = 0; i < s.rank; ++i) dims[i] = s.dims[i];
+  if (dt) { dt->dt = s.dt; dt->access = mlf_DIRECT; }
+  if (data) {
+    std::memcpy(data, s.ptr, s.bytes);
+    return data;
+  }
+  return s.ptr;
+}
+
+char* mlf_getinfo(MLF_OBJ* obj, int id, int type) {
+  EmObject* o = as_em(obj);
+  if (!o || id < 1 || id > 7) return nullptr;
+  Slot& s = o->slots[id - 1];
+  if (type == mlf_NAME) return const_cast<char*>(s.name.c_str());
+  if (type == mlf_FIELDS && s.has_fields) return const_cast<char*>(s.fields.c_str());
+  return nullptr;  // r_desc is never set on this path
+}
+
+int mlf_updatersc(MLF_OBJ* obj, int id, void* data) {
+  EmObject* o = as_em(obj);
+  if (!o || id < 1 || id > 7) return -1;
+  const Slot& s = o->slots[id - 1];
+  if (data) std::memcpy(s.ptr, data, s.bytes);
+  return 0;
+}
+
+int mlf_pushState(MLF_OBJ* handler, MLF_OBJ* obj, int override_) {
+  Hdf5Handle* h = as_h5(handler);
+  EmObject* o = as_em(obj);
+  if (!h || !o) return -1;
+  if (!h->writable) return mlf_FILEERROR;
+  // one dataset per allocated slot, named by r_name, dims reversed (src/mlf_hdf5.f90:696-736)
+  for (const Slot& s : o->slots) {
+    mlfh5::Dataset* dst = h->find(s.name);
+    if (dst && !override_) {
+      fprintf(stderr, "mlf_pushState: dataset %s exists (override not set)\n", s.name.c_str());
+      return mlf_FILEERROR;
+    }
+    mlfh5::Dataset nd;
+    nd.name = s.name;
+    nd.type = (s.dt == mlf_INT64) ? mlfh5::I64 : mlfh5::F64;
+    for (int i = s.rank - 1; i >= 0; --i) nd.dims.push_back((uint64_t)s.dims[i]);
+    nd.data.assign((const uint8_t*)s.ptr, (const uint8_t*)s.ptr + s.bytes);
+    if (dst) *dst = std::move(nd);
+    else h->ds.push_back(std::move(nd));
+  }
+  return h->flush();
+}
+
+int mlf_step(MLF_OBJ* obj, double* dt, int64_t* niter) {
+  EmObject* o = as_em(obj);
+  if (!o) return -1;
+  const int64_t n = niter ? *niter : 1;
+  // mlf_step_f (src/mlf_step_algo.f90:187-201): timers around stepF, counters accumulate
+  const auto t0 = std::chrono::steady_clock::now();
+  const std::clock_t c0 = std::clock();
+  int info = em_stepF(o, n);
+  const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  o->realTime() += el;
+  o->cpuTime() += (double)(std::clock() - c0) / CLOCKS_PER_SEC;
+  o->niter() += n;
+  if (dt) *dt = el;
+  if (info != mlf_STEP_OK) return info;
+  if (o->cpuTime() > o->cpuMax() || o->realTime() > o->realMax()) return mlf_STEP_STOP;
+  return mlf_STEP_OK;
+}
+
+int mlf_getNumClasses(MLF_OBJ* obj) {
+  EmObject* o = as_em(obj);
+  return o ? o->K : -1;
+}
+
+static int em_expect(EmObject* o, const double* X, int nX, int nIn, double* P, int* Cl) {
+  if (!o->initialized) return mlf_UNINIT;  // src/unsupervised/mlf_emgmm.f90:166-169
+  if (nX != o->d || nIn < 0) return -1;
+  int r = o->eng.upload_params(o->Mu.data(), o->Cov.data(), o->lambda.data());
+  if (r < 0) return r;
+  return o->eng.expectation(X, false, nIn, P, Cl);
+}
+
+int mlf_getClass(MLF_OBJ* obj, const double* X, int* Cl, int nX, int nIn) {
+  EmObject* o = as_em(obj);
+  if (!o) return -1;
+  return em_expect(o, X, nX, nIn, nullptr, Cl);
+}
+
+int mlf_getProba(MLF_OBJ* obj, const double* X, double* P, int nX, int nIn, int nCl) {
+  EmObject* o = as_em(obj);
+  if (!o) return -1;
+  if (nCl != o->K) return -1;
+  return em_expect(o, X, nX, nIn, P, nullptr);
+}
+
+MLF_OBJ* mlf_hdf5_createFile(const char* fname, int trunk) {
+  if (!fname) return nullptr;
+  if (trunk == 0) {  // H5F_ACC_EXCL_F: fail if the file exists (src/mlf_hdf5.f90:178-179)
+    FILE* f = fopen(fname, "rb");
+    if (f) { fclose(f); fprintf(stderr, "Error while creating file: %s\n", fname); return nullptr; }
+  }
+  std::unique_ptr<Hdf5Handle> h(new Hdf5Handle());
+  h->path = fname;
+  h->writable = true;
+  if (h->flush() < 0) { fprintf(stderr, "Error while creating file: %s\n", fname); return nullptr; }
+  return h.release();
+}
+
+MLF_OBJ* mlf_hdf5_openFile(const char* fname, int rw) {
+  if (!fname) return nullptr;
+  std::unique_ptr<Hdf5Handle> h(new Hdf5Handle());
+  h->path = fname;
+  h->writable = rw != 0;
+  if (mlfh5::read_file(h->path, h->ds) < 0) { fprintf(stderr, "Error while opening file: %s\n", fname); return nullptr; }
+  return h.release();
+}
+
+MLF_OBJ* mlf_emgmm_c(double* X, int nX, int nY, int nC, double minProba, MLF_OBJ* handler) {
+  return em_create(X, nX, nY, nC, minProba, handler, -1, 0);
+}
+
+MLF_OBJ* mlf_b200_emgmm_create(const double* X, int64_t nX, int nY, int nC, double minProba, MLF_OBJ* handler, int device,
+                               unsigned flags) {
+  return em_create(X, nX, nY, nC, minProba, handler, device, flags);
+}
+
+int mlf_b200_set_allreduce(MLF_OBJ* obj, mlf_b200_allreduce_fn fn, void* ctx, int rank, int world) {
+  EmObject* o = as_em(obj);
+  if (!o) return -1;
+  o->eng.set_allreduce(fn, ctx);
+  o->rank = rank;
+  o->world = world;
+  return 0;
+}
+
+int mlf_b200_set_initialized(MLF_OBJ* obj, int initialized) {
+  EmObject* o = as_em(obj);
+  if (!o) return -1;
+  o->initialized = initialized != 0;
+  return 0;
+}
+int mlf_b200_get_initialized(MLF_OBJ* obj) {
+  EmObject* o = as_em(obj);
+  return o ? (o->initialized ? 1 : 0) : -1;
+}
+
+int mlf_b200_refresh_x(MLF_OBJ* obj, const double* X) {
+  EmObject* o = as_em(obj);
+  if (!o) return -1;
+  o->X = X;
+  return o->eng.refresh_x(X, o->x_on_device);
+}
+
+const char* mlf_b200_last_error(MLF_OBJ* obj) {
+  EmObject* o = as_em(obj);
+  if (!o) return "invalid handle";
+  return o->err.empty() ? o->eng.last_error().c_str() : o->err.c_str();
+}
+
+int64_t mlf_b200_sumll_trace(MLF_OBJ* obj, double* out, int64_t n) {
+  EmObject* o = as_em(obj);
+  if (!o) return -1;
+  const int64_t m = (int64_t)o->trace.size();
+  if (out)
+    for (int64_t i = 0; i < m && i < n; ++i) out[i] = o->trace[(size_t)i];
+  return m;
+}
+
+int mlf_b200_resident_proba(MLF_OBJ* obj, double* P) {
+  EmObject* o = as_em(obj);
+  if (!o || !P) return -1;
+  if (o->N == 0) return 0;
+  cudaError_t e = cudaMemcpy2DAsync(P, (size_t)o->N * sizeof(double), o->eng.gamma_device(), (size_t)o->eng.gamma_ld() * sizeof(double),
+                                    (size_t)o->N * sizeof(double), o->K, cudaMemcpyDeviceToHost, o->eng.stream());
+  if (e == cudaSuccess) e = cudaStreamSynchronize(o->eng.stream());
+  return e == cudaSuccess ? 0 : mlf_OTHERERROR;
+}
+
+int mlf_b200_resident_labels(MLF_OBJ* obj, int* Cl) {
+  EmObject* o = as_em(obj);
+  if (!o || !Cl) return -1;
+  if (!o->initialized) return mlf_UNINIT;
+  int r = o->eng.upload_params(o->Mu.data(), o->Cov.data(), o->lambda.data());
+  if (r < 0) return r;
+  return o->eng.resident_labels(Cl);
+}
+
+int mlf_b200_set_profile(MLF_OBJ* obj, int on) {
+  EmObject* o = as_em(obj);
+  if (!o) return -1;
+  o->eng.set_profile(on != 0);
+  return 0;
+}
+int mlf_b200_get_times(MLF_OBJ* obj, double out[6]) {
+  EmObject* o = as_em(obj);
+  if (!o || !out) return -1;
+  const mlfb200::EngineTimes& t = o->eng.times();
+  out[0] = t.refresh; out[1] = t.estep; out[2] = t.mid; out[3] = t.mstep; out[4] = t.fin; out[5] = (double)t.iters;
+  return 0;
+}
+int64_t mlf_b200_launch_count(MLF_OBJ* obj) {
+  EmObject* o = as_em(obj);
+  return o ? o->eng.launches() : -1;
+}
+void* mlf_b200_stream(MLF_OBJ* obj) {
+  EmObject* o = as_em(obj);
+  return o ? (void*)o->eng.stream() : nullptr;
+}
+int64_t mlf_b200_global_points(MLF_OBJ* obj) {
+  EmObject* o = as_em(obj);
+  return o ? o->eng.n_global() : -1;
+}
+
+// Single-component entry points: to be wired to the device kernels.
+int mlf_evalGaussian(int, int, const double*, double*, const double*, const double*, double, double*) {
+  fprintf(stderr, "mlf_evalGaussian: not built yet in mlfortran_b200\n");
+  return mlf_OTHERERROR;
+}
+double mlf_maxGaussian(int, int, const double*, const double*, double*, double*) {
+  fprintf(stderr, "mlf_maxGaussian: not built yet in mlfortran_b200\n");
+  return std::numeric_limits<double>::quiet_NaN();
+}
+
+}  // extern "C"
