@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Benchmark of the EM-GMM hot path (BASELINE.json: EM iter/s & point*comp evals/s, N=1e8 d=16 K=64 full cov).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, one process per GPU)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm on the host cores
+
+A step is one EM iteration (ExpStep + MaxStep, src/unsupervised/mlf_emgmm.f90:147-149) over the whole synthetic
+data set (sharded over the ranks).  `value` is timed with inputs resident in HBM; `e2e` goes through the same C-ABI
+with HOST buffers: every step re-uploads the rank's X from pinned memory, runs mlf_step(1) and reads the
+parameters and sumLL back.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "EM point*component evaluations/s (N=1e8, d=16, K=64 full covariance); em_iter_per_s alongside"
+UNIT = "point*comp/s"
+SIGMA_C, SIGMA_X, SEED = 8.0, 1.0, 3
+
+
+def flops_e(d):  # E = d^2 + 4d + 6 flops + one exp (40 flops) per (point, component)
+    return d * d + 4 * d + 6 + 40
+
+
+def flops_m(d):  # M = d^2 + 3d + 4
+    return d * d + 3 * d + 4
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, ln in self.rows:
+            if t0 is not None and not (t0 <= ts <= t1 + 0.3):
+                continue
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_rate(d, K, n_cpu, min_proba, steps, warmup, threads=None):
+    """Times the CPU restatement of the reference algorithm (oracle/, kind "port") on a bounded sample."""
+    from mlfortran_b200 import synth
+    from oracle.emgmm_oracle import get
+
+    orc = get()
+    nthr = threads or min(K, os.cpu_count() or 1)
+    orc.set_threads(nthr)
+    data = synth.make_mixture(d, K, max(n_cpu // K, 1), SIGMA_C, SIGMA_X, SEED)
+    X = data["X"]
+    Mu, Cov, lam = synth.injected_init(data["centres"], SEED)
+    if warmup > 0:
+        Mu, Cov, lam, _ = orc.em_iterations(X, Mu, Cov, lam, min_proba, warmup)
+    per = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        Mu, Cov, lam, _ = orc.em_iterations(X, Mu, Cov, lam, min_proba, 1)
+        per.append(time.perf_counter() - t0)
+    n = X.shape[0]
+    tot = float(np.sum(per))
+    return {"value": n * K * steps / tot, "sec_per_step": tot / steps, "n": int(n), "threads": int(nthr), "lapack": bool(orc.has_lapack)}
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the reference's own CPU algorithm for this path on the box's host cores.  The reference
+    itself (Fortran + LAPACK + HDF5) cannot be compiled in this image, so this times the oracle port."""
+    if rank != 0:
+        return
+    d, K = args.dims, args.comps
+    n_cpu = args.cpu_points
+    r = cpu_oracle_rate(d, K, n_cpu, args.min_proba, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["sec_per_step"] * 1e3 * (args.points / r["n"]), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "em_iter_per_s": r["value"] / (args.points * K),
+        "config": {"workload": f"synthetic GMM N={args.points:.0e} d={d} K={K} full covariance (BASELINE configs[2])", "N": args.points, "d": d,
+                   "K": K, "minProba": args.min_proba, "note": "ms_per_step and em_iter_per_s are linear extrapolations from the CPU sample to N"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+                         "sample": f"N_cpu={r['n']} points of the same d={d}, K={K} mixture, {args.steps} EM iterations, OpenMP over components, "
+                                   f"LAPACK={'OpenBLAS(scipy)' if r['lapack'] else 'built-in Jacobi'}; reference layout needs 8*N*K bytes so N=1e8 cannot run on the host"},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=float, default=1e8, help="total points N (all ranks)")
+    ap.add_argument("--dims", type=int, default=16)
+    ap.add_argument("--comps", type=int, default=64)
+    ap.add_argument("--min-proba", type=float, default=1.0, help="minProba as in tests/test_emgmm.f90:125")
+    ap.add_argument("--cpu-points", type=int, default=256000, help="bounded CPU sample for cpu_baseline / --impl reference")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.points = int(args.points)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = max(args.warmup, 1)  # the driver's default is >= 3; tiny dev runs may pass less
+
+    import torch
+    import torch.distributed as dist
+
+    from mlfortran_b200 import mlf_algo_emgmm, parallel, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (mlfortran_b200 has no CPU fallback)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    d, K, N = args.dims, args.comps, args.points
+    lo, hi = parallel.shard_bounds(N, rank, world)
+    n_loc = hi - lo
+    # same mixture on every rank (seed), rank-specific sample stream
+    X, centres, _ = synth.make_mixture_torch(d, K, n_loc, SIGMA_C, SIGMA_X, SEED, dev, stream_seed=SEED + 1000 * rank)
+    Mu0, Cov0, lam0 = synth.injected_init(centres, SEED)
+
+    em = mlf_algo_emgmm()
+    if em.init(X, K, args.min_proba) != 0:
+        raise SystemExit("bench.py: init failed")
+    if world > 1:
+        em.set_allreduce(parallel.make_allreduce(None, dev), rank, world)
+    em.inject(Mu0, Cov0, lam0)
+    info, _ = em.step(args.warmup)
+    if info < 0:
+        raise SystemExit(f"bench.py: warm-up failed: {em.last_error()}")
+
+    est = torch.cuda.ExternalStream(em.stream(), device=dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    em.set_profile(True)
+    l0 = em.launch_count()
+    barrier()
+    tw0 = time.perf_counter()
+    ev0.record(est)
+    info, _ = em.step(args.steps)
+    ev1.record(est)
+    torch.cuda.synchronize(dev)
+    tw1 = time.perf_counter()
+    barrier()
+    if info < 0:
+        raise SystemExit(f"bench.py: timed step failed: {em.last_error()}")
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop(tw0, tw1) if sampler else None
+    launches = em.launch_count() - l0
+    times = em.times()
+    em.set_profile(False)
+    sumll = em.sumLL
+    value = N * K * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (E-pass), CUDA events on the engine's stream inside the timed region ------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")))
+    except Exception:
+        pass
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    hbm_src = "MEASURED_PEAKS.json" if hbm_peak else "fallback 6650 GB/s (B200_PROFILING.md)"
+    hbm_peak = hbm_peak or 6650.0
+    it = max(times["iters"], 1)
+    e_ms, m_ms = times["estep_ms"] / it, times["mstep_ms"] / it
+    peak_tf = peaks.get("dmma_tflops", 37.16)
+    ach_tf = flops_e(d) * n_loc * K / (e_ms * 1e-3) * 1e-12 if e_ms > 0 else 0.0
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "estep_traffic.json")))
+        traffic = tj["dram_bytes_per_point"] * n_loc if (tj.get("d") == d and tj.get("K") == K) else None
+    except Exception:
+        pass
+    roofline = {
+        "kernel": "k_estep (E-pass: whitening DMMA + log-sum-exp + pass-A statistics)", "bound": "tensor",
+        "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None, "traffic": traffic,
+        "peak_source": "fp64 DMMA (mma.sync m8n8k4.f64) measured on this pool by bench/micro/fp64_peaks.cu -> profiles/fp64_peaks_r01.json; "
+                       "MEASURED_PEAKS.json has no fp64 figure (bf16 tensor peak does not apply to an fp64 path)",
+        "algorithmic_flops_per_launch": flops_e(d) * n_loc * K, "ms_per_launch": e_ms,
+        "hbm": {"achieved_gbs": (8.0 * n_loc * d + 8.0 * n_loc * K) / (e_ms * 1e-3) * 1e-9 if e_ms > 0 else 0.0, "peak_gbs": hbm_peak,
+                "peak_source": hbm_src, "note": "E-pass reads X once and writes the responsibilities once; fp64-bound, not HBM-bound"},
+        "mstep": {"ms_per_launch": m_ms, "algorithmic_bytes": 8.0 * n_loc * K + 8.0 * n_loc * d,
+                  "achieved_gbs": (8.0 * n_loc * K + 8.0 * n_loc * d) / (m_ms * 1e-3) * 1e-9 if m_ms > 0 else 0.0},
+        "per_iteration_ms": {k: v / it for k, v in times.items() if k != "iters"},
+    }
+
+    # ---- e2e: same C-ABI, HOST buffers; H2D of X (pinned) + mlf_step(1) + D2H of parameters every step --------------
+    e2e = None
+    if not args.no_e2e:
+        e_steps = args.e2e_steps or min(args.steps, 5)
+        Xh = torch.empty((n_loc, d), dtype=torch.float64, pin_memory=True)
+        Xh.copy_(X)
+        torch.cuda.synchronize(dev)
+        em.finalize()
+        del X
+        torch.cuda.empty_cache()
+        Xn = Xh.numpy()
+        em = mlf_algo_emgmm()
+        if em.init(Xn, K, args.min_proba, device=local_rank) != 0:
+            raise SystemExit("bench.py: e2e init failed")
+        if world > 1:
+            em.set_allreduce(parallel.make_allreduce(None, dev), rank, world)
+        em.inject(Mu0, Cov0, lam0)
+        em.step(1)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            if em._lib.mlf_b200_refresh_x(em._h, Xn.ctypes.data) != 0:
+                raise SystemExit("bench.py: refresh_x failed")
+            info, _ = em.step(1)
+            if info < 0:
+                raise SystemExit(f"bench.py: e2e step failed: {em.last_error()}")
+        torch.cuda.synchronize(dev)
+        el = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        pbytes = 8 * (K * d + K * d * d + K)
+        e2e = {"value": N * K * e_steps / el, "unit": UNIT, "h2d_bytes_per_step": int(8 * n_loc * d + pbytes), "d2h_bytes_per_step": int(pbytes + 8),
+               "steps": e_steps, "ms_per_step": el / e_steps * 1e3, "em_iter_per_s": e_steps / el,
+               "note": "per rank and step: pinned-host X -> HBM, parameters up, mlf_step(1), parameters + sumLL down"}
+    em.finalize()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_oracle_rate(d, K, args.cpu_points, args.min_proba, 3, 1)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+               "sample": f"oracle (C restatement of the reference, OpenMP over components) on N_cpu={r['n']} points of the same d={d}, K={K} mixture, "
+                         f"3 EM iterations after 1 warm-up; {r['sec_per_step']:.2f} s/iteration"}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "em_iter_per_s": args.steps / (ms * 1e-3), "sumLL_last": sumll,
+            "config": {"workload": f"synthetic GMM N={N:.0e} d={d} K={K} full covariance, points sharded over {world} GPU(s) (BASELINE configs[2])",
+                       "N": N, "d": d, "K": K, "minProba": args.min_proba, "points_per_gpu": n_loc, "parallelism": f"points-sharded x{world}",
+                       "l2": "inputs larger than L2 (X + responsibilities >> 126 MB per GPU); no explicit flush",
+                       "timing": "CUDA events on the engine stream, max over ranks"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -33,7 +33,7 @@ EmgmmEngine::~EmgmmEngine() {
     if (b) cudaFree(b);
   if (dInfo_) cudaFree(dInfo_);
   if (dLabels_) cudaFree(dLabels_);
-  for (auto& e : ev_)
+  for (auto& e : pev_)
     if (e) cudaEventDestroy(e);
   if (own_stream_ && st_) cudaStreamDestroy(st_);
 }
@@ -74,7 +74,6 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   if (ldg_ == 0) ldg_ = 32;
   CKE(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking), "cudaStreamCreate");
   own_stream_ = true;
-  for (auto& e : ev_) CKE(cudaEventCreate(&e), "cudaEventCreate");
   const Geom& g = geom_;
   const int KP = g.K8 * 8;
   const int64_t etiles = (n_ + kEstepTilePts - 1) / kEstepTilePts;
@@ -215,7 +214,17 @@ int EmgmmEngine::iterate(int64_t niter, double minProba, double* sumLL_last, dou
     CKE(cudaMalloc((void**)&dSumLL_, trace_cap_ * sizeof(double)), "cudaMalloc trace");
   }
   const double minW = 1e-3 / (double)(float)nglob_;  // 1d-3/real(NX)  (src/unsupervised/mlf_gaussian.f90:50)
+  const bool prof = profile_ && niter <= 4096;
+  if (prof) {
+    while ((int64_t)pev_.size() < 6 * niter) {
+      cudaEvent_t e;
+      CKE(cudaEventCreate(&e), "cudaEventCreate");
+      pev_.push_back(e);
+    }
+  }
   for (int64_t it = 0; it < niter; ++it) {
+    cudaEvent_t* ev_ = prof ? &pev_[(size_t)6 * it] : nullptr;
+    const bool profile_ = prof;
     if (profile_) cudaEventRecord(ev_[0], st_);
     CKE(launch_refresh(g, dMu_, dCov_, dLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_),
         "refresh");
@@ -235,21 +244,23 @@ int EmgmmEngine::iterate(int64_t niter, double minProba, double* sumLL_last, dou
     if (profile_) cudaEventRecord(ev_[4], st_);
     CKE(launch_finalize(g, dStatsA_, dStatsB_, minProba, dCov_, dLambda_, st_), "finalize");
     ++launches_;
-    if (profile_) {
-      cudaEventRecord(ev_[5], st_);
-      CKE(cudaEventSynchronize(ev_[5]), "event sync");
-      float ms;
-      cudaEventElapsedTime(&ms, ev_[0], ev_[1]); times_.refresh += ms;
-      cudaEventElapsedTime(&ms, ev_[1], ev_[2]); times_.estep += ms;
-      cudaEventElapsedTime(&ms, ev_[2], ev_[3]); times_.mid += ms;
-      cudaEventElapsedTime(&ms, ev_[3], ev_[4]); times_.mstep += ms;
-      cudaEventElapsedTime(&ms, ev_[4], ev_[5]); times_.fin += ms;
-      times_.iters += 1;
-    }
+    if (profile_) cudaEventRecord(ev_[5], st_);
   }
   std::vector<double> tr((size_t)niter);
   CKE(cudaMemcpyAsync(tr.data(), dSumLL_, niter * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H sumLL");
   CKE(cudaStreamSynchronize(st_), "sync");
+  if (prof) {  // read the per-iteration events only after the single sync: no host stalls inside the loop
+    for (int64_t it = 0; it < niter; ++it) {
+      cudaEvent_t* e = &pev_[(size_t)6 * it];
+      float ms;
+      cudaEventElapsedTime(&ms, e[0], e[1]); times_.refresh += ms;
+      cudaEventElapsedTime(&ms, e[1], e[2]); times_.estep += ms;
+      cudaEventElapsedTime(&ms, e[2], e[3]); times_.mid += ms;
+      cudaEventElapsedTime(&ms, e[3], e[4]); times_.mstep += ms;
+      cudaEventElapsedTime(&ms, e[4], e[5]); times_.fin += ms;
+      times_.iters += 1;
+    }
+  }
   if (sumLL_last) *sumLL_last = tr[(size_t)niter - 1];
   if (sumLL_trace) std::memcpy(sumLL_trace, tr.data(), niter * sizeof(double));
   return 0;

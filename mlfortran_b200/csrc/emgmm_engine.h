@@ -60,6 +60,7 @@ class EmgmmEngine {
   cudaStream_t stream() const { return st_; }
   const std::string& last_error() const { return err_; }
   EngineTimes& times() { return times_; }
+  void reset_times() { times_ = EngineTimes(); }
   void set_profile(bool on) { profile_ = on; }
   int64_t launches() const { return launches_; }
 
@@ -94,7 +95,7 @@ class EmgmmEngine {
   EngineTimes times_;
   bool profile_ = false;
   int64_t launches_ = 0;
-  cudaEvent_t ev_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> pev_;  // 6 profiling events per iteration (only when set_profile(true))
 };
 
 }  // namespace mlfb200

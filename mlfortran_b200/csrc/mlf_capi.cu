@@ -456,6 +456,7 @@ int mlf_b200_set_profile(MLF_OBJ* obj, int on) {
   EmObject* o = as_em(obj);
   if (!o) return -1;
   o->eng.set_profile(on != 0);
+  o->eng.reset_times();
   return 0;
 }
 int mlf_b200_get_times(MLF_OBJ* obj, double out[6]) {

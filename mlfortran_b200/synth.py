@@ -53,7 +53,8 @@ def injected_init(centres: np.ndarray, seed: int, jitter: float = 0.5):
     return Mu, Cov, lam
 
 
-def make_mixture_torch(d: int, K: int, N: int, sigma_c: float, sigma_x: float, seed: int, device, chunk: int = 1 << 22):
+def make_mixture_torch(d: int, K: int, N: int, sigma_c: float, sigma_x: float, seed: int, device, chunk: int = 1 << 22,
+                       stream_seed: int | None = None):
     """Device generator for the large bench shapes (same distribution; component of point i is
     drawn uniformly, which is what shuffling equal-sized blocks yields in the limit).
     Returns (X [N,d] float64 on device, centres [K,d] numpy, C12 [K,d,d] numpy)."""
@@ -64,7 +65,7 @@ def make_mixture_torch(d: int, K: int, N: int, sigma_c: float, sigma_x: float, s
     w = spectrum(d, sigma_x)
     C12 = np.stack([haar_orthogonal(rng, d) * w for _ in range(K)])
     g = torch.Generator(device=device)
-    g.manual_seed(seed)
+    g.manual_seed(seed if stream_seed is None else stream_seed)  # mixture from `seed`, sample stream per rank
     X = torch.empty((N, d), dtype=torch.float64, device=device)
     tXC = torch.as_tensor(XC, device=device)
     tC12T = torch.as_tensor(np.ascontiguousarray(C12.transpose(0, 2, 1)), device=device)
