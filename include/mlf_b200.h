@@ -108,6 +108,13 @@ void *mlf_b200_stream(MLF_OBJ *obj);
 int64_t mlf_b200_global_points(MLF_OBJ *obj);
 const char *mlf_b200_version(void);
 
+/* Generic dataset access on a checkpoint handle (root group; int64 / float64; dims in file (C) order, i.e. the
+ * reverse of the Fortran shape).  mlf_b200_h5_get with data == NULL only reports type/rank/dims. */
+int mlf_b200_h5_put(MLF_OBJ *handler, const char *name, int dtype, int rank, const int64_t *dims, const void *data, int override_);
+int mlf_b200_h5_get(MLF_OBJ *handler, const char *name, int *dtype, int *rank, int64_t *dims, void *data, int64_t capacity_bytes);
+int mlf_b200_h5_count(MLF_OBJ *handler);
+const char *mlf_b200_h5_name(MLF_OBJ *handler, int idx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,10 @@ SYMBOLS = {
     "mlf_b200_stream": (C.c_void_p, [C.c_void_p]),
     "mlf_b200_global_points": (C.c_int64, [C.c_void_p]),
     "mlf_b200_version": (C.c_char_p, []),
+    "mlf_b200_h5_put": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, c_int64_p, C.c_void_p, C.c_int]),
+    "mlf_b200_h5_get": (C.c_int, [C.c_void_p, C.c_char_p, c_int_p, c_int_p, c_int64_p, C.c_void_p, C.c_int64]),
+    "mlf_b200_h5_count": (C.c_int, [C.c_void_p]),
+    "mlf_b200_h5_name": (C.c_char_p, [C.c_void_p, C.c_int]),
 }
 
 _lib = None

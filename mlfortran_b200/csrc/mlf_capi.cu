@@ -479,6 +479,52 @@ int64_t mlf_b200_global_points(MLF_OBJ* obj) {
   return o ? o->eng.n_global() : -1;
 }
 
+int mlf_b200_h5_put(MLF_OBJ* handler, const char* name, int dtype, int rank, const int64_t* dims, const void* data, int override_) {
+  Hdf5Handle* h = as_h5(handler);
+  if (!h || !name || rank < 1 || rank > MLF_MAXRANK || !dims || !data) return -1;
+  if (!h->writable) return mlf_FILEERROR;
+  if (dtype != mlf_INT64 && dtype != mlf_DOUBLE) return mlf_WRONGTYPE;
+  mlfh5::Dataset nd;
+  nd.name = name;
+  nd.type = dtype == mlf_INT64 ? mlfh5::I64 : mlfh5::F64;
+  for (int i = 0; i < rank; ++i) {
+    if (dims[i] < 1) return mlf_WRONGRANK;
+    nd.dims.push_back((uint64_t)dims[i]);
+  }
+  nd.data.assign((const uint8_t*)data, (const uint8_t*)data + nd.count() * 8);
+  mlfh5::Dataset* dst = h->find(nd.name);
+  if (dst && !override_) return mlf_FILEERROR;
+  if (dst) *dst = std::move(nd);
+  else h->ds.push_back(std::move(nd));
+  return h->flush();
+}
+
+int mlf_b200_h5_get(MLF_OBJ* handler, const char* name, int* dtype, int* rank, int64_t* dims, void* data, int64_t capacity_bytes) {
+  Hdf5Handle* h = as_h5(handler);
+  if (!h || !name) return -1;
+  mlfh5::Dataset* s = h->find(name);
+  if (!s) return mlf_FILENOTFOUND;
+  if (dtype) *dtype = s->type == mlfh5::I64 ? mlf_INT64 : mlf_DOUBLE;
+  if (rank) *rank = (int)s->dims.size();
+  if (dims)
+    for (size_t i = 0; i < s->dims.size() && i < MLF_MAXRANK; ++i) dims[i] = (int64_t)s->dims[i];
+  if (data) {
+    if ((int64_t)s->data.size() > capacity_bytes) return mlf_WRONGRANK;
+    std::memcpy(data, s->data.data(), s->data.size());
+  }
+  return 0;
+}
+
+int mlf_b200_h5_count(MLF_OBJ* handler) {
+  Hdf5Handle* h = as_h5(handler);
+  return h ? (int)h->ds.size() : -1;
+}
+const char* mlf_b200_h5_name(MLF_OBJ* handler, int idx) {
+  Hdf5Handle* h = as_h5(handler);
+  if (!h || idx < 0 || idx >= (int)h->ds.size()) return nullptr;
+  return h->ds[(size_t)idx].name.c_str();
+}
+
 // Single-component entry points: to be wired to the device kernels.
 int mlf_evalGaussian(int, int, const double*, double*, const double*, const double*, double, double*) {
   fprintf(stderr, "mlf_evalGaussian: not built yet in mlfortran_b200\n");

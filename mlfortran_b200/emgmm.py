@@ -55,6 +55,34 @@ class mlf_hdf5_file:
             _lib.load().mlf_dealloc(self._h)
             self._h = None
 
+    # generic dataset access (extension; dims in file/C order)
+    def put(self, name: str, arr: np.ndarray, override: bool = False) -> int:
+        arr = np.ascontiguousarray(arr)
+        if arr.dtype == np.int64:
+            dt = mlf_INT64
+        elif arr.dtype == np.float64:
+            dt = mlf_DOUBLE
+        else:
+            return -3
+        dims = (C.c_int64 * arr.ndim)(*arr.shape)
+        return _lib.load().mlf_b200_h5_put(self._h, name.encode(), dt, arr.ndim, dims, arr.ctypes.data, 1 if override else 0)
+
+    def get(self, name: str):
+        lib = _lib.load()
+        dt, rank = C.c_int(), C.c_int()
+        dims = (C.c_int64 * 15)()
+        if lib.mlf_b200_h5_get(self._h, name.encode(), C.byref(dt), C.byref(rank), dims, None, 0) != 0:
+            return None
+        shape = tuple(dims[i] for i in range(rank.value))
+        out = np.empty(shape, dtype=np.int64 if dt.value == mlf_INT64 else np.float64)
+        if lib.mlf_b200_h5_get(self._h, name.encode(), None, None, None, out.ctypes.data, out.nbytes) != 0:
+            return None
+        return out
+
+    def names(self):
+        lib = _lib.load()
+        return [lib.mlf_b200_h5_name(self._h, i).decode() for i in range(max(lib.mlf_b200_h5_count(self._h), 0))]
+
     def __del__(self):
         try:
             self.finalize()
