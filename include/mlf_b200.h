@@ -100,6 +100,8 @@ int64_t mlf_b200_sumll_trace(MLF_OBJ *obj, double *out, int64_t n);
 /* Responsibilities (ProbaC(N,K), P[k*N+i]) and labels of the resident shard, as of the last E-pass. */
 int mlf_b200_resident_proba(MLF_OBJ *obj, double *P);
 int mlf_b200_resident_labels(MLF_OBJ *obj, int *Cl);
+/* Device pointer of the resident responsibilities (component k starts at k * *ld doubles; columns >= N are zero). */
+const double *mlf_b200_resident_proba_device(MLF_OBJ *obj, int64_t *ld);
 /* Profiling counters: out[0..5] = ms in refresh, E-pass, mid, M-pass, finalize, and iterations counted. */
 int mlf_b200_set_profile(MLF_OBJ *obj, int on);
 int mlf_b200_get_times(MLF_OBJ *obj, double out[6]);

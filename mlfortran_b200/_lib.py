@@ -50,6 +50,7 @@ SYMBOLS = {
     "mlf_b200_sumll_trace": (C.c_int64, [C.c_void_p, c_double_p, C.c_int64]),
     "mlf_b200_resident_proba": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mlf_b200_resident_labels": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mlf_b200_resident_proba_device": (C.c_void_p, [C.c_void_p, c_int64_p]),
     "mlf_b200_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "mlf_b200_get_times": (C.c_int, [C.c_void_p, c_double_p]),
     "mlf_b200_launch_count": (C.c_int64, [C.c_void_p]),

@@ -443,6 +443,13 @@ int mlf_b200_resident_proba(MLF_OBJ* obj, double* P) {
   return e == cudaSuccess ? 0 : mlf_OTHERERROR;
 }
 
+const double* mlf_b200_resident_proba_device(MLF_OBJ* obj, int64_t* ld) {
+  EmObject* o = as_em(obj);
+  if (!o) return nullptr;
+  if (ld) *ld = o->eng.gamma_ld();
+  return o->eng.gamma_device();
+}
+
 int mlf_b200_resident_labels(MLF_OBJ* obj, int* Cl) {
   EmObject* o = as_em(obj);
   if (!o || !Cl) return -1;
