@@ -93,6 +93,8 @@ int mlf_b200_set_allreduce(MLF_OBJ *obj, mlf_b200_allreduce_fn fn, void *ctx, in
 
 int mlf_b200_set_initialized(MLF_OBJ *obj, int initialized); /* the Fortran API exposes %initialized directly */
 int mlf_b200_get_initialized(MLF_OBJ *obj);
+/* Seed of the k-means initialiser's random stream (the reference uses an unseeded RANDOM_NUMBER, src/mlf_rand.f90:173-182). */
+int mlf_b200_set_seed(MLF_OBJ *obj, uint64_t seed);
 int mlf_b200_refresh_x(MLF_OBJ *obj, const double *X);        /* re-copy X after the caller changed it */
 const char *mlf_b200_last_error(MLF_OBJ *obj);
 /* sumLL of each EM iteration of the most recent mlf_step call (at most n values); returns how many exist. */
@@ -109,6 +111,27 @@ int64_t mlf_b200_launch_count(MLF_OBJ *obj);
 void *mlf_b200_stream(MLF_OBJ *obj);
 int64_t mlf_b200_global_points(MLF_OBJ *obj);
 const char *mlf_b200_version(void);
+
+/* ---- engine-level entry points: what a Fortran extension type binds with iso_c_binding --------------------------
+ * Deliverable form (A) of INTEGRATION.md: fortran/mlf_emgmm_b200.f90 declares a type extending the reference's
+ * mlf_step_obj whose init/reinit/stepF forward here, so that the reference's generic handle functions, HDF5
+ * checkpoint and resource slots keep working unchanged on Fortran-owned host arrays.  The engine owns only device
+ * state; Mu/Cov/lambda are caller arrays in the reference layout (uploaded at the start of a call, downloaded at
+ * its end), replacing ExpStep/MaxStep of src/unsupervised/mlf_emgmm.f90:174-207. */
+typedef void MLF_B200_ENGINE;
+MLF_B200_ENGINE *mlf_b200_engine_create(const double *X, int64_t nX, int nY, int nC, int device, unsigned flags);
+void mlf_b200_engine_destroy(MLF_B200_ENGINE *eng);
+/* niter x (ExpStep + MaxStep) from the caller's current Mu/Cov/lambda; sumLL of the last iteration. 0 or negative. */
+int mlf_b200_engine_step(MLF_B200_ENGINE *eng, int64_t niter, double minProba, double *Mu, double *Cov, double *lambda, double *sumLL);
+/* km_algo%init + stepF(nkm) + Cov = I + lambda = 1/nC  (src/unsupervised/mlf_emgmm.f90:135-145). */
+int mlf_b200_engine_kmeans_init(MLF_B200_ENGINE *eng, int nkm, uint64_t seed, double *Mu, double *Cov, double *lambda);
+/* ExpStep on caller data with the given parameters: P (nullable) as Proba(nIn,nC), Cl (nullable) 1-based MAXLOC. */
+int mlf_b200_engine_expectation(MLF_B200_ENGINE *eng, const double *Mu, const double *Cov, const double *lambda,
+                                const double *Xq, int64_t nIn, double *P, int *Cl);
+/* ProbaC(nX,nC) of the resident points as of the last ExpStep (the Fortran type's public ProbaC component). */
+int mlf_b200_engine_proba(MLF_B200_ENGINE *eng, double *ProbaC);
+int mlf_b200_engine_set_allreduce(MLF_B200_ENGINE *eng, mlf_b200_allreduce_fn fn, void *ctx, int rank, int world);
+const char *mlf_b200_engine_last_error(MLF_B200_ENGINE *eng);
 
 /* Generic dataset access on a checkpoint handle (root group; int64 / float64; dims in file (C) order, i.e. the
  * reverse of the Fortran shape).  mlf_b200_h5_get with data == NULL only reports type/rank/dims. */

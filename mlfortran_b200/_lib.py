@@ -45,6 +45,7 @@ SYMBOLS = {
     "mlf_b200_set_allreduce": (C.c_int, [C.c_void_p, ALLREDUCE_FN, C.c_void_p, C.c_int, C.c_int]),
     "mlf_b200_set_initialized": (C.c_int, [C.c_void_p, C.c_int]),
     "mlf_b200_get_initialized": (C.c_int, [C.c_void_p]),
+    "mlf_b200_set_seed": (C.c_int, [C.c_void_p, C.c_uint64]),
     "mlf_b200_refresh_x": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mlf_b200_last_error": (C.c_char_p, [C.c_void_p]),
     "mlf_b200_sumll_trace": (C.c_int64, [C.c_void_p, c_double_p, C.c_int64]),
@@ -57,6 +58,14 @@ SYMBOLS = {
     "mlf_b200_stream": (C.c_void_p, [C.c_void_p]),
     "mlf_b200_global_points": (C.c_int64, [C.c_void_p]),
     "mlf_b200_version": (C.c_char_p, []),
+    "mlf_b200_engine_create": (C.c_void_p, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint]),
+    "mlf_b200_engine_destroy": (None, [C.c_void_p]),
+    "mlf_b200_engine_step": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, c_double_p]),
+    "mlf_b200_engine_kmeans_init": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mlf_b200_engine_expectation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "mlf_b200_engine_proba": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mlf_b200_engine_set_allreduce": (C.c_int, [C.c_void_p, ALLREDUCE_FN, C.c_void_p, C.c_int, C.c_int]),
+    "mlf_b200_engine_last_error": (C.c_char_p, [C.c_void_p]),
     "mlf_b200_h5_put": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, c_int64_p, C.c_void_p, C.c_int]),
     "mlf_b200_h5_get": (C.c_int, [C.c_void_p, C.c_char_p, c_int_p, c_int_p, c_int64_p, C.c_void_p, C.c_int64]),
     "mlf_b200_h5_count": (C.c_int, [C.c_void_p]),

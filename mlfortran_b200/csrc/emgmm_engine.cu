@@ -190,11 +190,11 @@ int EmgmmEngine::download_params(double* Mu, double* Cov, double* lambda) {
   return 0;
 }
 
-int EmgmmEngine::run_estep(const double* X, int64_t n, double* gamma, int64_t ldg, int32_t* labels, bool want_stats) {
+int EmgmmEngine::run_estep(const double* X, int64_t n, double* gamma, int64_t ldg, int32_t* labels, bool want_stats, bool raw) {
   const Geom& g = geom_;
   const int64_t etiles = (n + kEstepTilePts - 1) / kEstepTilePts;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sms_, etiles));
-  CKE(launch_estep(g, X, n, dPack_, gamma, ldg, labels, dPartA_, grid, smem_limit_, st_), "estep");
+  CKE(launch_estep(g, X, n, dPack_, gamma, ldg, labels, dPartA_, grid, smem_limit_, raw ? 1 : 0, st_), "estep");
   ++launches_;
   if (want_stats) {
     CKE(launch_reduce_partials(dPartA_, grid, (int64_t)g.K8 * 8 * g.DS, dStatsA_, st_), "reduce statsA");
@@ -311,6 +311,15 @@ int EmgmmEngine::expectation(const double* Xq, bool on_device, int64_t nq, doubl
   return rc;
 }
 
+int EmgmmEngine::resident_proba(double* P_host) {
+  CKE(cudaSetDevice(device_), "cudaSetDevice");
+  if (n_ == 0) return 0;
+  CKE(cudaMemcpy2DAsync(P_host, (size_t)n_ * sizeof(double), dGamma_, (size_t)ldg_ * sizeof(double), (size_t)n_ * sizeof(double),
+                        geom_.K, cudaMemcpyDeviceToHost, st_), "D2H ProbaC");
+  CKE(cudaStreamSynchronize(st_), "sync");
+  return 0;
+}
+
 int EmgmmEngine::resident_labels(int32_t* labels_host) {
   CKE(cudaSetDevice(device_), "cudaSetDevice");
   if (n_ == 0) return 0;
@@ -326,9 +335,171 @@ int EmgmmEngine::resident_labels(int32_t* labels_host) {
   return 0;
 }
 
-int EmgmmEngine::kmeans_init(int /*nkm*/, uint64_t /*seed*/) {
-  err_ = "k-means initialiser not built yet: inject Mu/Cov/lambda (mlf_updatersc + mlf_b200_emgmm_set_initialized)";
-  return -7;
+// mlf_EvalGaussian for the single component of a K = 1 engine (src/unsupervised/mlf_gaussian.f90:63-79):
+// P_i = lambda * exp(-maha_i/2 - lnDet) (not normalised) and LL = N (log lambda - lnDet) + sum_i (-maha_i/2).
+int EmgmmEngine::eval_gaussian_raw(double* P_host, double* sumLL) {
+  CKE(cudaSetDevice(device_), "cudaSetDevice");
+  if (geom_.K != 1) { err_ = "eval_gaussian_raw needs a single-component engine"; return -7; }
+  if (int r = ensure_moments()) return r;
+  CKE(launch_refresh(geom_, dMu_, dCov_, dLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_), "refresh");
+  ++launches_;
+  if (n_ > 0)
+    if (int r = run_estep(dX_, n_, dGamma_, ldg_, nullptr, false, true)) return r;
+  if (P_host && n_ > 0) CKE(cudaMemcpyAsync(P_host, dGamma_, (size_t)n_ * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H P");
+  if (sumLL) CKE(cudaMemcpyAsync(sumLL, dSumLLk_, sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H LL");
+  CKE(cudaStreamSynchronize(st_), "sync");
+  return 0;
+}
+
+// mlf_MaxGaussian for given weights (src/unsupervised/mlf_gaussian.f90:41-51): W = P/sum(P); GECovMatrix with
+// minW = 1d-3/real(NX).  K = 1 engine; returns sum(P).
+int EmgmmEngine::max_gaussian(const double* Proba_host, double* mu_host, double* C_host, double* sumPi) {
+  CKE(cudaSetDevice(device_), "cudaSetDevice");
+  if (geom_.K != 1) { err_ = "max_gaussian needs a single-component engine"; return -7; }
+  const Geom& g = geom_;
+  if (n_ > 0) CKE(cudaMemcpyAsync(dGamma_, Proba_host, (size_t)n_ * sizeof(double), cudaMemcpyHostToDevice, st_), "H2D Proba");
+  const int grid = std::max(1, std::min<int>(sms_, (int)((n_ + 255) / 256)));
+  CKE(launch_stats_from_gamma(g, dX_, n_, dGamma_, dPartA_, grid, st_), "stats_from_gamma");
+  CKE(launch_reduce_partials(dPartA_, grid, g.DS, dStatsA_, st_), "reduce");
+  const double minW = 1e-3 / (double)(float)n_;
+  CKE(launch_mid(g, dStatsA_, minW, dMu_, dMupad_, dThr_, st_), "mid");
+  CKE(launch_mstep(g, dX_, n_, dGamma_, ldg_, dMupad_, dThr_, dPartB_, mgx_, st_), "mstep");
+  CKE(launch_reduce_partials(dPartB_, mgx_, (int64_t)g.K * g.MS, dStatsB_, st_), "reduce statsB");
+  CKE(launch_finalize(g, dStatsA_, dStatsB_, 0.0, dCov_, dLambda_, st_), "finalize");
+  launches_ += 6;
+  CKE(cudaMemcpyAsync(mu_host, dMu_, g.d * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H mu");
+  CKE(cudaMemcpyAsync(C_host, dCov_, (size_t)g.d * g.d * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H C");
+  if (sumPi) CKE(cudaMemcpyAsync(sumPi, dStatsA_, sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H sum");
+  CKE(cudaStreamSynchronize(st_), "sync");
+  return 0;
+}
+
+namespace {
+// splitmix64: the host-side stream that replaces the reference's unseeded RANDOM_NUMBER (src/mlf_rand.f90:173-182).
+// Every rank draws the same numbers from the same seed, so all ranks agree on the sampled point.
+inline double next_uniform(uint64_t& st) {
+  uint64_t z = (st += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+}  // namespace
+
+// mlf_GetFarPoint (src/unsupervised/mlf_kmeans.f90:140-149): draw a data point with probability proportional to
+// minDist^2 over the *global* data set.  dPart holds this rank's per-block sums; the owning rank copies the
+// point into dOut (d doubles), the others contribute zeros, and a sum all-reduce broadcasts it.
+int EmgmmEngine::draw_far_point(double u, int grid, int64_t chunk, double* dMinDist, double* dPart, double* dOut) {
+  const int d = geom_.d;
+  std::vector<double> part((size_t)grid);
+  CKE(cudaMemcpyAsync(part.data(), dPart, grid * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H seed partials");
+  CKE(cudaStreamSynchronize(st_), "sync");
+  double local = 0;
+  for (double v : part) local += v;
+  std::vector<double> tot((size_t)world_, 0.0);
+  tot[(size_t)rank_] = local;
+  if (world_ > 1) {
+    CKE(cudaMemcpyAsync(dOut, tot.data(), world_ * sizeof(double), cudaMemcpyHostToDevice, st_), "H2D totals");
+    if (int r = allreduce(dOut, world_)) return r;
+    CKE(cudaMemcpyAsync(tot.data(), dOut, world_ * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H totals");
+    CKE(cudaStreamSynchronize(st_), "sync");
+  }
+  double all = 0;
+  for (double v : tot) all += v;
+  double target = u * all;  // r*W(size(W)) (src/mlf_rand.f90:180)
+  int owner = world_ - 1;
+  while (owner > 0 && tot[(size_t)owner] <= 0) --owner;   // last rank with any weight
+  for (int r = 0; r < world_; ++r) {
+    if (tot[(size_t)r] > 0 && target <= tot[(size_t)r]) { owner = r; break; }
+    target -= tot[(size_t)r];
+  }
+  if (all <= 0) { owner = 0; target = 0; }  // degenerate: every point coincides with a centre -> first point
+  CKE(cudaMemsetAsync(dOut, 0, (size_t)std::max(d, world_) * sizeof(double), st_), "memset");
+  if (owner == rank_ && n_ > 0) {
+    int b = grid - 1;
+    while (b > 0 && part[(size_t)b] <= 0) --b;
+    double t = target;
+    for (int i = 0; i < grid; ++i) {
+      if (part[(size_t)i] > 0 && t <= part[(size_t)i]) { b = i; break; }
+      t -= part[(size_t)i];
+    }
+    if (t > part[(size_t)b]) t = part[(size_t)b];
+    const int64_t lo = (int64_t)b * chunk, hi = std::min<int64_t>(n_, lo + chunk);
+    CKE(launch_seed_pick(dX_, d, dMinDist, lo, hi, t, dOut, st_), "seed_pick");
+    ++launches_;
+  }
+  if (world_ > 1)
+    if (int r = allreduce(dOut, d)) return r;
+  return 0;
+}
+
+// km_algo%init + km_algo%stepF(nkm) + Cov = I + lambda = 1/K  (src/unsupervised/mlf_emgmm.f90:135-145):
+// one seeding pass (mlf_InitKMeans) followed by nkm-1 Lloyd steps (src/unsupervised/mlf_kmeans_naive.f90:55-96).
+// The reference draws from an unseeded RANDOM_NUMBER stream; here the stream is splitmix64(seed), so parity with the
+// reference is distributional only.  Empty clusters are re-seeded with mlf_GetFarPoint
+// against the finished centres (the reference mixes finished centres and raw sums at that point, :86-92).
+int EmgmmEngine::kmeans_init(int nkm, uint64_t seed) {
+  CKE(cudaSetDevice(device_), "cudaSetDevice");
+  if (int r = ensure_moments()) return r;
+  const Geom& g = geom_;
+  const int d = g.d, K = g.K;
+  if (nglob_ < 1) { err_ = "k-means initialiser needs at least one point"; return -7; }
+  uint64_t rng = seed;
+  const int grid = sms_;
+  const int64_t chunk = std::max<int64_t>(1, (n_ + grid - 1) / grid);
+  double *dMinDist = nullptr, *dPart = nullptr, *dOut = nullptr, *dCnt = nullptr;
+  CKE(cudaMalloc((void**)&dMinDist, std::max<int64_t>(n_, 1) * sizeof(double)), "cudaMalloc minDist");
+  CKE(cudaMalloc((void**)&dPart, grid * sizeof(double)), "cudaMalloc");
+  CKE(cudaMalloc((void**)&dOut, (size_t)std::max(d, world_) * sizeof(double)), "cudaMalloc");
+  CKE(cudaMalloc((void**)&dCnt, K * sizeof(double)), "cudaMalloc");
+  int rc = 0;
+  auto seed_pass = [&](const double* centre, int first) -> int {
+    CKE(launch_seed_update(dX_, n_, d, centre, dMinDist, first, chunk, grid, dPart, st_), "seed_update");
+    ++launches_;
+    return 0;
+  };
+  // Mu(:,1) = mean(X,2); Mu(:,1) = GetFarPoint(X, Mu(:,1:1)); Mu(:,i) = GetFarPoint(X, Mu(:,1:i-1))
+  for (int i = 0; i < K && rc == 0; ++i) {
+    const double* centre = (i == 0) ? dMean_ : dMu_ + (size_t)(i - 1) * d;
+    rc = seed_pass(centre, i <= 1 ? 1 : 0);
+    if (rc == 0) rc = draw_far_point(next_uniform(rng), grid, chunk, dMinDist, dPart, dOut);
+    if (rc == 0 && cudaMemcpyAsync(dMu_ + (size_t)i * d, dOut, d * sizeof(double), cudaMemcpyDeviceToDevice, st_) != cudaSuccess) rc = -7;
+  }
+  std::vector<double> cnt((size_t)K);
+  for (int it = 1; it < nkm && rc == 0; ++it) {
+    // mlf_EvaluateClass + EvaluateCentres
+    if (launch_kmeans_assign(dX_, n_, d, K, dMu_, nullptr, nullptr, dPartA_, grid, st_) != cudaSuccess) { rc = -7; break; }
+    if (launch_reduce_partials(dPartA_, grid, (int64_t)K * (d + 1), dStatsA_, st_) != cudaSuccess) { rc = -7; break; }
+    launches_ += 2;
+    if ((rc = allreduce(dStatsA_, (int64_t)K * (d + 1)))) break;
+    if (launch_kmeans_centres(dStatsA_, K, d, dMu_, dCnt, st_) != cudaSuccess) { rc = -7; break; }
+    ++launches_;
+    if (cudaMemcpyAsync(cnt.data(), dCnt, K * sizeof(double), cudaMemcpyDeviceToHost, st_) != cudaSuccess ||
+        cudaStreamSynchronize(st_) != cudaSuccess) { rc = -7; break; }
+    bool any_empty = false;
+    for (double c : cnt) any_empty |= !(c > 0);
+    if (!any_empty) continue;
+    // distances to the finished centres (empty ones sit at +inf and attract nothing)
+    if (launch_kmeans_assign(dX_, n_, d, K, dMu_, nullptr, dMinDist, nullptr, grid, st_) != cudaSuccess) { rc = -7; break; }
+    ++launches_;
+    bool have_part = false;
+    for (int k = 0; k < K && rc == 0; ++k) {
+      if (cnt[(size_t)k] > 0) continue;
+      if (!have_part) {  // per-block sums of the current minDist^2: min with an infinitely far "centre" changes nothing
+        rc = seed_pass(dMu_ + (size_t)k * d, 0);
+        have_part = true;
+      }
+      if (rc == 0) rc = draw_far_point(next_uniform(rng), grid, chunk, dMinDist, dPart, dOut);
+      if (rc == 0 && cudaMemcpyAsync(dMu_ + (size_t)k * d, dOut, d * sizeof(double), cudaMemcpyDeviceToDevice, st_) != cudaSuccess) rc = -7;
+      if (rc == 0) rc = seed_pass(dMu_ + (size_t)k * d, 0);
+    }
+  }
+  if (rc == 0 && launch_identity_cov(K, d, dCov_, dLambda_, st_) != cudaSuccess) rc = -7;
+  ++launches_;
+  cudaStreamSynchronize(st_);
+  cudaFree(dMinDist); cudaFree(dPart); cudaFree(dOut); cudaFree(dCnt);
+  if (rc != 0 && err_.empty()) err_ = "k-means initialiser failed";
+  return rc;
 }
 
 }  // namespace mlfb200

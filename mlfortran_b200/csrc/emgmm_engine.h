@@ -30,7 +30,9 @@ class EmgmmEngine {
   // X: N_local x d, point-major (Fortran X(d,N)).  x_on_device: X is a device pointer that the caller keeps
   // alive (borrowed, like the reference's `this%X => X`); otherwise it is copied host->device here.
   int init(const double* X, bool x_on_device, int64_t n_local, int d, int K, int device);
-  void set_allreduce(allreduce_fn fn, void* ctx) { ar_ = fn; ar_ctx_ = ctx; moments_ready_ = false; }
+  void set_allreduce(allreduce_fn fn, void* ctx, int rank, int world) {
+    ar_ = fn; ar_ctx_ = ctx; rank_ = rank; world_ = world < 1 ? 1 : world; moments_ready_ = false;
+  }
   void set_stream(cudaStream_t st);
   int refresh_x(const double* X, bool x_on_device);
 
@@ -46,8 +48,13 @@ class EmgmmEngine {
   int expectation(const double* Xq, bool on_device, int64_t nq, double* P_host, int32_t* labels_host);
   // Labels / responsibilities of the resident shard from the most recent E-pass parameters.
   int resident_labels(int32_t* labels_host);
+  int resident_proba(double* P_host);  // ProbaC(N,K): P[k*N + i]
   const double* gamma_device() const { return dGamma_; }
   int64_t gamma_ld() const { return ldg_; }
+
+  // Single-component entry points (K = 1 engines): see emgmm_engine.cu.
+  int eval_gaussian_raw(double* P_host, double* sumLL);
+  int max_gaussian(const double* Proba_host, double* mu_host, double* C_host, double* sumPi);
 
   // k-means initialiser (src/unsupervised/mlf_emgmm.f90:135-145): seeding + nkm-1 Lloyd steps, Cov=I, lambda=1/K.
   int kmeans_init(int nkm, uint64_t seed);
@@ -67,8 +74,9 @@ class EmgmmEngine {
  private:
   int fail(const char* what, cudaError_t e);
   int ensure_moments();
-  int run_estep(const double* X, int64_t n, double* gamma, int64_t ldg, int32_t* labels, bool want_stats);
+  int run_estep(const double* X, int64_t n, double* gamma, int64_t ldg, int32_t* labels, bool want_stats, bool raw = false);
   int allreduce(double* buf, int64_t count);
+  int draw_far_point(double u, int grid, int64_t chunk, double* dMinDist, double* dPart, double* dOut);
 
   Geom geom_{};
   int device_ = 0, sms_ = 148;
@@ -90,6 +98,7 @@ class EmgmmEngine {
   int egrid_ = 0, mgx_ = 0, mgy_ = 0;
   bool moments_ready_ = false;
   allreduce_fn ar_ = nullptr;
+  int rank_ = 0, world_ = 1;
   void* ar_ctx_ = nullptr;
   std::string err_;
   EngineTimes times_;

@@ -252,7 +252,7 @@ cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, c
 template <int DM, int CBMAX>
 __global__ void __launch_bounds__(kEstepThreads, 1)
 k_estep(const double* __restrict__ X, int64_t N, int d, int K, int K8, int S, const double* __restrict__ pack,
-        double* __restrict__ gamma, int64_t ldg, int32_t* __restrict__ labels, double* __restrict__ partial) {
+        double* __restrict__ gamma, int64_t ldg, int32_t* __restrict__ labels, double* __restrict__ partial, int raw) {
   constexpr int DN = (DM + 1) / 2;
   constexpr int NB = blk_off(DM);
   constexpr int PS = NB * 32 + 4 * DM + 4;
@@ -351,6 +351,7 @@ k_estep(const double* __restrict__ X, int64_t N, int d, int K, int K8, int S, co
         const int oa = __shfl_xor_sync(0xffffffffu, am, sh);
         if (om > m || (om == m && oa < am)) { m = om; am = oa; }
       }
+      if (raw) m = 0.0;  // mlf_evalGaussian: P = lambda*exp(v - lnDet), not normalised (src/unsupervised/mlf_gaussian.f90:77)
       double sum = 0;
       for (int k4 = 0; k4 < K4; ++k4) {
         const double e = exp(row[grp][4 * k4 + t] - m);
@@ -359,7 +360,7 @@ k_estep(const double* __restrict__ X, int64_t N, int d, int K, int K8, int S, co
       }
       sum += shfl_xor_d(sum, 1);
       sum += shfl_xor_d(sum, 2);
-      const double inv = valid ? 1.0 / sum : 0.0;
+      const double inv = valid ? (raw ? 1.0 : 1.0 / sum) : 0.0;
       for (int k4 = 0; k4 < K4; ++k4) {
         const int k = 4 * k4 + t;
         const double gk = row[grp][k] * inv;
@@ -419,37 +420,37 @@ int estep_cbmax(const Geom& g) { return g.K8 <= 8 ? 1 : (g.K8 <= 16 ? 2 : (g.K8 
 
 template <int DM, int CBMAX>
 static cudaError_t launch_estep_t(const Geom& g, const double* X, int64_t N, const double* pack, double* gamma, int64_t ldg,
-                                  int32_t* labels, double* partial, int grid, size_t smem, cudaStream_t st) {
+                                  int32_t* labels, double* partial, int grid, size_t smem, int raw, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(k_estep<DM, CBMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_estep<DM, CBMAX><<<grid, kEstepThreads, smem, st>>>(X, N, g.d, g.K, g.K8, g.S, pack, gamma, ldg, labels, partial);
+  k_estep<DM, CBMAX><<<grid, kEstepThreads, smem, st>>>(X, N, g.d, g.K, g.K8, g.S, pack, gamma, ldg, labels, partial, raw);
   return cudaGetLastError();
 }
 
 template <int DM>
 static cudaError_t launch_estep_dm(const Geom& g, const double* X, int64_t N, const double* pack, double* gamma, int64_t ldg,
-                                   int32_t* labels, double* partial, int grid, size_t smem, cudaStream_t st) {
+                                   int32_t* labels, double* partial, int grid, size_t smem, int raw, cudaStream_t st) {
   switch (estep_cbmax(g)) {
-    case 1: return launch_estep_t<DM, 1>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
-    case 2: return launch_estep_t<DM, 2>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
-    case 4: return launch_estep_t<DM, 4>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
-    default: return launch_estep_t<DM, 8>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
+    case 1: return launch_estep_t<DM, 1>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, raw, st);
+    case 2: return launch_estep_t<DM, 2>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, raw, st);
+    case 4: return launch_estep_t<DM, 4>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, raw, st);
+    default: return launch_estep_t<DM, 8>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, raw, st);
   }
 }
 
 cudaError_t launch_estep(const Geom& g, const double* X, int64_t N, const double* pack, double* gamma, int64_t ldg,
-                         int32_t* labels, double* partial, int grid, size_t smem_limit, cudaStream_t st) {
+                         int32_t* labels, double* partial, int grid, size_t smem_limit, int raw, cudaStream_t st) {
   const size_t smem = estep_smem_bytes(g);
   if (smem > smem_limit || g.K8 > 64) return cudaErrorInvalidConfiguration;
   switch (g.DM) {
-    case 1: return launch_estep_dm<1>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
-    case 2: return launch_estep_dm<2>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
-    case 3: return launch_estep_dm<3>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
-    case 4: return launch_estep_dm<4>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
-    case 5: return launch_estep_dm<5>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
-    case 6: return launch_estep_dm<6>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
-    case 7: return launch_estep_dm<7>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
-    case 8: return launch_estep_dm<8>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, st);
+    case 1: return launch_estep_dm<1>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, raw, st);
+    case 2: return launch_estep_dm<2>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, raw, st);
+    case 3: return launch_estep_dm<3>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, raw, st);
+    case 4: return launch_estep_dm<4>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, raw, st);
+    case 5: return launch_estep_dm<5>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, raw, st);
+    case 6: return launch_estep_dm<6>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, raw, st);
+    case 7: return launch_estep_dm<7>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, raw, st);
+    case 8: return launch_estep_dm<8>(g, X, N, pack, gamma, ldg, labels, partial, grid, smem, raw, st);
     default: return cudaErrorInvalidConfiguration;
   }
 }
@@ -466,6 +467,46 @@ __global__ void k_reduce_partials(const double* __restrict__ partial, int nblock
 }
 cudaError_t launch_reduce_partials(const double* partial, int nblocks, int64_t n, double* out, cudaStream_t st) {
   k_reduce_partials<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(partial, nblocks, n, out);
+  return cudaGetLastError();
+}
+
+// Pass-A statistics of ONE component from given weights (mlf_maxGaussian entry point, src/unsupervised/mlf_gaussian.f90:41-51):
+// partial[block][DS] = [sum g, sum g^2, sum g x].  Thread = (point lane, dimension).
+__global__ void __launch_bounds__(256) k_stats_from_gamma(const double* __restrict__ X, int64_t N, int d, int DS,
+                                                          const double* __restrict__ gamma, double* __restrict__ partial) {
+  __shared__ double red[3][256];
+  const int tid = threadIdx.x;
+  const int lanes = 256 / d;
+  const int a = tid % d, pl = tid / d;
+  double sx = 0, sg = 0, sg2 = 0;
+  if (pl < lanes)
+    for (int64_t p = (int64_t)blockIdx.x * lanes + pl; p < N; p += (int64_t)gridDim.x * lanes) {
+      const double gv = gamma[p];
+      sx = fma(gv, X[p * d + a], sx);
+      if (a == 0) { sg += gv; sg2 = fma(gv, gv, sg2); }
+    }
+  red[0][tid] = (pl < lanes) ? sx : 0.0;
+  red[1][tid] = sg;
+  red[2][tid] = sg2;
+  __syncthreads();
+  double* o = partial + (size_t)blockIdx.x * DS;
+  if (tid < d) {
+    double r = 0;
+    for (int j = 0; j < lanes; ++j) r += red[0][j * d + tid];
+    o[2 + tid] = r;
+  } else if (tid < DS - 2) {
+    o[2 + tid] = 0.0;
+  }
+  if (tid == 0) {
+    double r1 = 0, r2 = 0;
+    for (int j = 0; j < lanes; ++j) { r1 += red[1][j * d]; r2 += red[2][j * d]; }
+    o[0] = r1;
+    o[1] = r2;
+  }
+}
+cudaError_t launch_stats_from_gamma(const Geom& g, const double* X, int64_t N, const double* gamma, double* partial, int grid,
+                                    cudaStream_t st) {
+  k_stats_from_gamma<<<grid, 256, 0, st>>>(X, N, g.d, g.DS, gamma, partial);
   return cudaGetLastError();
 }
 
@@ -728,6 +769,119 @@ cudaError_t launch_kmeans_assign(const double* X, int64_t N, int d, int K, const
     if (e != cudaSuccess) return e;
   }
   k_kmeans_assign<<<grid, 256, smem, st>>>(X, N, d, K, Mu, cl, minDist, partial);
+  return cudaGetLastError();
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// k-means seeding (mlf_InitKMeans / mlf_GetFarPoint, src/unsupervised/mlf_kmeans.f90:140-149,168-182): the next
+// centre is a data point drawn with probability proportional to minDist^2.  Block b owns the contiguous
+// chunk [b*chunk, (b+1)*chunk) so that the host can locate the drawn point from the per-block sums.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_seed_update(const double* __restrict__ X, int64_t N, int d,
+                                                     const double* __restrict__ centre, double* __restrict__ minDist,
+                                                     int first, int64_t chunk, double* __restrict__ partial) {
+  __shared__ double sc[128];
+  __shared__ double red[256];
+  const int tid = threadIdx.x;
+  for (int a = tid; a < d; a += 256) sc[a] = centre[a];
+  __syncthreads();
+  const int64_t lo = (int64_t)blockIdx.x * chunk;
+  const int64_t hi = (lo + chunk < N) ? lo + chunk : N;
+  double s = 0;
+  for (int64_t p = lo + tid; p < hi; p += 256) {
+    const double* x = X + p * d;
+    double q = 0;
+    for (int a = 0; a < d; ++a) { const double t = x[a] - sc[a]; q = fma(t, t, q); }
+    double m = sqrt(q);  // norm2 (src/unsupervised/mlf_kmeans.f90:160)
+    if (!first) m = fmin(minDist[p], m);
+    minDist[p] = m;
+    s = fma(m, m, s);
+  }
+  red[tid] = s;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (tid < st) red[tid] += red[tid + st];
+    __syncthreads();
+  }
+  if (tid == 0) partial[blockIdx.x] = red[0];
+}
+cudaError_t launch_seed_update(const double* X, int64_t N, int d, const double* centre, double* minDist, int first,
+                               int64_t chunk, int grid, double* partial, cudaStream_t st) {
+  k_seed_update<<<grid, 256, 0, st>>>(X, N, d, centre, minDist, first, chunk, partial);
+  return cudaGetLastError();
+}
+
+// First index i in [lo, hi) whose running sum of minDist^2 reaches `target` (mlf_rand_class / mlf_di_search on the
+// cumulative vector, src/mlf_rand.f90:173-182); copies that point into out[0..d).  One block.
+__global__ void __launch_bounds__(256) k_seed_pick(const double* __restrict__ X, int d, const double* __restrict__ minDist,
+                                                   int64_t lo, int64_t hi, double target, double* __restrict__ out) {
+  __shared__ double loc[256], pre[256];
+  __shared__ long long s_idx;
+  const int tid = threadIdx.x;
+  const int64_t n = hi - lo, sub = (n + 255) / 256;
+  const int64_t a0 = lo + tid * sub, a1 = (a0 + sub < hi) ? a0 + sub : hi;
+  double s = 0;
+  for (int64_t p = a0; p < a1; ++p) { const double m = minDist[p]; s = fma(m, m, s); }
+  loc[tid] = s;
+  __syncthreads();
+  if (tid == 0) {
+    double run = 0;
+    int owner = -1, lastnz = -1;
+    for (int t = 0; t < 256; ++t) {
+      pre[t] = run;
+      run += loc[t];
+      if (loc[t] > 0) lastnz = t;
+      if (owner < 0 && loc[t] > 0 && run >= target) owner = t;
+    }
+    if (owner < 0) owner = lastnz;
+    s_idx = (owner < 0) ? (long long)lo : -(long long)owner - 1;  // negative: thread -(v+1) scans its slice
+  }
+  __syncthreads();
+  const long long code = s_idx;
+  if (code < 0 && tid == (int)(-code - 1)) {
+    double run = pre[tid];
+    long long idx = -1, lastnz = a0;
+    for (int64_t p = a0; p < a1; ++p) {
+      const double m = minDist[p];
+      if (m > 0) lastnz = p;
+      run = fma(m, m, run);
+      if (m > 0 && run >= target) { idx = p; break; }
+    }
+    s_idx = idx >= 0 ? idx : lastnz;
+  }
+  __syncthreads();
+  const int64_t idx = s_idx;
+  for (int a = tid; a < d; a += 256) out[a] = X[idx * d + a];
+}
+cudaError_t launch_seed_pick(const double* X, int d, const double* minDist, int64_t lo, int64_t hi, double target,
+                             double* out, cudaStream_t st) {
+  k_seed_pick<<<1, 256, 0, st>>>(X, d, minDist, lo, hi, target, out);
+  return cudaGetLastError();
+}
+
+// EvaluateCentres (src/unsupervised/mlf_kmeans_naive.f90:74-96): Mu_k = sum_k / n_k; empty clusters are flagged
+// (count 0) and given an infinite centre so that they attract no point until re-seeded by the host logic.
+__global__ void k_kmeans_centres(const double* __restrict__ sums, int K, int d, double* __restrict__ Mu,
+                                 double* __restrict__ counts) {
+  const int k = blockIdx.x;
+  const double n = sums[(size_t)k * (d + 1) + d];
+  for (int a = threadIdx.x; a < d; a += blockDim.x) Mu[(size_t)k * d + a] = n > 0 ? sums[(size_t)k * (d + 1) + a] / n : INFINITY;
+  if (threadIdx.x == 0) counts[k] = n;
+}
+cudaError_t launch_kmeans_centres(const double* sums, int K, int d, double* Mu, double* counts, cudaStream_t st) {
+  k_kmeans_centres<<<K, 32, 0, st>>>(sums, K, d, Mu, counts);
+  return cudaGetLastError();
+}
+
+// Cov_k = I (IdentityMatrix, src/mlf_matrix.f90:90-95), lambda_k = 1/K  (src/unsupervised/mlf_emgmm.f90:141-145)
+__global__ void k_identity_cov(int K, int d, double* __restrict__ Cov, double* __restrict__ lambda) {
+  const int k = blockIdx.x;
+  for (int i = threadIdx.x; i < d * d; i += blockDim.x) Cov[(size_t)k * d * d + i] = (i % d == i / d) ? 1.0 : 0.0;
+  if (threadIdx.x == 0) lambda[k] = 1.0 / (double)K;
+}
+cudaError_t launch_identity_cov(int K, int d, double* Cov, double* lambda, cudaStream_t st) {
+  k_identity_cov<<<K, 128, 0, st>>>(K, d, Cov, lambda);
   return cudaGetLastError();
 }
 

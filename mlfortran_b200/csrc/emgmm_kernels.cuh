@@ -37,9 +37,13 @@ cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, c
 // E-pass: responsibilities (component-major gamma[k*ldg + i]), optional 1-based labels, and per-block
 // partial pass-A statistics partial[block][K8*8][DS].  Returns the grid size used through *grid_out.
 cudaError_t launch_estep(const Geom& g, const double* X, int64_t N, const double* pack, double* gamma, int64_t ldg,
-                         int32_t* labels, double* partial, int grid, size_t smem_limit, cudaStream_t st);
+                         int32_t* labels, double* partial, int grid, size_t smem_limit, int raw, cudaStream_t st);
 size_t estep_smem_bytes(const Geom& g);
 int estep_cbmax(const Geom& g);
+
+// Pass-A statistics of a single component from given weights gamma[0..N): partial[grid][DS].
+cudaError_t launch_stats_from_gamma(const Geom& g, const double* X, int64_t N, const double* gamma, double* partial, int grid,
+                                    cudaStream_t st);
 
 // Fixed-order reduction over blocks: out[j] = sum_b partial[b*n + j].
 cudaError_t launch_reduce_partials(const double* partial, int nblocks, int64_t n, double* out, cudaStream_t st);
@@ -70,5 +74,15 @@ cudaError_t launch_sum_k(const double* v, int K, double* out, cudaStream_t st);
 // (src/unsupervised/mlf_kmeans.f90:151-165, mlf_kmeans_naive.f90:74-96).
 cudaError_t launch_kmeans_assign(const double* X, int64_t N, int d, int K, const double* Mu, int32_t* cl, double* minDist,
                                  double* partial /*[grid][K][d+1]*/, int grid, cudaStream_t st);
+
+
+// k-means seeding: minDist[p] = first ? |x_p - c| : min(minDist[p], |x_p - c|); partial[b] = sum over block b's
+// contiguous chunk of minDist^2.  k_seed_pick copies the point at which the running sum reaches `target`.
+cudaError_t launch_seed_update(const double* X, int64_t N, int d, const double* centre, double* minDist, int first,
+                               int64_t chunk, int grid, double* partial, cudaStream_t st);
+cudaError_t launch_seed_pick(const double* X, int d, const double* minDist, int64_t lo, int64_t hi, double target,
+                             double* out, cudaStream_t st);
+cudaError_t launch_kmeans_centres(const double* sums, int K, int d, double* Mu, double* counts, cudaStream_t st);
+cudaError_t launch_identity_cov(int K, int d, double* Cov, double* lambda, cudaStream_t st);
 
 }  // namespace mlfb200

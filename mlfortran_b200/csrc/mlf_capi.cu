@@ -394,7 +394,7 @@ MLF_OBJ* mlf_b200_emgmm_create(const double* X, int64_t nX, int nY, int nC, doub
 int mlf_b200_set_allreduce(MLF_OBJ* obj, mlf_b200_allreduce_fn fn, void* ctx, int rank, int world) {
   EmObject* o = as_em(obj);
   if (!o) return -1;
-  o->eng.set_allreduce(fn, ctx);
+  o->eng.set_allreduce(fn, ctx, rank, world);
   o->rank = rank;
   o->world = world;
   return 0;
@@ -409,6 +409,13 @@ int mlf_b200_set_initialized(MLF_OBJ* obj, int initialized) {
 int mlf_b200_get_initialized(MLF_OBJ* obj) {
   EmObject* o = as_em(obj);
   return o ? (o->initialized ? 1 : 0) : -1;
+}
+
+int mlf_b200_set_seed(MLF_OBJ* obj, uint64_t seed) {
+  EmObject* o = as_em(obj);
+  if (!o) return -1;
+  o->seed = seed;
+  return 0;
 }
 
 int mlf_b200_refresh_x(MLF_OBJ* obj, const double* X) {
@@ -436,11 +443,7 @@ int64_t mlf_b200_sumll_trace(MLF_OBJ* obj, double* out, int64_t n) {
 int mlf_b200_resident_proba(MLF_OBJ* obj, double* P) {
   EmObject* o = as_em(obj);
   if (!o || !P) return -1;
-  if (o->N == 0) return 0;
-  cudaError_t e = cudaMemcpy2DAsync(P, (size_t)o->N * sizeof(double), o->eng.gamma_device(), (size_t)o->eng.gamma_ld() * sizeof(double),
-                                    (size_t)o->N * sizeof(double), o->K, cudaMemcpyDeviceToHost, o->eng.stream());
-  if (e == cudaSuccess) e = cudaStreamSynchronize(o->eng.stream());
-  return e == cudaSuccess ? 0 : mlf_OTHERERROR;
+  return o->eng.resident_proba(P);
 }
 
 const double* mlf_b200_resident_proba_device(MLF_OBJ* obj, int64_t* ld) {
@@ -532,14 +535,82 @@ const char* mlf_b200_h5_name(MLF_OBJ* handler, int idx) {
   return h->ds[(size_t)idx].name.c_str();
 }
 
-// Single-component entry points: to be wired to the device kernels.
-int mlf_evalGaussian(int, int, const double*, double*, const double*, const double*, double, double*) {
-  fprintf(stderr, "mlf_evalGaussian: not built yet in mlfortran_b200\n");
-  return mlf_OTHERERROR;
+// ---- engine-level entry points (bound by fortran/mlf_emgmm_b200.f90) ---------------------------------------------
+MLF_B200_ENGINE* mlf_b200_engine_create(const double* X, int64_t nX, int nY, int nC, int device, unsigned flags) {
+  if ((!X && nX > 0) || nX < 0 || nY < 1 || nC < 1) return nullptr;
+  std::unique_ptr<EmgmmEngine> e(new EmgmmEngine());
+  if (device < 0 && cudaGetDevice(&device) != cudaSuccess) device = 0;
+  if (e->init(X, (flags & MLF_B200_X_ON_DEVICE) != 0, nX, nY, nC, device) < 0) {
+    fprintf(stderr, "mlf_b200_engine_create: %s\n", e->last_error().c_str());
+    return nullptr;
+  }
+  return e.release();
 }
-double mlf_maxGaussian(int, int, const double*, const double*, double*, double*) {
-  fprintf(stderr, "mlf_maxGaussian: not built yet in mlfortran_b200\n");
-  return std::numeric_limits<double>::quiet_NaN();
+void mlf_b200_engine_destroy(MLF_B200_ENGINE* eng) { delete static_cast<EmgmmEngine*>(eng); }
+int mlf_b200_engine_step(MLF_B200_ENGINE* eng, int64_t niter, double minProba, double* Mu, double* Cov, double* lambda, double* sumLL) {
+  EmgmmEngine* e = static_cast<EmgmmEngine*>(eng);
+  if (!e || !Mu || !Cov || !lambda) return -1;
+  if (niter <= 0) return 0;
+  int r = e->upload_params(Mu, Cov, lambda);
+  if (r == 0) r = e->iterate(niter, minProba, sumLL, nullptr);
+  if (r == 0) r = e->download_params(Mu, Cov, lambda);
+  return r;
+}
+int mlf_b200_engine_kmeans_init(MLF_B200_ENGINE* eng, int nkm, uint64_t seed, double* Mu, double* Cov, double* lambda) {
+  EmgmmEngine* e = static_cast<EmgmmEngine*>(eng);
+  if (!e || !Mu || !Cov || !lambda) return -1;
+  int r = e->kmeans_init(nkm, seed);
+  if (r == 0) r = e->download_params(Mu, Cov, lambda);
+  return r;
+}
+int mlf_b200_engine_expectation(MLF_B200_ENGINE* eng, const double* Mu, const double* Cov, const double* lambda, const double* Xq,
+                                int64_t nIn, double* P, int* Cl) {
+  EmgmmEngine* e = static_cast<EmgmmEngine*>(eng);
+  if (!e || !Mu || !Cov || !lambda || nIn < 0 || (!Xq && nIn > 0)) return -1;
+  int r = e->upload_params(Mu, Cov, lambda);
+  if (r == 0) r = e->expectation(Xq, false, nIn, P, Cl);
+  return r;
+}
+int mlf_b200_engine_proba(MLF_B200_ENGINE* eng, double* ProbaC) {
+  EmgmmEngine* e = static_cast<EmgmmEngine*>(eng);
+  if (!e || !ProbaC) return -1;
+  return e->resident_proba(ProbaC);
+}
+int mlf_b200_engine_set_allreduce(MLF_B200_ENGINE* eng, mlf_b200_allreduce_fn fn, void* ctx, int rank, int world) {
+  EmgmmEngine* e = static_cast<EmgmmEngine*>(eng);
+  if (!e) return -1;
+  e->set_allreduce(fn, ctx, rank, world);
+  return 0;
+}
+const char* mlf_b200_engine_last_error(MLF_B200_ENGINE* eng) {
+  EmgmmEngine* e = static_cast<EmgmmEngine*>(eng);
+  return e ? e->last_error().c_str() : "invalid engine";
+}
+
+// Single-component entry points (src/unsupervised/mlf_gaussian.f90:53-59,81-88): a temporary K = 1 engine over the
+// caller's X runs the same kernels as the step object.
+int mlf_evalGaussian(int ND, int NX, const double* X, double* P, const double* mu, const double* C, double lambda, double* sumLL) {
+  if (ND < 1 || NX < 0 || !X || !mu || !C) return mlf_OTHERERROR;
+  EmgmmEngine eng;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  if (eng.init(X, false, NX, ND, 1, dev) < 0) { fprintf(stderr, "mlf_evalGaussian: %s\n", eng.last_error().c_str()); return mlf_OTHERERROR; }
+  if (eng.upload_params(mu, C, &lambda) < 0) return mlf_OTHERERROR;
+  double ll = 0;
+  if (eng.eval_gaussian_raw(P, &ll) < 0) return mlf_OTHERERROR;
+  if (sumLL) *sumLL = ll;
+  return 0;
+}
+double mlf_maxGaussian(int ND, int NX, const double* X, const double* Proba, double* mu, double* C) {
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  if (ND < 1 || NX < 0 || !X || !Proba || !mu || !C) return nan;
+  EmgmmEngine eng;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  if (eng.init(X, false, NX, ND, 1, dev) < 0) { fprintf(stderr, "mlf_maxGaussian: %s\n", eng.last_error().c_str()); return nan; }
+  double s = nan;
+  if (eng.max_gaussian(Proba, mu, C, &s) < 0) return nan;
+  return s;
 }
 
 }  // extern "C"

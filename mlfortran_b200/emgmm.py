@@ -264,6 +264,10 @@ class mlf_algo_emgmm:
         self._lambda[...] = lam
         self.initialized = True
 
+    def set_seed(self, seed: int) -> None:
+        """Seed of the k-means initialiser's random stream (reference: unseeded RANDOM_NUMBER)."""
+        self._lib.mlf_b200_set_seed(self._h, int(seed) & (2 ** 64 - 1))
+
     def labels(self) -> np.ndarray:
         cl = np.zeros(int(self._X.shape[0]), dtype=np.int32)
         info = self._lib.mlf_b200_resident_labels(self._h, cl.ctypes.data)
@@ -311,3 +315,29 @@ class mlf_algo_emgmm:
 
         self._cb = _lib.ALLREDUCE_FN(_tramp)
         self._lib.mlf_b200_set_allreduce(self._h, self._cb, None, rank, world)
+
+
+def mlf_evalGaussian(X, mu, C, lam):
+    """info, P, sumLL = mlf_evalGaussian(ND, NX, X, P, mu, C, lambda, sumLL) (src/unsupervised/mlf_gaussian.f90:81-88)."""
+    import ctypes as _C
+    lib = _lib.load()
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    n, d = X.shape
+    mu = np.ascontiguousarray(mu, dtype=np.float64)
+    Cm = np.ascontiguousarray(C, dtype=np.float64)
+    P = np.empty(n)
+    ll = _C.c_double()
+    info = lib.mlf_evalGaussian(d, n, X.ctypes.data, P.ctypes.data, mu.ctypes.data, Cm.ctypes.data, float(lam), _C.byref(ll))
+    return info, P, ll.value
+
+
+def mlf_maxGaussian(X, Proba):
+    """sumPi, mu, C = mlf_maxGaussian(ND, NX, X, Proba, mu, C) (src/unsupervised/mlf_gaussian.f90:53-59)."""
+    lib = _lib.load()
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    n, d = X.shape
+    Proba = np.ascontiguousarray(Proba, dtype=np.float64)
+    mu = np.empty(d)
+    Cm = np.empty((d, d))
+    s = lib.mlf_maxGaussian(d, n, X.ctypes.data, Proba.ctypes.data, mu.ctypes.data, Cm.ctypes.data)
+    return s, mu, Cm

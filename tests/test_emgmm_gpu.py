@@ -326,6 +326,113 @@ def test_run_to_run_determinism():
         np.testing.assert_array_equal(x, y)
 
 
+# ---- fresh object: the first step is the k-means initialiser (src/unsupervised/mlf_emgmm.f90:134-145) -----------------
+def _inertia(oracle, X, Mu):
+    _, md = oracle.kmeans_evaluate_class(X, Mu)
+    return float((md * md).sum())
+
+
+def test_fresh_object_first_step_is_kmeans_init(oracle):
+    # four unit-variance clusters at the corners of a 200 x 200 square: a D^2 seeding misses a cluster with
+    # probability ~1e-4, so Lloyd must end at the true partition
+    rng = np.random.default_rng(71)
+    centres = np.array([[-100.0, -100.0], [-100.0, 100.0], [100.0, -100.0], [100.0, 100.0]])
+    X = np.ascontiguousarray((centres[:, None, :] + rng.standard_normal((4, 500, 2))).reshape(-1, 2)[rng.permutation(2000)])
+    data = {"X": X, "centres": centres}
+    em = mlf_algo_emgmm()
+    assert em.init(X, 4, 1.0) == 0
+    em.set_seed(1234)
+    assert not em.initialized
+    info, _ = em.step(1)
+    assert info == 0, em.last_error()
+    assert em.initialized and em.niter == 1
+    np.testing.assert_array_equal(em.Cov, np.tile(np.eye(2), (4, 1, 1)))     # IdentityMatrix
+    np.testing.assert_array_equal(em.lambda_, np.full(4, 0.25))              # 1/nC
+    Mu_km = em.Mu.copy()
+    assert np.isfinite(Mu_km).all()
+    # distributional parity only (the reference's stream is an unseeded RANDOM_NUMBER): Lloyd from a D^2 seeding on
+    # well-separated clusters must reach the quality of the true centres
+    assert _inertia(oracle, X, Mu_km) <= 1.05 * _inertia(oracle, X, data["centres"])
+    # the centres are a fixed point of the reference's Lloyd step (EvaluateClass + EvaluateCentres)
+    cl, _ = oracle.kmeans_evaluate_class(X, Mu_km)
+    Mu_next, empty = oracle.kmeans_evaluate_centres(X, cl, 4)
+    assert empty == 0 and np.abs(Mu_next - Mu_km).max() <= 1e-9
+    # step(n) on a fresh object = initialiser + (n-1) EM iterations
+    em2 = mlf_algo_emgmm()
+    assert em2.init(X, 4, 1.0) == 0
+    em2.set_seed(1234)
+    assert em2.step(5)[0] == 0 and em2.niter == 5 and len(em2.sumLL_trace()) == 4
+    oMu, oCov, olam, otr = oracle.em_iterations(X, Mu_km, np.tile(np.eye(2), (4, 1, 1)), np.full(4, 0.25), 1.0, 4)
+    check_against(em2, oMu, oCov, olam, otr)
+    # reinit() returns to the uninitialised state (src/unsupervised/mlf_emgmm.f90:115-122)
+    em2.reinit()
+    assert not em2.initialized and em2.niter == 0 and (em2.Mu == 0).all()
+    em.finalize(); em2.finalize()
+
+
+def test_kmeans_init_more_clusters_than_structure():
+    # K larger than the number of real clusters and duplicate points: every centre must still be finite and distinct rows
+    rng = np.random.default_rng(72)
+    X = np.ascontiguousarray(np.repeat(rng.standard_normal((40, 3)), 5, axis=0))
+    em = mlf_algo_emgmm()
+    assert em.init(X, 12, 0.0) == 0
+    assert em.step(1)[0] == 0, em.last_error()
+    assert np.isfinite(em.Mu).all()
+    em.finalize()
+
+
+# ---- single-component C entry points (src/unsupervised/mlf_gaussian.f90:53-59,81-88) ---------------------------------
+def test_eval_and_max_gaussian_entry_points(oracle):
+    from mlfortran_b200 import mlf_evalGaussian, mlf_maxGaussian
+
+    rng = np.random.default_rng(81)
+    for d, n in ((2, 1000), (5, 333), (16, 2000)):
+        A = rng.standard_normal((d, d))
+        Cm = A @ A.T / d + 0.3 * np.eye(d)
+        mu = rng.standard_normal(d)
+        X = np.ascontiguousarray(rng.standard_normal((n, d)) @ np.linalg.cholesky(Cm).T + mu)
+        info, P, ll = mlf_evalGaussian(X, mu, Cm, 0.37)
+        oinfo, oP, oll = oracle.eval_gaussian(X, mu, Cm, 0.37)
+        assert info == 0 and oinfo == 0
+        np.testing.assert_allclose(P, oP, rtol=1e-11, atol=1e-300)
+        assert abs(ll - oll) <= LL_RTOL * abs(oll)
+        w = rng.random(n) ** 8      # many tiny weights: exercises the W < 1e-3/N threshold
+        s, m, Cn = mlf_maxGaussian(X, w)
+        os_, om, oC = oracle.max_gaussian(X, w)
+        assert abs(s - os_) <= 1e-12 * os_
+        np.testing.assert_allclose(m, om, rtol=0, atol=PAR_RTOL * np.abs(om).max())
+        np.testing.assert_allclose(Cn, oC, rtol=0, atol=PAR_RTOL * np.abs(oC).max())
+
+
+# ---- engine-level entry points (what fortran/mlf_emgmm_b200.f90 binds) ------------------------------------------------
+def test_engine_level_abi_matches_handle_level(oracle):
+    lib = _lib.load()
+    data = synth.make_mixture(3, 5, 400, 6.0, 1.0, 91)
+    X = data["X"]
+    n, d, K = X.shape[0], 3, 5
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 91)
+    oMu, oCov, olam, otr, oP = oracle.em_iterations(X, Mu0, Cov0, lam0, 0.0, 4, return_proba=True)
+    eng = lib.mlf_b200_engine_create(X.ctypes.data, n, d, K, 0, 0)
+    assert eng
+    Mu, Cov, lam = Mu0.copy(), Cov0.copy(), lam0.copy()     # caller-owned arrays in the reference layout
+    ll = C.c_double()
+    assert lib.mlf_b200_engine_step(eng, 4, 0.0, Mu.ctypes.data, Cov.ctypes.data, lam.ctypes.data, C.byref(ll)) == 0
+    assert abs(ll.value - otr[-1]) <= LL_RTOL * abs(otr[-1])
+    assert rel(Mu, oMu) <= PAR_RTOL and rel(Cov, oCov) <= PAR_RTOL and np.abs(lam - olam).max() <= PAR_RTOL
+    P = np.empty((K, n))
+    assert lib.mlf_b200_engine_proba(eng, P.ctypes.data) == 0
+    assert np.abs(P - oP).max() <= 1e-9
+    Pq = np.empty((K, 100)); cl = np.zeros(100, dtype=np.int32)
+    assert lib.mlf_b200_engine_expectation(eng, Mu.ctypes.data, Cov.ctypes.data, lam.ctypes.data, X.ctypes.data, 100,
+                                           Pq.ctypes.data, cl.ctypes.data) == 0
+    _, Pn, _ = oracle.exp_step(X[:100], Mu, Cov, lam)
+    assert np.abs(Pq - Pn).max() <= 1e-11 and (cl == oracle.get_class(Pn)).all()
+    Mk, Ck, lk = np.empty((K, d)), np.empty((K, d, d)), np.empty(K)
+    assert lib.mlf_b200_engine_kmeans_init(eng, 16, 7, Mk.ctypes.data, Ck.ctypes.data, lk.ctypes.data) == 0
+    assert np.isfinite(Mk).all() and (Ck == np.eye(d)).all() and (lk == 1.0 / K).all()
+    lib.mlf_b200_engine_destroy(eng)
+
+
 # ---- sharded protocol on one GPU: two objects, each with half the points, host-side all-reduce between them ---------
 def test_two_shards_equal_single_object(oracle):
     import torch
