@@ -240,9 +240,16 @@ def main():
     hbm_src = "MEASURED_PEAKS.json" if hbm_peak else "fallback 6650 GB/s (B200_PROFILING.md)"
     hbm_peak = hbm_peak or 6650.0
     it = max(times["iters"], 1)
-    e_ms, m_ms = times["estep_ms"] / it, times["mstep_ms"] / it
+    fused = times.get("sweeps", 0) > 0
+    sweeps = max(times.get("sweeps", 0), 1) if fused else it
+    # ev1..ev2 brackets the sweep(s) + the statistics all-reduce; with the fused path it holds `sweeps` launches of k_em
+    e_ms, m_ms = times["estep_ms"] / sweeps, times["mstep_ms"] / it
     peak_tf = peaks.get("dmma_tflops", 37.16)
-    ach_tf = flops_e(d) * n_loc * K / (e_ms * 1e-3) * 1e-12 if e_ms > 0 else 0.0
+    # algorithmic flops per (point, component): E = d^2+4d+6 (+40 for the exp); the fused sweep also does the dense
+    # part of M (sum g, sum g^2, sum g x: 3d+4).  The d^2 scatter term is only owed for pairs that pass the
+    # reference's W >= minW test, a data-dependent handful per point, and is left out (conservative).
+    fl_pair = flops_e(d) + ((3 * d + 4) if fused else 0)
+    ach_tf = fl_pair * n_loc * K / (e_ms * 1e-3) * 1e-12 if e_ms > 0 else 0.0
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "estep_traffic.json")))
@@ -250,13 +257,16 @@ def main():
     except Exception:
         pass
     roofline = {
-        "kernel": "k_estep (E-pass: whitening DMMA + log-sum-exp + pass-A statistics)", "bound": "tensor",
+        "kernel": ("k_em<4,1,true> (fused sweep: whitening DMMA + log-sum-exp + pass-A statistics + thresholded covariance scatter)" if fused
+                   else "k_em/k_estep (E-pass: whitening DMMA + log-sum-exp + pass-A statistics)"), "bound": "tensor",
+        "sweeps_per_iteration": sweeps / it if fused else 1.0, "side_list_pairs": times.get("side_list_pairs", 0),
         "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None, "traffic": traffic,
         "peak_source": "fp64 DMMA (mma.sync m8n8k4.f64) measured on this pool by bench/micro/fp64_peaks.cu -> profiles/fp64_peaks_r01.json; "
                        "MEASURED_PEAKS.json has no fp64 figure (bf16 tensor peak does not apply to an fp64 path)",
-        "algorithmic_flops_per_launch": flops_e(d) * n_loc * K, "ms_per_launch": e_ms,
-        "hbm": {"achieved_gbs": (8.0 * n_loc * d + 8.0 * n_loc * K) / (e_ms * 1e-3) * 1e-9 if e_ms > 0 else 0.0, "peak_gbs": hbm_peak,
-                "peak_source": hbm_src, "note": "E-pass reads X once and writes the responsibilities once; fp64-bound, not HBM-bound"},
+        "algorithmic_flops_per_launch": fl_pair * n_loc * K, "flops_per_pair": fl_pair, "ms_per_launch": e_ms,
+        "hbm": {"achieved_gbs": (8.0 * n_loc * d + (0.0 if fused else 8.0 * n_loc * K)) / (e_ms * 1e-3) * 1e-9 if e_ms > 0 else 0.0, "peak_gbs": hbm_peak,
+                "peak_source": hbm_src, "note": ("fused sweep reads X once and writes nothing per point" if fused else
+                                                 "E-pass reads X once and writes the responsibilities once") + "; fp64-bound, not HBM-bound"},
         "mstep": {"ms_per_launch": m_ms, "algorithmic_bytes": 8.0 * n_loc * K + 8.0 * n_loc * d,
                   "achieved_gbs": (8.0 * n_loc * K + 8.0 * n_loc * d) / (m_ms * 1e-3) * 1e-9 if m_ms > 0 else 0.0},
         "per_iteration_ms": {k: v / it for k, v in times.items() if k != "iters"},
@@ -310,7 +320,7 @@ def main():
             "data": "synthetic", "em_iter_per_s": args.steps / (ms * 1e-3), "sumLL_last": sumll,
             "config": {"workload": f"synthetic GMM N={N:.0e} d={d} K={K} full covariance, points sharded over {world} GPU(s) (BASELINE configs[2])",
                        "N": N, "d": d, "K": K, "minProba": args.min_proba, "points_per_gpu": n_loc, "parallelism": f"points-sharded x{world}",
-                       "l2": "inputs larger than L2 (X + responsibilities >> 126 MB per GPU); no explicit flush",
+                       "l2": "inputs larger than L2 (X is 12.8 GB per 1e8 points >> 126 MB); no explicit flush",
                        "timing": "CUDA events on the engine stream, max over ranks"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }

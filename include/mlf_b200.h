@@ -104,9 +104,11 @@ int mlf_b200_resident_proba(MLF_OBJ *obj, double *P);
 int mlf_b200_resident_labels(MLF_OBJ *obj, int *Cl);
 /* Device pointer of the resident responsibilities (component k starts at k * *ld doubles; columns >= N are zero). */
 const double *mlf_b200_resident_proba_device(MLF_OBJ *obj, int64_t *ld);
-/* Profiling counters: out[0..5] = ms in refresh, E-pass, mid, M-pass, finalize, and iterations counted. */
+/* Profiling counters: out[0..5] = ms in refresh, sweep / E-pass, mid, M-pass / side-list resolution, finalize, and iterations
+ * counted; out[6] = sweeps over X (the fused path needs 2 in an iteration whose threshold band missed), out[7] = pairs settled
+ * through the side list. */
 int mlf_b200_set_profile(MLF_OBJ *obj, int on);
-int mlf_b200_get_times(MLF_OBJ *obj, double out[6]);
+int mlf_b200_get_times(MLF_OBJ *obj, double out[8]);
 int64_t mlf_b200_launch_count(MLF_OBJ *obj);
 void *mlf_b200_stream(MLF_OBJ *obj);
 int64_t mlf_b200_global_points(MLF_OBJ *obj);

@@ -31,6 +31,11 @@ EmgmmEngine::~EmgmmEngine() {
                     dStatsA_, dStatsB_, dPartA_, dPartB_, dSc_, dMean_, dNglob_};
   for (double* b : bufs)
     if (b) cudaFree(b);
+  double* fb[] = {dPack2_, dMuOld_, dTlo_, dThi_, dAB_, dPartB2_, dStatsC_, dPrevMu_, dPrevCov_, dPrevLambda_};
+  for (double* b : fb)
+    if (b) cudaFree(b);
+  if (dAmb_) cudaFree(dAmb_);
+  if (dAmbCount_) cudaFree(dAmbCount_);
   if (dInfo_) cudaFree(dInfo_);
   if (dLabels_) cudaFree(dLabels_);
   for (auto& e : pev_)
@@ -64,10 +69,17 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   sms_ = prop.multiProcessorCount;
   smem_limit_ = prop.sharedMemPerBlockOptin;
   geom_ = make_geom(d, K);
-  if (estep_smem_bytes(geom_) > smem_limit_) {
+  fgeom_ = make_fused_geom(geom_);
+  {
+    const char* lg = getenv("MLF_B200_LEGACY");
+    legacy_estep_ = lg && lg[0] == '1';
+  }
+  if (!legacy_estep_ && fgeom_.smem > smem_limit_) legacy_estep_ = true;  // fused pack does not fit: first-generation E-pass
+  if (legacy_estep_ && estep_smem_bytes(geom_) > smem_limit_) {
     err_ = "K*d^2 parameter pack + logit tile exceed shared memory for this (d,K)";
     return -7;
   }
+  fused_ = !legacy_estep_ && fgeom_.scatter_ok;
   n_ = n_local;
   nglob_ = n_local;
   ldg_ = ((n_ + 31) / 32) * 32;
@@ -80,7 +92,24 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   egrid_ = (int)std::max<int64_t>(1, std::min<int64_t>(sms_, etiles));
   mstep_grid(g, sms_, n_, &mgx_, &mgy_);
   auto A = [&](double** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(double)); };
-  CKE(A(&dGamma_, (size_t)K * ldg_), "cudaMalloc gamma (N*K responsibilities)");
+  if (!fused_) {
+    if (int r = ensure_gamma()) return r;  // two-pass path keeps ProbaC(N,K) resident; the fused sweep never stores it
+  }
+  CKE(A(&dPack2_, (size_t)KP * fgeom_.PSF), "cudaMalloc");
+  CKE(A(&dMuOld_, (size_t)KP * 8 * g.DN), "cudaMalloc");
+  CKE(A(&dTlo_, KP), "cudaMalloc");
+  CKE(A(&dThi_, KP), "cudaMalloc");
+  CKE(A(&dAB_, (size_t)KP * g.DS + (size_t)KP * fgeom_.MSF + 8), "cudaMalloc");
+  CKE(A(&dStatsC_, (size_t)K * (d * d + d + 1)), "cudaMalloc");
+  CKE(A(&dPrevMu_, (size_t)K * d), "cudaMalloc");
+  CKE(A(&dPrevCov_, (size_t)K * d * d), "cudaMalloc");
+  CKE(A(&dPrevLambda_, K), "cudaMalloc");
+  if (fused_) {
+    CKE(A(&dPartB2_, (size_t)sms_ * KP * fgeom_.MSF), "cudaMalloc");
+    CKE(cudaMalloc((void**)&dAmb_, (size_t)sms_ * (kEstepThreads / 32) * amb_cap_ * sizeof(AmbEntry)), "cudaMalloc side list");
+    CKE(cudaMalloc((void**)&dAmbCount_, (size_t)sms_ * (kEstepThreads / 32) * sizeof(int)), "cudaMalloc");
+    CKE(cudaMemsetAsync(dAmbCount_, 0, (size_t)sms_ * (kEstepThreads / 32) * sizeof(int), st_), "memset");
+  }
   CKE(A(&dMu_, (size_t)K * d), "cudaMalloc");
   CKE(A(&dCov_, (size_t)K * d * d), "cudaMalloc");
   CKE(A(&dLambda_, K), "cudaMalloc");
@@ -97,8 +126,22 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   CKE(A(&dMean_, (size_t)8 * g.DN + 8), "cudaMalloc");
   CKE(A(&dNglob_, 8), "cudaMalloc");
   CKE(cudaMalloc((void**)&dInfo_, sizeof(int) * KP), "cudaMalloc");
-  CKE(cudaMemsetAsync(dGamma_, 0, (size_t)K * ldg_ * sizeof(double), st_), "memset gamma");
   return refresh_x(X, x_on_device);
+}
+
+int EmgmmEngine::ensure_gamma() {
+  if (dGamma_) return 0;
+  CKE(cudaMalloc((void**)&dGamma_, std::max<size_t>((size_t)geom_.K * ldg_, 1) * sizeof(double)), "cudaMalloc gamma (N*K responsibilities)");
+  CKE(cudaMemsetAsync(dGamma_, 0, (size_t)geom_.K * ldg_ * sizeof(double), st_), "memset gamma");
+  return 0;
+}
+
+// InverseSymMatrix eigen branch + packing for both kernel generations (k_refresh).
+int EmgmmEngine::do_refresh() {
+  CKE(launch_refresh(geom_, dMu_, dCov_, dLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_, dPack2_, dMuOld_),
+      "refresh");
+  ++launches_;
+  return 0;
 }
 
 int EmgmmEngine::refresh_x(const double* X, bool x_on_device) {
@@ -194,7 +237,16 @@ int EmgmmEngine::run_estep(const double* X, int64_t n, double* gamma, int64_t ld
   const Geom& g = geom_;
   const int64_t etiles = (n + kEstepTilePts - 1) / kEstepTilePts;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sms_, etiles));
-  CKE(launch_estep(g, X, n, dPack_, gamma, ldg, labels, dPartA_, grid, smem_limit_, raw ? 1 : 0, st_), "estep");
+  if (legacy_estep_) {
+    CKE(launch_estep(g, X, n, dPack_, gamma, ldg, labels, dPartA_, grid, smem_limit_, raw ? 1 : 0, st_), "estep");
+  } else {
+    EmArgs a{};
+    a.X = X; a.N = n; a.d = g.d; a.K = g.K; a.K8 = g.K8; a.S = g.S;
+    a.pack2 = dPack2_; a.shift = dMean_; a.muold = dMuOld_; a.tlo = nullptr; a.thi = nullptr;
+    a.gamma = gamma; a.ldg = ldg; a.labels = labels; a.raw = raw ? 1 : 0;
+    a.partA = dPartA_; a.partB = nullptr; a.amb = nullptr; a.amb_cap = 0; a.amb_count = nullptr;
+    CKE(launch_em(g, fgeom_, a, false, grid, smem_limit_, st_), "em sweep (E-pass)");
+  }
   ++launches_;
   if (want_stats) {
     CKE(launch_reduce_partials(dPartA_, grid, (int64_t)g.K8 * 8 * g.DS, dStatsA_, st_), "reduce statsA");
@@ -207,13 +259,11 @@ int EmgmmEngine::iterate(int64_t niter, double minProba, double* sumLL_last, dou
   if (niter <= 0) return 0;
   CKE(cudaSetDevice(device_), "cudaSetDevice");
   if (int r = ensure_moments()) return r;
-  const Geom& g = geom_;
   if (trace_cap_ < niter) {
     if (dSumLL_) cudaFree(dSumLL_);
     trace_cap_ = std::max<int64_t>(niter, 64);
     CKE(cudaMalloc((void**)&dSumLL_, trace_cap_ * sizeof(double)), "cudaMalloc trace");
   }
-  const double minW = 1e-3 / (double)(float)nglob_;  // 1d-3/real(NX)  (src/unsupervised/mlf_gaussian.f90:50)
   const bool prof = profile_ && niter <= 4096;
   if (prof) {
     while ((int64_t)pev_.size() < 6 * niter) {
@@ -222,34 +272,11 @@ int EmgmmEngine::iterate(int64_t niter, double minProba, double* sumLL_last, dou
       pev_.push_back(e);
     }
   }
-  for (int64_t it = 0; it < niter; ++it) {
-    cudaEvent_t* ev_ = prof ? &pev_[(size_t)6 * it] : nullptr;
-    const bool profile_ = prof;
-    if (profile_) cudaEventRecord(ev_[0], st_);
-    CKE(launch_refresh(g, dMu_, dCov_, dLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_),
-        "refresh");
-    CKE(launch_sum_k(dSumLLk_, g.K, dSumLL_ + it, st_), "sum_k");
-    launches_ += 2;
-    if (profile_) cudaEventRecord(ev_[1], st_);
-    if (int r = run_estep(dX_, n_, dGamma_, ldg_, nullptr, true)) return r;
-    if (int r = allreduce(dStatsA_, (int64_t)g.K8 * 8 * g.DS)) return r;
-    if (profile_) cudaEventRecord(ev_[2], st_);
-    CKE(launch_mid(g, dStatsA_, minW, dMu_, dMupad_, dThr_, st_), "mid");
-    ++launches_;
-    if (profile_) cudaEventRecord(ev_[3], st_);
-    CKE(launch_mstep(g, dX_, n_, dGamma_, ldg_, dMupad_, dThr_, dPartB_, mgx_, st_), "mstep");
-    CKE(launch_reduce_partials(dPartB_, mgx_, (int64_t)g.K * g.MS, dStatsB_, st_), "reduce statsB");
-    launches_ += 2;
-    if (int r = allreduce(dStatsB_, (int64_t)g.K * g.MS)) return r;
-    if (profile_) cudaEventRecord(ev_[4], st_);
-    CKE(launch_finalize(g, dStatsA_, dStatsB_, minProba, dCov_, dLambda_, st_), "finalize");
-    ++launches_;
-    if (profile_) cudaEventRecord(ev_[5], st_);
-  }
+  if (int r = fused_ ? iterate_fused(niter, minProba, prof) : iterate_two_pass(niter, minProba, prof)) return r;
   std::vector<double> tr((size_t)niter);
   CKE(cudaMemcpyAsync(tr.data(), dSumLL_, niter * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H sumLL");
   CKE(cudaStreamSynchronize(st_), "sync");
-  if (prof) {  // read the per-iteration events only after the single sync: no host stalls inside the loop
+  if (prof) {  // read the per-iteration events only after the final sync
     for (int64_t it = 0; it < niter; ++it) {
       cudaEvent_t* e = &pev_[(size_t)6 * it];
       float ms;
@@ -266,15 +293,138 @@ int EmgmmEngine::iterate(int64_t niter, double minProba, double* sumLL_last, dou
   return 0;
 }
 
+// Two-pass iteration with the responsibilities stored in HBM: E-pass -> all-reduce -> thresholds -> M-pass -> all-reduce.
+// Used where the fused sweep's scatter accumulators do not fit the register file (d > 16, or d > 8 with K > 64).
+int EmgmmEngine::iterate_two_pass(int64_t niter, double minProba, bool prof) {
+  const Geom& g = geom_;
+  if (int r = ensure_gamma()) return r;
+  const double minW = 1e-3 / (double)(float)nglob_;  // 1d-3/real(NX)  (src/unsupervised/mlf_gaussian.f90:50)
+  for (int64_t it = 0; it < niter; ++it) {
+    cudaEvent_t* ev_ = prof ? &pev_[(size_t)6 * it] : nullptr;
+    if (prof) cudaEventRecord(ev_[0], st_);
+    if (int r = do_refresh()) return r;
+    CKE(launch_sum_k(dSumLLk_, g.K, dSumLL_ + it, st_), "sum_k");
+    ++launches_;
+    if (prof) cudaEventRecord(ev_[1], st_);
+    if (int r = run_estep(dX_, n_, dGamma_, ldg_, nullptr, true)) return r;
+    if (int r = allreduce(dStatsA_, (int64_t)g.K8 * 8 * g.DS)) return r;
+    if (prof) cudaEventRecord(ev_[2], st_);
+    CKE(launch_mid(g, dStatsA_, minW, dMu_, dMupad_, dThr_, st_), "mid");
+    ++launches_;
+    if (prof) cudaEventRecord(ev_[3], st_);
+    CKE(launch_mstep(g, dX_, n_, dGamma_, ldg_, dMupad_, dThr_, dPartB_, mgx_, st_), "mstep");
+    CKE(launch_reduce_partials(dPartB_, mgx_, (int64_t)g.K * g.MS, dStatsB_, st_), "reduce statsB");
+    launches_ += 2;
+    if (int r = allreduce(dStatsB_, (int64_t)g.K * g.MS)) return r;
+    if (prof) cudaEventRecord(ev_[4], st_);
+    CKE(launch_finalize(g, dStatsA_, dStatsB_, minProba, dCov_, dLambda_, st_), "finalize");
+    ++launches_;
+    if (prof) cudaEventRecord(ev_[5], st_);
+  }
+  gamma_current_ = true;
+  return 0;
+}
+
+// Single-sweep iteration (emgmm_fused.cu).  Per iteration: refresh -> one sweep over X that produces the pass-A
+// statistics AND the covariance scatter of the certainly-kept pairs -> ONE all-reduce of both -> host check that the
+// finished s_k lies inside the predicted threshold band (repeat the sweep with the exact threshold otherwise) ->
+// side-list resolution (+ a second, tiny all-reduce only if any pair was listed) -> finalize.
+int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
+  const Geom& g = geom_;
+  const FusedGeom& f = fgeom_;
+  const int K = g.K, KP = g.K8 * 8, d = g.d;
+  const int nlists = egrid_ * (kEstepThreads / 32);
+  const int64_t nA = (int64_t)KP * g.DS, nB = (int64_t)KP * f.MSF;
+  const double minW = 1e-3 / (double)(float)nglob_;  // 1d-3/real(NX)  (src/unsupervised/mlf_gaussian.f90:50)
+  double* dFlags = dAB_ + nA + nB;                    // [listed pairs, overflowing lists] ride in the same all-reduce
+  std::vector<double> hA((size_t)nA + 0), hflag(2), tlo((size_t)KP), thi((size_t)KP), sk((size_t)K);
+  gamma_current_ = false;
+  for (int64_t it = 0; it < niter; ++it) {
+    cudaEvent_t* ev_ = prof ? &pev_[(size_t)6 * it] : nullptr;
+    if (prof) cudaEventRecord(ev_[0], st_);
+    // parameters this E-step is evaluated with (what ProbaC refers to after the step)
+    CKE(cudaMemcpyAsync(dPrevMu_, dMu_, (size_t)K * d * sizeof(double), cudaMemcpyDeviceToDevice, st_), "copy");
+    CKE(cudaMemcpyAsync(dPrevCov_, dCov_, (size_t)K * d * d * sizeof(double), cudaMemcpyDeviceToDevice, st_), "copy");
+    CKE(cudaMemcpyAsync(dPrevLambda_, dLambda_, (size_t)K * sizeof(double), cudaMemcpyDeviceToDevice, st_), "copy");
+    prev_valid_ = true;
+    if (int r = do_refresh()) return r;
+    CKE(launch_sum_k(dSumLLk_, K, dSumLL_ + it, st_), "sum_k");
+    ++launches_;
+    if (prof) cudaEventRecord(ev_[1], st_);
+    // threshold band [tlo, thi] = minW * [s_lo, s_hi]; s_k predicted from the previous iterations
+    bool exact = false;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int k = 0; k < KP; ++k) {
+        double lo, hi;
+        if (k >= K) { lo = hi = INFINITY; }
+        else if (exact) { lo = hi = minW * sk[(size_t)k]; }
+        else {
+          double sp, rho;
+          if (s_prev_.empty()) { sp = (double)nglob_ / K; rho = 0.5; }
+          else {
+            sp = s_prev_[(size_t)k];
+            rho = s_prev2_.empty() ? 0.25 : 8.0 * std::fabs(sp - s_prev2_[(size_t)k]) / std::max(std::fabs(sp), 1e-300);
+            rho = std::min(0.5, std::max(rho, 1e-6));
+          }
+          lo = minW * sp * (1.0 - rho);
+          hi = minW * sp * (1.0 + rho);
+        }
+        tlo[(size_t)k] = lo; thi[(size_t)k] = hi;
+      }
+      CKE(cudaMemcpyAsync(dTlo_, tlo.data(), KP * sizeof(double), cudaMemcpyHostToDevice, st_), "H2D tlo");
+      CKE(cudaMemcpyAsync(dThi_, thi.data(), KP * sizeof(double), cudaMemcpyHostToDevice, st_), "H2D thi");
+      EmArgs a{};
+      a.X = dX_; a.N = n_; a.d = d; a.K = K; a.K8 = g.K8; a.S = g.S;
+      a.pack2 = dPack2_; a.shift = dMean_; a.muold = dMuOld_; a.tlo = dTlo_; a.thi = dThi_;
+      a.gamma = nullptr; a.ldg = 0; a.labels = nullptr; a.raw = 0;
+      a.partA = dPartA_; a.partB = dPartB2_; a.amb = dAmb_; a.amb_cap = amb_cap_; a.amb_count = dAmbCount_;
+      CKE(launch_em(g, f, a, true, egrid_, smem_limit_, st_), "em sweep (fused)");
+      CKE(launch_reduce_partials(dPartA_, egrid_, nA, dAB_, st_), "reduce statsA");
+      CKE(launch_reduce_partials(dPartB2_, egrid_, nB, dAB_ + nA, st_), "reduce statsB");
+      CKE(launch_amb_summary(dAmbCount_, nlists, amb_cap_, dFlags, st_), "amb summary");
+      launches_ += 4;
+      times_.sweeps += 1;
+      if (int r = allreduce(dAB_, nA + nB + 2)) return r;
+      // verification needs s_k and the list flags on the host: one small D2H + sync per sweep
+      CKE(cudaMemcpyAsync(hA.data(), dAB_, nA * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H statsA");
+      CKE(cudaMemcpyAsync(hflag.data(), dFlags, 2 * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H flags");
+      CKE(cudaStreamSynchronize(st_), "sync");
+      bool ok = hflag[1] == 0.0 && hflag[0] <= 200000.0;
+      for (int k = 0; k < K; ++k) {
+        sk[(size_t)k] = hA[(size_t)k * g.DS];
+        const double tau = minW * sk[(size_t)k];
+        if (!(tlo[(size_t)k] <= tau && tau <= thi[(size_t)k])) ok = false;  // also catches NaN
+      }
+      if (ok || exact) break;
+      exact = true;  // s_k is known now: repeat the sweep with tlo == thi == minW*s_k (the side list stays empty)
+    }
+    if (prof) cudaEventRecord(ev_[2], st_);
+    if (prof) cudaEventRecord(ev_[3], st_);
+    const double* statsC = nullptr;
+    if (hflag[0] > 0.0) {
+      CKE(launch_amb_resolve(g, dX_, dAmb_, amb_cap_, dAmbCount_, nlists, dAB_, minW, dMuOld_, dStatsC_, st_), "amb resolve");
+      ++launches_;
+      if (int r = allreduce(dStatsC_, (int64_t)K * (d * d + d + 1))) return r;
+      statsC = dStatsC_;
+      times_.amb_pairs += (int64_t)hflag[0];
+    }
+    if (prof) cudaEventRecord(ev_[4], st_);
+    CKE(launch_finalize_fused(g, f, dAB_, dAB_ + nA, statsC, dMuOld_, minProba, dMu_, dCov_, dLambda_, st_), "finalize");
+    ++launches_;
+    if (prof) cudaEventRecord(ev_[5], st_);
+    s_prev2_ = s_prev_;
+    s_prev_ = sk;
+  }
+  return 0;
+}
+
 int EmgmmEngine::expectation(const double* Xq, bool on_device, int64_t nq, double* P_host, int32_t* labels_host) {
   CKE(cudaSetDevice(device_), "cudaSetDevice");
   if (nq <= 0) return 0;
   if (int r = ensure_moments()) return r;
   const Geom& g = geom_;
   const int d = g.d, K = g.K;
-  CKE(launch_refresh(g, dMu_, dCov_, dLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_),
-      "refresh");
-  ++launches_;
+  if (int r = do_refresh()) return r;
   const int64_t chunk = std::min<int64_t>(nq, (int64_t)1 << 20);
   const int64_t ldq = ((chunk + 31) / 32) * 32;
   double *dxq = nullptr, *dpq = nullptr;
@@ -311,9 +461,31 @@ int EmgmmEngine::expectation(const double* Xq, bool on_device, int64_t nq, doubl
   return rc;
 }
 
+// The fused sweep never stores ProbaC(N,K); it is re-evaluated on demand with the parameters the last E-step used.
+int EmgmmEngine::materialize_gamma() {
+  CKE(cudaSetDevice(device_), "cudaSetDevice");
+  if (gamma_current_) return 0;
+  if (int r = ensure_gamma()) return r;
+  if (!prev_valid_ || n_ == 0) return 0;  // no E-step yet: ProbaC = 0 (src/unsupervised/mlf_emgmm.f90:119)
+  if (int r = ensure_moments()) return r;
+  CKE(launch_refresh(geom_, dPrevMu_, dPrevCov_, dPrevLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_,
+                     dPack2_, dMuOld_), "refresh");
+  ++launches_;
+  if (int r = run_estep(dX_, n_, dGamma_, ldg_, nullptr, false)) return r;
+  gamma_current_ = true;
+  return 0;
+}
+
+const double* EmgmmEngine::gamma_device() {
+  if (materialize_gamma() != 0) return nullptr;
+  cudaStreamSynchronize(st_);
+  return dGamma_;
+}
+
 int EmgmmEngine::resident_proba(double* P_host) {
   CKE(cudaSetDevice(device_), "cudaSetDevice");
   if (n_ == 0) return 0;
+  if (int r = materialize_gamma()) return r;
   CKE(cudaMemcpy2DAsync(P_host, (size_t)n_ * sizeof(double), dGamma_, (size_t)ldg_ * sizeof(double), (size_t)n_ * sizeof(double),
                         geom_.K, cudaMemcpyDeviceToHost, st_), "D2H ProbaC");
   CKE(cudaStreamSynchronize(st_), "sync");
@@ -326,10 +498,12 @@ int EmgmmEngine::resident_labels(int32_t* labels_host) {
   if (int r = ensure_moments()) return r;
   const Geom& g = geom_;
   if (!dLabels_) CKE(cudaMalloc((void**)&dLabels_, (size_t)n_ * sizeof(int32_t)), "cudaMalloc labels");
-  CKE(launch_refresh(g, dMu_, dCov_, dLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_),
-      "refresh");
-  ++launches_;
-  if (int r = run_estep(dX_, n_, dGamma_, ldg_, dLabels_, false)) return r;
+  if (int r = do_refresh()) return r;
+  if (legacy_estep_) {
+    if (int r = ensure_gamma()) return r;
+    gamma_current_ = false;
+  }
+  if (int r = run_estep(dX_, n_, legacy_estep_ ? dGamma_ : nullptr, ldg_, dLabels_, false)) return r;
   CKE(cudaMemcpyAsync(labels_host, dLabels_, (size_t)n_ * sizeof(int32_t), cudaMemcpyDeviceToHost, st_), "D2H labels");
   CKE(cudaStreamSynchronize(st_), "sync");
   return 0;
@@ -341,8 +515,9 @@ int EmgmmEngine::eval_gaussian_raw(double* P_host, double* sumLL) {
   CKE(cudaSetDevice(device_), "cudaSetDevice");
   if (geom_.K != 1) { err_ = "eval_gaussian_raw needs a single-component engine"; return -7; }
   if (int r = ensure_moments()) return r;
-  CKE(launch_refresh(geom_, dMu_, dCov_, dLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_), "refresh");
-  ++launches_;
+  if (int r = do_refresh()) return r;
+  if (int r = ensure_gamma()) return r;
+  gamma_current_ = false;
   if (n_ > 0)
     if (int r = run_estep(dX_, n_, dGamma_, ldg_, nullptr, false, true)) return r;
   if (P_host && n_ > 0) CKE(cudaMemcpyAsync(P_host, dGamma_, (size_t)n_ * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H P");
@@ -357,6 +532,8 @@ int EmgmmEngine::max_gaussian(const double* Proba_host, double* mu_host, double*
   CKE(cudaSetDevice(device_), "cudaSetDevice");
   if (geom_.K != 1) { err_ = "max_gaussian needs a single-component engine"; return -7; }
   const Geom& g = geom_;
+  if (int r = ensure_gamma()) return r;
+  gamma_current_ = false;
   if (n_ > 0) CKE(cudaMemcpyAsync(dGamma_, Proba_host, (size_t)n_ * sizeof(double), cudaMemcpyHostToDevice, st_), "H2D Proba");
   const int grid = std::max(1, std::min<int>(sms_, (int)((n_ + 255) / 256)));
   CKE(launch_stats_from_gamma(g, dX_, n_, dGamma_, dPartA_, grid, st_), "stats_from_gamma");

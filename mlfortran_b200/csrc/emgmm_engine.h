@@ -18,6 +18,8 @@ typedef int (*allreduce_fn)(void* ctx, double* buf, int64_t count, void* stream)
 struct EngineTimes {  // CUDA-event milliseconds accumulated over iterate() calls (profiling counters)
   double refresh = 0, estep = 0, mid = 0, mstep = 0, fin = 0;
   int64_t iters = 0;
+  int64_t sweeps = 0;     // fused path: sweeps over X (1 per iteration when the threshold band held, 2 otherwise)
+  int64_t amb_pairs = 0;  // fused path: pairs settled through the side list
 };
 
 class EmgmmEngine {
@@ -49,7 +51,8 @@ class EmgmmEngine {
   // Labels / responsibilities of the resident shard from the most recent E-pass parameters.
   int resident_labels(int32_t* labels_host);
   int resident_proba(double* P_host);  // ProbaC(N,K): P[k*N + i]
-  const double* gamma_device() const { return dGamma_; }
+  const double* gamma_device();   // materialises ProbaC on demand
+  int materialize_gamma();
   int64_t gamma_ld() const { return ldg_; }
 
   // Single-component entry points (K = 1 engines): see emgmm_engine.cu.
@@ -76,9 +79,16 @@ class EmgmmEngine {
   int ensure_moments();
   int run_estep(const double* X, int64_t n, double* gamma, int64_t ldg, int32_t* labels, bool want_stats, bool raw = false);
   int allreduce(double* buf, int64_t count);
+  int iterate_fused(int64_t niter, double minProba, bool prof);
+  int iterate_two_pass(int64_t niter, double minProba, bool prof);
+  int ensure_gamma();
+  int do_refresh();
   int draw_far_point(double u, int grid, int64_t chunk, double* dMinDist, double* dPart, double* dOut);
 
   Geom geom_{};
+  FusedGeom fgeom_{};
+  bool fused_ = false;        // single-sweep path available for this (d, K)
+  bool legacy_estep_ = false; // MLF_B200_LEGACY=1: first-generation kernels (A/B comparisons)
   int device_ = 0, sms_ = 148;
   size_t smem_limit_ = 0;
   cudaStream_t st_ = nullptr;
@@ -94,6 +104,15 @@ class EmgmmEngine {
   double *dStatsA_ = nullptr, *dStatsB_ = nullptr, *dPartA_ = nullptr, *dPartB_ = nullptr;
   double *dSc_ = nullptr, *dMean_ = nullptr, *dNglob_ = nullptr;
   int* dInfo_ = nullptr;
+  // fused path
+  double *dPack2_ = nullptr, *dMuOld_ = nullptr, *dTlo_ = nullptr, *dThi_ = nullptr, *dAB_ = nullptr, *dPartB2_ = nullptr, *dStatsC_ = nullptr;
+  double *dPrevMu_ = nullptr, *dPrevCov_ = nullptr, *dPrevLambda_ = nullptr;  // parameters at the start of the last iteration (ProbaC)
+  bool prev_valid_ = false;
+  bool gamma_current_ = false;  // dGamma_ holds the responsibilities of the last E-step
+  AmbEntry* dAmb_ = nullptr;
+  int* dAmbCount_ = nullptr;
+  int amb_cap_ = 1024;
+  std::vector<double> s_prev_, s_prev2_;
   int32_t* dLabels_ = nullptr;
   int egrid_ = 0, mgx_ = 0, mgy_ = 0;
   bool moments_ready_ = false;

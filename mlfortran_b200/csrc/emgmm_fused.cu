@@ -1,0 +1,496 @@
+// Fused single-pass EM kernel for sm_100a (reference: ExpStep + MaxStep, src/unsupervised/mlf_emgmm.f90:174-207;
+// mlf_EvalGaussian / mlf_MaxGaussian, src/unsupervised/mlf_gaussian.f90:41-79; GECovMatrix, src/mlf_matrix.f90:99-147).
+//
+// One sweep over X per iteration, responsibilities never leave the SM:
+//   P1  whitening  u = L_k^T (x - m) - L_k^T (mu_k - m)  as [8 points x 4 dims] x [4 dims x 8 coords] DMMA tiles whose
+//       accumulators start at the per-component bias (m = global mean of the data, so nothing is subtracted per
+//       component); maha = |u|^2; logits log(lambda_k) - lnDet_k - maha/2 into a shared-memory tile;
+//   P2  log-sum-exp over the components, responsibilities in place (optionally stored / labelled);
+//   P3  pass-A statistics sum g, sum g^2, sum g x as [8 comps x 4 points] x [4 points x 8 dims] DMMA, and -- fused --
+//       the covariance scatter sum g (x - mu_k)(x - mu_k)^T of the points that pass the reference's
+//       "W(i) < minW -> CYCLE" test (src/mlf_matrix.f90:135), centred at the *current* mean and re-centred exactly
+//       at the new mean by k_finalize_fused.
+//
+// The reference's threshold needs s_k = sum_i g_ik of the *finished* E-step.  The kernel therefore classifies
+// against a band [tlo_k, thi_k] that brackets minW*s_k: g >= thi is certainly kept (accumulated here), g < tlo is
+// certainly dropped, and the rare pairs in between go to a per-warp side list that k_amb_resolve settles once the
+// all-reduced s_k is known.  With tlo == thi (s_k known exactly) the list stays empty.  The host checks that the
+// finished s_k lies inside the band it predicted and repeats the sweep with the exact threshold otherwise, so the
+// result is always the reference's.
+#include "emgmm_kernels.cuh"
+
+#include <cmath>
+
+namespace mlfb200 {
+
+namespace {
+
+__host__ __device__ constexpr int f_blk_off(int mb) {
+  int s = 0;
+  for (int m = 0; m < mb; ++m) s += m / 2 + 1;
+  return s;
+}
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr double kExpZero = -746.0;  // exp(x) == 0 in fp64 for x < -745.14
+
+}  // namespace
+
+FusedGeom make_fused_geom(const Geom& g) {
+  FusedGeom f{};
+  f.OFFB = g.NB * 32;
+  f.OFFC = f.OFFB + 8 * g.DN;
+  f.PSF = f.OFFC + 4;
+  f.XS = 8 * g.DN + 4;
+  f.MSF = g.MB * 64 + 8 * g.DN + 2;
+  f.CBMAX = g.K8 <= 8 ? 1 : (g.K8 <= 16 ? 2 : (g.K8 <= 32 ? 4 : 8));
+  f.smem = ((size_t)g.K8 * 8 * f.PSF + (size_t)g.K8 * 8 * 8 * g.DN + (size_t)kEstepTilePts * f.XS + (size_t)kEstepTilePts * g.S) * sizeof(double);
+  // scatter accumulators: 8 comps x CBMAX x MB blocks x 2 doubles per lane must stay in registers
+  f.scatter_ok = (16 * f.CBMAX * g.MB <= 64) && g.K8 <= 64;
+  return f;
+}
+
+template <int DM, int CBMAX, bool SCATTER>
+__global__ void __launch_bounds__(kEstepThreads, 1) k_em(EmArgs A) {
+  constexpr int DN = (DM + 1) / 2;
+  constexpr int NB = f_blk_off(DM);
+  constexpr int OFFB = NB * 32, OFFC = OFFB + 8 * DN, PSF = OFFC + 4;
+  constexpr int XS = 8 * DN + 4;
+  constexpr int MB = DN * (DN + 1) / 2;
+  constexpr int DS = 8 * DN + 2;
+  constexpr int MSF = MB * 64 + 8 * DN + 2;
+  constexpr int SC = SCATTER ? CBMAX : 1;
+  extern __shared__ __align__(16) double smem[];
+  const int K8 = A.K8, KP = K8 * 8, K4 = 2 * K8, S = A.S, d = A.d, K = A.K;
+  const int64_t N = A.N;
+  double* sp = smem;                                  // [KP][PSF]  L fragments | -L^T(mu-m) | log(lambda)-lnDet
+  double* smu = sp + (size_t)KP * PSF;                // [KP][8 DN] current means (scatter centre)
+  double* xs = smu + (size_t)KP * 8 * DN;             // [128][XS]  raw points of the tile
+  double* tile = xs + (size_t)kEstepTilePts * XS;     // [128][S]   logits -> responsibilities
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+
+  for (int i = tid; i < KP * PSF; i += kEstepThreads) sp[i] = A.pack2[i];
+  for (int i = tid; i < KP * 8 * DN; i += kEstepThreads) smu[i] = A.muold[i];
+  double sh[DM];
+#pragma unroll
+  for (int mb = 0; mb < DM; ++mb) sh[mb] = A.shift[4 * mb + t];
+  __syncthreads();
+
+  double accA[CBMAX][DN][2], sg[CBMAX], sg2[CBMAX];
+  double accK[SC][DN][2], sk[SC], thi_r[SC], tlo_r[SC];
+  double accS[SC][8][MB][2];
+#pragma unroll
+  for (int c = 0; c < CBMAX; ++c) {
+    sg[c] = 0; sg2[c] = 0;
+#pragma unroll
+    for (int b = 0; b < DN; ++b) { accA[c][b][0] = 0; accA[c][b][1] = 0; }
+  }
+#pragma unroll
+  for (int c = 0; c < SC; ++c) {
+    sk[c] = 0;
+    const int cb = warp + 8 * c;
+    thi_r[c] = (SCATTER && cb < K8) ? A.thi[8 * cb + g] : INFINITY;
+    tlo_r[c] = (SCATTER && cb < K8) ? A.tlo[8 * cb + g] : INFINITY;
+#pragma unroll
+    for (int b = 0; b < DN; ++b) { accK[c][b][0] = 0; accK[c][b][1] = 0; }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int b = 0; b < MB; ++b) { accS[c][q][b][0] = 0; accS[c][q][b][1] = 0; }
+  }
+  int nAmb = 0;
+  AmbEntry* ambw = SCATTER ? A.amb + ((size_t)blockIdx.x * (kEstepThreads / 32) + warp) * A.amb_cap : nullptr;
+
+  const int64_t ntiles = (N + kEstepTilePts - 1) / kEstepTilePts;
+  for (int64_t bt = blockIdx.x; bt < ntiles; bt += gridDim.x) {
+    const int64_t p0 = bt * kEstepTilePts + warp * 16;
+    // ---- P1: logits of this warp's 16 points against every component ---------------------------------------------
+    double xa[2][DM];
+#pragma unroll
+    for (int grp = 0; grp < 2; ++grp) {
+      const int64_t p = p0 + 8 * grp + g;
+      double* xr = xs + (size_t)(warp * 16 + 8 * grp + g) * XS;
+#pragma unroll
+      for (int mb = 0; mb < DM; ++mb) {
+        const int a = 4 * mb + t;
+        const double x = (p < N && a < d) ? A.X[p * d + a] : 0.0;
+        xr[a] = x;
+        xa[grp][mb] = x - sh[mb];
+      }
+      if (8 * DN > 4 * DM) xr[4 * DM + t] = 0.0;  // zero padding up to 8*DN
+    }
+    double* row[2] = {tile + (size_t)(warp * 16 + g) * S, tile + (size_t)(warp * 16 + 8 + g) * S};
+    double rmax[2] = {-INFINITY, -INFINITY};
+    int rarg[2] = {0, 0};
+    for (int k4 = 0; k4 < K4; ++k4) {
+      double part[2][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double* pk = sp + (size_t)(4 * k4 + j) * PSF;
+        double Lf[NB];
+        double2 nb2[DN];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) Lf[b] = pk[b * 32 + lane];
+#pragma unroll
+        for (int nb = 0; nb < DN; ++nb) nb2[nb] = *reinterpret_cast<const double2*>(pk + OFFB + 8 * nb + 2 * t);
+#pragma unroll
+        for (int grp = 0; grp < 2; ++grp) {
+          double c[DN][2];
+#pragma unroll
+          for (int nb = 0; nb < DN; ++nb) { c[nb][0] = nb2[nb].x; c[nb][1] = nb2[nb].y; }
+#pragma unroll
+          for (int mb = 0; mb < DM; ++mb)
+#pragma unroll
+            for (int nb = 0; nb <= mb / 2; ++nb) dmma(c[nb], xa[grp][mb], Lf[f_blk_off(mb) + nb]);
+          double s = c[0][0] * c[0][0];
+          s = fma(c[0][1], c[0][1], s);
+#pragma unroll
+          for (int nb = 1; nb < DN; ++nb) { s = fma(c[nb][0], c[nb][0], s); s = fma(c[nb][1], c[nb][1], s); }
+          part[grp][j] = s;
+        }
+      }
+      const double ck = sp[(size_t)(4 * k4 + t) * PSF + OFFC];
+#pragma unroll
+      for (int grp = 0; grp < 2; ++grp) {
+        // transposed reduction over the quad: lane t ends with the full |u|^2 of component 4*k4+t
+        const bool hi2 = (t & 2) != 0, hi1 = (t & 1) != 0;
+        const double send0 = hi2 ? part[grp][0] : part[grp][2];
+        const double send1 = hi2 ? part[grp][1] : part[grp][3];
+        const double keep0 = hi2 ? part[grp][2] : part[grp][0];
+        const double keep1 = hi2 ? part[grp][3] : part[grp][1];
+        const double a0 = keep0 + shx(send0, 2);
+        const double a1 = keep1 + shx(send1, 2);
+        const double maha = (hi1 ? a1 : a0) + shx(hi1 ? a0 : a1, 1);
+        const double logit = fma(-0.5, maha, ck);
+        row[grp][4 * k4 + t] = logit;
+        if (logit > rmax[grp]) { rmax[grp] = logit; rarg[grp] = 4 * k4 + t; }
+      }
+    }
+    // ---- P2: log-sum-exp over the components (4 independent exp chains per lane) --------------------------------
+    double mx[2], inv[2];
+    int am[2];
+#pragma unroll
+    for (int grp = 0; grp < 2; ++grp) {
+      double m = rmax[grp];
+      int a = rarg[grp];
+#pragma unroll
+      for (int s2 = 1; s2 <= 2; s2 <<= 1) {
+        const double om = shx(m, s2);
+        const int oa = __shfl_xor_sync(kFull, a, s2);
+        if (om > m || (om == m && oa < a)) { m = om; a = oa; }
+      }
+      mx[grp] = A.raw ? 0.0 : m;  // raw: P = lambda*exp(v - lnDet) un-normalised (src/unsupervised/mlf_gaussian.f90:77)
+      am[grp] = a;
+    }
+    double sum0 = 0, sum1 = 0;
+    for (int k4 = 0; k4 < K4; k4 += 2) {
+      const double a00 = row[0][4 * k4 + t] - mx[0], a01 = row[0][4 * k4 + 4 + t] - mx[0];
+      const double a10 = row[1][4 * k4 + t] - mx[1], a11 = row[1][4 * k4 + 4 + t] - mx[1];
+      double e00 = 0, e01 = 0, e10 = 0, e11 = 0;
+      const bool live = (a00 > kExpZero) | (a01 > kExpZero) | (a10 > kExpZero) | (a11 > kExpZero) | (a00 != a00) | (a10 != a10) |
+                        (a01 != a01) | (a11 != a11);
+      if (__any_sync(kFull, live)) {  // exp() of anything below kExpZero is exactly 0: skipping it changes no bit
+        e00 = exp(a00); e01 = exp(a01); e10 = exp(a10); e11 = exp(a11);
+      }
+      row[0][4 * k4 + t] = e00; row[0][4 * k4 + 4 + t] = e01;
+      row[1][4 * k4 + t] = e10; row[1][4 * k4 + 4 + t] = e11;
+      sum0 += e00; sum0 += e01;
+      sum1 += e10; sum1 += e11;
+    }
+    sum0 += shx(sum0, 1); sum0 += shx(sum0, 2);
+    sum1 += shx(sum1, 1); sum1 += shx(sum1, 2);
+    {
+      const bool v0 = (p0 + g) < N, v1 = (p0 + 8 + g) < N;
+      inv[0] = v0 ? (A.raw ? 1.0 : 1.0 / sum0) : 0.0;
+      inv[1] = v1 ? (A.raw ? 1.0 : 1.0 / sum1) : 0.0;
+    }
+#pragma unroll
+    for (int grp = 0; grp < 2; ++grp) {
+      const int64_t p = p0 + 8 * grp + g;
+      const bool valid = p < N;
+      for (int k4 = 0; k4 < K4; ++k4) {
+        const int k = 4 * k4 + t;
+        const double e = row[grp][k];
+        const double gk = e * inv[grp];
+        row[grp][k] = gk;
+        if (A.gamma != nullptr && valid && k < K) A.gamma[(size_t)k * A.ldg + p] = gk;
+      }
+      if (A.labels != nullptr && valid && t == 0) A.labels[p] = am[grp] + 1;  // MAXLOC: first maximum, 1-based
+    }
+    __syncthreads();
+    // ---- P3: statistics of the block tile; warp w owns component blocks w, w+8, ... ------------------------------
+#pragma unroll
+    for (int ci = 0; ci < CBMAX; ++ci) {
+      const int cb = warp + 8 * ci;
+      if (cb < K8) {
+        const int64_t q0 = bt * kEstepTilePts;
+#pragma unroll 1
+        for (int pb = 0; pb < kEstepTilePts / 4; ++pb) {
+          const double a = tile[(size_t)(4 * pb + t) * S + 8 * cb + g];
+          sg[ci] += a;
+          sg2[ci] = fma(a, a, sg2[ci]);
+          double b[DN];
+#pragma unroll
+          for (int db = 0; db < DN; ++db) {
+            b[db] = xs[(size_t)(4 * pb + t) * XS + 8 * db + g];
+            dmma(accA[ci][db], a, b[db]);
+          }
+          if (SCATTER) {
+            constexpr int cs = SCATTER ? 1 : 0;
+            const int c2 = ci * cs;
+            // "If(W(i) < minW0) CYCLE" (src/mlf_matrix.f90:135); g == 0 adds nothing and is never listed
+            const bool hi = !(a < thi_r[c2]) && a != 0.0;
+            const bool mid = !hi && !(a < tlo_r[c2]) && a != 0.0;
+            const double ahi = hi ? a : 0.0;
+            sk[c2] += ahi;
+            const unsigned mh = __ballot_sync(kFull, hi);
+            const unsigned mm = __ballot_sync(kFull, mid);
+            if (mh) {
+#pragma unroll
+              for (int db = 0; db < DN; ++db) dmma(accK[c2][db], ahi, b[db]);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                if (mh & (0xFu << (4 * q))) {  // some point of this 4-group is kept by component 8*cb+q
+                  const double w = __shfl_sync(kFull, ahi, 4 * q + t);
+                  const double* mq = smu + (size_t)(8 * cb + q) * 8 * DN;
+                  double z[DN], wz[DN];
+#pragma unroll
+                  for (int ab = 0; ab < DN; ++ab) {
+                    z[ab] = b[ab] - mq[8 * ab + g];
+                    wz[ab] = w * z[ab];
+                  }
+#pragma unroll
+                  for (int ab = 0; ab < DN; ++ab)
+#pragma unroll
+                    for (int bb = 0; bb <= ab; ++bb) dmma(accS[c2][q][ab * (ab + 1) / 2 + bb], wz[ab], z[bb]);
+                }
+              }
+            }
+            if (mm) {  // undecided until s_k is final: side list, settled by k_amb_resolve
+              const int slot = nAmb + __popc(mm & ((1u << lane) - 1u));
+              if (mid && slot < A.amb_cap) {
+                AmbEntry e;
+                e.g = a;
+                e.key = (long long)(q0 + 4 * pb + t) * 1024 + (8 * cb + g);
+                ambw[slot] = e;
+              }
+              nAmb += __popc(mm);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- per-block partials ----------------------------------------------------------------------------------------
+  double* outA = A.partA + (size_t)blockIdx.x * KP * DS;
+#pragma unroll
+  for (int ci = 0; ci < CBMAX; ++ci) {
+    const int cb = warp + 8 * ci;
+    if (cb < K8) {
+      double a = sg[ci], b = sg2[ci];
+      a += shx(a, 1); a += shx(a, 2);
+      b += shx(b, 1); b += shx(b, 2);
+      double* o = outA + (size_t)(8 * cb + g) * DS;
+      if (t == 0) { o[0] = a; o[1] = b; }
+#pragma unroll
+      for (int db = 0; db < DN; ++db) {
+        o[2 + 8 * db + 2 * t] = accA[ci][db][0];
+        o[2 + 8 * db + 2 * t + 1] = accA[ci][db][1];
+      }
+    }
+  }
+  if (SCATTER) {
+    double* outB = A.partB + (size_t)blockIdx.x * KP * MSF;
+#pragma unroll
+    for (int ci = 0; ci < SC; ++ci) {
+      const int cb = warp + 8 * ci;
+      if (cb < K8) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          double* o = outB + (size_t)(8 * cb + q) * MSF;
+#pragma unroll
+          for (int b = 0; b < MB; ++b) {
+            o[b * 64 + g * 8 + 2 * t] = accS[ci][q][b][0];
+            o[b * 64 + g * 8 + 2 * t + 1] = accS[ci][q][b][1];
+          }
+        }
+        double* o = outB + (size_t)(8 * cb + g) * MSF + MB * 64;
+#pragma unroll
+        for (int db = 0; db < DN; ++db) {
+          o[8 * db + 2 * t] = accK[ci][db][0];
+          o[8 * db + 2 * t + 1] = accK[ci][db][1];
+        }
+        double s = sk[ci];
+        s += shx(s, 1); s += shx(s, 2);
+        if (t == 0) { o[8 * DN] = s; o[8 * DN + 1] = 0.0; }
+      }
+    }
+    if (lane == 0) A.amb_count[blockIdx.x * (kEstepThreads / 32) + warp] = nAmb;
+  }
+}
+
+template <int DM, int CBMAX, bool SCATTER>
+static cudaError_t launch_em_t(const EmArgs& a, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(k_em<DM, CBMAX, SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_em<DM, CBMAX, SCATTER><<<grid, kEstepThreads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <int DM>
+static cudaError_t launch_em_dm(const EmArgs& a, int cbmax, bool scatter, int grid, size_t smem, cudaStream_t st) {
+  constexpr int DN = (DM + 1) / 2;
+  constexpr int MB = DN * (DN + 1) / 2;
+  if (scatter) {
+    // instantiate the fused variant only where its accumulators fit the register file
+    if constexpr (16 * 1 * MB <= 64) { if (cbmax == 1) return launch_em_t<DM, 1, true>(a, grid, smem, st); }
+    if constexpr (16 * 2 * MB <= 64) { if (cbmax == 2) return launch_em_t<DM, 2, true>(a, grid, smem, st); }
+    if constexpr (16 * 4 * MB <= 64) { if (cbmax == 4) return launch_em_t<DM, 4, true>(a, grid, smem, st); }
+    return cudaErrorInvalidConfiguration;
+  }
+  switch (cbmax) {
+    case 1: return launch_em_t<DM, 1, false>(a, grid, smem, st);
+    case 2: return launch_em_t<DM, 2, false>(a, grid, smem, st);
+    case 4: return launch_em_t<DM, 4, false>(a, grid, smem, st);
+    default: return launch_em_t<DM, 8, false>(a, grid, smem, st);
+  }
+}
+
+cudaError_t launch_em(const Geom& g, const FusedGeom& f, const EmArgs& a, bool scatter, int grid, size_t smem_limit, cudaStream_t st) {
+  if (f.smem > smem_limit || g.K8 > 64) return cudaErrorInvalidConfiguration;
+  if (scatter && !f.scatter_ok) return cudaErrorInvalidConfiguration;
+  switch (g.DM) {
+    case 1: return launch_em_dm<1>(a, f.CBMAX, scatter, grid, f.smem, st);
+    case 2: return launch_em_dm<2>(a, f.CBMAX, scatter, grid, f.smem, st);
+    case 3: return launch_em_dm<3>(a, f.CBMAX, scatter, grid, f.smem, st);
+    case 4: return launch_em_dm<4>(a, f.CBMAX, scatter, grid, f.smem, st);
+    case 5: return launch_em_dm<5>(a, f.CBMAX, scatter, grid, f.smem, st);
+    case 6: return launch_em_dm<6>(a, f.CBMAX, scatter, grid, f.smem, st);
+    case 7: return launch_em_dm<7>(a, f.CBMAX, scatter, grid, f.smem, st);
+    case 8: return launch_em_dm<8>(a, f.CBMAX, scatter, grid, f.smem, st);
+    default: return cudaErrorInvalidConfiguration;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// side list of undecided pairs: settle against the exact threshold minW * s_k, accumulate their contribution
+// relative to the current mean.  One block per component, thread (a,b) owns one scatter entry; entries are visited
+// in list order, so the sums are deterministic.  outC[k] = [d*d scatter (column-major) | d sum g z | sum g].
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_amb_resolve(int d, int K, int DS, const double* __restrict__ X, const AmbEntry* __restrict__ amb, int cap,
+                              const int* __restrict__ counts, int nlists, const double* __restrict__ statsA, double minW,
+                              const double* __restrict__ muold, int ldmu, double* __restrict__ outC) {
+  const int k = blockIdx.x;
+  const int nt = blockDim.x;
+  const double thr = minW * statsA[(size_t)k * DS];
+  const double* mu = muold + (size_t)k * ldmu;
+  double* o = outC + (size_t)k * (d * d + d + 1);
+  for (int e = threadIdx.x; e < d * d + d + 1; e += nt) {
+    const int a = (e < d * d) ? e % d : (e - d * d);
+    const int b = (e < d * d) ? e / d : -1;
+    double acc = 0;
+    for (int l = 0; l < nlists; ++l) {
+      const int n = counts[l] < cap ? counts[l] : cap;
+      const AmbEntry* list = amb + (size_t)l * cap;
+      for (int j = 0; j < n; ++j) {
+        const AmbEntry en = list[j];
+        if ((int)(en.key & 1023) != k || en.g < thr) continue;
+        const long long p = en.key >> 10;
+        if (e == d * d + d) acc += en.g;
+        else if (b < 0) acc = fma(en.g, X[p * d + a] - mu[a], acc);
+        else acc = fma(en.g * (X[p * d + a] - mu[a]), X[p * d + b] - mu[b], acc);
+      }
+    }
+    o[e] = acc;
+  }
+}
+cudaError_t launch_amb_resolve(const Geom& g, const double* X, const AmbEntry* amb, int cap, const int* counts, int nlists,
+                               const double* statsA, double minW, const double* muold, double* outC, cudaStream_t st) {
+  k_amb_resolve<<<g.K, 256, 0, st>>>(g.d, g.K, g.DS, X, amb, cap, counts, nlists, statsA, minW, muold, 8 * g.DN, outC);
+  return cudaGetLastError();
+}
+
+// flags[0] = listed pairs on this rank, flags[1] = lists that overflowed their capacity (both all-reduced as doubles)
+__global__ void k_amb_summary(const int* __restrict__ counts, int nlists, int cap, double* __restrict__ flags) {
+  long long tot = 0;
+  int over = 0;
+  for (int l = 0; l < nlists; ++l) {
+    tot += counts[l];
+    over += counts[l] > cap;
+  }
+  flags[0] = (double)tot;
+  flags[1] = (double)over;
+}
+cudaError_t launch_amb_summary(const int* counts, int nlists, int cap, double* flags, cudaStream_t st) {
+  k_amb_summary<<<1, 1, 0, st>>>(counts, nlists, cap, flags);
+  return cudaGetLastError();
+}
+
+// GECovMatrix epilogue for the fused sweep: Mu_k = sum g x / s_k; the scatter was centred at the current mean mu0,
+// so with delta = Mu_k - mu0, m = sum_kept g (x - mu0), sK = sum_kept g:
+//   sum_kept g (x-Mu)(x-Mu)^T = S - delta m^T - m delta^T + sK delta delta^T            (exact algebra)
+// then C_k = ms^2/s_k * that (src/mlf_matrix.f90:119,137,145-146), lambda floor + normalise (mlf_emgmm.f90:184-187).
+__global__ void k_finalize_fused(Geom g, int MSF, const double* __restrict__ statsA, const double* __restrict__ statsB,
+                                 const double* __restrict__ statsC /*nullable*/, const double* __restrict__ muold,
+                                 double minProba, double* __restrict__ Mu, double* __restrict__ Cov, double* __restrict__ lambda) {
+  const int d = g.d;
+  __shared__ double s_mu[128], s_dl[128], s_m[128];
+  for (int k = blockIdx.x; k < g.K; k += gridDim.x) {
+    const double* sa = statsA + (size_t)k * g.DS;
+    const double* sb = statsB + (size_t)k * MSF;
+    const double* sc = statsC ? statsC + (size_t)k * (d * d + d + 1) : nullptr;
+    const double* m0 = muold + (size_t)k * 8 * g.DN;
+    const double s = sa[0];
+    const double sK = sb[g.MB * 64 + 8 * g.DN] + (sc ? sc[d * d + d] : 0.0);
+    for (int a = threadIdx.x; a < d; a += blockDim.x) {
+      const double mu = sa[2 + a] / s;
+      s_mu[a] = mu;
+      s_dl[a] = mu - m0[a];
+      s_m[a] = (sb[g.MB * 64 + a] - sb[g.MB * 64 + 8 * g.DN] * m0[a]) + (sc ? sc[d * d + a] : 0.0);
+      Mu[(size_t)k * d + a] = mu;
+    }
+    __syncthreads();
+    const double sw2 = sa[1] / (s * s);
+    const double ms = 1.0 / (1.0 - sw2);
+    const double scale = ms * ms / s;
+    double* Ck = Cov + (size_t)k * d * d;
+    for (int i = threadIdx.x; i < d * d; i += blockDim.x) {
+      const int a = i % d, b = i / d;
+      if (a < b) continue;
+      const int ab = a >> 3, bb = b >> 3;
+      double S = sb[(ab * (ab + 1) / 2 + bb) * 64 + (a & 7) * 8 + (b & 7)];
+      if (sc) S += sc[(size_t)b * d + a];
+      const double v = scale * (S - s_dl[a] * s_m[b] - s_m[a] * s_dl[b] + sK * s_dl[a] * s_dl[b]);
+      Ck[(size_t)b * d + a] = v;
+      Ck[(size_t)a * d + b] = v;
+    }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double mx = -INFINITY;
+    for (int k = 0; k < g.K; ++k) mx = fmax(mx, statsA[(size_t)k * g.DS]);
+    double sum = 0;
+    for (int k = 0; k < g.K; ++k) {
+      double l = statsA[(size_t)k * g.DS];
+      if (minProba > 0 && !(l >= minProba * mx)) l = minProba * mx;
+      lambda[k] = l;
+      sum += l;
+    }
+    for (int k = 0; k < g.K; ++k) lambda[k] /= sum;
+  }
+}
+cudaError_t launch_finalize_fused(const Geom& g, const FusedGeom& f, const double* statsA, const double* statsB, const double* statsC,
+                                  const double* muold, double minProba, double* Mu, double* Cov, double* lambda, cudaStream_t st) {
+  k_finalize_fused<<<g.K < 148 ? g.K : 148, 128, 0, st>>>(g, f.MSF, statsA, statsB, statsC, muold, minProba, Mu, Cov, lambda);
+  return cudaGetLastError();
+}
+
+}  // namespace mlfb200

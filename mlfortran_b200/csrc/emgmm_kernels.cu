@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(128) k_refresh(Geom g, const double* __restric
                                                  const double* __restrict__ lambda, const double* __restrict__ Sc,
                                                  const double* __restrict__ mean, double Nglob, double* __restrict__ scratch,
                                                  double* __restrict__ pack, double* __restrict__ sumLLk,
-                                                 int* __restrict__ info) {
+                                                 int* __restrict__ info, double* __restrict__ pack2, double* __restrict__ muold,
+                                                 int PSF, int OFFB2, int OFFC2) {
   const int k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, d = g.d;
   const int OFFMU = g.NB * 32, OFFC = OFFMU + 4 * g.DM;
   double* pk = pack + (size_t)k * g.PS;
@@ -84,6 +85,11 @@ __global__ void __launch_bounds__(128) k_refresh(Geom g, const double* __restric
     for (int i = tid; i < g.PS; i += nt) pk[i] = 0.0;
     __syncthreads();
     if (tid == 0) pk[OFFC] = -INFINITY;
+    if (pack2) {
+      double* p2 = pack2 + (size_t)k * PSF;
+      for (int i = tid; i < PSF; i += nt) p2[i] = (i == OFFC2) ? -INFINITY : 0.0;
+      for (int i = tid; i < 8 * g.DN; i += nt) muold[(size_t)k * 8 * g.DN + i] = 0.0;
+    }
     return;
   }
   double* A = scratch + (size_t)k * 3 * d * d;
@@ -220,6 +226,18 @@ __global__ void __launch_bounds__(128) k_refresh(Geom g, const double* __restric
   __syncthreads();
   const double ck = log(lambda[k]) - lnDet;
   if (tid == 0) pk[OFFC] = ck;
+  if (pack2) {  // fused-kernel pack: same fragments, accumulator bias -L^T(mu - m) with m the global mean, constant
+    double* p2 = pack2 + (size_t)k * PSF;
+    for (int i = tid; i < g.NB * 32; i += nt) p2[i] = pk[i];
+    for (int n = tid; n < 8 * g.DN; n += nt) {
+      double acc = 0;
+      if (n < d)
+        for (int m = n; m < d; ++m) acc = fma(W[(size_t)n * d + m], muk[m] - mean[m], acc);
+      p2[OFFB2 + n] = -acc;
+      muold[(size_t)k * 8 * g.DN + n] = (n < d) ? muk[n] : 0.0;
+    }
+    if (tid == 0) { p2[OFFC2] = ck; p2[OFFC2 + 1] = 0; p2[OFFC2 + 2] = 0; p2[OFFC2 + 3] = 0; }
+  }
 
   // closed form of sum_i (x_i-mu)^T invC (x_i-mu) = tr(L^T Sc L) + N |L^T (m - mu)|^2   (Sc = centred scatter)
   double part = 0;
@@ -241,8 +259,10 @@ __global__ void __launch_bounds__(128) k_refresh(Geom g, const double* __restric
 
 cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, const double* lambda, const double* Sc,
                            const double* mean, double Nglob, double* scratch, double* pack, double* sumLLk, int* info,
-                           cudaStream_t st) {
-  k_refresh<<<g.K8 * 8, 128, 0, st>>>(g, Mu, Cov, lambda, Sc, mean, Nglob, scratch, pack, sumLLk, info);
+                           cudaStream_t st, double* pack2, double* muold) {
+  const FusedGeom f = make_fused_geom(g);
+  k_refresh<<<g.K8 * 8, 128, 0, st>>>(g, Mu, Cov, lambda, Sc, mean, Nglob, scratch, pack, sumLLk, info, pack2, muold, f.PSF, f.OFFB,
+                                      f.OFFC);
   return cudaGetLastError();
 }
 

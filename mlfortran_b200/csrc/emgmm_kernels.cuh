@@ -23,6 +23,36 @@ struct Geom {
 
 Geom make_geom(int d, int K);
 
+// Geometry of the fused single-pass kernel (emgmm_fused.cu).
+struct FusedGeom {
+  int OFFB;       // offset of the accumulator bias -L^T(mu - m) inside a component's pack (= NB*32)
+  int OFFC;       // offset of log(lambda) - lnDet
+  int PSF;        // doubles per component in the fused pack
+  int XS;         // row stride of the shared-memory X tile (8*DN + 4, conflict-free for both fragment shapes)
+  int MSF;        // doubles per component of the fused pass-B statistics: [MB*64 scatter | 8*DN sum_kept g x | sum_kept g, pad]
+  int CBMAX;      // component blocks (of 8) per warp
+  size_t smem;    // dynamic shared memory of k_em
+  bool scatter_ok;  // the scatter accumulators fit the register file for this (d, K)
+};
+FusedGeom make_fused_geom(const Geom& g);
+
+struct AmbEntry {  // pair whose keep/drop decision waits for the all-reduced s_k
+  double g;
+  long long key;   // point index * 1024 + component
+};
+
+struct EmArgs {
+  const double* X; long long N; int d, K, K8, S;
+  const double* pack2;   // [K8*8][PSF]
+  const double* shift;   // [>= 4*DM] global mean of the data, zero padded
+  const double* muold;   // [K8*8][8*DN] current means, zero padded
+  const double* tlo; const double* thi;   // [K8*8] band around minW*s_k (dummy components: +inf)
+  double* gamma; long long ldg; int* labels; int raw;
+  double* partA;         // [grid][K8*8][DS]
+  double* partB;         // [grid][K8*8][MSF]
+  AmbEntry* amb; int amb_cap; int* amb_count;   // [grid*8][amb_cap], [grid*8]
+};
+
 constexpr int kEstepThreads = 256;      // 8 warps per persistent block
 constexpr int kEstepTilePts = 128;      // 16 points per warp
 constexpr int kMstepThreads = 256;
@@ -32,7 +62,15 @@ constexpr int kMstepTilePts = 2048;     // points per block tile of the M-pass s
 //   scratch: K * 3*d*d doubles.  Sc (d*d, column-major) / mean (d) / Nglob describe the whole data set.
 cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, const double* lambda, const double* Sc,
                            const double* mean, double Nglob, double* scratch, double* pack, double* sumLLk, int* info,
-                           cudaStream_t st);
+                           cudaStream_t st, double* pack2 = nullptr, double* muold = nullptr);
+
+// Fused sweep (scatter = true) or E-pass + pass-A statistics only (scatter = false); see emgmm_fused.cu.
+cudaError_t launch_em(const Geom& g, const FusedGeom& f, const EmArgs& a, bool scatter, int grid, size_t smem_limit, cudaStream_t st);
+cudaError_t launch_amb_resolve(const Geom& g, const double* X, const AmbEntry* amb, int cap, const int* counts, int nlists,
+                               const double* statsA, double minW, const double* muold, double* outC, cudaStream_t st);
+cudaError_t launch_amb_summary(const int* counts, int nlists, int cap, double* flags, cudaStream_t st);
+cudaError_t launch_finalize_fused(const Geom& g, const FusedGeom& f, const double* statsA, const double* statsB, const double* statsC,
+                                  const double* muold, double minProba, double* Mu, double* Cov, double* lambda, cudaStream_t st);
 
 // E-pass: responsibilities (component-major gamma[k*ldg + i]), optional 1-based labels, and per-block
 // partial pass-A statistics partial[block][K8*8][DS].  Returns the grid size used through *grid_out.

@@ -469,11 +469,12 @@ int mlf_b200_set_profile(MLF_OBJ* obj, int on) {
   o->eng.reset_times();
   return 0;
 }
-int mlf_b200_get_times(MLF_OBJ* obj, double out[6]) {
+int mlf_b200_get_times(MLF_OBJ* obj, double out[8]) {
   EmObject* o = as_em(obj);
   if (!o || !out) return -1;
   const mlfb200::EngineTimes& t = o->eng.times();
   out[0] = t.refresh; out[1] = t.estep; out[2] = t.mid; out[3] = t.mstep; out[4] = t.fin; out[5] = (double)t.iters;
+  out[6] = (double)t.sweeps; out[7] = (double)t.amb_pairs;
   return 0;
 }
 int64_t mlf_b200_launch_count(MLF_OBJ* obj) {

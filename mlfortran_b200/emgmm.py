@@ -289,9 +289,9 @@ class mlf_algo_emgmm:
         self._lib.mlf_b200_set_profile(self._h, 1 if on else 0)
 
     def times(self) -> dict:
-        out = (C.c_double * 6)()
+        out = (C.c_double * 8)()
         self._lib.mlf_b200_get_times(self._h, out)
-        return dict(zip(["refresh_ms", "estep_ms", "mid_ms", "mstep_ms", "finalize_ms", "iters"], list(out)))
+        return dict(zip(["refresh_ms", "estep_ms", "mid_ms", "mstep_ms", "finalize_ms", "iters", "sweeps", "side_list_pairs"], list(out)))
 
     def launch_count(self) -> int:
         return int(self._lib.mlf_b200_launch_count(self._h))

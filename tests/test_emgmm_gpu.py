@@ -224,6 +224,29 @@ def test_labels_ties_resolve_to_lowest_index():
     em.finalize()
 
 
+# ---- fused sweep: threshold band, side list, exact repeat ---------------------------------------------------------------
+def test_fused_sweep_band_and_side_list(oracle):
+    """Heavily overlapping clusters: many pairs sit near the reference's W >= 1e-3/N threshold, the first iterations
+    mispredict s_k (repeat with the exact threshold) and later ones settle listed pairs; every path must give the
+    reference's numbers."""
+    data = synth.make_mixture(4, 6, 1500, 1.5, 1.0, 101)
+    X = data["X"]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 101)
+    iters = 12
+    oMu, oCov, olam, otr, oP = oracle.em_iterations(X, Mu0, Cov0, lam0, 0.0, iters, return_proba=True)
+    em = make_em(X, 6, 0.0, Mu0, Cov0, lam0)
+    em.set_profile(True)
+    for _ in range(iters):          # one iteration per call: the prediction state must survive across calls
+        assert em.step(1)[0] == 0, em.last_error()
+    t = em.times()
+    assert rel(em.Mu, oMu) <= PAR_RTOL and rel(em.Cov, oCov) <= PAR_RTOL and np.abs(em.lambda_ - olam).max() <= PAR_RTOL
+    assert abs(em.sumLL - otr[-1]) <= LL_RTOL * abs(otr[-1])
+    assert np.abs(em.ProbaC - oP).max() <= 1e-9     # re-evaluated on demand with the parameters of the last E-step
+    assert t["sweeps"] >= iters                      # counters are live (fused path) ...
+    assert t["sweeps"] < 2 * iters                   # ... and the band held in at least one iteration
+    em.finalize()
+
+
 # ---- edge cases ------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [1, 2, 31, 127, 128, 129, 2049])
 def test_tiny_and_ragged_point_counts(n, oracle):
