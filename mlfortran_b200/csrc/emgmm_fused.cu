@@ -39,7 +39,39 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 __device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr double kExpZero = -746.0;  // exp(x) == 0 in fp64 for x < -745.14
+
+// Branch-free fp64 exp for the softmax (arguments are logit - max <= 0, or raw logits): Cody-Waite reduction
+// r = a - n ln2 with |r| <= ln2/2, degree-13 Taylor polynomial (truncation 4e-18 relative), and a two-factor power of
+// two so that results in the denormal range round correctly.  Branch-free, so the compiler interleaves the eight
+// evaluations a lane has in flight; libm-style exp() carries three data-dependent branches per call.
+__device__ __forceinline__ double exp_bf(double a) {
+  a = (a < -750.0) ? -750.0 : a;   // exp(-750) underflows to 0 below; NaN stays NaN, +inf handled by the caller's data
+  a = (a > 710.0) ? 710.0 : a;     // 2^1024 overflows to +inf through the scaling
+  const double magic = 6755399441055744.0;  // 1.5 * 2^52
+  double t = fma(a, 1.4426950408889634074, magic);
+  const int n = __double2loint(t);
+  t -= magic;
+  double r = fma(t, -6.93147180369123816490e-01, a);
+  r = fma(t, -1.90821492927058770002e-10, r);
+  double p = 1.6059043836821614599e-10;            // 1/13!
+  p = fma(p, r, 2.0876756987868098979e-09);        // 1/12!
+  p = fma(p, r, 2.5052108385441718775e-08);        // 1/11!
+  p = fma(p, r, 2.7557319223985890653e-07);        // 1/10!
+  p = fma(p, r, 2.7557319223985892510e-06);        // 1/9!
+  p = fma(p, r, 2.4801587301587301566e-05);        // 1/8!
+  p = fma(p, r, 1.9841269841269841253e-04);        // 1/7!
+  p = fma(p, r, 1.3888888888888889419e-03);        // 1/6!
+  p = fma(p, r, 8.3333333333333332177e-03);        // 1/5!
+  p = fma(p, r, 4.1666666666666664354e-02);        // 1/4!
+  p = fma(p, r, 1.6666666666666665741e-01);        // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const int n1 = n >> 1, n2 = n - n1;
+  const double s1 = __hiloint2double((n1 + 1023) << 20, 0);
+  const double s2 = __hiloint2double((n2 + 1023) << 20, 0);
+  return (p * s1) * s2;
+}
 
 }  // namespace
 
@@ -190,15 +222,11 @@ __global__ void __launch_bounds__(kEstepThreads, 1) k_em(EmArgs A) {
       am[grp] = a;
     }
     double sum0 = 0, sum1 = 0;
-    for (int k4 = 0; k4 < K4; k4 += 2) {
+#pragma unroll 2
+    for (int k4 = 0; k4 < K4; k4 += 2) {   // K4 is even; 4 independent exp chains per trip, 2 trips unrolled
       const double a00 = row[0][4 * k4 + t] - mx[0], a01 = row[0][4 * k4 + 4 + t] - mx[0];
       const double a10 = row[1][4 * k4 + t] - mx[1], a11 = row[1][4 * k4 + 4 + t] - mx[1];
-      double e00 = 0, e01 = 0, e10 = 0, e11 = 0;
-      const bool live = (a00 > kExpZero) | (a01 > kExpZero) | (a10 > kExpZero) | (a11 > kExpZero) | (a00 != a00) | (a10 != a10) |
-                        (a01 != a01) | (a11 != a11);
-      if (__any_sync(kFull, live)) {  // exp() of anything below kExpZero is exactly 0: skipping it changes no bit
-        e00 = exp(a00); e01 = exp(a01); e10 = exp(a10); e11 = exp(a11);
-      }
+      const double e00 = exp_bf(a00), e01 = exp_bf(a01), e10 = exp_bf(a10), e11 = exp_bf(a11);
       row[0][4 * k4 + t] = e00; row[0][4 * k4 + 4 + t] = e01;
       row[1][4 * k4 + t] = e10; row[1][4 * k4 + 4 + t] = e11;
       sum0 += e00; sum0 += e01;
@@ -226,25 +254,29 @@ __global__ void __launch_bounds__(kEstepThreads, 1) k_em(EmArgs A) {
     }
     __syncthreads();
     // ---- P3: statistics of the block tile; warp w owns component blocks w, w+8, ... ------------------------------
+    // Loop A (branch-light, pipelined): pass-A DMMA for every 4-point group pb, kept/undecided classification; lane pb
+    // remembers which of the warp's 8 components keep a point of group pb.  Loop B: per component (static index, so
+    // its accumulators stay in named registers) walk only the groups that component keeps.
 #pragma unroll
     for (int ci = 0; ci < CBMAX; ++ci) {
       const int cb = warp + 8 * ci;
       if (cb < K8) {
+        constexpr int cs = SCATTER ? 1 : 0;
+        const int c2 = ci * cs;
         const int64_t q0 = bt * kEstepTilePts;
-#pragma unroll 1
+        const double* tcol = tile + 8 * cb + g;
+        unsigned act = 0;  // lane pb: bit q set <=> component 8*cb+q keeps some point of group pb
+#pragma unroll 4
         for (int pb = 0; pb < kEstepTilePts / 4; ++pb) {
-          const double a = tile[(size_t)(4 * pb + t) * S + 8 * cb + g];
-          sg[ci] += a;
-          sg2[ci] = fma(a, a, sg2[ci]);
+          const double a = tcol[(size_t)(4 * pb + t) * S];
           double b[DN];
 #pragma unroll
-          for (int db = 0; db < DN; ++db) {
-            b[db] = xs[(size_t)(4 * pb + t) * XS + 8 * db + g];
-            dmma(accA[ci][db], a, b[db]);
-          }
+          for (int db = 0; db < DN; ++db) b[db] = xs[(size_t)(4 * pb + t) * XS + 8 * db + g];
+          sg[ci] += a;
+          sg2[ci] = fma(a, a, sg2[ci]);
+#pragma unroll
+          for (int db = 0; db < DN; ++db) dmma(accA[ci][db], a, b[db]);
           if (SCATTER) {
-            constexpr int cs = SCATTER ? 1 : 0;
-            const int c2 = ci * cs;
             // "If(W(i) < minW0) CYCLE" (src/mlf_matrix.f90:135); g == 0 adds nothing and is never listed
             const bool hi = !(a < thi_r[c2]) && a != 0.0;
             const bool mid = !hi && !(a < tlo_r[c2]) && a != 0.0;
@@ -255,23 +287,13 @@ __global__ void __launch_bounds__(kEstepThreads, 1) k_em(EmArgs A) {
             if (mh) {
 #pragma unroll
               for (int db = 0; db < DN; ++db) dmma(accK[c2][db], ahi, b[db]);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                if (mh & (0xFu << (4 * q))) {  // some point of this 4-group is kept by component 8*cb+q
-                  const double w = __shfl_sync(kFull, ahi, 4 * q + t);
-                  const double* mq = smu + (size_t)(8 * cb + q) * 8 * DN;
-                  double z[DN], wz[DN];
-#pragma unroll
-                  for (int ab = 0; ab < DN; ++ab) {
-                    z[ab] = b[ab] - mq[8 * ab + g];
-                    wz[ab] = w * z[ab];
-                  }
-#pragma unroll
-                  for (int ab = 0; ab < DN; ++ab)
-#pragma unroll
-                    for (int bb = 0; bb <= ab; ++bb) dmma(accS[c2][q][ab * (ab + 1) / 2 + bb], wz[ab], z[bb]);
-                }
-              }
+              unsigned cm = mh | (mh >> 1);
+              cm |= cm >> 2;
+              cm &= 0x11111111u;                       // bit 4q: component q keeps a point of this group
+              cm = (cm | (cm >> 3)) & 0x03030303u;     // compress the 8 nibble flags into 8 contiguous bits
+              cm = (cm | (cm >> 6)) & 0x000f000fu;
+              cm = (cm | (cm >> 12)) & 0xffu;
+              if (lane == pb) act = cm;
             }
             if (mm) {  // undecided until s_k is final: side list, settled by k_amb_resolve
               const int slot = nAmb + __popc(mm & ((1u << lane) - 1u));
@@ -282,6 +304,35 @@ __global__ void __launch_bounds__(kEstepThreads, 1) k_em(EmArgs A) {
                 ambw[slot] = e;
               }
               nAmb += __popc(mm);
+            }
+          }
+        }
+        if (SCATTER) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            unsigned pm = __ballot_sync(kFull, (act >> q) & 1u);   // groups kept by component 8*cb+q
+            if (pm == 0) continue;
+            const double thq = __shfl_sync(kFull, thi_r[c2], 4 * q);
+            const double* mq = smu + (size_t)(8 * cb + q) * 8 * DN;
+            double mu_q[DN];
+#pragma unroll
+            for (int ab = 0; ab < DN; ++ab) mu_q[ab] = mq[8 * ab + g];
+            const double* tq = tile + 8 * cb + q;
+            while (pm) {
+              const int pb = __ffs(pm) - 1;
+              pm &= pm - 1;
+              const double aq = tq[(size_t)(4 * pb + t) * S];
+              const double w = (!(aq < thq) && aq != 0.0) ? aq : 0.0;
+              double z[DN], wz[DN];
+#pragma unroll
+              for (int ab = 0; ab < DN; ++ab) {
+                z[ab] = xs[(size_t)(4 * pb + t) * XS + 8 * ab + g] - mu_q[ab];
+                wz[ab] = w * z[ab];
+              }
+#pragma unroll
+              for (int ab = 0; ab < DN; ++ab)
+#pragma unroll
+                for (int bb = 0; bb <= ab; ++bb) dmma(accS[c2][q][ab * (ab + 1) / 2 + bb], wz[ab], z[bb]);
             }
           }
         }
