@@ -304,7 +304,9 @@ def main():
         pbytes = 8 * (K * d + K * d * d + K)
         e2e = {"value": N * K * e_steps / el, "unit": UNIT, "h2d_bytes_per_step": int(8 * n_loc * d + pbytes), "d2h_bytes_per_step": int(pbytes + 8),
                "steps": e_steps, "ms_per_step": el / e_steps * 1e3, "em_iter_per_s": e_steps / el,
-               "note": "per rank and step: pinned-host X -> HBM, parameters up, mlf_step(1), parameters + sumLL down"}
+               "note": "per rank and step: mlf_b200_refresh_x(pinned host X) + mlf_step(1) + parameters/sumLL back; the X upload is "
+                       "chunked underneath the step's sweep, so the step is PCIe-bound (h2d_bytes / ms_per_step = achieved H2D GB/s)",
+               "h2d_gbs": (8 * n_loc * d + pbytes) / (el / e_steps) * 1e-9}
     em.finalize()
 
     cpu = None

@@ -31,7 +31,10 @@ EmgmmEngine::~EmgmmEngine() {
                     dStatsA_, dStatsB_, dPartA_, dPartB_, dSc_, dMean_, dNglob_};
   for (double* b : bufs)
     if (b) cudaFree(b);
-  double* fb[] = {dPack2_, dMuOld_, dTlo_, dThi_, dAB_, dPartB2_, dStatsC_, dPrevMu_, dPrevCov_, dPrevLambda_};
+  double* fb[] = {dPack2_, dMuOld_, dTlo_, dThi_, dAB_, dPartB2_, dStatsC_, dPrevMu_, dPrevCov_, dPrevLambda_, dShift_, dMomPart_, dMomRaw_};
+  for (auto& e : cev_)
+    if (e) cudaEventDestroy(e);
+  if (cst_) cudaStreamDestroy(cst_);
   for (double* b : fb)
     if (b) cudaFree(b);
   if (dAmb_) cudaFree(dAmb_);
@@ -101,6 +104,10 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   CKE(A(&dThi_, KP), "cudaMalloc");
   CKE(A(&dAB_, (size_t)KP * g.DS + (size_t)KP * fgeom_.MSF + 8), "cudaMalloc");
   CKE(A(&dStatsC_, (size_t)K * (d * d + d + 1)), "cudaMalloc");
+  CKE(A(&dShift_, (size_t)8 * g.DN + 8), "cudaMalloc");
+  CKE(A(&dMomPart_, (size_t)sms_ * std::max(g.MB * 64 + 8 * g.DN, d + 1)), "cudaMalloc");
+  CKE(A(&dMomRaw_, (size_t)g.MB * 64 + 8 * g.DN), "cudaMalloc");
+  CKE(cudaStreamCreateWithFlags(&cst_, cudaStreamNonBlocking), "cudaStreamCreate");
   CKE(A(&dPrevMu_, (size_t)K * d), "cudaMalloc");
   CKE(A(&dPrevCov_, (size_t)K * d * d), "cudaMalloc");
   CKE(A(&dPrevLambda_, K), "cudaMalloc");
@@ -137,9 +144,9 @@ int EmgmmEngine::ensure_gamma() {
 }
 
 // InverseSymMatrix eigen branch + packing for both kernel generations (k_refresh).
-int EmgmmEngine::do_refresh() {
-  CKE(launch_refresh(geom_, dMu_, dCov_, dLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_, dPack2_, dMuOld_),
-      "refresh");
+int EmgmmEngine::do_refresh(bool with_sumll) {
+  CKE(launch_refresh(geom_, dMu_, dCov_, dLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_, dPack2_, dMuOld_,
+                     dShift_, with_sumll ? 1 : 0), "refresh");
   ++launches_;
   return 0;
 }
@@ -147,14 +154,27 @@ int EmgmmEngine::do_refresh() {
 int EmgmmEngine::refresh_x(const double* X, bool x_on_device) {
   CKE(cudaSetDevice(device_), "cudaSetDevice");
   const size_t bytes = (size_t)n_ * geom_.d * sizeof(double);
+  pending_host_ = nullptr;
   if (x_on_device) {
     dX_ = X;
   } else {
     if (!dXown_) CKE(cudaMalloc((void**)&dXown_, std::max<size_t>(bytes, 8)), "cudaMalloc X");
-    if (bytes) CKE(cudaMemcpyAsync(dXown_, X, bytes, cudaMemcpyHostToDevice, st_), "H2D X");
     dX_ = dXown_;
+    if (fused_ && shift_ready_ && n_ >= (int64_t)kStreamChunks * 4096) {
+      pending_host_ = X;   // uploaded chunk by chunk underneath the next sweep (iterate_fused), not here
+    } else if (bytes) {
+      CKE(cudaMemcpyAsync(dXown_, X, bytes, cudaMemcpyHostToDevice, st_), "H2D X");
+    }
   }
   moments_ready_ = false;
+  return 0;
+}
+
+int EmgmmEngine::flush_pending() {
+  if (!pending_host_) return 0;
+  const size_t bytes = (size_t)n_ * geom_.d * sizeof(double);
+  CKE(cudaMemcpyAsync(dXown_, pending_host_, bytes, cudaMemcpyHostToDevice, st_), "H2D X");
+  pending_host_ = nullptr;
   return 0;
 }
 
@@ -165,50 +185,47 @@ int EmgmmEngine::allreduce(double* buf, int64_t count) {
   return 0;
 }
 
-// One-time global moments: N, mean m and centred scatter Sc = sum_i (x_i-m)(x_i-m)^T, used by the closed form of
-// sum_i maha_ik in k_refresh (sumLL, src/unsupervised/mlf_gaussian.f90:73-76).
+// Global moments of the data: N, exact mean m and centred scatter Sc = sum_i (x_i-m)(x_i-m)^T, used by the closed form
+// of sum_i maha_ik (sumLL, src/unsupervised/mlf_gaussian.f90:73-76).  The first call fixes the shift vector (the global
+// mean at that time): the sweep whitens x - shift, and later moments are taken about the same shift in ONE pass.
 int EmgmmEngine::ensure_moments() {
   if (moments_ready_) return 0;
+  if (int r = flush_pending()) return r;
   const Geom& g = geom_;
   const int d = g.d;
-  const int grid = std::max(1, std::min<int>(sms_, (int)((n_ + 255) / 256)));
-  CKE(launch_colsum(dX_, n_, d, dPartB_, grid, st_), "colsum");
-  CKE(launch_reduce_partials(dPartB_, grid, d, dMean_, st_), "reduce colsum");
+  if (!shift_ready_) {
+    const int grid = std::max(1, std::min<int>(sms_, (int)((n_ + 255) / 256)));
+    CKE(launch_colsum(dX_, n_, d, dMomPart_, grid, st_), "colsum");
+    CKE(launch_reduce_partials(dMomPart_, grid, d, dShift_, st_), "reduce colsum");
+    launches_ += 2;
+    const double nl = (double)n_;
+    CKE(cudaMemcpyAsync(dShift_ + d, &nl, sizeof(double), cudaMemcpyHostToDevice, st_), "H2D n");
+    CKE(cudaStreamSynchronize(st_), "sync");
+    if (int r = allreduce(dShift_, d + 1)) return r;
+    std::vector<double> h(8 * g.DN + 8, 0.0);
+    CKE(cudaMemcpyAsync(h.data(), dShift_, (d + 1) * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H mean");
+    CKE(cudaStreamSynchronize(st_), "sync");
+    nglob_ = (int64_t)llround(h[d]);
+    const double ng = h[d];
+    for (int a = 0; a < d; ++a) h[a] /= ng;
+    for (size_t a = d; a < h.size(); ++a) h[a] = 0.0;
+    CKE(cudaMemcpyAsync(dShift_, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, st_), "H2D shift");
+    CKE(cudaStreamSynchronize(st_), "sync");
+    shift_ready_ = true;
+  }
+  const int grid = std::max(1, std::min<int>(sms_, (int)((n_ + 127) / 128)));
+  CKE(launch_moments(g, dX_, n_, dShift_, dMomPart_, grid, 0, st_), "moments");
+  ++launches_;
+  return finish_moments(grid);
+}
+
+int EmgmmEngine::finish_moments(int grid) {
+  const Geom& g = geom_;
+  const int PM = g.MB * 64 + 8 * g.DN;
+  CKE(launch_reduce_partials(dMomPart_, grid, PM, dMomRaw_, st_), "reduce moments");
+  if (int r = allreduce(dMomRaw_, PM)) return r;
+  CKE(launch_moments_finish(g, dMomRaw_, dShift_, (double)nglob_, dMean_, dSc_, st_), "moments finish");
   launches_ += 2;
-  const double nl = (double)n_;
-  CKE(cudaMemcpyAsync(dMean_ + d, &nl, sizeof(double), cudaMemcpyHostToDevice, st_), "H2D n");
-  CKE(cudaStreamSynchronize(st_), "sync");
-  if (int r = allreduce(dMean_, d + 1)) return r;
-  std::vector<double> h(8 * g.DN + 8, 0.0);
-  CKE(cudaMemcpyAsync(h.data(), dMean_, (d + 1) * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H mean");
-  CKE(cudaStreamSynchronize(st_), "sync");
-  nglob_ = (int64_t)llround(h[d]);
-  const double ng = h[d];
-  for (int a = 0; a < d; ++a) h[a] /= ng;
-  for (size_t a = d; a < h.size(); ++a) h[a] = 0.0;
-  CKE(cudaMemcpyAsync(dMean_, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, st_), "H2D mean");
-  // centred scatter through the M-pass kernel with unit weights and a single "component" centred at m
-  Geom g1 = make_geom(d, 1);
-  int gx, gy;
-  mstep_grid(g1, sms_, n_, &gx, &gy);
-  const double zero = 0.0;
-  CKE(cudaMemcpyAsync(dThr_, &zero, sizeof(double), cudaMemcpyHostToDevice, st_), "H2D thr");
-  CKE(launch_mstep(g1, dX_, n_, nullptr, 0, dMean_, dThr_, dPartB_, gx, st_), "mstep(moments)");
-  CKE(launch_reduce_partials(dPartB_, gx, g1.MS, dStatsB_, st_), "reduce moments");
-  launches_ += 2;
-  if (int r = allreduce(dStatsB_, g1.MS)) return r;
-  std::vector<double> sb(g1.MS), sc((size_t)d * d);
-  CKE(cudaMemcpyAsync(sb.data(), dStatsB_, g1.MS * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H moments");
-  CKE(cudaStreamSynchronize(st_), "sync");
-  for (int a = 0; a < d; ++a)
-    for (int b = 0; b <= a; ++b) {
-      const int ab = a >> 3, bb = b >> 3;
-      const double v = sb[(size_t)(ab * (ab + 1) / 2 + bb) * 64 + (a & 7) * 8 + (b & 7)];
-      sc[(size_t)b * d + a] = v;
-      sc[(size_t)a * d + b] = v;
-    }
-  CKE(cudaMemcpyAsync(dSc_, sc.data(), sc.size() * sizeof(double), cudaMemcpyHostToDevice, st_), "H2D Sc");
-  CKE(cudaStreamSynchronize(st_), "sync");
   moments_ready_ = true;
   return 0;
 }
@@ -242,9 +259,10 @@ int EmgmmEngine::run_estep(const double* X, int64_t n, double* gamma, int64_t ld
   } else {
     EmArgs a{};
     a.X = X; a.N = n; a.d = g.d; a.K = g.K; a.K8 = g.K8; a.S = g.S;
-    a.pack2 = dPack2_; a.shift = dMean_; a.muold = dMuOld_; a.tlo = nullptr; a.thi = nullptr;
+    a.pack2 = dPack2_; a.shift = dShift_; a.muold = dMuOld_; a.tlo = nullptr; a.thi = nullptr;
     a.gamma = gamma; a.ldg = ldg; a.labels = labels; a.raw = raw ? 1 : 0;
     a.partA = dPartA_; a.partB = nullptr; a.amb = nullptr; a.amb_cap = 0; a.amb_count = nullptr;
+    a.accumulate = 0; a.p_offset = 0;
     CKE(launch_em(g, fgeom_, a, false, grid, smem_limit_, st_), "em sweep (E-pass)");
   }
   ++launches_;
@@ -258,7 +276,11 @@ int EmgmmEngine::run_estep(const double* X, int64_t n, double* gamma, int64_t ld
 int EmgmmEngine::iterate(int64_t niter, double minProba, double* sumLL_last, double* sumLL_trace) {
   if (niter <= 0) return 0;
   CKE(cudaSetDevice(device_), "cudaSetDevice");
-  if (int r = ensure_moments()) return r;
+  if (!fused_) {
+    if (int r = flush_pending()) return r;
+  }
+  if (!(fused_ && pending_host_ && shift_ready_))
+    if (int r = ensure_moments()) return r;
   if (trace_cap_ < niter) {
     if (dSumLL_) cudaFree(dSumLL_);
     trace_cap_ = std::max<int64_t>(niter, 64);
@@ -325,6 +347,50 @@ int EmgmmEngine::iterate_two_pass(int64_t niter, double minProba, bool prof) {
   return 0;
 }
 
+// First sweep after refresh_x(host pointer): the shard is uploaded in kStreamChunks pieces on a copy stream while the
+// compute stream sweeps the pieces already there; every piece adds to the same per-block partials (fixed order, so the
+// result is deterministic) and to the global moments about the fixed shift.
+int EmgmmEngine::streamed_sweep(const EmArgs& base) {
+  const Geom& g = geom_;
+  const FusedGeom& f = fgeom_;
+  const int d = g.d, KP = g.K8 * 8;
+  const int PM = g.MB * 64 + 8 * g.DN;
+  const int nlists = sms_ * (kEstepThreads / 32);
+  while ((int)cev_.size() < kStreamChunks + 1) {
+    cudaEvent_t e;
+    CKE(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+    cev_.push_back(e);
+  }
+  CKE(cudaMemsetAsync(dPartA_, 0, (size_t)sms_ * KP * g.DS * sizeof(double), st_), "memset");
+  CKE(cudaMemsetAsync(dPartB2_, 0, (size_t)sms_ * KP * f.MSF * sizeof(double), st_), "memset");
+  CKE(cudaMemsetAsync(dAmbCount_, 0, (size_t)nlists * sizeof(int), st_), "memset");
+  CKE(cudaMemsetAsync(dMomPart_, 0, (size_t)sms_ * PM * sizeof(double), st_), "memset");
+  // the copy may not overwrite X before everything queued so far (earlier sweeps) has read it
+  CKE(cudaEventRecord(cev_[kStreamChunks], st_), "event");
+  CKE(cudaStreamWaitEvent(cst_, cev_[kStreamChunks], 0), "wait");
+  int64_t chunk = (n_ + kStreamChunks - 1) / kStreamChunks;
+  chunk = ((chunk + kEstepTilePts - 1) / kEstepTilePts) * kEstepTilePts;
+  int c = 0;
+  for (int64_t off = 0; off < n_; off += chunk, ++c) {
+    const int64_t n = std::min(chunk, n_ - off);
+    CKE(cudaMemcpyAsync(dXown_ + (size_t)off * d, pending_host_ + (size_t)off * d, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice, cst_),
+        "H2D X chunk");
+    CKE(cudaEventRecord(cev_[c], cst_), "event");
+    CKE(cudaStreamWaitEvent(st_, cev_[c], 0), "wait");
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sms_, (n + kEstepTilePts - 1) / kEstepTilePts));
+    CKE(launch_moments(g, dXown_ + (size_t)off * d, n, dShift_, dMomPart_, grid, 1, st_), "moments chunk");
+    EmArgs a = base;
+    a.X = dXown_ + (size_t)off * d;
+    a.N = n;
+    a.accumulate = 1;
+    a.p_offset = off;
+    CKE(launch_em(g, f, a, true, grid, smem_limit_, st_), "em sweep (streamed chunk)");
+    launches_ += 2;
+  }
+  pending_host_ = nullptr;
+  return finish_moments(sms_);
+}
+
 // Single-sweep iteration (emgmm_fused.cu).  Per iteration: refresh -> one sweep over X that produces the pass-A
 // statistics AND the covariance scatter of the certainly-kept pairs -> ONE all-reduce of both -> host check that the
 // finished s_k lies inside the predicted threshold band (repeat the sweep with the exact threshold otherwise) ->
@@ -347,9 +413,14 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
     CKE(cudaMemcpyAsync(dPrevCov_, dCov_, (size_t)K * d * d * sizeof(double), cudaMemcpyDeviceToDevice, st_), "copy");
     CKE(cudaMemcpyAsync(dPrevLambda_, dLambda_, (size_t)K * sizeof(double), cudaMemcpyDeviceToDevice, st_), "copy");
     prev_valid_ = true;
-    if (int r = do_refresh()) return r;
-    CKE(launch_sum_k(dSumLLk_, K, dSumLL_ + it, st_), "sum_k");
-    ++launches_;
+    // X was refreshed from host memory: its upload runs chunk by chunk underneath this iteration's first sweep, and the
+    // global moments (hence sumLL) become final only after it
+    const bool streamed = pending_host_ != nullptr;
+    if (int r = do_refresh(!streamed)) return r;
+    if (!streamed) {
+      CKE(launch_sum_k(dSumLLk_, K, dSumLL_ + it, st_), "sum_k");
+      ++launches_;
+    }
     if (prof) cudaEventRecord(ev_[1], st_);
     // threshold band [tlo, thi] = minW * [s_lo, s_hi]; s_k predicted from the previous iterations
     bool exact = false;
@@ -375,14 +446,23 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
       CKE(cudaMemcpyAsync(dThi_, thi.data(), KP * sizeof(double), cudaMemcpyHostToDevice, st_), "H2D thi");
       EmArgs a{};
       a.X = dX_; a.N = n_; a.d = d; a.K = K; a.K8 = g.K8; a.S = g.S;
-      a.pack2 = dPack2_; a.shift = dMean_; a.muold = dMuOld_; a.tlo = dTlo_; a.thi = dThi_;
+      a.pack2 = dPack2_; a.shift = dShift_; a.muold = dMuOld_; a.tlo = dTlo_; a.thi = dThi_;
       a.gamma = nullptr; a.ldg = 0; a.labels = nullptr; a.raw = 0;
       a.partA = dPartA_; a.partB = dPartB2_; a.amb = dAmb_; a.amb_cap = amb_cap_; a.amb_count = dAmbCount_;
-      CKE(launch_em(g, f, a, true, egrid_, smem_limit_, st_), "em sweep (fused)");
+      a.accumulate = 0; a.p_offset = 0;
+      if (streamed && pass == 0) {
+        if (int r = streamed_sweep(a)) return r;
+        CKE(launch_sumll(g, dMu_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, st_), "sumll");
+        CKE(launch_sum_k(dSumLLk_, K, dSumLL_ + it, st_), "sum_k");
+        launches_ += 2;
+      } else {
+        CKE(launch_em(g, f, a, true, egrid_, smem_limit_, st_), "em sweep (fused)");
+        ++launches_;
+      }
       CKE(launch_reduce_partials(dPartA_, egrid_, nA, dAB_, st_), "reduce statsA");
       CKE(launch_reduce_partials(dPartB2_, egrid_, nB, dAB_ + nA, st_), "reduce statsB");
       CKE(launch_amb_summary(dAmbCount_, nlists, amb_cap_, dFlags, st_), "amb summary");
-      launches_ += 4;
+      launches_ += 3;
       times_.sweeps += 1;
       if (int r = allreduce(dAB_, nA + nB + 2)) return r;
       // verification needs s_k and the list flags on the host: one small D2H + sync per sweep
@@ -469,7 +549,7 @@ int EmgmmEngine::materialize_gamma() {
   if (!prev_valid_ || n_ == 0) return 0;  // no E-step yet: ProbaC = 0 (src/unsupervised/mlf_emgmm.f90:119)
   if (int r = ensure_moments()) return r;
   CKE(launch_refresh(geom_, dPrevMu_, dPrevCov_, dPrevLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_,
-                     dPack2_, dMuOld_), "refresh");
+                     dPack2_, dMuOld_, dShift_, 1), "refresh");
   ++launches_;
   if (int r = run_estep(dX_, n_, dGamma_, ldg_, nullptr, false)) return r;
   gamma_current_ = true;

@@ -33,7 +33,7 @@ class EmgmmEngine {
   // alive (borrowed, like the reference's `this%X => X`); otherwise it is copied host->device here.
   int init(const double* X, bool x_on_device, int64_t n_local, int d, int K, int device);
   void set_allreduce(allreduce_fn fn, void* ctx, int rank, int world) {
-    ar_ = fn; ar_ctx_ = ctx; rank_ = rank; world_ = world < 1 ? 1 : world; moments_ready_ = false;
+    ar_ = fn; ar_ctx_ = ctx; rank_ = rank; world_ = world < 1 ? 1 : world; moments_ready_ = false; shift_ready_ = false;
   }
   void set_stream(cudaStream_t st);
   int refresh_x(const double* X, bool x_on_device);
@@ -82,7 +82,10 @@ class EmgmmEngine {
   int iterate_fused(int64_t niter, double minProba, bool prof);
   int iterate_two_pass(int64_t niter, double minProba, bool prof);
   int ensure_gamma();
-  int do_refresh();
+  int do_refresh(bool with_sumll = true);
+  int flush_pending();
+  int finish_moments(int grid);
+  int streamed_sweep(const EmArgs& base);
   int draw_far_point(double u, int grid, int64_t chunk, double* dMinDist, double* dPart, double* dOut);
 
   Geom geom_{};
@@ -108,6 +111,13 @@ class EmgmmEngine {
   double *dPack2_ = nullptr, *dMuOld_ = nullptr, *dTlo_ = nullptr, *dThi_ = nullptr, *dAB_ = nullptr, *dPartB2_ = nullptr, *dStatsC_ = nullptr;
   double *dPrevMu_ = nullptr, *dPrevCov_ = nullptr, *dPrevLambda_ = nullptr;  // parameters at the start of the last iteration (ProbaC)
   bool prev_valid_ = false;
+  // streamed refresh of X: host pointer waiting to be uploaded underneath the next sweep
+  static constexpr int kStreamChunks = 16;
+  const double* pending_host_ = nullptr;
+  double *dShift_ = nullptr, *dMomPart_ = nullptr, *dMomRaw_ = nullptr;
+  bool shift_ready_ = false;
+  cudaStream_t cst_ = nullptr;
+  std::vector<cudaEvent_t> cev_;
   bool gamma_current_ = false;  // dGamma_ holds the responsibilities of the last E-step
   AmbEntry* dAmb_ = nullptr;
   int* dAmbCount_ = nullptr;

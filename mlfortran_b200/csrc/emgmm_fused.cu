@@ -118,26 +118,47 @@ __global__ void __launch_bounds__(kEstepThreads, 1) k_em(EmArgs A) {
   double accA[CBMAX][DN][2], sg[CBMAX], sg2[CBMAX];
   double accK[SC][DN][2], sk[SC], thi_r[SC], tlo_r[SC];
   double accS[SC][8][MB][2];
+  // accumulators start at zero, or -- chunked sweep of a streamed X -- at what this block's partial slots hold
+  const bool accu = A.accumulate != 0;
+  double* outA = A.partA + (size_t)blockIdx.x * KP * DS;
+  double* outB = SCATTER ? A.partB + (size_t)blockIdx.x * KP * MSF : nullptr;
 #pragma unroll
   for (int c = 0; c < CBMAX; ++c) {
-    sg[c] = 0; sg2[c] = 0;
+    const int cb = warp + 8 * c;
+    const bool ld = accu && cb < K8;
+    const double* o = outA + (size_t)(8 * cb + g) * DS;
+    sg[c] = (ld && t == 0) ? o[0] : 0.0;
+    sg2[c] = (ld && t == 0) ? o[1] : 0.0;
 #pragma unroll
-    for (int b = 0; b < DN; ++b) { accA[c][b][0] = 0; accA[c][b][1] = 0; }
+    for (int b = 0; b < DN; ++b) {
+      accA[c][b][0] = ld ? o[2 + 8 * b + 2 * t] : 0.0;
+      accA[c][b][1] = ld ? o[2 + 8 * b + 2 * t + 1] : 0.0;
+    }
   }
 #pragma unroll
   for (int c = 0; c < SC; ++c) {
-    sk[c] = 0;
     const int cb = warp + 8 * c;
+    const bool ld = SCATTER && accu && cb < K8;
     thi_r[c] = (SCATTER && cb < K8) ? A.thi[8 * cb + g] : INFINITY;
     tlo_r[c] = (SCATTER && cb < K8) ? A.tlo[8 * cb + g] : INFINITY;
+    const double* ok = ld ? outB + (size_t)(8 * cb + g) * MSF + MB * 64 : nullptr;
+    sk[c] = (ld && t == 0) ? ok[8 * DN] : 0.0;
 #pragma unroll
-    for (int b = 0; b < DN; ++b) { accK[c][b][0] = 0; accK[c][b][1] = 0; }
+    for (int b = 0; b < DN; ++b) {
+      accK[c][b][0] = ld ? ok[8 * b + 2 * t] : 0.0;
+      accK[c][b][1] = ld ? ok[8 * b + 2 * t + 1] : 0.0;
+    }
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
+    for (int q = 0; q < 8; ++q) {
+      const double* oq = ld ? outB + (size_t)(8 * cb + q) * MSF : nullptr;
 #pragma unroll
-      for (int b = 0; b < MB; ++b) { accS[c][q][b][0] = 0; accS[c][q][b][1] = 0; }
+      for (int b = 0; b < MB; ++b) {
+        accS[c][q][b][0] = ld ? oq[b * 64 + g * 8 + 2 * t] : 0.0;
+        accS[c][q][b][1] = ld ? oq[b * 64 + g * 8 + 2 * t + 1] : 0.0;
+      }
+    }
   }
-  int nAmb = 0;
+  int nAmb = (SCATTER && accu) ? A.amb_count[blockIdx.x * (kEstepThreads / 32) + warp] : 0;
   AmbEntry* ambw = SCATTER ? A.amb + ((size_t)blockIdx.x * (kEstepThreads / 32) + warp) * A.amb_cap : nullptr;
 
   const int64_t ntiles = (N + kEstepTilePts - 1) / kEstepTilePts;
@@ -300,7 +321,7 @@ __global__ void __launch_bounds__(kEstepThreads, 1) k_em(EmArgs A) {
               if (mid && slot < A.amb_cap) {
                 AmbEntry e;
                 e.g = a;
-                e.key = (long long)(q0 + 4 * pb + t) * 1024 + (8 * cb + g);
+                e.key = (long long)(A.p_offset + q0 + 4 * pb + t) * 1024 + (8 * cb + g);
                 ambw[slot] = e;
               }
               nAmb += __popc(mm);
@@ -341,7 +362,6 @@ __global__ void __launch_bounds__(kEstepThreads, 1) k_em(EmArgs A) {
     __syncthreads();
   }
   // ---- per-block partials ----------------------------------------------------------------------------------------
-  double* outA = A.partA + (size_t)blockIdx.x * KP * DS;
 #pragma unroll
   for (int ci = 0; ci < CBMAX; ++ci) {
     const int cb = warp + 8 * ci;
@@ -359,7 +379,6 @@ __global__ void __launch_bounds__(kEstepThreads, 1) k_em(EmArgs A) {
     }
   }
   if (SCATTER) {
-    double* outB = A.partB + (size_t)blockIdx.x * KP * MSF;
 #pragma unroll
     for (int ci = 0; ci < SC; ++ci) {
       const int cb = warp + 8 * ci;

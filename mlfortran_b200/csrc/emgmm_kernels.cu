@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(128) k_refresh(Geom g, const double* __restric
                                                  const double* __restrict__ mean, double Nglob, double* __restrict__ scratch,
                                                  double* __restrict__ pack, double* __restrict__ sumLLk,
                                                  int* __restrict__ info, double* __restrict__ pack2, double* __restrict__ muold,
-                                                 int PSF, int OFFB2, int OFFC2) {
+                                                 int PSF, int OFFB2, int OFFC2, const double* __restrict__ shift, int do_sumll) {
   const int k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, d = g.d;
   const int OFFMU = g.NB * 32, OFFC = OFFMU + 4 * g.DM;
   double* pk = pack + (size_t)k * g.PS;
@@ -232,13 +232,14 @@ __global__ void __launch_bounds__(128) k_refresh(Geom g, const double* __restric
     for (int n = tid; n < 8 * g.DN; n += nt) {
       double acc = 0;
       if (n < d)
-        for (int m = n; m < d; ++m) acc = fma(W[(size_t)n * d + m], muk[m] - mean[m], acc);
+        for (int m = n; m < d; ++m) acc = fma(W[(size_t)n * d + m], muk[m] - shift[m], acc);
       p2[OFFB2 + n] = -acc;
       muold[(size_t)k * 8 * g.DN + n] = (n < d) ? muk[n] : 0.0;
     }
     if (tid == 0) { p2[OFFC2] = ck; p2[OFFC2 + 1] = 0; p2[OFFC2 + 2] = 0; p2[OFFC2 + 3] = 0; }
   }
 
+  if (!do_sumll) return;   // streamed refresh of X: the moments are not final yet, k_sumll runs after the sweep
   // closed form of sum_i (x_i-mu)^T invC (x_i-mu) = tr(L^T Sc L) + N |L^T (m - mu)|^2   (Sc = centred scatter)
   double part = 0;
   for (int n = tid; n < d; n += nt) {
@@ -259,10 +260,135 @@ __global__ void __launch_bounds__(128) k_refresh(Geom g, const double* __restric
 
 cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, const double* lambda, const double* Sc,
                            const double* mean, double Nglob, double* scratch, double* pack, double* sumLLk, int* info,
-                           cudaStream_t st, double* pack2, double* muold) {
+                           cudaStream_t st, double* pack2, double* muold, const double* shift, int do_sumll) {
   const FusedGeom f = make_fused_geom(g);
   k_refresh<<<g.K8 * 8, 128, 0, st>>>(g, Mu, Cov, lambda, Sc, mean, Nglob, scratch, pack, sumLLk, info, pack2, muold, f.PSF, f.OFFB,
-                                      f.OFFC);
+                                      f.OFFC, shift ? shift : mean, do_sumll);
+  return cudaGetLastError();
+}
+
+// sumLL_k from the global moments, for the case where they become final only after the sweep (streamed X):
+// same closed form as the tail of k_refresh, reading L (scratch W) and log(lambda_k) - lnDet_k (pack) it left behind.
+__global__ void __launch_bounds__(128) k_sumll(Geom g, const double* __restrict__ Mu, const double* __restrict__ Sc,
+                                               const double* __restrict__ mean, double Nglob, const double* __restrict__ scratch,
+                                               const double* __restrict__ pack, double* __restrict__ sumLLk) {
+  const int k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, d = g.d;
+  __shared__ double s_red[128];
+  const double* W = scratch + (size_t)k * 3 * d * d + 2 * (size_t)d * d;
+  const double* muk = Mu + (size_t)k * d;
+  const double ck = pack[(size_t)k * g.PS + g.NB * 32 + 4 * g.DM];
+  double part = 0;
+  for (int n = tid; n < d; n += nt) {
+    double y = 0, q = 0;
+    for (int a = n; a < d; ++a) {
+      const double lan = W[(size_t)n * d + a];
+      y += lan * (mean[a] - muk[a]);
+      double tsum = 0;
+      for (int b = n; b < d; ++b) tsum += Sc[(size_t)b * d + a] * W[(size_t)n * d + b];
+      q += lan * tsum;
+    }
+    part += q + Nglob * y * y;
+  }
+  part = block_sum(part, s_red);
+  if (tid == 0) sumLLk[k] = Nglob * ck - 0.5 * part;
+}
+cudaError_t launch_sumll(const Geom& g, const double* Mu, const double* Sc, const double* mean, double Nglob, const double* scratch,
+                         const double* pack, double* sumLLk, cudaStream_t st) {
+  k_sumll<<<g.K, 128, 0, st>>>(g, Mu, Sc, mean, Nglob, scratch, pack, sumLLk);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// global moments of the data about a fixed shift vector: sum (x - sh), sum (x - sh)(x - sh)^T (lower 8x8 blocks) as
+// [8 dims x 4 points] x [4 points x 8 dims] DMMA tiles.  partial[block][PM], PM = MB*64 + 8*DN; `accumulate` adds to
+// what the slot already holds (chunked upload of X).  Used for the closed form of sum_i maha_ik (sumLL).
+// ---------------------------------------------------------------------------------------------------------------
+template <int DN>
+__global__ void __launch_bounds__(256) k_moments(const double* __restrict__ X, int64_t N, int d, const double* __restrict__ shift,
+                                                 double* __restrict__ partial, int accumulate) {
+  constexpr int MB = DN * (DN + 1) / 2;
+  constexpr int PM = MB * 64 + 8 * DN;
+  __shared__ double red[8][PM];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  double sh[DN], zs[DN], acc[MB][2];
+#pragma unroll
+  for (int ab = 0; ab < DN; ++ab) { sh[ab] = (8 * ab + g < d) ? shift[8 * ab + g] : 0.0; zs[ab] = 0; }
+#pragma unroll
+  for (int b = 0; b < MB; ++b) { acc[b][0] = 0; acc[b][1] = 0; }
+  const int64_t ngroups = (N + 3) / 4;
+  const int64_t stride = (int64_t)gridDim.x * 8;
+#pragma unroll 4
+  for (int64_t gi = (int64_t)blockIdx.x * 8 + warp; gi < ngroups; gi += stride) {
+    const int64_t p = 4 * gi + t;
+    double z[DN];
+#pragma unroll
+    for (int ab = 0; ab < DN; ++ab) {
+      const int dim = 8 * ab + g;
+      z[ab] = (p < N && dim < d) ? X[p * d + dim] - sh[ab] : 0.0;
+      zs[ab] += z[ab];
+    }
+#pragma unroll
+    for (int ab = 0; ab < DN; ++ab)
+#pragma unroll
+      for (int bb = 0; bb <= ab; ++bb) dmma884(acc[ab * (ab + 1) / 2 + bb], z[ab], z[bb]);
+  }
+#pragma unroll
+  for (int b = 0; b < MB; ++b) {
+    red[warp][b * 64 + g * 8 + 2 * t] = acc[b][0];
+    red[warp][b * 64 + g * 8 + 2 * t + 1] = acc[b][1];
+  }
+#pragma unroll
+  for (int ab = 0; ab < DN; ++ab) {
+    double v = zs[ab];
+    v += shfl_xor_d(v, 1);
+    v += shfl_xor_d(v, 2);
+    if (t == 0) red[warp][MB * 64 + 8 * ab + g] = v;
+  }
+  __syncthreads();
+  double* o = partial + (size_t)blockIdx.x * PM;
+  for (int i = threadIdx.x; i < PM; i += 256) {
+    double v = accumulate ? o[i] : 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][i];
+    o[i] = v;
+  }
+}
+cudaError_t launch_moments(const Geom& g, const double* X, int64_t N, const double* shift, double* partial, int grid, int accumulate,
+                           cudaStream_t st) {
+  switch (g.DN) {
+    case 1: k_moments<1><<<grid, 256, 0, st>>>(X, N, g.d, shift, partial, accumulate); break;
+    case 2: k_moments<2><<<grid, 256, 0, st>>>(X, N, g.d, shift, partial, accumulate); break;
+    case 3: k_moments<3><<<grid, 256, 0, st>>>(X, N, g.d, shift, partial, accumulate); break;
+    case 4: k_moments<4><<<grid, 256, 0, st>>>(X, N, g.d, shift, partial, accumulate); break;
+    default: return cudaErrorInvalidConfiguration;
+  }
+  return cudaGetLastError();
+}
+
+// raw = [MB*64 scatter blocks about shift | 8*DN sum (x - shift)] (all-reduced); writes the exact mean (zero padded,
+// 8*DN + 8 doubles) and the centred scatter Sc (d x d, column-major): Sc = S - N delta delta^T, delta = mean - shift.
+__global__ void k_moments_finish(Geom g, const double* __restrict__ raw, const double* __restrict__ shift, double Nglob,
+                                 double* __restrict__ mean, double* __restrict__ Sc) {
+  const int d = g.d;
+  __shared__ double dl[128];
+  for (int a = threadIdx.x; a < 8 * g.DN + 8; a += blockDim.x) {
+    const double del = (a < d) ? raw[g.MB * 64 + a] / Nglob : 0.0;
+    if (a < 128) dl[a] = del;
+    mean[a] = (a < d) ? shift[a] + del : 0.0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d * d; i += blockDim.x) {
+    const int a = i % d, b = i / d;
+    if (a < b) continue;
+    const int ab = a >> 3, bb = b >> 3;
+    const double v = raw[(ab * (ab + 1) / 2 + bb) * 64 + (a & 7) * 8 + (b & 7)] - Nglob * dl[a] * dl[b];
+    Sc[(size_t)b * d + a] = v;
+    Sc[(size_t)a * d + b] = v;
+  }
+}
+cudaError_t launch_moments_finish(const Geom& g, const double* raw, const double* shift, double Nglob, double* mean, double* Sc,
+                                  cudaStream_t st) {
+  k_moments_finish<<<1, 256, 0, st>>>(g, raw, shift, Nglob, mean, Sc);
   return cudaGetLastError();
 }
 

@@ -51,6 +51,8 @@ struct EmArgs {
   double* partA;         // [grid][K8*8][DS]
   double* partB;         // [grid][K8*8][MSF]
   AmbEntry* amb; int amb_cap; int* amb_count;   // [grid*8][amb_cap], [grid*8]
+  int accumulate;        // start from the partials / list counts already stored (chunked sweep of a streamed X)
+  long long p_offset;    // index of X[0] inside the rank's shard (side-list keys)
 };
 
 constexpr int kEstepThreads = 256;      // 8 warps per persistent block
@@ -62,7 +64,15 @@ constexpr int kMstepTilePts = 2048;     // points per block tile of the M-pass s
 //   scratch: K * 3*d*d doubles.  Sc (d*d, column-major) / mean (d) / Nglob describe the whole data set.
 cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, const double* lambda, const double* Sc,
                            const double* mean, double Nglob, double* scratch, double* pack, double* sumLLk, int* info,
-                           cudaStream_t st, double* pack2 = nullptr, double* muold = nullptr);
+                           cudaStream_t st, double* pack2 = nullptr, double* muold = nullptr, const double* shift = nullptr,
+                           int do_sumll = 1);
+cudaError_t launch_sumll(const Geom& g, const double* Mu, const double* Sc, const double* mean, double Nglob, const double* scratch,
+                         const double* pack, double* sumLLk, cudaStream_t st);
+// Global moments about `shift`: partial[grid][MB*64 + 8*DN]; finish turns the all-reduced sums into mean and centred scatter.
+cudaError_t launch_moments(const Geom& g, const double* X, int64_t N, const double* shift, double* partial, int grid, int accumulate,
+                           cudaStream_t st);
+cudaError_t launch_moments_finish(const Geom& g, const double* raw, const double* shift, double Nglob, double* mean, double* Sc,
+                                  cudaStream_t st);
 
 // Fused sweep (scatter = true) or E-pass + pass-A statistics only (scatter = false); see emgmm_fused.cu.
 cudaError_t launch_em(const Geom& g, const FusedGeom& f, const EmArgs& a, bool scatter, int grid, size_t smem_limit, cudaStream_t st);

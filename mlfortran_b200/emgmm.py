@@ -264,6 +264,14 @@ class mlf_algo_emgmm:
         self._lambda[...] = lam
         self.initialized = True
 
+    def refresh_x(self, X: np.ndarray) -> int:
+        """Tell the object that the caller's X changed (the reference reads `this%X => X` on every step; here X lives in
+        HBM).  The upload is streamed underneath the next step's first sweep."""
+        if X.dtype != np.float64 or X.ndim != 2 or not X.flags.c_contiguous or X.shape != tuple(self._X.shape):
+            return mlf_OTHERERROR
+        self._X = X
+        return self._lib.mlf_b200_refresh_x(self._h, X.ctypes.data)
+
     def set_seed(self, seed: int) -> None:
         """Seed of the k-means initialiser's random stream (reference: unseeded RANDOM_NUMBER)."""
         self._lib.mlf_b200_set_seed(self._h, int(seed) & (2 ** 64 - 1))

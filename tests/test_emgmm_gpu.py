@@ -247,6 +247,31 @@ def test_fused_sweep_band_and_side_list(oracle):
     em.finalize()
 
 
+def test_streamed_refresh_of_x(oracle):
+    """refresh_x(host X) + step: the upload is chunked underneath the first sweep and the global moments (sumLL) are
+    re-accumulated about the old shift; results must equal a fresh run on the new data."""
+    d, K = 4, 5
+    data = synth.make_mixture(d, K, 16000, 6.0, 1.0, 111)       # 80 000 points >= the streaming threshold
+    X1 = data["X"]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 111)
+    em = make_em(X1, K, 0.0, Mu0, Cov0, lam0)
+    assert em.step(2)[0] == 0
+    rng = np.random.default_rng(112)
+    X2 = np.ascontiguousarray(X1 + 0.05 * rng.standard_normal(X1.shape) + 0.3)   # changed data, shifted mean
+    Mu1, Cov1, lam1 = em.Mu.copy(), em.Cov.copy(), em.lambda_.copy()
+    assert em.refresh_x(X2) == 0
+    assert em.step(3)[0] == 0, em.last_error()
+    oMu, oCov, olam, otr = oracle.em_iterations(X2, Mu1, Cov1, lam1, 0.0, 3)
+    check_against(em, oMu, oCov, olam, otr)
+    info, cl = em.getClass(X2[:500])
+    _, Pn, _ = oracle.exp_step(X2[:500], em.Mu, em.Cov, em.lambda_)
+    assert info == 0 and (cl == oracle.get_class(Pn)).all()
+    # refresh followed directly by a query (no step in between) must see the new data too
+    assert em.refresh_x(X1) == 0
+    np.testing.assert_array_equal(em.labels()[:500], em.getClass(X1[:500])[1])
+    em.finalize()
+
+
 # ---- edge cases ------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [1, 2, 31, 127, 128, 129, 2049])
 def test_tiny_and_ragged_point_counts(n, oracle):
