@@ -1,0 +1,343 @@
+// Large-shape kernels of the EM-GMM path for sm_100a: 32 < d <= 128 (BASELINE config 4: d = 128, K = 32), or any
+// (d, K) whose parameter pack does not fit shared memory next to the logit tile (e.g. d = 8, K = 256).
+// Reference: mlf_EvalGaussian / mlf_MaxGaussian (src/unsupervised/mlf_gaussian.f90:41-79), GECovMatrix
+// (src/mlf_matrix.f90:99-147).
+//
+//   k_estep_big : same arithmetic as the fused kernel's P1-P3 (whitening u = L^T(x-m) - L^T(mu-m) as DMMA tiles whose
+//                 accumulators start at the bias, log-sum-exp, pass-A statistics), but the Cholesky fragments of one
+//                 component (69.6 KB at d = 128) are streamed from L2 through L1 instead of living in shared memory,
+//                 8 points per warp, 64 points per block tile.
+//   k_mstep_big : thresholded centred scatter sum g (x-mu)(x-mu)^T with the lower-triangular 8x8 output blocks
+//                 (136 at d = 128) distributed over the 8 warps of a block; a 32-point strip of (x - mu) is staged in
+//                 shared memory, strips without a kept point are skipped.
+// The responsibilities are stored (two-pass iteration); the fused single sweep covers d <= 16.
+#include "emgmm_kernels.cuh"
+
+#include <cmath>
+
+namespace mlfb200 {
+
+namespace {
+
+__host__ __device__ constexpr int b_blk_off(int mb) {
+  int s = 0;
+  for (int m = 0; m < mb; ++m) s += m / 2 + 1;
+  return s;
+}
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+constexpr unsigned kFull = 0xffffffffu;
+
+// same branch-free exp as the fused kernel (see emgmm_fused.cu)
+__device__ __forceinline__ double exp_bf(double a) {
+  a = (a < -750.0) ? -750.0 : a;
+  a = (a > 710.0) ? 710.0 : a;
+  const double magic = 6755399441055744.0;
+  double t = fma(a, 1.4426950408889634074, magic);
+  const int n = __double2loint(t);
+  t -= magic;
+  double r = fma(t, -6.93147180369123816490e-01, a);
+  r = fma(t, -1.90821492927058770002e-10, r);
+  double p = 1.6059043836821614599e-10;
+  p = fma(p, r, 2.0876756987868098979e-09);
+  p = fma(p, r, 2.5052108385441718775e-08);
+  p = fma(p, r, 2.7557319223985890653e-07);
+  p = fma(p, r, 2.7557319223985892510e-06);
+  p = fma(p, r, 2.4801587301587301566e-05);
+  p = fma(p, r, 1.9841269841269841253e-04);
+  p = fma(p, r, 1.3888888888888889419e-03);
+  p = fma(p, r, 8.3333333333333332177e-03);
+  p = fma(p, r, 4.1666666666666664354e-02);
+  p = fma(p, r, 1.6666666666666665741e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const int n1 = n >> 1, n2 = n - n1;
+  return (p * __hiloint2double((n1 + 1023) << 20, 0)) * __hiloint2double((n2 + 1023) << 20, 0);
+}
+
+constexpr int kBigTile = 64;  // points per block tile (8 per warp)
+
+}  // namespace
+
+size_t estep_big_smem(const Geom& g) {
+  const int XS = 8 * g.DN + 4;
+  const int S = ((g.K8 * 8 + 15) / 16) * 16 + 4;
+  return ((size_t)kBigTile * XS + (size_t)kBigTile * S) * sizeof(double);
+}
+int estep_big_cb(const Geom& g) { return (g.K8 + 7) / 8; }
+bool estep_big_ok(const Geom& g, size_t smem_limit) {
+  const int cb = estep_big_cb(g);
+  const bool inst = (g.DM == 1 || g.DM == 2 || g.DM == 4 || g.DM == 8 || g.DM == 12 || g.DM == 16 || g.DM == 24 || g.DM == 32);
+  return inst && cb * g.DN <= 16 && (cb == 1 || cb == 2 || cb == 4) && estep_big_smem(g) <= smem_limit;
+}
+
+// pack2 layout per component (FusedGeom): [NB*32 L fragments | 8*DN bias -L^T(mu-m) | log(lambda)-lnDet, pad]
+template <int DM, int CB>
+__global__ void __launch_bounds__(256, 1) k_estep_big(EmArgs A) {
+  constexpr int DN = (DM + 1) / 2;
+  constexpr int NB = b_blk_off(DM);
+  constexpr int OFFB = NB * 32, OFFC = OFFB + 8 * DN, PSF = OFFC + 4;
+  constexpr int XS = 8 * DN + 4;
+  constexpr int DS = 8 * DN + 2;
+  extern __shared__ __align__(16) double smem[];
+  const int K8 = A.K8, KP = K8 * 8, S = A.S, d = A.d, K = A.K;
+  const int64_t N = A.N;
+  double* xs = smem;                          // [64][XS] raw points of the tile
+  double* tile = xs + (size_t)kBigTile * XS;  // [64][S]  logits -> responsibilities
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+
+  double accA[CB][DN][2], sg[CB], sg2[CB];
+#pragma unroll
+  for (int c = 0; c < CB; ++c) {
+    sg[c] = 0; sg2[c] = 0;
+#pragma unroll
+    for (int b = 0; b < DN; ++b) { accA[c][b][0] = 0; accA[c][b][1] = 0; }
+  }
+  const int64_t ntiles = (N + kBigTile - 1) / kBigTile;
+  for (int64_t bt = blockIdx.x; bt < ntiles; bt += gridDim.x) {
+    const int64_t p = bt * kBigTile + warp * 8 + g;
+    // ---- P1: logits of this warp's 8 points against every component -------------------------------------------
+    double xa[DM];
+    {
+      double* xr = xs + (size_t)(warp * 8 + g) * XS;
+#pragma unroll
+      for (int mb = 0; mb < DM; ++mb) {
+        const int a = 4 * mb + t;
+        const double x = (p < N && a < d) ? A.X[p * d + a] : 0.0;
+        xr[a] = x;
+        xa[mb] = x - A.shift[a];
+      }
+      if (8 * DN > 4 * DM) xr[4 * DM + t] = 0.0;
+    }
+    double* row = tile + (size_t)(warp * 8 + g) * S;
+    double rmax = -INFINITY;
+    int rarg = 0;
+    for (int k = 0; k < KP; ++k) {
+      const double* pk = A.pack2 + (size_t)k * PSF;
+      double c[DN][2];
+#pragma unroll
+      for (int nb = 0; nb < DN; ++nb) {
+        const double2 v = *reinterpret_cast<const double2*>(pk + OFFB + 8 * nb + 2 * t);
+        c[nb][0] = v.x; c[nb][1] = v.y;
+      }
+#pragma unroll
+      for (int mb = 0; mb < DM; ++mb)
+#pragma unroll
+        for (int nb = 0; nb <= mb / 2; ++nb) dmma(c[nb], xa[mb], __ldg(pk + (b_blk_off(mb) + nb) * 32 + lane));
+      double s = 0;
+#pragma unroll
+      for (int nb = 0; nb < DN; ++nb) { s = fma(c[nb][0], c[nb][0], s); s = fma(c[nb][1], c[nb][1], s); }
+      s += shx(s, 1);
+      s += shx(s, 2);
+      const double logit = fma(-0.5, s, pk[OFFC]);
+      if (t == 0) row[k] = logit;
+      if (logit > rmax) { rmax = logit; rarg = k; }  // k ascending: first maximum wins (MAXLOC)
+    }
+    __syncwarp();
+    // ---- P2: log-sum-exp over the components; lane t handles components t, t+4, ... ----------------------------
+    const double mx = A.raw ? 0.0 : rmax;
+    double sum = 0;
+#pragma unroll 4
+    for (int k = t; k < KP; k += 4) {
+      const double e = exp_bf(row[k] - mx);
+      row[k] = e;
+      sum += e;
+    }
+    sum += shx(sum, 1);
+    sum += shx(sum, 2);
+    const bool valid = p < N;
+    const double inv = valid ? (A.raw ? 1.0 : 1.0 / sum) : 0.0;
+    for (int k = t; k < KP; k += 4) {
+      const double gk = row[k] * inv;
+      row[k] = gk;
+      if (A.gamma != nullptr && valid && k < K) A.gamma[(size_t)k * A.ldg + p] = gk;
+    }
+    if (A.labels != nullptr && valid && t == 0) A.labels[p] = rarg + 1;
+    __syncthreads();
+    // ---- P3: pass-A statistics; warp w owns component blocks w, w+8, ... -----------------------------------------
+#pragma unroll
+    for (int ci = 0; ci < CB; ++ci) {
+      const int cb = warp + 8 * ci;
+      if (cb < K8) {
+#pragma unroll 2
+        for (int pb = 0; pb < kBigTile / 4; ++pb) {
+          const double a = tile[(size_t)(4 * pb + t) * S + 8 * cb + g];
+          sg[ci] += a;
+          sg2[ci] = fma(a, a, sg2[ci]);
+#pragma unroll
+          for (int db = 0; db < DN; ++db) dmma(accA[ci][db], a, xs[(size_t)(4 * pb + t) * XS + 8 * db + g]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  double* outA = A.partA + (size_t)blockIdx.x * KP * DS;
+#pragma unroll
+  for (int ci = 0; ci < CB; ++ci) {
+    const int cb = warp + 8 * ci;
+    if (cb < K8) {
+      double a = sg[ci], b = sg2[ci];
+      a += shx(a, 1); a += shx(a, 2);
+      b += shx(b, 1); b += shx(b, 2);
+      double* o = outA + (size_t)(8 * cb + g) * DS;
+      if (t == 0) { o[0] = a; o[1] = b; }
+#pragma unroll
+      for (int db = 0; db < DN; ++db) {
+        o[2 + 8 * db + 2 * t] = accA[ci][db][0];
+        o[2 + 8 * db + 2 * t + 1] = accA[ci][db][1];
+      }
+    }
+  }
+}
+
+template <int DM, int CB>
+static cudaError_t launch_big_t(const EmArgs& a, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(k_estep_big<DM, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_estep_big<DM, CB><<<grid, 256, smem, st>>>(a);
+  return cudaGetLastError();
+}
+template <int DM>
+static cudaError_t launch_big_dm(const EmArgs& a, int cb, int grid, size_t smem, cudaStream_t st) {
+  constexpr int DN = (DM + 1) / 2;
+  if constexpr (1 * DN <= 16) { if (cb == 1) return launch_big_t<DM, 1>(a, grid, smem, st); }
+  if constexpr (2 * DN <= 16) { if (cb == 2) return launch_big_t<DM, 2>(a, grid, smem, st); }
+  if constexpr (4 * DN <= 16) { if (cb == 4) return launch_big_t<DM, 4>(a, grid, smem, st); }
+  return cudaErrorInvalidConfiguration;
+}
+cudaError_t launch_estep_big(const Geom& g, EmArgs a, int grid, size_t smem_limit, cudaStream_t st) {
+  if (!estep_big_ok(g, smem_limit)) return cudaErrorInvalidConfiguration;
+  const size_t smem = estep_big_smem(g);
+  a.S = ((g.K8 * 8 + 15) / 16) * 16 + 4;
+  const int cb = estep_big_cb(g);
+  switch (g.DM) {
+    case 1: return launch_big_dm<1>(a, cb, grid, smem, st);
+    case 2: return launch_big_dm<2>(a, cb, grid, smem, st);
+    case 4: return launch_big_dm<4>(a, cb, grid, smem, st);
+    case 8: return launch_big_dm<8>(a, cb, grid, smem, st);
+    case 12: return launch_big_dm<12>(a, cb, grid, smem, st);
+    case 16: return launch_big_dm<16>(a, cb, grid, smem, st);
+    case 24: return launch_big_dm<24>(a, cb, grid, smem, st);
+    case 32: return launch_big_dm<32>(a, cb, grid, smem, st);
+    default: return cudaErrorInvalidConfiguration;
+  }
+}
+int estep_big_tile() { return kBigTile; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// M-pass for large d.  grid = (point chunks, components); block = 8 warps; warp w owns the lower-triangular 8x8 output
+// blocks w, w+8, ... of the scatter matrix (<= 17 at d = 128).  partial[chunk][K][MS] as k_mstep.
+// gamma == nullptr: unit weights (global moments).
+// ---------------------------------------------------------------------------------------------------------------
+template <int DN>
+__global__ void __launch_bounds__(256) k_mstep_big(const double* __restrict__ X, int64_t N, int d, int K,
+                                                   const double* __restrict__ gamma, int64_t ldg, const double* __restrict__ mupad,
+                                                   const double* __restrict__ thr, double* __restrict__ partial, int MS,
+                                                   int64_t chunk) {
+  constexpr int MB = DN * (DN + 1) / 2;
+  constexpr int OWN = (MB + 7) / 8;
+  constexpr int ZS = 8 * DN + 4;
+  __shared__ double zs[32][ZS];   // (x - mu) of a 32-point strip
+  __shared__ double ws[32];       // kept weight of each point (0 if dropped)
+  __shared__ double smu[8 * DN];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int k = blockIdx.y;
+  for (int a = tid; a < 8 * DN; a += 256) smu[a] = mupad[(size_t)k * 8 * DN + a];
+  const double th = thr[k];
+  const double* gk = gamma ? gamma + (size_t)k * ldg : nullptr;
+  double acc[OWN][2];
+  int oa[OWN], ob[OWN];
+#pragma unroll
+  for (int o = 0; o < OWN; ++o) {
+    acc[o][0] = 0; acc[o][1] = 0;
+    const int blk = warp + 8 * o;
+    int ab = 0;
+    while ((ab + 1) * (ab + 2) / 2 <= blk) ++ab;
+    oa[o] = ab;
+    ob[o] = blk - ab * (ab + 1) / 2;
+  }
+  double sg2 = 0;
+  __syncthreads();
+  const int64_t lo = (int64_t)blockIdx.x * chunk;
+  const int64_t hi = (lo + chunk < N) ? lo + chunk : N;
+  for (int64_t i0 = lo; i0 < hi; i0 += 32) {
+    // weight of the strip's points: every warp evaluates the same ballot (uniform decision, no extra barrier)
+    const int64_t pl = i0 + lane;
+    const double gv = (pl < hi) ? (gk ? gk[pl] : 1.0) : 0.0;
+    if (warp == 0) sg2 = fma(gv, gv, sg2);               // SUM(W*W) runs over all points (src/mlf_matrix.f90:119)
+    const bool kept = !(gv < th) && pl < hi && gv != 0.0;  // "If(W(i) < minW0) CYCLE" (:135)
+    const unsigned mask = __ballot_sync(kFull, kept);
+    if (mask == 0) continue;
+    __syncthreads();  // previous strip fully consumed
+    if (warp == 0) ws[lane] = kept ? gv : 0.0;
+    for (int i = tid; i < 32 * 8 * DN; i += 256) {
+      const int pt = i / (8 * DN), a = i % (8 * DN);
+      const int64_t pp = i0 + pt;
+      zs[pt][a] = (pp < hi && a < d) ? X[pp * d + a] - smu[a] : 0.0;
+    }
+    __syncthreads();
+    unsigned gm = mask | (mask >> 1);
+    gm |= gm >> 2;
+    gm &= 0x11111111u;  // bit 4q: 4-point group q holds a kept point
+    while (gm) {
+      const int q = (__ffs(gm) - 1) >> 2;
+      gm &= gm - 1;
+      const double w = ws[4 * q + t];
+#pragma unroll
+      for (int o = 0; o < OWN; ++o) {
+        if (warp + 8 * o < MB) {
+          const double za = zs[4 * q + t][8 * oa[o] + g];
+          const double zb = zs[4 * q + t][8 * ob[o] + g];
+          dmma(acc[o], w * za, zb);
+        }
+      }
+    }
+  }
+  double* out = partial + ((size_t)blockIdx.x * K + k) * MS;
+#pragma unroll
+  for (int o = 0; o < OWN; ++o) {
+    const int blk = warp + 8 * o;
+    if (blk < MB) {
+      out[(size_t)blk * 64 + g * 8 + 2 * t] = acc[o][0];
+      out[(size_t)blk * 64 + g * 8 + 2 * t + 1] = acc[o][1];
+    }
+  }
+  if (warp == 0) {
+    double s = sg2;
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) s += shx(s, sh);
+    if (lane == 0) { out[(size_t)MB * 64] = s; out[(size_t)MB * 64 + 1] = 0.0; }
+  }
+}
+
+void mstep_big_grid(const Geom& g, int sms, int64_t N, int* gx, int64_t* chunk) {
+  int x = sms * 2 / (g.K > 0 ? g.K : 1);
+  if (x < 1) x = 1;
+  int64_t c = (N + x - 1) / x;
+  c = ((c + 31) / 32) * 32;
+  if (c < 32) c = 32;
+  x = (int)((N + c - 1) / c);
+  if (x < 1) x = 1;
+  *gx = x;
+  *chunk = c;
+}
+
+cudaError_t launch_mstep_big(const Geom& g, const double* X, int64_t N, const double* gamma, int64_t ldg, const double* mupad,
+                             const double* thr, double* partial, int gx, int64_t chunk, cudaStream_t st) {
+  const dim3 grid(gx, g.K);
+#define MLF_MB(DNv) \
+  case DNv: k_mstep_big<DNv><<<grid, 256, 0, st>>>(X, N, g.d, g.K, gamma, ldg, mupad, thr, partial, g.MS, chunk); break;
+  switch (g.DN) {
+    MLF_MB(1) MLF_MB(2) MLF_MB(4) MLF_MB(6) MLF_MB(8) MLF_MB(12) MLF_MB(16)
+    default: return cudaErrorInvalidConfiguration;
+  }
+#undef MLF_MB
+  return cudaGetLastError();
+}
+
+}  // namespace mlfb200

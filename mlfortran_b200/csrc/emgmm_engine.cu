@@ -57,7 +57,7 @@ void EmgmmEngine::set_stream(cudaStream_t st) {
 
 int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d, int K, int device) {
   if (n_local < 0 || d < 1 || K < 1) { err_ = "invalid shape"; return -7; }
-  if (d > 32) { err_ = "d > 32 is not supported by this build (DMMA fragment-resident path covers d <= 32)"; return -7; }
+  if (d > 128) { err_ = "d > 128 is not supported by this build"; return -7; }
   int ndev = 0;
   cudaError_t e0 = cudaGetDeviceCount(&ndev);
   if (e0 != cudaSuccess || ndev == 0) {
@@ -76,13 +76,24 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   {
     const char* lg = getenv("MLF_B200_LEGACY");
     legacy_estep_ = lg && lg[0] == '1';
+    const char* bg = getenv("MLF_B200_BIG");
+    big_ = bg && bg[0] == '1';
   }
-  if (!legacy_estep_ && fgeom_.smem > smem_limit_) legacy_estep_ = true;  // fused pack does not fit: first-generation E-pass
-  if (legacy_estep_ && estep_smem_bytes(geom_) > smem_limit_) {
-    err_ = "K*d^2 parameter pack + logit tile exceed shared memory for this (d,K)";
-    return -7;
+  // kernel generation for this shape: fused single sweep (pack + tile in shared memory, scatter accumulators in
+  // registers) > resident-pack E-pass + stored responsibilities > large-shape kernels (pack streamed through L1)
+  if (d > 32 || (fgeom_.smem > smem_limit_ && estep_smem_bytes(geom_) > smem_limit_)) big_ = true;
+  if (big_) {
+    geom_ = make_geom(d, K, true);
+    fgeom_ = make_fused_geom(geom_);
+    if (!estep_big_ok(geom_, smem_limit_)) {
+      err_ = "this (d, K) is outside the shapes the large-shape kernels are built for (K <= 256 at d <= 32, K*d <= 8192 beyond)";
+      return -7;
+    }
+    legacy_estep_ = false;
+  } else if (!legacy_estep_ && fgeom_.smem > smem_limit_) {
+    legacy_estep_ = true;  // fused pack does not fit: first-generation E-pass
   }
-  fused_ = !legacy_estep_ && fgeom_.scatter_ok;
+  fused_ = !big_ && !legacy_estep_ && fgeom_.scatter_ok;
   n_ = n_local;
   nglob_ = n_local;
   ldg_ = ((n_ + 31) / 32) * 32;
@@ -94,6 +105,10 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   const int64_t etiles = (n_ + kEstepTilePts - 1) / kEstepTilePts;
   egrid_ = (int)std::max<int64_t>(1, std::min<int64_t>(sms_, etiles));
   mstep_grid(g, sms_, n_, &mgx_, &mgy_);
+  if (big_) {
+    egrid_ = (int)std::max<int64_t>(1, std::min<int64_t>(sms_, (n_ + estep_big_tile() - 1) / estep_big_tile()));
+    mstep_big_grid(g, sms_, n_, &mgx_, &mchunk_);
+  }
   auto A = [&](double** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(double)); };
   if (!fused_) {
     if (int r = ensure_gamma()) return r;  // two-pass path keeps ProbaC(N,K) resident; the fused sweep never stores it
@@ -128,7 +143,7 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   CKE(A(&dStatsA_, (size_t)KP * g.DS), "cudaMalloc");
   CKE(A(&dStatsB_, (size_t)K * g.MS), "cudaMalloc");
   CKE(A(&dPartA_, (size_t)sms_ * KP * g.DS), "cudaMalloc");
-  CKE(A(&dPartB_, (size_t)sms_ * K * g.MS), "cudaMalloc");
+  CKE(A(&dPartB_, (size_t)(2 * sms_ + K + 2) * g.MS), "cudaMalloc");
   CKE(A(&dSc_, (size_t)d * d), "cudaMalloc");
   CKE(A(&dMean_, (size_t)8 * g.DN + 8), "cudaMalloc");
   CKE(A(&dNglob_, 8), "cudaMalloc");
@@ -167,6 +182,7 @@ int EmgmmEngine::refresh_x(const double* X, bool x_on_device) {
     }
   }
   moments_ready_ = false;
+  if (!fused_) shift_ready_ = false;  // the shift is re-taken as the exact mean of the new data
   return 0;
 }
 
@@ -213,10 +229,43 @@ int EmgmmEngine::ensure_moments() {
     CKE(cudaStreamSynchronize(st_), "sync");
     shift_ready_ = true;
   }
+  if (g.DN > 4) {
+    // large d: scatter about the shift through the large-shape M-pass kernel with unit weights.  Without the fused
+    // path the shift is re-taken at every refresh of X, so sum (x - shift) is zero by construction.
+    Geom g1 = make_geom(d, 1, true);
+    int gx;
+    int64_t chunk;
+    mstep_big_grid(g1, sms_, n_, &gx, &chunk);
+    const double zero = 0.0;
+    CKE(cudaMemcpyAsync(dThr_, &zero, sizeof(double), cudaMemcpyHostToDevice, st_), "H2D thr");
+    CKE(launch_mstep_big(g1, dX_, n_, nullptr, 0, dShift_, dThr_, dPartB_, gx, chunk, st_), "moments (large shape)");
+    CKE(launch_reduce_partials(dPartB_, gx, (int64_t)g1.MS, dMomRaw_, st_), "reduce moments");  // MS = MB*64 + 2 <= PM
+    CKE(cudaMemsetAsync(dMomRaw_ + (size_t)g.MB * 64, 0, (size_t)8 * g.DN * sizeof(double), st_), "memset");
+    launches_ += 2;
+    const int PM = g.MB * 64 + 8 * g.DN;
+    if (int r = allreduce(dMomRaw_, PM)) return r;
+    CKE(launch_moments_finish(g, dMomRaw_, dShift_, (double)nglob_, dMean_, dSc_, st_), "moments finish");
+    ++launches_;
+    moments_ready_ = true;
+    return 0;
+  }
   const int grid = std::max(1, std::min<int>(sms_, (int)((n_ + 127) / 128)));
   CKE(launch_moments(g, dX_, n_, dShift_, dMomPart_, grid, 0, st_), "moments");
   ++launches_;
   return finish_moments(grid);
+}
+
+// M-pass dispatch: thresholded centred scatter of every component into dStatsB_ (fixed-order reduction over chunks).
+int EmgmmEngine::run_mstep(const double* gamma) {
+  const Geom& g = geom_;
+  if (big_) {
+    CKE(launch_mstep_big(g, dX_, n_, gamma, ldg_, dMupad_, dThr_, dPartB_, mgx_, mchunk_, st_), "mstep (large shape)");
+  } else {
+    CKE(launch_mstep(g, dX_, n_, gamma, ldg_, dMupad_, dThr_, dPartB_, mgx_, st_), "mstep");
+  }
+  CKE(launch_reduce_partials(dPartB_, mgx_, (int64_t)g.K * g.MS, dStatsB_, st_), "reduce statsB");
+  launches_ += 2;
+  return 0;
 }
 
 int EmgmmEngine::finish_moments(int grid) {
@@ -254,6 +303,19 @@ int EmgmmEngine::run_estep(const double* X, int64_t n, double* gamma, int64_t ld
   const Geom& g = geom_;
   const int64_t etiles = (n + kEstepTilePts - 1) / kEstepTilePts;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sms_, etiles));
+  if (big_) {
+    EmArgs a{};
+    a.X = X; a.N = n; a.d = g.d; a.K = g.K; a.K8 = g.K8; a.S = g.S;
+    a.pack2 = dPack2_; a.shift = dShift_; a.gamma = gamma; a.ldg = ldg; a.labels = labels; a.raw = raw ? 1 : 0; a.partA = dPartA_;
+    const int bgrid = (int)std::max<int64_t>(1, std::min<int64_t>(sms_, (n + estep_big_tile() - 1) / estep_big_tile()));
+    CKE(launch_estep_big(g, a, bgrid, smem_limit_, st_), "estep (large shape)");
+    ++launches_;
+    if (want_stats) {
+      CKE(launch_reduce_partials(dPartA_, bgrid, (int64_t)g.K8 * 8 * g.DS, dStatsA_, st_), "reduce statsA");
+      ++launches_;
+    }
+    return 0;
+  }
   if (legacy_estep_) {
     CKE(launch_estep(g, X, n, dPack_, gamma, ldg, labels, dPartA_, grid, smem_limit_, raw ? 1 : 0, st_), "estep");
   } else {
@@ -334,9 +396,7 @@ int EmgmmEngine::iterate_two_pass(int64_t niter, double minProba, bool prof) {
     CKE(launch_mid(g, dStatsA_, minW, dMu_, dMupad_, dThr_, st_), "mid");
     ++launches_;
     if (prof) cudaEventRecord(ev_[3], st_);
-    CKE(launch_mstep(g, dX_, n_, dGamma_, ldg_, dMupad_, dThr_, dPartB_, mgx_, st_), "mstep");
-    CKE(launch_reduce_partials(dPartB_, mgx_, (int64_t)g.K * g.MS, dStatsB_, st_), "reduce statsB");
-    launches_ += 2;
+    if (int r = run_mstep(dGamma_)) return r;
     if (int r = allreduce(dStatsB_, (int64_t)g.K * g.MS)) return r;
     if (prof) cudaEventRecord(ev_[4], st_);
     CKE(launch_finalize(g, dStatsA_, dStatsB_, minProba, dCov_, dLambda_, st_), "finalize");
@@ -620,10 +680,9 @@ int EmgmmEngine::max_gaussian(const double* Proba_host, double* mu_host, double*
   CKE(launch_reduce_partials(dPartA_, grid, g.DS, dStatsA_, st_), "reduce");
   const double minW = 1e-3 / (double)(float)n_;
   CKE(launch_mid(g, dStatsA_, minW, dMu_, dMupad_, dThr_, st_), "mid");
-  CKE(launch_mstep(g, dX_, n_, dGamma_, ldg_, dMupad_, dThr_, dPartB_, mgx_, st_), "mstep");
-  CKE(launch_reduce_partials(dPartB_, mgx_, (int64_t)g.K * g.MS, dStatsB_, st_), "reduce statsB");
+  if (int r = run_mstep(dGamma_)) return r;
   CKE(launch_finalize(g, dStatsA_, dStatsB_, 0.0, dCov_, dLambda_, st_), "finalize");
-  launches_ += 6;
+  launches_ += 4;
   CKE(cudaMemcpyAsync(mu_host, dMu_, g.d * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H mu");
   CKE(cudaMemcpyAsync(C_host, dCov_, (size_t)g.d * g.d * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H C");
   if (sumPi) CKE(cudaMemcpyAsync(sumPi, dStatsA_, sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H sum");

@@ -83,6 +83,7 @@ class EmgmmEngine {
   int iterate_two_pass(int64_t niter, double minProba, bool prof);
   int ensure_gamma();
   int do_refresh(bool with_sumll = true);
+  int run_mstep(const double* gamma);
   int flush_pending();
   int finish_moments(int grid);
   int streamed_sweep(const EmArgs& base);
@@ -92,6 +93,8 @@ class EmgmmEngine {
   FusedGeom fgeom_{};
   bool fused_ = false;        // single-sweep path available for this (d, K)
   bool legacy_estep_ = false; // MLF_B200_LEGACY=1: first-generation kernels (A/B comparisons)
+  bool big_ = false;          // large-shape kernels (d > 32 or pack too large for shared memory; MLF_B200_BIG=1 forces them)
+  int64_t mchunk_ = 0;
   int device_ = 0, sms_ = 148;
   size_t smem_limit_ = 0;
   cudaStream_t st_ = nullptr;

@@ -27,11 +27,16 @@ __host__ __device__ constexpr int blk_off(int mb) {  // fragment blocks before k
   return s;
 }
 
-Geom make_geom(int d, int K) {
+Geom make_geom(int d, int K, bool big) {
   Geom g{};
   g.d = d;
   g.K = K;
   g.DM = (d + 3) / 4;
+  if (big) {  // large-shape kernels are instantiated for these k-block counts only; extra dimensions are zero padding
+    const int sizes[] = {1, 2, 4, 8, 12, 16, 24, 32};
+    for (int s : sizes)
+      if (s >= g.DM) { g.DM = s; break; }
+  }
   g.DN = (g.DM + 1) / 2;
   g.NB = blk_off(g.DM);
   g.PS = g.NB * 32 + 4 * g.DM + 4;

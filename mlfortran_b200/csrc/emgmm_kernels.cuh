@@ -21,7 +21,7 @@ struct Geom {
   int MS;       // doubles per component of the pass-B statistics: [MB*64 scatter blocks, sum g^2] padded
 };
 
-Geom make_geom(int d, int K);
+Geom make_geom(int d, int K, bool big = false);
 
 // Geometry of the fused single-pass kernel (emgmm_fused.cu).
 struct FusedGeom {
@@ -81,6 +81,15 @@ cudaError_t launch_amb_resolve(const Geom& g, const double* X, const AmbEntry* a
 cudaError_t launch_amb_summary(const int* counts, int nlists, int cap, double* flags, cudaStream_t st);
 cudaError_t launch_finalize_fused(const Geom& g, const FusedGeom& f, const double* statsA, const double* statsB, const double* statsC,
                                   const double* muold, double minProba, double* Mu, double* Cov, double* lambda, cudaStream_t st);
+
+// Large-shape path (emgmm_big.cu): 32 < d <= 128, or packs that do not fit shared memory.
+size_t estep_big_smem(const Geom& g);
+bool estep_big_ok(const Geom& g, size_t smem_limit);
+int estep_big_tile();
+cudaError_t launch_estep_big(const Geom& g, EmArgs a, int grid, size_t smem_limit, cudaStream_t st);
+void mstep_big_grid(const Geom& g, int sms, int64_t N, int* gx, int64_t* chunk);
+cudaError_t launch_mstep_big(const Geom& g, const double* X, int64_t N, const double* gamma, int64_t ldg, const double* mupad,
+                             const double* thr, double* partial, int gx, int64_t chunk, cudaStream_t st);
 
 // E-pass: responsibilities (component-major gamma[k*ldg + i]), optional 1-based labels, and per-block
 // partial pass-A statistics partial[block][K8*8][DS].  Returns the grid size used through *grid_out.

@@ -272,6 +272,52 @@ def test_streamed_refresh_of_x(oracle):
     em.finalize()
 
 
+# ---- large shapes: d up to 128 (BASELINE configs[3] shape) and packs too large for shared memory ---------------------
+BIG_CASES = [
+    # d, K, n_per_comp, sigma_c, seed, minProba, iters
+    (128, 4, 700, 3.0, 121, 1.0, 3),      # config-4 dimension: DMMA whitening with streamed Cholesky fragments
+    (48, 5, 400, 4.0, 122, 0.0, 3),       # padded to 12 k-blocks
+    (33, 3, 300, 4.0, 123, 1.0, 2),
+    (64, 9, 300, 4.0, 124, 0.5, 3),
+    (8, 256, 60, 6.0, 125, 1.0, 2),       # config-5 shape (as full covariances): K*d^2 pack + logit tile exceed shared memory
+    (32, 40, 200, 5.0, 126, 0.0, 2),
+]
+
+
+@pytest.mark.parametrize("case", BIG_CASES, ids=[f"d{c[0]}_K{c[1]}" for c in BIG_CASES])
+def test_large_shapes_match_oracle(case, oracle):
+    d, K, npc, sc, seed, mp, iters = case
+    data = synth.make_mixture(d, K, npc, sc, 1.0, seed)
+    X = data["X"]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], seed)
+    oMu, oCov, olam, otr, oP = oracle.em_iterations(X, Mu0, Cov0, lam0, mp, iters, return_proba=True)
+    em = make_em(X, K, mp, Mu0, Cov0, lam0)
+    info, _ = em.step(iters)
+    assert info == 0, em.last_error()
+    check_against(em, oMu, oCov, olam, otr)
+    assert np.abs(em.ProbaC - oP).max() <= 1e-9
+    info, cl = em.getClass(X[:300])
+    _, Pn, _ = oracle.exp_step(X[:300], em.Mu, em.Cov, em.lambda_)
+    bad = cl != oracle.get_class(Pn)
+    if bad.any():
+        assert near_tie_mask(oracle, X[:300], em.Mu, em.Cov, em.lambda_)[bad].all()
+    em.finalize()
+
+
+def test_large_shape_kernels_forced_on_a_small_shape(oracle, monkeypatch):
+    """MLF_B200_BIG=1 routes a shape the fused sweep normally handles through the large-shape kernels: same numbers."""
+    monkeypatch.setenv("MLF_B200_BIG", "1")
+    data = synth.make_mixture(16, 8, 500, 8.0, 1.0, 131)
+    X = data["X"]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 131)
+    oMu, oCov, olam, otr = oracle.em_iterations(X, Mu0, Cov0, lam0, 1.0, 3)
+    em = make_em(X, 8, 1.0, Mu0, Cov0, lam0)
+    assert em.step(3)[0] == 0, em.last_error()
+    check_against(em, oMu, oCov, olam, otr)
+    assert em.times()["sweeps"] == 0     # not the fused path
+    em.finalize()
+
+
 # ---- edge cases ------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [1, 2, 31, 127, 128, 129, 2049])
 def test_tiny_and_ragged_point_counts(n, oracle):
