@@ -95,6 +95,9 @@ int mlf_b200_set_initialized(MLF_OBJ *obj, int initialized); /* the Fortran API 
 int mlf_b200_get_initialized(MLF_OBJ *obj);
 /* Seed of the k-means initialiser's random stream (the reference uses an unseeded RANDOM_NUMBER, src/mlf_rand.f90:173-182). */
 int mlf_b200_set_seed(MLF_OBJ *obj, uint64_t seed);
+/* EXTENSION (the reference has full covariances only): cov_type 0 = full (default, reference behaviour), 1 = diagonal --
+ * the E-step reads diag(C_k) only and the M-step keeps the diagonal of the reference's C_k (BASELINE config 5). */
+int mlf_b200_set_cov_type(MLF_OBJ *obj, int cov_type);
 int mlf_b200_refresh_x(MLF_OBJ *obj, const double *X);        /* re-copy X after the caller changed it */
 const char *mlf_b200_last_error(MLF_OBJ *obj);
 /* sumLL of each EM iteration of the most recent mlf_step call (at most n values); returns how many exist. */

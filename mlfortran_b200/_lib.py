@@ -46,6 +46,7 @@ SYMBOLS = {
     "mlf_b200_set_initialized": (C.c_int, [C.c_void_p, C.c_int]),
     "mlf_b200_get_initialized": (C.c_int, [C.c_void_p]),
     "mlf_b200_set_seed": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "mlf_b200_set_cov_type": (C.c_int, [C.c_void_p, C.c_int]),
     "mlf_b200_refresh_x": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mlf_b200_last_error": (C.c_char_p, [C.c_void_p]),
     "mlf_b200_sumll_trace": (C.c_int64, [C.c_void_p, c_double_p, C.c_int64]),

@@ -242,8 +242,9 @@ __global__ void __launch_bounds__(256) k_mstep_big(const double* __restrict__ X,
   constexpr int MB = DN * (DN + 1) / 2;
   constexpr int OWN = (MB + 7) / 8;
   constexpr int ZS = 8 * DN + 4;
-  __shared__ double zs[32][ZS];   // (x - mu) of a 32-point strip
-  __shared__ double ws[32];       // kept weight of each point (0 if dropped)
+  __shared__ double zs[32][ZS];     // (x - mu) of up to 8 kept 4-point groups, compacted across strips
+  __shared__ double ws[32];         // kept weight of each staged point (0 if dropped)
+  __shared__ long long pidx[32];    // global index of each staged point (-1: none)
   __shared__ double smu[8 * DN];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int k = blockIdx.y;
@@ -262,31 +263,30 @@ __global__ void __launch_bounds__(256) k_mstep_big(const double* __restrict__ X,
     ob[o] = blk - ab * (ab + 1) / 2;
   }
   double sg2 = 0;
+  int cnt = 0;  // staged groups; every warp evaluates the same ballots, so cnt is uniform over the block
   __syncthreads();
   const int64_t lo = (int64_t)blockIdx.x * chunk;
   const int64_t hi = (lo + chunk < N) ? lo + chunk : N;
-  for (int64_t i0 = lo; i0 < hi; i0 += 32) {
-    // weight of the strip's points: every warp evaluates the same ballot (uniform decision, no extra barrier)
-    const int64_t pl = i0 + lane;
-    const double gv = (pl < hi) ? (gk ? gk[pl] : 1.0) : 0.0;
-    if (warp == 0) sg2 = fma(gv, gv, sg2);               // SUM(W*W) runs over all points (src/mlf_matrix.f90:119)
-    const bool kept = !(gv < th) && pl < hi && gv != 0.0;  // "If(W(i) < minW0) CYCLE" (:135)
-    const unsigned mask = __ballot_sync(kFull, kept);
-    if (mask == 0) continue;
-    __syncthreads();  // previous strip fully consumed
-    if (warp == 0) ws[lane] = kept ? gv : 0.0;
-    for (int i = tid; i < 32 * 8 * DN; i += 256) {
+  auto flush = [&]() {
+    __syncthreads();  // pidx / ws of this batch are written
+    // 32 * 8*DN / 256 = DN loads per thread, all issued before the first is used
+    double xv[DN];
+#pragma unroll
+    for (int u = 0; u < DN; ++u) {
+      const int i = tid + 256 * u;
       const int pt = i / (8 * DN), a = i % (8 * DN);
-      const int64_t pp = i0 + pt;
-      zs[pt][a] = (pp < hi && a < d) ? X[pp * d + a] - smu[a] : 0.0;
+      const long long pp = pt < 4 * cnt ? pidx[pt] : -1;
+      xv[u] = (pp >= 0 && pp < hi && a < d) ? X[pp * d + a] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < DN; ++u) {
+      const int i = tid + 256 * u;
+      const int pt = i / (8 * DN), a = i % (8 * DN);
+      const long long pp = pt < 4 * cnt ? pidx[pt] : -1;
+      zs[pt][a] = (pp >= 0 && pp < hi && a < d) ? xv[u] - smu[a] : 0.0;
     }
     __syncthreads();
-    unsigned gm = mask | (mask >> 1);
-    gm |= gm >> 2;
-    gm &= 0x11111111u;  // bit 4q: 4-point group q holds a kept point
-    while (gm) {
-      const int q = (__ffs(gm) - 1) >> 2;
-      gm &= gm - 1;
+    for (int q = 0; q < cnt; ++q) {
       const double w = ws[4 * q + t];
 #pragma unroll
       for (int o = 0; o < OWN; ++o) {
@@ -297,7 +297,31 @@ __global__ void __launch_bounds__(256) k_mstep_big(const double* __restrict__ X,
         }
       }
     }
+    __syncthreads();  // batch consumed before the next one is listed
+    cnt = 0;
+  };
+  for (int64_t i0 = lo; i0 < hi; i0 += 32) {
+    const int64_t pl = i0 + lane;
+    const double gv = (pl < hi) ? (gk ? gk[pl] : 1.0) : 0.0;
+    if (warp == 0) sg2 = fma(gv, gv, sg2);               // SUM(W*W) runs over all points (src/mlf_matrix.f90:119)
+    const bool kept = !(gv < th) && pl < hi && gv != 0.0;  // "If(W(i) < minW0) CYCLE" (:135)
+    const unsigned mask = __ballot_sync(kFull, kept);
+    if (mask == 0) continue;
+    unsigned gm = mask | (mask >> 1);
+    gm |= gm >> 2;
+    gm &= 0x11111111u;  // bit 4q: 4-point group q holds a kept point
+    while (gm) {
+      const int q = (__ffs(gm) - 1) >> 2;
+      gm &= gm - 1;
+      const double wq = __shfl_sync(kFull, kept ? gv : 0.0, 4 * q + (lane & 3));
+      if (warp == 0 && lane < 4) {
+        ws[4 * cnt + lane] = wq;
+        pidx[4 * cnt + lane] = i0 + 4 * q + lane;
+      }
+      if (++cnt == 8) flush();
+    }
   }
+  if (cnt) flush();
   double* out = partial + ((size_t)blockIdx.x * K + k) * MS;
 #pragma unroll
   for (int o = 0; o < OWN; ++o) {

@@ -161,7 +161,7 @@ int EmgmmEngine::ensure_gamma() {
 // InverseSymMatrix eigen branch + packing for both kernel generations (k_refresh).
 int EmgmmEngine::do_refresh(bool with_sumll) {
   CKE(launch_refresh(geom_, dMu_, dCov_, dLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_, dPack2_, dMuOld_,
-                     dShift_, with_sumll ? 1 : 0), "refresh");
+                     dShift_, with_sumll ? 1 : 0, cov_diag_ ? 1 : 0), "refresh");
   ++launches_;
   return 0;
 }
@@ -399,7 +399,7 @@ int EmgmmEngine::iterate_two_pass(int64_t niter, double minProba, bool prof) {
     if (int r = run_mstep(dGamma_)) return r;
     if (int r = allreduce(dStatsB_, (int64_t)g.K * g.MS)) return r;
     if (prof) cudaEventRecord(ev_[4], st_);
-    CKE(launch_finalize(g, dStatsA_, dStatsB_, minProba, dCov_, dLambda_, st_), "finalize");
+    CKE(launch_finalize(g, dStatsA_, dStatsB_, minProba, dCov_, dLambda_, st_, cov_diag_ ? 1 : 0), "finalize");
     ++launches_;
     if (prof) cudaEventRecord(ev_[5], st_);
   }
@@ -549,7 +549,7 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
       times_.amb_pairs += (int64_t)hflag[0];
     }
     if (prof) cudaEventRecord(ev_[4], st_);
-    CKE(launch_finalize_fused(g, f, dAB_, dAB_ + nA, statsC, dMuOld_, minProba, dMu_, dCov_, dLambda_, st_), "finalize");
+    CKE(launch_finalize_fused(g, f, dAB_, dAB_ + nA, statsC, dMuOld_, minProba, dMu_, dCov_, dLambda_, st_, cov_diag_ ? 1 : 0), "finalize");
     ++launches_;
     if (prof) cudaEventRecord(ev_[5], st_);
     s_prev2_ = s_prev_;
@@ -609,7 +609,7 @@ int EmgmmEngine::materialize_gamma() {
   if (!prev_valid_ || n_ == 0) return 0;  // no E-step yet: ProbaC = 0 (src/unsupervised/mlf_emgmm.f90:119)
   if (int r = ensure_moments()) return r;
   CKE(launch_refresh(geom_, dPrevMu_, dPrevCov_, dPrevLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_,
-                     dPack2_, dMuOld_, dShift_, 1), "refresh");
+                     dPack2_, dMuOld_, dShift_, 1, cov_diag_ ? 1 : 0), "refresh");
   ++launches_;
   if (int r = run_estep(dX_, n_, dGamma_, ldg_, nullptr, false)) return r;
   gamma_current_ = true;

@@ -72,6 +72,10 @@ class EmgmmEngine {
   EngineTimes& times() { return times_; }
   void reset_times() { times_ = EngineTimes(); }
   void set_profile(bool on) { profile_ = on; }
+  // EXTENSION (no reference semantics): diagonal covariances -- the E-step reads diag(C_k) only and the
+  // M-step keeps the diagonal of the reference's C_k.  Default: full covariances (reference behaviour).
+  void set_cov_diag(bool on) { cov_diag_ = on; }
+  bool cov_diag() const { return cov_diag_; }
   int64_t launches() const { return launches_; }
 
  private:
@@ -135,6 +139,7 @@ class EmgmmEngine {
   std::string err_;
   EngineTimes times_;
   bool profile_ = false;
+  bool cov_diag_ = false;
   int64_t launches_ = 0;
   std::vector<cudaEvent_t> pev_;  // 6 profiling events per iteration (only when set_profile(true))
 };

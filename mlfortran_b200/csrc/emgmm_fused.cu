@@ -510,7 +510,8 @@ cudaError_t launch_amb_summary(const int* counts, int nlists, int cap, double* f
 // then C_k = ms^2/s_k * that (src/mlf_matrix.f90:119,137,145-146), lambda floor + normalise (mlf_emgmm.f90:184-187).
 __global__ void k_finalize_fused(Geom g, int MSF, const double* __restrict__ statsA, const double* __restrict__ statsB,
                                  const double* __restrict__ statsC /*nullable*/, const double* __restrict__ muold,
-                                 double minProba, double* __restrict__ Mu, double* __restrict__ Cov, double* __restrict__ lambda) {
+                                 double minProba, double* __restrict__ Mu, double* __restrict__ Cov, double* __restrict__ lambda,
+                                 int cov_diag) {
   const int d = g.d;
   __shared__ double s_mu[128], s_dl[128], s_m[128];
   for (int k = blockIdx.x; k < g.K; k += gridDim.x) {
@@ -538,7 +539,7 @@ __global__ void k_finalize_fused(Geom g, int MSF, const double* __restrict__ sta
       const int ab = a >> 3, bb = b >> 3;
       double S = sb[(ab * (ab + 1) / 2 + bb) * 64 + (a & 7) * 8 + (b & 7)];
       if (sc) S += sc[(size_t)b * d + a];
-      const double v = scale * (S - s_dl[a] * s_m[b] - s_m[a] * s_dl[b] + sK * s_dl[a] * s_dl[b]);
+      const double v = (cov_diag && a != b) ? 0.0 : scale * (S - s_dl[a] * s_m[b] - s_m[a] * s_dl[b] + sK * s_dl[a] * s_dl[b]);
       Ck[(size_t)b * d + a] = v;
       Ck[(size_t)a * d + b] = v;
     }
@@ -558,8 +559,9 @@ __global__ void k_finalize_fused(Geom g, int MSF, const double* __restrict__ sta
   }
 }
 cudaError_t launch_finalize_fused(const Geom& g, const FusedGeom& f, const double* statsA, const double* statsB, const double* statsC,
-                                  const double* muold, double minProba, double* Mu, double* Cov, double* lambda, cudaStream_t st) {
-  k_finalize_fused<<<g.K < 148 ? g.K : 148, 128, 0, st>>>(g, f.MSF, statsA, statsB, statsC, muold, minProba, Mu, Cov, lambda);
+                                  const double* muold, double minProba, double* Mu, double* Cov, double* lambda, cudaStream_t st,
+                                  int cov_diag) {
+  k_finalize_fused<<<g.K < 148 ? g.K : 148, 128, 0, st>>>(g, f.MSF, statsA, statsB, statsC, muold, minProba, Mu, Cov, lambda, cov_diag);
   return cudaGetLastError();
 }
 

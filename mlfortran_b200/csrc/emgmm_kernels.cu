@@ -77,12 +77,13 @@ __device__ double block_sum(double v, double* red) {
 // One block (128 threads) per component.  Matrices are column-major M(a,b) = M[b*d + a] in global scratch.
 // Follows InverseSymMatrix(C, invC, lnDet, .TRUE.)  (src/mlf_matrix.f90:256-298) with a cyclic Jacobi
 // eigensolver in place of dsytrd/dorgtr/dsteqr (only invC and lnDet enter the result, not the eigenvectors).
-__global__ void __launch_bounds__(128) k_refresh(Geom g, const double* __restrict__ Mu, const double* __restrict__ Cov,
+__global__ void __launch_bounds__(256) k_refresh(Geom g, const double* __restrict__ Mu, const double* __restrict__ Cov,
                                                  const double* __restrict__ lambda, const double* __restrict__ Sc,
                                                  const double* __restrict__ mean, double Nglob, double* __restrict__ scratch,
                                                  double* __restrict__ pack, double* __restrict__ sumLLk,
                                                  int* __restrict__ info, double* __restrict__ pack2, double* __restrict__ muold,
-                                                 int PSF, int OFFB2, int OFFC2, const double* __restrict__ shift, int do_sumll) {
+                                                 int PSF, int OFFB2, int OFFC2, const double* __restrict__ shift, int do_sumll, int use_smem,
+                                                 int cov_diag) {
   const int k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, d = g.d;
   const int OFFMU = g.NB * 32, OFFC = OFFMU + 4 * g.DM;
   double* pk = pack + (size_t)k * g.PS;
@@ -97,11 +98,14 @@ __global__ void __launch_bounds__(128) k_refresh(Geom g, const double* __restric
     }
     return;
   }
-  double* A = scratch + (size_t)k * 3 * d * d;
-  double* V = A + (size_t)d * d;
+  extern __shared__ __align__(16) double s_dyn[];
+  // the working copy A of the Jacobi sweeps lives in shared memory for large d (global scratch round trips dominated
+  // the refresh at d = 128); V and W stay in global scratch
+  double* A = use_smem ? s_dyn : scratch + (size_t)k * 3 * d * d;
+  double* V = scratch + (size_t)k * 3 * d * d + (size_t)d * d;
   double* W = V + (size_t)d * d;
   const double* Ck = Cov + (size_t)k * d * d;
-  __shared__ double s_c[64], s_s[64], s_red[128], s_f[128];
+  __shared__ double s_c[64], s_s[64], s_red[256], s_f[128];
   __shared__ int s_p[64], s_q[64];
   __shared__ int s_flag;
 
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(128) k_refresh(Geom g, const double* __restric
   for (int i = tid; i < d * d; i += nt) {
     const int a = i % d, b = i / d;
     const int lo = a < b ? a : b, hi = a < b ? b : a;
-    A[i] = Ck[(size_t)hi * d + lo];
+    A[i] = (cov_diag && a != b) ? 0.0 : Ck[(size_t)hi * d + lo];  // cov_diag: extension, diagonal of C only
     V[i] = (a == b) ? 1.0 : 0.0;
   }
   __syncthreads();
@@ -265,10 +269,16 @@ __global__ void __launch_bounds__(128) k_refresh(Geom g, const double* __restric
 
 cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, const double* lambda, const double* Sc,
                            const double* mean, double Nglob, double* scratch, double* pack, double* sumLLk, int* info,
-                           cudaStream_t st, double* pack2, double* muold, const double* shift, int do_sumll) {
+                           cudaStream_t st, double* pack2, double* muold, const double* shift, int do_sumll, int cov_diag) {
   const FusedGeom f = make_fused_geom(g);
-  k_refresh<<<g.K8 * 8, 128, 0, st>>>(g, Mu, Cov, lambda, Sc, mean, Nglob, scratch, pack, sumLLk, info, pack2, muold, f.PSF, f.OFFB,
-                                      f.OFFC, shift ? shift : mean, do_sumll);
+  const bool large = g.d > 32;
+  const size_t dyn = large ? (size_t)g.d * g.d * sizeof(double) : 0;
+  if (large) {
+    cudaError_t e = cudaFuncSetAttribute(k_refresh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+  }
+  k_refresh<<<g.K8 * 8, large ? 256 : 128, dyn, st>>>(g, Mu, Cov, lambda, Sc, mean, Nglob, scratch, pack, sumLLk, info, pack2, muold,
+                                                     f.PSF, f.OFFB, f.OFFC, shift ? shift : mean, do_sumll, large ? 1 : 0, cov_diag);
   return cudaGetLastError();
 }
 
@@ -683,7 +693,7 @@ cudaError_t launch_mid(const Geom& g, const double* statsA, double minW, double*
 
 // GECovMatrix epilogue + MaxStep tail (src/mlf_matrix.f90:119,137,145-146; src/unsupervised/mlf_emgmm.f90:184-187).
 __global__ void k_finalize(Geom g, const double* __restrict__ statsA, const double* __restrict__ statsB, double minProba,
-                           double* __restrict__ Cov, double* __restrict__ lambda) {
+                           double* __restrict__ Cov, double* __restrict__ lambda, int cov_diag) {
   const int d = g.d;
   for (int k = blockIdx.x; k < g.K; k += gridDim.x) {
     const double s = statsA[(size_t)k * g.DS];
@@ -696,7 +706,7 @@ __global__ void k_finalize(Geom g, const double* __restrict__ statsA, const doub
       const int a = i % d, b = i / d;
       if (a < b) continue;  // lower triangle a >= b, mirrored (SymmetrizeMatrix, src/mlf_matrix.f90:56-63)
       const int ab = a >> 3, bb = b >> 3;
-      const double v = scale * sb[(ab * (ab + 1) / 2 + bb) * 64 + (a & 7) * 8 + (b & 7)];
+      const double v = (cov_diag && a != b) ? 0.0 : scale * sb[(ab * (ab + 1) / 2 + bb) * 64 + (a & 7) * 8 + (b & 7)];
       Ck[(size_t)b * d + a] = v;
       Ck[(size_t)a * d + b] = v;
     }
@@ -715,8 +725,8 @@ __global__ void k_finalize(Geom g, const double* __restrict__ statsA, const doub
   }
 }
 cudaError_t launch_finalize(const Geom& g, const double* statsA, const double* statsB, double minProba, double* Cov,
-                            double* lambda, cudaStream_t st) {
-  k_finalize<<<g.K < 148 ? g.K : 148, 128, 0, st>>>(g, statsA, statsB, minProba, Cov, lambda);
+                            double* lambda, cudaStream_t st, int cov_diag) {
+  k_finalize<<<g.K < 148 ? g.K : 148, 128, 0, st>>>(g, statsA, statsB, minProba, Cov, lambda, cov_diag);
   return cudaGetLastError();
 }
 

@@ -65,7 +65,7 @@ constexpr int kMstepTilePts = 2048;     // points per block tile of the M-pass s
 cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, const double* lambda, const double* Sc,
                            const double* mean, double Nglob, double* scratch, double* pack, double* sumLLk, int* info,
                            cudaStream_t st, double* pack2 = nullptr, double* muold = nullptr, const double* shift = nullptr,
-                           int do_sumll = 1);
+                           int do_sumll = 1, int cov_diag = 0);
 cudaError_t launch_sumll(const Geom& g, const double* Mu, const double* Sc, const double* mean, double Nglob, const double* scratch,
                          const double* pack, double* sumLLk, cudaStream_t st);
 // Global moments about `shift`: partial[grid][MB*64 + 8*DN]; finish turns the all-reduced sums into mean and centred scatter.
@@ -80,7 +80,8 @@ cudaError_t launch_amb_resolve(const Geom& g, const double* X, const AmbEntry* a
                                const double* statsA, double minW, const double* muold, double* outC, cudaStream_t st);
 cudaError_t launch_amb_summary(const int* counts, int nlists, int cap, double* flags, cudaStream_t st);
 cudaError_t launch_finalize_fused(const Geom& g, const FusedGeom& f, const double* statsA, const double* statsB, const double* statsC,
-                                  const double* muold, double minProba, double* Mu, double* Cov, double* lambda, cudaStream_t st);
+                                  const double* muold, double minProba, double* Mu, double* Cov, double* lambda, cudaStream_t st,
+                                  int cov_diag = 0);
 
 // Large-shape path (emgmm_big.cu): 32 < d <= 128, or packs that do not fit shared memory.
 size_t estep_big_smem(const Geom& g);
@@ -119,7 +120,7 @@ void mstep_grid(const Geom& g, int sms, int64_t N, int* gx, int* gy);
 
 // After pass B (and its all-reduce): Cov_k = ms^2/s_k * S_k (lower triangle mirrored), lambda floor + normalise.
 cudaError_t launch_finalize(const Geom& g, const double* statsA, const double* statsB, double minProba, double* Cov,
-                            double* lambda, cudaStream_t st);
+                            double* lambda, cudaStream_t st, int cov_diag = 0);
 
 // sum over points of x (per block partials [grid][d]) for the one-time global mean.
 cudaError_t launch_colsum(const double* X, int64_t N, int d, double* partial, int grid, cudaStream_t st);

@@ -411,6 +411,13 @@ int mlf_b200_get_initialized(MLF_OBJ* obj) {
   return o ? (o->initialized ? 1 : 0) : -1;
 }
 
+int mlf_b200_set_cov_type(MLF_OBJ* obj, int cov_type) {
+  EmObject* o = as_em(obj);
+  if (!o || (cov_type != 0 && cov_type != 1)) return -1;
+  o->eng.set_cov_diag(cov_type == 1);
+  return 0;
+}
+
 int mlf_b200_set_seed(MLF_OBJ* obj, uint64_t seed) {
   EmObject* o = as_em(obj);
   if (!o) return -1;

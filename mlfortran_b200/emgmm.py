@@ -272,6 +272,10 @@ class mlf_algo_emgmm:
         self._X = X
         return self._lib.mlf_b200_refresh_x(self._h, X.ctypes.data)
 
+    def set_cov_type(self, cov_type: str) -> int:
+        """EXTENSION: 'full' (reference behaviour, default) or 'diag' (diagonal covariances, BASELINE config 5)."""
+        return self._lib.mlf_b200_set_cov_type(self._h, {"full": 0, "diag": 1}[cov_type])
+
     def set_seed(self, seed: int) -> None:
         """Seed of the k-means initialiser's random stream (reference: unseeded RANDOM_NUMBER)."""
         self._lib.mlf_b200_set_seed(self._h, int(seed) & (2 ** 64 - 1))

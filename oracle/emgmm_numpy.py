@@ -22,14 +22,14 @@ def inverse_sym_matrix(Cm):
     return (V * f) @ V.T, lnDet
 
 
-def exp_step(X, Mu, Cov, lam):
-    """src/unsupervised/mlf_emgmm.f90:191-207 + mlf_gaussian.f90:63-79."""
+def exp_step(X, Mu, Cov, lam, cov_diag=False):
+    """src/unsupervised/mlf_emgmm.f90:191-207 + mlf_gaussian.f90:63-79.  cov_diag: extension (diagonal of Cov only)."""
     N, d = X.shape
     K = Mu.shape[0]
     P = np.empty((K, N))
     sumLL = 0.0
     for k in range(K):
-        invC, lnDet = inverse_sym_matrix(Cov[k])
+        invC, lnDet = inverse_sym_matrix(np.diag(np.diag(Cov[k])) if cov_diag else Cov[k])
         Z = X - Mu[k]
         v = -0.5 * np.einsum("ia,ab,ib->i", Z, invC, Z)
         with np.errstate(divide="ignore"):
@@ -40,7 +40,7 @@ def exp_step(X, Mu, Cov, lam):
     return P, sumLL
 
 
-def max_step(X, P, min_proba=0.0):
+def max_step(X, P, min_proba=0.0, cov_diag=False):
     """src/unsupervised/mlf_emgmm.f90:174-188 + mlf_gaussian.f90:41-51 + mlf_matrix.f90:99-147."""
     N, d = X.shape
     K = P.shape[0]
@@ -56,19 +56,21 @@ def max_step(X, P, min_proba=0.0):
         keep = ~(W < minW)
         B = (ms * np.sqrt(W[keep]))[:, None] * (X[keep] - Mu[k])
         Cov[k] = B.T @ B
+        if cov_diag:
+            Cov[k] = np.diag(np.diag(Cov[k]))
         lam[k] = s
     if min_proba > 0:
         lam = np.maximum(lam, min_proba * lam.max())
     return Mu, Cov, lam / lam.sum()
 
 
-def em_iterations(X, Mu, Cov, lam, min_proba, niter):
+def em_iterations(X, Mu, Cov, lam, min_proba, niter, cov_diag=False):
     trace = []
     P = None
     for _ in range(niter):
-        P, ll = exp_step(X, Mu, Cov, lam)
+        P, ll = exp_step(X, Mu, Cov, lam, cov_diag)
         trace.append(ll)
-        Mu, Cov, lam = max_step(X, P, min_proba)
+        Mu, Cov, lam = max_step(X, P, min_proba, cov_diag)
     return Mu, Cov, lam, np.array(trace), P
 
 

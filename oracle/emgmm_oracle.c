@@ -47,6 +47,11 @@ static dorgtr_fn p_dorgtr;
 static dsteqr_fn p_dsteqr;
 static dsyrk_fn p_dsyrk;
 static int g_use_lapack = 0;
+/* EXTENSION (not in the reference): diagonal covariances = Appendix A with every covariance restricted to
+ * its diagonal: the E-step sees diag(C_k) only, the M-step keeps diag of the reference's C_k. */
+static int g_cov_diag = 0;
+void orc_set_cov_diag(int on) { g_cov_diag = on != 0; }
+int orc_get_cov_diag(void) { return g_cov_diag; }
 
 /* Returns 0 when all four routines were found (tries "scipy_<name>_" then "<name>_"). */
 int orc_load_lapack(const char* path) {
@@ -172,7 +177,14 @@ int orc_eval_gaussian(int d, int64_t N, const double* X, double* P, const double
   double* z = (double*)malloc(sizeof(double) * 2 * d);
   double* t = z + d;
   double lnDet;
+  double* Cd = NULL;
+  if (g_cov_diag) { /* extension: off-diagonal entries are ignored */
+    Cd = (double*)calloc((size_t)d * d, sizeof(double));
+    for (int a = 0; a < d; ++a) Cd[a * d + a] = C[a * d + a];
+    C = Cd;
+  }
   int info = orc_inverse_sym_matrix(d, C, invC, &lnDet); /* :71 */
+  free(Cd);
   if (info != 0) { free(invC); free(z); return info; }
   double ll = (double)N * (log(lambda) - lnDet); /* :73 */
   for (int64_t i = 0; i < N; ++i) {               /* :74-78 */
@@ -214,6 +226,7 @@ void orc_ge_cov_matrix(int d, int64_t N, double* C, const double* A, double* Mu,
       for (int b = 0; b < d; ++b) { const double bb = B[jj * d + b]; for (int a = b; a < d; ++a) C[b * d + a] += B[jj * d + a] * bb; }
   }
   for (int b = 0; b < d; ++b) for (int a = b + 1; a < d; ++a) C[a * d + b] = C[b * d + a]; /* :146 SymmetrizeMatrix, :56-63 */
+  if (g_cov_diag) for (int b = 0; b < d; ++b) for (int a = 0; a < d; ++a) if (a != b) C[b * d + a] = 0.0; /* extension */
   free(B);
 }
 

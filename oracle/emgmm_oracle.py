@@ -67,6 +67,7 @@ class Oracle:
         lib.orc_kmeans_evaluate_class.restype = None
         lib.orc_kmeans_evaluate_centres.argtypes = [C.c_int, C.c_int64, C.c_int, _dp, _dp, _ip]
         lib.orc_set_threads.argtypes = [C.c_int]
+        lib.orc_set_cov_diag.argtypes = [C.c_int]
         self.lapack_path = None
         if use_lapack:
             p = _find_lapack()
@@ -81,6 +82,10 @@ class Oracle:
     @property
     def has_lapack(self) -> bool:
         return bool(self.lib.orc_has_lapack())
+
+    def set_cov_diag(self, on: bool) -> None:
+        """EXTENSION (no reference semantics): diagonal covariances, see emgmm_oracle.c."""
+        self.lib.orc_set_cov_diag(1 if on else 0)
 
     def set_threads(self, n: int) -> None:
         self.lib.orc_set_threads(int(n))

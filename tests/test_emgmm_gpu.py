@@ -318,6 +318,26 @@ def test_large_shape_kernels_forced_on_a_small_shape(oracle, monkeypatch):
     em.finalize()
 
 
+# ---- EXTENSION: diagonal covariances (BASELINE configs[4] shape; the reference has no such mode, parity vs our oracle) ----
+@pytest.mark.parametrize("shape", [(8, 16, 400, 5.0), (8, 256, 50, 6.0), (3, 4, 500, 3.0)], ids=["d8_K16", "d8_K256", "d3_K4"])
+def test_diagonal_covariance_extension(shape, oracle):
+    d, K, npc, sc = shape
+    data = synth.make_mixture(d, K, npc, sc, 1.0, 141)
+    X = data["X"]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 141)
+    oracle.set_cov_diag(True)
+    try:
+        oMu, oCov, olam, otr = oracle.em_iterations(X, Mu0, Cov0, lam0, 1.0, 4)
+    finally:
+        oracle.set_cov_diag(False)
+    em = make_em(X, K, 1.0, Mu0, Cov0, lam0)
+    assert em.set_cov_type("diag") == 0
+    assert em.step(4)[0] == 0, em.last_error()
+    check_against(em, oMu, oCov, olam, otr)
+    assert (em.Cov - np.stack([np.diag(np.diag(c)) for c in em.Cov]) == 0).all()
+    em.finalize()
+
+
 # ---- edge cases ------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [1, 2, 31, 127, 128, 129, 2049])
 def test_tiny_and_ragged_point_counts(n, oracle):

@@ -193,3 +193,24 @@ def test_shipped_test_shape_converges(oracle):
     true_cov = np.einsum("kab,kcb->kac", data["C12"], data["C12"])
     assert np.abs(Cov - true_cov).max() < 0.25
     np.testing.assert_allclose(lam, 1 / 3, rtol=1e-15)
+
+
+def test_diagonal_extension_c_vs_numpy(oracle):
+    # EXTENSION (no reference semantics, SURVEY fact 0.8 / BASELINE configs[4]): Appendix A with every covariance restricted
+    # to its diagonal.  The two independent restatements must agree, and the result must differ from the full-covariance run.
+    data = synth.make_mixture(4, 3, 300, 4.0, 1.0, 33)
+    X = data["X"]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 33)
+    oracle.set_cov_diag(True)
+    try:
+        Mu, Cov, lam, tr = oracle.em_iterations(X, Mu0, Cov0, lam0, 0.0, 5)
+    finally:
+        oracle.set_cov_diag(False)
+    nMu, nCov, nlam, ntr, _ = onp.em_iterations(X, Mu0, Cov0, lam0, 0.0, 5, cov_diag=True)
+    np.testing.assert_allclose(tr, ntr, rtol=1e-11)
+    np.testing.assert_allclose(Mu, nMu, rtol=0, atol=1e-10)
+    np.testing.assert_allclose(Cov, nCov, rtol=0, atol=1e-10)
+    off = Cov - np.stack([np.diag(np.diag(c)) for c in Cov])
+    assert (off == 0).all()
+    fMu, fCov, flam, ftr = oracle.em_iterations(X, Mu0, Cov0, lam0, 0.0, 5)
+    assert np.abs(fCov - Cov).max() > 1e-3      # the full-covariance reference path is a different computation
