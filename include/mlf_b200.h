@@ -82,6 +82,8 @@ MLF_OBJ *mlf_emgmm_c(double *X, int nX, int nY, int nC, double minProba, MLF_OBJ
 
 /* ---- B200-specific extensions ----------------------------------------------------------------------------------- */
 #define MLF_B200_X_ON_DEVICE 1u /* X is a device pointer (kept alive by the caller) */
+#define MLF_B200_COV_DIAG 2u    /* EXTENSION: diagonal covariances (as mlf_b200_set_cov_type(obj, 1), but known at construction, which
+                                   lets K = 256 at d = 8 run through the single-sweep kernel: BASELINE config 5) */
 
 /* As mlf_emgmm_c with 64-bit point count, device selection (-1 = current) and flags. */
 MLF_OBJ *mlf_b200_emgmm_create(const double *X, int64_t nX, int nY, int nC, double minProba, MLF_OBJ *handler, int device, unsigned flags);

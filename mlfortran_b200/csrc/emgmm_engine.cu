@@ -55,7 +55,8 @@ void EmgmmEngine::set_stream(cudaStream_t st) {
   own_stream_ = false;
 }
 
-int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d, int K, int device) {
+int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d, int K, int device, bool cov_diag) {
+  cov_diag_ = cov_diag;
   if (n_local < 0 || d < 1 || K < 1) { err_ = "invalid shape"; return -7; }
   if (d > 128) { err_ = "d > 128 is not supported by this build"; return -7; }
   int ndev = 0;
@@ -72,7 +73,7 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   sms_ = prop.multiProcessorCount;
   smem_limit_ = prop.sharedMemPerBlockOptin;
   geom_ = make_geom(d, K);
-  fgeom_ = make_fused_geom(geom_);
+  fgeom_ = make_fused_geom(geom_, cov_diag_, smem_limit_);
   {
     const char* lg = getenv("MLF_B200_LEGACY");
     legacy_estep_ = lg && lg[0] == '1';
@@ -84,7 +85,7 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   if (d > 32 || (fgeom_.smem > smem_limit_ && estep_smem_bytes(geom_) > smem_limit_)) big_ = true;
   if (big_) {
     geom_ = make_geom(d, K, true);
-    fgeom_ = make_fused_geom(geom_);
+    fgeom_ = make_fused_geom(geom_, false, smem_limit_);
     if (!estep_big_ok(geom_, smem_limit_)) {
       err_ = "this (d, K) is outside the shapes the large-shape kernels are built for (K <= 256 at d <= 32, K*d <= 8192 beyond)";
       return -7;
@@ -102,7 +103,8 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   own_stream_ = true;
   const Geom& g = geom_;
   const int KP = g.K8 * 8;
-  const int64_t etiles = (n_ + kEstepTilePts - 1) / kEstepTilePts;
+  const int tp = legacy_estep_ ? kEstepTilePts : fgeom_.TP;
+  const int64_t etiles = (n_ + tp - 1) / tp;
   egrid_ = (int)std::max<int64_t>(1, std::min<int64_t>(sms_, etiles));
   mstep_grid(g, sms_, n_, &mgx_, &mgy_);
   if (big_) {
@@ -161,7 +163,7 @@ int EmgmmEngine::ensure_gamma() {
 // InverseSymMatrix eigen branch + packing for both kernel generations (k_refresh).
 int EmgmmEngine::do_refresh(bool with_sumll) {
   CKE(launch_refresh(geom_, dMu_, dCov_, dLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_, dPack2_, dMuOld_,
-                     dShift_, with_sumll ? 1 : 0, cov_diag_ ? 1 : 0), "refresh");
+                     dShift_, with_sumll ? 1 : 0, cov_diag_ ? 1 : 0, &fgeom_), "refresh");
   ++launches_;
   return 0;
 }
@@ -301,7 +303,8 @@ int EmgmmEngine::download_params(double* Mu, double* Cov, double* lambda) {
 
 int EmgmmEngine::run_estep(const double* X, int64_t n, double* gamma, int64_t ldg, int32_t* labels, bool want_stats, bool raw) {
   const Geom& g = geom_;
-  const int64_t etiles = (n + kEstepTilePts - 1) / kEstepTilePts;
+  const int tp = legacy_estep_ ? kEstepTilePts : fgeom_.TP;
+  const int64_t etiles = (n + tp - 1) / tp;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sms_, etiles));
   if (big_) {
     EmArgs a{};
@@ -437,7 +440,7 @@ int EmgmmEngine::streamed_sweep(const EmArgs& base) {
         "H2D X chunk");
     CKE(cudaEventRecord(cev_[c], cst_), "event");
     CKE(cudaStreamWaitEvent(st_, cev_[c], 0), "wait");
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sms_, (n + kEstepTilePts - 1) / kEstepTilePts));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sms_, (n + f.TP - 1) / f.TP));
     CKE(launch_moments(g, dXown_ + (size_t)off * d, n, dShift_, dMomPart_, grid, 1, st_), "moments chunk");
     EmArgs a = base;
     a.X = dXown_ + (size_t)off * d;
@@ -609,7 +612,7 @@ int EmgmmEngine::materialize_gamma() {
   if (!prev_valid_ || n_ == 0) return 0;  // no E-step yet: ProbaC = 0 (src/unsupervised/mlf_emgmm.f90:119)
   if (int r = ensure_moments()) return r;
   CKE(launch_refresh(geom_, dPrevMu_, dPrevCov_, dPrevLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_,
-                     dPack2_, dMuOld_, dShift_, 1, cov_diag_ ? 1 : 0), "refresh");
+                     dPack2_, dMuOld_, dShift_, 1, cov_diag_ ? 1 : 0, &fgeom_), "refresh");
   ++launches_;
   if (int r = run_estep(dX_, n_, dGamma_, ldg_, nullptr, false)) return r;
   gamma_current_ = true;

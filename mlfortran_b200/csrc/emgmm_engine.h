@@ -31,7 +31,8 @@ class EmgmmEngine {
 
   // X: N_local x d, point-major (Fortran X(d,N)).  x_on_device: X is a device pointer that the caller keeps
   // alive (borrowed, like the reference's `this%X => X`); otherwise it is copied host->device here.
-  int init(const double* X, bool x_on_device, int64_t n_local, int d, int K, int device);
+  // cov_diag: diagonal-covariance extension, fixed at construction so that the kernel plan can use the compressed pack
+  int init(const double* X, bool x_on_device, int64_t n_local, int d, int K, int device, bool cov_diag = false);
   void set_allreduce(allreduce_fn fn, void* ctx, int rank, int world) {
     ar_ = fn; ar_ctx_ = ctx; rank_ = rank; world_ = world < 1 ? 1 : world; moments_ready_ = false; shift_ready_ = false;
   }

@@ -75,25 +75,43 @@ __device__ __forceinline__ double exp_bf(double a) {
 
 }  // namespace
 
-FusedGeom make_fused_geom(const Geom& g) {
+FusedGeom make_fused_geom(const Geom& g, bool cov_diag, size_t smem_limit) {
   FusedGeom f{};
-  f.OFFB = g.NB * 32;
-  f.OFFC = f.OFFB + 8 * g.DN;
-  f.PSF = f.OFFC + 4;
   f.XS = 8 * g.DN + 4;
   f.MSF = g.MB * 64 + 8 * g.DN + 2;
   f.CBMAX = g.K8 <= 8 ? 1 : (g.K8 <= 16 ? 2 : (g.K8 <= 32 ? 4 : 8));
-  f.smem = ((size_t)g.K8 * 8 * f.PSF + (size_t)g.K8 * 8 * 8 * g.DN + (size_t)kEstepTilePts * f.XS + (size_t)kEstepTilePts * g.S) * sizeof(double);
   // scatter accumulators: 8 comps x CBMAX x MB blocks x 2 doubles per lane must stay in registers
   f.scatter_ok = (16 * f.CBMAX * g.MB <= 64) && g.K8 <= 64;
+  auto plan = [&](int gpw, bool diag) {
+    f.GPW = gpw;
+    f.diag = diag;
+    f.TP = 64 * gpw;
+    f.OFFB = diag ? 8 * g.DN : g.NB * 32;
+    f.OFFC = f.OFFB + 8 * g.DN;
+    f.PSF = f.OFFC + 4;
+    f.smem = ((size_t)g.K8 * 8 * f.PSF + (size_t)g.K8 * 8 * 8 * g.DN + (size_t)f.TP * f.XS + (size_t)f.TP * g.S) * sizeof(double);
+    return f.smem <= smem_limit;
+  };
+  // preference: 128-point tiles with the full pack; 64-point tiles for large K at d <= 8; the diagonal-compressed
+  // pack (extension) when the caller asked for diagonal covariances and nothing else fits
+  if (plan(2, false)) return f;
+  const bool small = (g.DM <= 2) && (f.CBMAX == 2 || f.CBMAX == 4);
+  if (small && plan(1, false)) return f;
+  if (small && cov_diag && plan(1, true)) return f;
+  plan(2, false);
   return f;
 }
 
-template <int DM, int CBMAX, bool SCATTER>
+// GPW: 8-point groups per warp (2: 128-point tiles; 1: 64-point tiles for large K, whose logit tile would not fit).
+// DIAG: diagonal-covariance extension with the compressed pack [8*DN diag(L) | 8*DN bias | const]: the B fragments are
+// synthesised from the diagonal, which is what lets K = 256 at d = 8 (BASELINE config 5) fit shared memory.
+template <int DM, int CBMAX, bool SCATTER, int GPW, bool DIAG>
 __global__ void __launch_bounds__(kEstepThreads, 1) k_em(EmArgs A) {
   constexpr int DN = (DM + 1) / 2;
   constexpr int NB = f_blk_off(DM);
-  constexpr int OFFB = NB * 32, OFFC = OFFB + 8 * DN, PSF = OFFC + 4;
+  constexpr int OFFB = DIAG ? 8 * DN : NB * 32, OFFC = OFFB + 8 * DN, PSF = OFFC + 4;
+  constexpr int TP = 64 * GPW;   // points per block tile
+  constexpr int WP = 8 * GPW;    // points per warp
   constexpr int XS = 8 * DN + 4;
   constexpr int MB = DN * (DN + 1) / 2;
   constexpr int DS = 8 * DN + 2;
@@ -105,7 +123,7 @@ __global__ void __launch_bounds__(kEstepThreads, 1) k_em(EmArgs A) {
   double* sp = smem;                                  // [KP][PSF]  L fragments | -L^T(mu-m) | log(lambda)-lnDet
   double* smu = sp + (size_t)KP * PSF;                // [KP][8 DN] current means (scatter centre)
   double* xs = smu + (size_t)KP * 8 * DN;             // [128][XS]  raw points of the tile
-  double* tile = xs + (size_t)kEstepTilePts * XS;     // [128][S]   logits -> responsibilities
+  double* tile = xs + (size_t)TP * XS;                // [TP][S]    logits -> responsibilities
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
 
   for (int i = tid; i < KP * PSF; i += kEstepThreads) sp[i] = A.pack2[i];
@@ -161,15 +179,15 @@ __global__ void __launch_bounds__(kEstepThreads, 1) k_em(EmArgs A) {
   int nAmb = (SCATTER && accu) ? A.amb_count[blockIdx.x * (kEstepThreads / 32) + warp] : 0;
   AmbEntry* ambw = SCATTER ? A.amb + ((size_t)blockIdx.x * (kEstepThreads / 32) + warp) * A.amb_cap : nullptr;
 
-  const int64_t ntiles = (N + kEstepTilePts - 1) / kEstepTilePts;
+  const int64_t ntiles = (N + TP - 1) / TP;
   for (int64_t bt = blockIdx.x; bt < ntiles; bt += gridDim.x) {
-    const int64_t p0 = bt * kEstepTilePts + warp * 16;
+    const int64_t p0 = bt * TP + warp * WP;
     // ---- P1: logits of this warp's 16 points against every component ---------------------------------------------
-    double xa[2][DM];
+    double xa[GPW][DM];
 #pragma unroll
-    for (int grp = 0; grp < 2; ++grp) {
+    for (int grp = 0; grp < GPW; ++grp) {
       const int64_t p = p0 + 8 * grp + g;
-      double* xr = xs + (size_t)(warp * 16 + 8 * grp + g) * XS;
+      double* xr = xs + (size_t)(warp * WP + 8 * grp + g) * XS;
 #pragma unroll
       for (int mb = 0; mb < DM; ++mb) {
         const int a = 4 * mb + t;
@@ -179,22 +197,31 @@ __global__ void __launch_bounds__(kEstepThreads, 1) k_em(EmArgs A) {
       }
       if (8 * DN > 4 * DM) xr[4 * DM + t] = 0.0;  // zero padding up to 8*DN
     }
-    double* row[2] = {tile + (size_t)(warp * 16 + g) * S, tile + (size_t)(warp * 16 + 8 + g) * S};
-    double rmax[2] = {-INFINITY, -INFINITY};
-    int rarg[2] = {0, 0};
+    double* row[GPW];
+    double rmax[GPW];
+    int rarg[GPW];
+#pragma unroll
+    for (int grp = 0; grp < GPW; ++grp) { row[grp] = tile + (size_t)(warp * WP + 8 * grp + g) * S; rmax[grp] = -INFINITY; rarg[grp] = 0; }
     for (int k4 = 0; k4 < K4; ++k4) {
-      double part[2][4];
+      double part[GPW][4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const double* pk = sp + (size_t)(4 * k4 + j) * PSF;
         double Lf[NB];
         double2 nb2[DN];
+        if (DIAG) {  // lane (k = t, n = g) of block (mb, nb) holds L[4mb+t][8nb+g]: only the diagonal is non-zero
 #pragma unroll
-        for (int b = 0; b < NB; ++b) Lf[b] = pk[b * 32 + lane];
+          for (int mb = 0; mb < DM; ++mb)
+#pragma unroll
+            for (int nb = 0; nb <= mb / 2; ++nb) Lf[f_blk_off(mb) + nb] = (4 * mb + t == 8 * nb + g) ? pk[8 * nb + g] : 0.0;
+        } else {
+#pragma unroll
+          for (int b = 0; b < NB; ++b) Lf[b] = pk[b * 32 + lane];
+        }
 #pragma unroll
         for (int nb = 0; nb < DN; ++nb) nb2[nb] = *reinterpret_cast<const double2*>(pk + OFFB + 8 * nb + 2 * t);
 #pragma unroll
-        for (int grp = 0; grp < 2; ++grp) {
+        for (int grp = 0; grp < GPW; ++grp) {
           double c[DN][2];
 #pragma unroll
           for (int nb = 0; nb < DN; ++nb) { c[nb][0] = nb2[nb].x; c[nb][1] = nb2[nb].y; }
@@ -211,7 +238,7 @@ __global__ void __launch_bounds__(kEstepThreads, 1) k_em(EmArgs A) {
       }
       const double ck = sp[(size_t)(4 * k4 + t) * PSF + OFFC];
 #pragma unroll
-      for (int grp = 0; grp < 2; ++grp) {
+      for (int grp = 0; grp < GPW; ++grp) {
         // transposed reduction over the quad: lane t ends with the full |u|^2 of component 4*k4+t
         const bool hi2 = (t & 2) != 0, hi1 = (t & 1) != 0;
         const double send0 = hi2 ? part[grp][0] : part[grp][2];
@@ -227,10 +254,10 @@ __global__ void __launch_bounds__(kEstepThreads, 1) k_em(EmArgs A) {
       }
     }
     // ---- P2: log-sum-exp over the components (4 independent exp chains per lane) --------------------------------
-    double mx[2], inv[2];
-    int am[2];
+    double mx[GPW], inv[GPW], sum[GPW];
+    int am[GPW];
 #pragma unroll
-    for (int grp = 0; grp < 2; ++grp) {
+    for (int grp = 0; grp < GPW; ++grp) {
       double m = rmax[grp];
       int a = rarg[grp];
 #pragma unroll
@@ -241,33 +268,42 @@ __global__ void __launch_bounds__(kEstepThreads, 1) k_em(EmArgs A) {
       }
       mx[grp] = A.raw ? 0.0 : m;  // raw: P = lambda*exp(v - lnDet) un-normalised (src/unsupervised/mlf_gaussian.f90:77)
       am[grp] = a;
+      sum[grp] = 0;
     }
-    double sum0 = 0, sum1 = 0;
+    if constexpr (GPW == 2) {
 #pragma unroll 2
-    for (int k4 = 0; k4 < K4; k4 += 2) {   // K4 is even; 4 independent exp chains per trip, 2 trips unrolled
-      const double a00 = row[0][4 * k4 + t] - mx[0], a01 = row[0][4 * k4 + 4 + t] - mx[0];
-      const double a10 = row[1][4 * k4 + t] - mx[1], a11 = row[1][4 * k4 + 4 + t] - mx[1];
-      const double e00 = exp_bf(a00), e01 = exp_bf(a01), e10 = exp_bf(a10), e11 = exp_bf(a11);
-      row[0][4 * k4 + t] = e00; row[0][4 * k4 + 4 + t] = e01;
-      row[1][4 * k4 + t] = e10; row[1][4 * k4 + 4 + t] = e11;
-      sum0 += e00; sum0 += e01;
-      sum1 += e10; sum1 += e11;
-    }
-    sum0 += shx(sum0, 1); sum0 += shx(sum0, 2);
-    sum1 += shx(sum1, 1); sum1 += shx(sum1, 2);
-    {
-      const bool v0 = (p0 + g) < N, v1 = (p0 + 8 + g) < N;
-      inv[0] = v0 ? (A.raw ? 1.0 : 1.0 / sum0) : 0.0;
-      inv[1] = v1 ? (A.raw ? 1.0 : 1.0 / sum1) : 0.0;
+      for (int k4 = 0; k4 < K4; k4 += 2) {   // K4 is even; 4 independent exp chains per trip, 2 trips unrolled
+        const double a00 = row[0][4 * k4 + t] - mx[0], a01 = row[0][4 * k4 + 4 + t] - mx[0];
+        const double a10 = row[1][4 * k4 + t] - mx[1], a11 = row[1][4 * k4 + 4 + t] - mx[1];
+        const double e00 = exp_bf(a00), e01 = exp_bf(a01), e10 = exp_bf(a10), e11 = exp_bf(a11);
+        row[0][4 * k4 + t] = e00; row[0][4 * k4 + 4 + t] = e01;
+        row[1][4 * k4 + t] = e10; row[1][4 * k4 + 4 + t] = e11;
+        sum[0] += e00; sum[0] += e01;
+        sum[1] += e10; sum[1] += e11;
+      }
+    } else {
+#pragma unroll 2
+      for (int k4 = 0; k4 < K4; k4 += 2) {   // one group per warp: 2 chains per trip, 2 trips unrolled
+        const double a0 = row[0][4 * k4 + t] - mx[0], a1 = row[0][4 * k4 + 4 + t] - mx[0];
+        const double e0 = exp_bf(a0), e1 = exp_bf(a1);
+        row[0][4 * k4 + t] = e0; row[0][4 * k4 + 4 + t] = e1;
+        sum[0] += e0; sum[0] += e1;
+      }
     }
 #pragma unroll
-    for (int grp = 0; grp < 2; ++grp) {
+    for (int grp = 0; grp < GPW; ++grp) {
+      sum[grp] += shx(sum[grp], 1);
+      sum[grp] += shx(sum[grp], 2);
+      const bool v = (p0 + 8 * grp + g) < N;
+      inv[grp] = v ? (A.raw ? 1.0 : 1.0 / sum[grp]) : 0.0;
+    }
+#pragma unroll
+    for (int grp = 0; grp < GPW; ++grp) {
       const int64_t p = p0 + 8 * grp + g;
       const bool valid = p < N;
       for (int k4 = 0; k4 < K4; ++k4) {
         const int k = 4 * k4 + t;
-        const double e = row[grp][k];
-        const double gk = e * inv[grp];
+        const double gk = row[grp][k] * inv[grp];
         row[grp][k] = gk;
         if (A.gamma != nullptr && valid && k < K) A.gamma[(size_t)k * A.ldg + p] = gk;
       }
@@ -284,11 +320,11 @@ __global__ void __launch_bounds__(kEstepThreads, 1) k_em(EmArgs A) {
       if (cb < K8) {
         constexpr int cs = SCATTER ? 1 : 0;
         const int c2 = ci * cs;
-        const int64_t q0 = bt * kEstepTilePts;
+        const int64_t q0 = bt * TP;
         const double* tcol = tile + 8 * cb + g;
         unsigned act = 0;  // lane pb: bit q set <=> component 8*cb+q keeps some point of group pb
 #pragma unroll 4
-        for (int pb = 0; pb < kEstepTilePts / 4; ++pb) {
+        for (int pb = 0; pb < TP / 4; ++pb) {
           const double a = tcol[(size_t)(4 * pb + t) * S];
           double b[DN];
 #pragma unroll
@@ -407,36 +443,55 @@ __global__ void __launch_bounds__(kEstepThreads, 1) k_em(EmArgs A) {
   }
 }
 
-template <int DM, int CBMAX, bool SCATTER>
+template <int DM, int CBMAX, bool SCATTER, int GPW, bool DIAG>
 static cudaError_t launch_em_t(const EmArgs& a, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(k_em<DM, CBMAX, SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_em<DM, CBMAX, SCATTER, GPW, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_em<DM, CBMAX, SCATTER><<<grid, kEstepThreads, smem, st>>>(a);
+  k_em<DM, CBMAX, SCATTER, GPW, DIAG><<<grid, kEstepThreads, smem, st>>>(a);
   return cudaGetLastError();
 }
 
+// 128-point tiles, full pack: every (DM, CBMAX) the register file allows
 template <int DM>
 static cudaError_t launch_em_dm(const EmArgs& a, int cbmax, bool scatter, int grid, size_t smem, cudaStream_t st) {
   constexpr int DN = (DM + 1) / 2;
   constexpr int MB = DN * (DN + 1) / 2;
   if (scatter) {
     // instantiate the fused variant only where its accumulators fit the register file
-    if constexpr (16 * 1 * MB <= 64) { if (cbmax == 1) return launch_em_t<DM, 1, true>(a, grid, smem, st); }
-    if constexpr (16 * 2 * MB <= 64) { if (cbmax == 2) return launch_em_t<DM, 2, true>(a, grid, smem, st); }
-    if constexpr (16 * 4 * MB <= 64) { if (cbmax == 4) return launch_em_t<DM, 4, true>(a, grid, smem, st); }
+    if constexpr (16 * 1 * MB <= 64) { if (cbmax == 1) return launch_em_t<DM, 1, true, 2, false>(a, grid, smem, st); }
+    if constexpr (16 * 2 * MB <= 64) { if (cbmax == 2) return launch_em_t<DM, 2, true, 2, false>(a, grid, smem, st); }
+    if constexpr (16 * 4 * MB <= 64) { if (cbmax == 4) return launch_em_t<DM, 4, true, 2, false>(a, grid, smem, st); }
     return cudaErrorInvalidConfiguration;
   }
   switch (cbmax) {
-    case 1: return launch_em_t<DM, 1, false>(a, grid, smem, st);
-    case 2: return launch_em_t<DM, 2, false>(a, grid, smem, st);
-    case 4: return launch_em_t<DM, 4, false>(a, grid, smem, st);
-    default: return launch_em_t<DM, 8, false>(a, grid, smem, st);
+    case 1: return launch_em_t<DM, 1, false, 2, false>(a, grid, smem, st);
+    case 2: return launch_em_t<DM, 2, false, 2, false>(a, grid, smem, st);
+    case 4: return launch_em_t<DM, 4, false, 2, false>(a, grid, smem, st);
+    default: return launch_em_t<DM, 8, false, 2, false>(a, grid, smem, st);
   }
+}
+
+// 64-point tiles (large K at d <= 8), full or diagonal-compressed pack
+template <int DM, bool DIAG>
+static cudaError_t launch_em_small(const EmArgs& a, int cbmax, bool scatter, int grid, size_t smem, cudaStream_t st) {
+  if (scatter) {
+    if (cbmax == 2) return launch_em_t<DM, 2, true, 1, DIAG>(a, grid, smem, st);
+    if (cbmax == 4) return launch_em_t<DM, 4, true, 1, DIAG>(a, grid, smem, st);
+  } else {
+    if (cbmax == 2) return launch_em_t<DM, 2, false, 1, DIAG>(a, grid, smem, st);
+    if (cbmax == 4) return launch_em_t<DM, 4, false, 1, DIAG>(a, grid, smem, st);
+  }
+  return cudaErrorInvalidConfiguration;
 }
 
 cudaError_t launch_em(const Geom& g, const FusedGeom& f, const EmArgs& a, bool scatter, int grid, size_t smem_limit, cudaStream_t st) {
   if (f.smem > smem_limit || g.K8 > 64) return cudaErrorInvalidConfiguration;
   if (scatter && !f.scatter_ok) return cudaErrorInvalidConfiguration;
+  if (f.GPW == 1) {
+    if (g.DM == 1) return f.diag ? launch_em_small<1, true>(a, f.CBMAX, scatter, grid, f.smem, st) : launch_em_small<1, false>(a, f.CBMAX, scatter, grid, f.smem, st);
+    if (g.DM == 2) return f.diag ? launch_em_small<2, true>(a, f.CBMAX, scatter, grid, f.smem, st) : launch_em_small<2, false>(a, f.CBMAX, scatter, grid, f.smem, st);
+    return cudaErrorInvalidConfiguration;
+  }
   switch (g.DM) {
     case 1: return launch_em_dm<1>(a, f.CBMAX, scatter, grid, f.smem, st);
     case 2: return launch_em_dm<2>(a, f.CBMAX, scatter, grid, f.smem, st);

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) k_refresh(Geom g, const double* __restric
                                                  double* __restrict__ pack, double* __restrict__ sumLLk,
                                                  int* __restrict__ info, double* __restrict__ pack2, double* __restrict__ muold,
                                                  int PSF, int OFFB2, int OFFC2, const double* __restrict__ shift, int do_sumll, int use_smem,
-                                                 int cov_diag) {
+                                                 int cov_diag, int diag_pack) {
   const int k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, d = g.d;
   const int OFFMU = g.NB * 32, OFFC = OFFMU + 4 * g.DM;
   double* pk = pack + (size_t)k * g.PS;
@@ -237,7 +237,11 @@ __global__ void __launch_bounds__(256) k_refresh(Geom g, const double* __restric
   if (tid == 0) pk[OFFC] = ck;
   if (pack2) {  // fused-kernel pack: same fragments, accumulator bias -L^T(mu - m) with m the global mean, constant
     double* p2 = pack2 + (size_t)k * PSF;
-    for (int i = tid; i < g.NB * 32; i += nt) p2[i] = pk[i];
+    if (diag_pack) {  // diagonal-compressed pack: [8*DN diag(L) | bias | const]
+      for (int n = tid; n < 8 * g.DN; n += nt) p2[n] = (n < d) ? W[(size_t)n * d + n] : 0.0;
+    } else {
+      for (int i = tid; i < g.NB * 32; i += nt) p2[i] = pk[i];
+    }
     for (int n = tid; n < 8 * g.DN; n += nt) {
       double acc = 0;
       if (n < d)
@@ -269,8 +273,9 @@ __global__ void __launch_bounds__(256) k_refresh(Geom g, const double* __restric
 
 cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, const double* lambda, const double* Sc,
                            const double* mean, double Nglob, double* scratch, double* pack, double* sumLLk, int* info,
-                           cudaStream_t st, double* pack2, double* muold, const double* shift, int do_sumll, int cov_diag) {
-  const FusedGeom f = make_fused_geom(g);
+                           cudaStream_t st, double* pack2, double* muold, const double* shift, int do_sumll, int cov_diag,
+                           const FusedGeom* fg) {
+  const FusedGeom f = fg ? *fg : make_fused_geom(g);
   const bool large = g.d > 32;
   const size_t dyn = large ? (size_t)g.d * g.d * sizeof(double) : 0;
   if (large) {
@@ -278,7 +283,7 @@ cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, c
     if (e != cudaSuccess) return e;
   }
   k_refresh<<<g.K8 * 8, large ? 256 : 128, dyn, st>>>(g, Mu, Cov, lambda, Sc, mean, Nglob, scratch, pack, sumLLk, info, pack2, muold,
-                                                     f.PSF, f.OFFB, f.OFFC, shift ? shift : mean, do_sumll, large ? 1 : 0, cov_diag);
+                                                     f.PSF, f.OFFB, f.OFFC, shift ? shift : mean, do_sumll, large ? 1 : 0, cov_diag, f.diag ? 1 : 0);
   return cudaGetLastError();
 }
 

@@ -31,10 +31,13 @@ struct FusedGeom {
   int XS;         // row stride of the shared-memory X tile (8*DN + 4, conflict-free for both fragment shapes)
   int MSF;        // doubles per component of the fused pass-B statistics: [MB*64 scatter | 8*DN sum_kept g x | sum_kept g, pad]
   int CBMAX;      // component blocks (of 8) per warp
+  int GPW;        // 8-point groups per warp: 2 (128-point tiles) or 1 (64-point tiles, large K)
+  int TP;         // points per block tile = 64 * GPW
+  bool diag;      // diagonal-compressed pack [8*DN diag(L) | 8*DN bias | const] (diagonal-covariance extension)
   size_t smem;    // dynamic shared memory of k_em
   bool scatter_ok;  // the scatter accumulators fit the register file for this (d, K)
 };
-FusedGeom make_fused_geom(const Geom& g);
+FusedGeom make_fused_geom(const Geom& g, bool cov_diag = false, size_t smem_limit = 232448);
 
 struct AmbEntry {  // pair whose keep/drop decision waits for the all-reduced s_k
   double g;
@@ -65,7 +68,7 @@ constexpr int kMstepTilePts = 2048;     // points per block tile of the M-pass s
 cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, const double* lambda, const double* Sc,
                            const double* mean, double Nglob, double* scratch, double* pack, double* sumLLk, int* info,
                            cudaStream_t st, double* pack2 = nullptr, double* muold = nullptr, const double* shift = nullptr,
-                           int do_sumll = 1, int cov_diag = 0);
+                           int do_sumll = 1, int cov_diag = 0, const FusedGeom* fg = nullptr);
 cudaError_t launch_sumll(const Geom& g, const double* Mu, const double* Sc, const double* mean, double Nglob, const double* scratch,
                          const double* pack, double* sumLLk, cudaStream_t st);
 // Global moments about `shift`: partial[grid][MB*64 + 8*DN]; finish turns the all-reduced sums into mean and centred scatter.

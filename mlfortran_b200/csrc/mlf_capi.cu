@@ -217,7 +217,7 @@ MLF_OBJ* em_create(const double* X, int64_t nX, int nY, int nC, double minProba,
     if (cudaGetDevice(&cur) != cudaSuccess) cur = 0;
     device = cur;
   }
-  if (o->eng.init(X, o->x_on_device, nX, nY, K, device) < 0) {
+  if (o->eng.init(X, o->x_on_device, nX, nY, K, device, (flags & MLF_B200_COV_DIAG) != 0) < 0) {
     fprintf(stderr, "mlf_emgmm_c: %s\n", o->eng.last_error().c_str());
     return nullptr;
   }
@@ -548,7 +548,7 @@ MLF_B200_ENGINE* mlf_b200_engine_create(const double* X, int64_t nX, int nY, int
   if ((!X && nX > 0) || nX < 0 || nY < 1 || nC < 1) return nullptr;
   std::unique_ptr<EmgmmEngine> e(new EmgmmEngine());
   if (device < 0 && cudaGetDevice(&device) != cudaSuccess) device = 0;
-  if (e->init(X, (flags & MLF_B200_X_ON_DEVICE) != 0, nX, nY, nC, device) < 0) {
+  if (e->init(X, (flags & MLF_B200_X_ON_DEVICE) != 0, nX, nY, nC, device, (flags & MLF_B200_COV_DIAG) != 0) < 0) {
     fprintf(stderr, "mlf_b200_engine_create: %s\n", e->last_error().c_str());
     return nullptr;
   }

@@ -21,6 +21,7 @@ mlf_STEP_OK, mlf_STEP_STOP = 0, 1
 mlf_NAME, mlf_DESC, mlf_FIELDS = 1, 2, 3
 mlf_INT64, mlf_DOUBLE, mlf_DIRECT = 3, 6, 1
 X_ON_DEVICE = 1
+COV_DIAG = 2
 
 
 def mlf_init() -> int:
@@ -101,14 +102,14 @@ class mlf_algo_emgmm:
 
     # -- init / lifetime ------------------------------------------------------------------------------------------
     def init(self, X, nC: int, minProba: float | None = None, data_handler: mlf_hdf5_file | None = None,
-             device: int = -1) -> int:
+             device: int = -1, cov_type: str = "full") -> int:
         """info = this%init(X, nC, minProba, data_handler) (src/unsupervised/mlf_emgmm.f90:76-112).
 
         X: NumPy (N,d) float64 C-contiguous (borrowed, copied once to HBM) or a CUDA torch tensor of that shape
         (borrowed on the device).  With a data_handler the number of components comes from the checkpoint."""
         self.finalize()
         self._lib = lib = _lib.load()
-        flags = 0
+        flags = COV_DIAG if cov_type == "diag" else 0   # extension; "full" is the reference behaviour
         if isinstance(X, np.ndarray):
             if X.dtype != np.float64 or X.ndim != 2 or not X.flags.c_contiguous:
                 return mlf_OTHERERROR

@@ -338,6 +338,48 @@ def test_diagonal_covariance_extension(shape, oracle):
     em.finalize()
 
 
+def test_config5_shape_runs_through_the_single_sweep_kernel(oracle):
+    """d=8, K=256 diagonal (BASELINE configs[4] shape), cov_type fixed at construction: 64-point tiles + diagonal-compressed
+    pack keep the whole mixture in shared memory, so no N*K responsibility buffer is needed (256 GB per GPU at full size)."""
+    d, K = 8, 256
+    data = synth.make_mixture(d, K, 40, 6.0, 1.0, 151)
+    X = data["X"]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 151)
+    oracle.set_cov_diag(True)
+    try:
+        oMu, oCov, olam, otr = oracle.em_iterations(X, Mu0, Cov0, lam0, 1.0, 4)
+    finally:
+        oracle.set_cov_diag(False)
+    em = mlf_algo_emgmm()
+    assert em.init(X, K, 1.0, cov_type="diag") == 0
+    em.inject(Mu0, Cov0, lam0)
+    assert em.step(4)[0] == 0, em.last_error()
+    check_against(em, oMu, oCov, olam, otr)
+    assert em.times()["sweeps"] >= 4          # fused path
+    info, cl = em.getClass(X[:400])
+    oracle.set_cov_diag(True)
+    try:
+        _, Pn, _ = oracle.exp_step(X[:400], em.Mu, em.Cov, em.lambda_)
+    finally:
+        oracle.set_cov_diag(False)
+    assert info == 0 and (cl == oracle.get_class(Pn)).all()
+    em.finalize()
+
+
+def test_64_point_tiles_full_covariance_large_k(oracle):
+    # d=8, K=128 full covariances: the pack fits shared memory only with 64-point tiles (one 8-point group per warp)
+    data = synth.make_mixture(8, 128, 60, 6.0, 1.0, 152)
+    X = data["X"]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 152)
+    oMu, oCov, olam, otr, oP = oracle.em_iterations(X, Mu0, Cov0, lam0, 0.0, 3, return_proba=True)
+    em = make_em(X, 128, 0.0, Mu0, Cov0, lam0)
+    assert em.step(3)[0] == 0, em.last_error()
+    check_against(em, oMu, oCov, olam, otr)
+    assert em.times()["sweeps"] >= 3
+    assert np.abs(em.ProbaC - oP).max() <= 1e-9
+    em.finalize()
+
+
 # ---- edge cases ------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [1, 2, 31, 127, 128, 129, 2049])
 def test_tiny_and_ragged_point_counts(n, oracle):
