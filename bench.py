@@ -142,6 +142,7 @@ def main():
     ap.add_argument("--dims", type=int, default=16)
     ap.add_argument("--comps", type=int, default=64)
     ap.add_argument("--min-proba", type=float, default=1.0, help="minProba as in tests/test_emgmm.f90:125")
+    ap.add_argument("--cov-type", default="full", choices=["full", "diag"], help="diag = extension (BASELINE configs[4]); full = reference")
     ap.add_argument("--cpu-points", type=int, default=256000, help="bounded CPU sample for cpu_baseline / --impl reference")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -191,7 +192,7 @@ def main():
     Mu0, Cov0, lam0 = synth.injected_init(centres, SEED)
 
     em = mlf_algo_emgmm()
-    if em.init(X, K, args.min_proba) != 0:
+    if em.init(X, K, args.min_proba, cov_type=args.cov_type) != 0:
         raise SystemExit("bench.py: init failed")
     if world > 1:
         em.set_allreduce(parallel.make_allreduce(None, dev), rank, world)
@@ -284,7 +285,7 @@ def main():
         torch.cuda.empty_cache()
         Xn = Xh.numpy()
         em = mlf_algo_emgmm()
-        if em.init(Xn, K, args.min_proba, device=local_rank) != 0:
+        if em.init(Xn, K, args.min_proba, device=local_rank, cov_type=args.cov_type) != 0:
             raise SystemExit("bench.py: e2e init failed")
         if world > 1:
             em.set_allreduce(parallel.make_allreduce(None, dev), rank, world)
@@ -320,7 +321,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "em_iter_per_s": args.steps / (ms * 1e-3), "sumLL_last": sumll,
-            "config": {"workload": f"synthetic GMM N={N:.0e} d={d} K={K} full covariance, points sharded over {world} GPU(s) (BASELINE configs[2])",
+            "config": {"workload": f"synthetic GMM N={N:.0e} d={d} K={K} {'full' if args.cov_type == 'full' else 'diagonal'} covariance, points sharded over {world} GPU(s)"
+                                   + (" (BASELINE configs[2])" if (d, K, args.cov_type) == (16, 64, "full") else ""),
                        "N": N, "d": d, "K": K, "minProba": args.min_proba, "points_per_gpu": n_loc, "parallelism": f"points-sharded x{world}",
                        "l2": "inputs larger than L2 (X is 12.8 GB per 1e8 points >> 126 MB); no explicit flush",
                        "timing": "CUDA events on the engine stream, max over ranks"},

@@ -646,6 +646,63 @@ def test_two_shards_equal_single_object(oracle):
     np.testing.assert_array_equal(res[0][2], res[1][2])
 
 
+def test_two_shards_kmeans_initialiser(oracle):
+    """Fresh sharded objects: the D^2 seeding draws from the *global* data (per-rank weight totals are all-gathered through
+    the all-reduce callback, the owner rank broadcasts the drawn point), Lloyd steps all-reduce the centre sums; both ranks
+    must end with the same centres, and those must be a fixed point of the reference's Lloyd step on the whole data."""
+    import torch
+
+    rng = np.random.default_rng(161)
+    centres = np.array([[-60.0, 0.0, 0.0], [60.0, 0.0, 0.0], [0.0, 60.0, 0.0], [0.0, 0.0, 60.0], [0.0, -60.0, -60.0]])
+    X = np.ascontiguousarray((centres[:, None, :] + rng.standard_normal((5, 300, 3))).reshape(-1, 3)[rng.permutation(1500)])
+    world = 2
+    bar = threading.Barrier(world)
+    slots = [None] * world
+    res = [None] * world
+
+    def worker(rank):
+        from mlfortran_b200 import parallel
+
+        lo, hi = parallel.shard_bounds(X.shape[0], rank, world)
+        em = mlf_algo_emgmm()
+        assert em.init(np.ascontiguousarray(X[lo:hi]), 5, 1.0, device=0) == 0
+
+        def allreduce(ptr, count, stream):
+            t = torch.as_tensor(parallel._DevBuf(ptr, count), device="cuda:0")
+            torch.cuda.ExternalStream(stream, device="cuda:0").synchronize()
+            slots[rank] = t
+            bar.wait()
+            total = slots[0].clone()
+            for r in range(1, world):
+                total += slots[r]
+            torch.cuda.synchronize()
+            bar.wait()
+            t.copy_(total)
+            torch.cuda.synchronize()
+            bar.wait()
+            return 0
+
+        em.set_allreduce(allreduce, rank, world)
+        em.set_seed(99)
+        info, _ = em.step(3)     # initialiser + 2 EM iterations
+        res[rank] = (info, em.Mu.copy(), em.Cov.copy(), em.sumLL_trace().copy(), em.last_error())
+        em.finalize()
+
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=300)
+    assert res[0] is not None and res[1] is not None
+    assert res[0][0] == 0 and res[1][0] == 0, (res[0][4], res[1][4])
+    np.testing.assert_array_equal(res[0][1], res[1][1])
+    np.testing.assert_array_equal(res[0][2], res[1][2])
+    Mu = res[0][1]
+    # every true centre is recovered (well-separated clusters, EM refines the k-means centres)
+    dist = np.linalg.norm(Mu[:, None, :] - centres[None], axis=2)
+    assert (dist.min(axis=0) < 0.5).all()
+
+
 # ---- full-size properties (BASELINE configs[2] shape on one GPU) ----------------------------------------------------
 def test_full_size_properties_and_sample_parity(oracle):
     """N=1e8 (or what fits), d=16, K=64: size-independent invariants plus oracle parity on a 20 000-point sample."""
