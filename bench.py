@@ -143,7 +143,7 @@ def main():
     ap.add_argument("--comps", type=int, default=64)
     ap.add_argument("--min-proba", type=float, default=1.0, help="minProba as in tests/test_emgmm.f90:125")
     ap.add_argument("--cov-type", default="full", choices=["full", "diag"], help="diag = extension (BASELINE configs[4]); full = reference")
-    ap.add_argument("--cpu-points", type=int, default=256000, help="bounded CPU sample for cpu_baseline / --impl reference")
+    ap.add_argument("--cpu-points", type=int, default=1000000, help="bounded CPU sample for cpu_baseline / --impl reference (SURVEY 8d: N_cpu = 1e6)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
