@@ -155,6 +155,87 @@ static void run(const double* dpack, const double* dX, int tiles, double* dout, 
   printf("{\"variant\": \"%s\", \"ms\": %.4f, \"ns_per_pair\": %.5f, \"dmma_tflops\": %.3f, \"frac_of_37.16\": %.3f}\n", name, best, best * 1e6 / pairs, tf, tf / 37.16);
 }
 
+// NW warps per block, GPW 8-point groups per warp (tile = NW*8*GPW points): does more warps per scheduler fill the gaps?
+template <int NW, int GPW>
+__global__ void __launch_bounds__(NW * 32, 1) k_p1w(const double* __restrict__ pack, const double* __restrict__ X, int tiles, double* __restrict__ out) {
+  extern __shared__ __align__(16) double smem[];
+  double* sp = smem;
+  double* tile = smem + K * PSF;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < K * PSF; i += NW * 32) sp[i] = pack[i];
+  __syncthreads();
+  constexpr int TP = NW * 8 * GPW;
+  double acc = 0;
+  for (int bt = 0; bt < tiles; ++bt) {
+    double xa[GPW][DM];
+#pragma unroll
+    for (int grp = 0; grp < GPW; ++grp)
+#pragma unroll
+      for (int mb = 0; mb < DM; ++mb) xa[grp][mb] = X[(((size_t)(blockIdx.x * tiles + bt) * TP + warp * 8 * GPW + 8 * grp + g) % (148u * 200u * 128u)) * 16 + 4 * mb + t];
+    double* row[GPW];
+    double rmax[GPW];
+    int rarg[GPW];
+#pragma unroll
+    for (int grp = 0; grp < GPW; ++grp) { row[grp] = tile + (size_t)(warp * 8 * GPW + 8 * grp + g) * S; rmax[grp] = -1e300; rarg[grp] = 0; }
+    for (int k4 = 0; k4 < K4; ++k4) {
+      double part[GPW][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double* pk = sp + (size_t)(4 * k4 + j) * PSF;
+        double Lf[NB];
+        double2 nb2[DN];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) Lf[b] = pk[b * 32 + lane];
+#pragma unroll
+        for (int nb = 0; nb < DN; ++nb) nb2[nb] = *reinterpret_cast<const double2*>(pk + OFFB + 8 * nb + 2 * t);
+#pragma unroll
+        for (int grp = 0; grp < GPW; ++grp) {
+          double c[DN][2];
+#pragma unroll
+          for (int nb = 0; nb < DN; ++nb) { c[nb][0] = nb2[nb].x; c[nb][1] = nb2[nb].y; }
+#pragma unroll
+          for (int mb = 0; mb < DM; ++mb)
+#pragma unroll
+            for (int nb = 0; nb <= mb / 2; ++nb) dmma_v(c[nb], xa[grp][mb], Lf[blk_off(mb) + nb]);
+          double s2 = c[0][0] * c[0][0];
+          s2 = fma(c[0][1], c[0][1], s2);
+#pragma unroll
+          for (int nb = 1; nb < DN; ++nb) { s2 = fma(c[nb][0], c[nb][0], s2); s2 = fma(c[nb][1], c[nb][1], s2); }
+          part[grp][j] = s2;
+        }
+      }
+      const double ck = sp[(size_t)(4 * k4 + t) * PSF + OFFC];
+#pragma unroll
+      for (int grp = 0; grp < GPW; ++grp) reduce_store(part[grp], ck, row[grp], k4, t, rmax[grp], rarg[grp]);
+    }
+#pragma unroll
+    for (int grp = 0; grp < GPW; ++grp) acc += rmax[grp] + rarg[grp];
+  }
+  if (acc == 1.2345e-300) out[0] = acc + tile[tid];
+}
+
+template <int NW, int GPW>
+static void runw(const double* dpack, const double* dX, int tiles, double* dout, const char* name) {
+  const size_t smem = ((size_t)K * PSF + (size_t)NW * 8 * GPW * S) * 8;
+  CK(cudaFuncSetAttribute(k_p1w<NW, GPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  k_p1w<NW, GPW><<<148, NW * 32, smem>>>(dpack, dX, tiles, dout);
+  CK(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int r = 0; r < 3; ++r) {
+    CK(cudaEventRecord(e0));
+    k_p1w<NW, GPW><<<148, NW * 32, smem>>>(dpack, dX, tiles, dout);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  const double pairs = 148.0 * tiles * NW * 8 * GPW * K;
+  const double tf = pairs * 6 / 8 * 512 / (best * 1e-3) * 1e-12;
+  printf("{\"variant\": \"%s\", \"ms\": %.4f, \"ns_per_pair\": %.5f, \"dmma_tflops\": %.3f, \"frac_of_37.16\": %.3f}\n", name, best, best * 1e6 / pairs, tf, tf / 37.16);
+}
+
 int main() {
   const int tiles = 200;
   std::vector<double> hp((size_t)K * PSF), hx((size_t)148 * tiles * 128 * 16);
@@ -170,6 +251,11 @@ int main() {
   run<2>(dp, dx, tiles, dout, smem, "2 pipelined tail");
   run<3>(dp, dx, tiles, dout, smem, "3 non-volatile asm");
   run<4>(dp, dx, tiles, dout, smem, "4 pipelined tail + non-volatile");
+  runw<8, 2>(dp, dx, tiles, dout, "8 warps x 16 points (= variant 0 structure)");
+  runw<16, 1>(dp, dx, tiles, dout, "16 warps x 8 points");
+  runw<12, 2>(dp, dx, tiles, dout, "12 warps x 16 points");
+  runw<12, 1>(dp, dx, tiles, dout, "12 warps x 8 points");
+  runw<8, 1>(dp, dx, tiles, dout, "8 warps x 8 points");
   {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     const int iters = 20000;

@@ -140,22 +140,26 @@ __global__ void __launch_bounds__(256, 1) k_estep_big(EmArgs A) {
     }
     __syncwarp();
     // ---- P2: log-sum-exp over the components; lane t handles components t, t+4, ... ----------------------------
-    const double mx = A.raw ? 0.0 : rmax;
-    double sum = 0;
-#pragma unroll 4
-    for (int k = t; k < KP; k += 4) {
-      const double e = exp_bf(row[k] - mx);
-      row[k] = e;
-      sum += e;
-    }
-    sum += shx(sum, 1);
-    sum += shx(sum, 2);
     const bool valid = p < N;
-    const double inv = valid ? (A.raw ? 1.0 : 1.0 / sum) : 0.0;
-    for (int k = t; k < KP; k += 4) {
-      const double gk = row[k] * inv;
-      row[k] = gk;
-      if (A.gamma != nullptr && valid && k < K) A.gamma[(size_t)k * A.ldg + p] = gk;
+    if (A.hard) {  // k-means assignment: one-hot of the nearest centre (see emgmm_fused.cu)
+      for (int k = t; k < KP; k += 4) row[k] = (valid && k == rarg) ? 1.0 : 0.0;
+    } else {
+      const double mx = A.raw ? 0.0 : rmax;
+      double sum = 0;
+#pragma unroll 4
+      for (int k = t; k < KP; k += 4) {
+        const double e = exp_bf(row[k] - mx);
+        row[k] = e;
+        sum += e;
+      }
+      sum += shx(sum, 1);
+      sum += shx(sum, 2);
+      const double inv = valid ? (A.raw ? 1.0 : 1.0 / sum) : 0.0;
+      for (int k = t; k < KP; k += 4) {
+        const double gk = row[k] * inv;
+        row[k] = gk;
+        if (A.gamma != nullptr && valid && k < K) A.gamma[(size_t)k * A.ldg + p] = gk;
+      }
     }
     if (A.labels != nullptr && valid && t == 0) A.labels[p] = rarg + 1;
     __syncthreads();

@@ -301,7 +301,7 @@ int EmgmmEngine::download_params(double* Mu, double* Cov, double* lambda) {
   return 0;
 }
 
-int EmgmmEngine::run_estep(const double* X, int64_t n, double* gamma, int64_t ldg, int32_t* labels, bool want_stats, bool raw) {
+int EmgmmEngine::run_estep(const double* X, int64_t n, double* gamma, int64_t ldg, int32_t* labels, bool want_stats, bool raw, bool hard) {
   const Geom& g = geom_;
   const int tp = legacy_estep_ ? kEstepTilePts : fgeom_.TP;
   const int64_t etiles = (n + tp - 1) / tp;
@@ -310,6 +310,7 @@ int EmgmmEngine::run_estep(const double* X, int64_t n, double* gamma, int64_t ld
     EmArgs a{};
     a.X = X; a.N = n; a.d = g.d; a.K = g.K; a.K8 = g.K8; a.S = g.S;
     a.pack2 = dPack2_; a.shift = dShift_; a.gamma = gamma; a.ldg = ldg; a.labels = labels; a.raw = raw ? 1 : 0; a.partA = dPartA_;
+    a.hard = hard ? 1 : 0;
     const int bgrid = (int)std::max<int64_t>(1, std::min<int64_t>(sms_, (n + estep_big_tile() - 1) / estep_big_tile()));
     CKE(launch_estep_big(g, a, bgrid, smem_limit_, st_), "estep (large shape)");
     ++launches_;
@@ -327,7 +328,7 @@ int EmgmmEngine::run_estep(const double* X, int64_t n, double* gamma, int64_t ld
     a.pack2 = dPack2_; a.shift = dShift_; a.muold = dMuOld_; a.tlo = nullptr; a.thi = nullptr;
     a.gamma = gamma; a.ldg = ldg; a.labels = labels; a.raw = raw ? 1 : 0;
     a.partA = dPartA_; a.partB = nullptr; a.amb = nullptr; a.amb_cap = 0; a.amb_count = nullptr;
-    a.accumulate = 0; a.p_offset = 0;
+    a.accumulate = 0; a.p_offset = 0; a.hard = hard ? 1 : 0;
     CKE(launch_em(g, fgeom_, a, false, grid, smem_limit_, st_), "em sweep (E-pass)");
   }
   ++launches_;
@@ -787,11 +788,21 @@ int EmgmmEngine::kmeans_init(int nkm, uint64_t seed) {
   std::vector<double> cnt((size_t)K);
   for (int it = 1; it < nkm && rc == 0; ++it) {
     // mlf_EvaluateClass + EvaluateCentres
-    if (launch_kmeans_assign(dX_, n_, d, K, dMu_, nullptr, nullptr, dPartA_, grid, st_) != cudaSuccess) { rc = -7; break; }
-    if (launch_reduce_partials(dPartA_, grid, (int64_t)K * (d + 1), dStatsA_, st_) != cudaSuccess) { rc = -7; break; }
-    launches_ += 2;
-    if ((rc = allreduce(dStatsA_, (int64_t)K * (d + 1)))) break;
-    if (launch_kmeans_centres(dStatsA_, K, d, dMu_, dCnt, st_) != cudaSuccess) { rc = -7; break; }
+    if (legacy_estep_) {
+      if (launch_kmeans_assign(dX_, n_, d, K, dMu_, nullptr, nullptr, dPartA_, grid, st_) != cudaSuccess) { rc = -7; break; }
+      if (launch_reduce_partials(dPartA_, grid, (int64_t)K * (d + 1), dStatsA_, st_) != cudaSuccess) { rc = -7; break; }
+      launches_ += 2;
+      if ((rc = allreduce(dStatsA_, (int64_t)K * (d + 1)))) break;
+      if (launch_kmeans_centres(dStatsA_, K, d, dMu_, dCnt, st_) != cudaSuccess) { rc = -7; break; }
+    } else {
+      // assignment through the E-pass kernel in hard mode: distances as DMMA tiles, one-hot labels, and the cluster
+      // counts / coordinate sums from the same fixed-order pass-A statistics as EM (deterministic, no atomics)
+      if (launch_pack_kmeans(g, fgeom_, dMu_, dShift_, dPack2_, st_) != cudaSuccess) { rc = -7; break; }
+      ++launches_;
+      if ((rc = run_estep(dX_, n_, nullptr, ldg_, nullptr, true, false, true))) break;
+      if ((rc = allreduce(dStatsA_, (int64_t)g.K8 * 8 * g.DS))) break;
+      if (launch_kmeans_centres_a(g, dStatsA_, dMu_, dCnt, st_) != cudaSuccess) { rc = -7; break; }
+    }
     ++launches_;
     if (cudaMemcpyAsync(cnt.data(), dCnt, K * sizeof(double), cudaMemcpyDeviceToHost, st_) != cudaSuccess ||
         cudaStreamSynchronize(st_) != cudaSuccess) { rc = -7; break; }

@@ -82,7 +82,8 @@ class EmgmmEngine {
  private:
   int fail(const char* what, cudaError_t e);
   int ensure_moments();
-  int run_estep(const double* X, int64_t n, double* gamma, int64_t ldg, int32_t* labels, bool want_stats, bool raw = false);
+  int run_estep(const double* X, int64_t n, double* gamma, int64_t ldg, int32_t* labels, bool want_stats, bool raw = false,
+                bool hard = false);
   int allreduce(double* buf, int64_t count);
   int iterate_fused(int64_t niter, double minProba, bool prof);
   int iterate_two_pass(int64_t niter, double minProba, bool prof);

@@ -270,44 +270,62 @@ __global__ void __launch_bounds__(kEstepThreads, 1) k_em(EmArgs A) {
       am[grp] = a;
       sum[grp] = 0;
     }
-    if constexpr (GPW == 2) {
-#pragma unroll 2
-      for (int k4 = 0; k4 < K4; k4 += 2) {   // K4 is even; 4 independent exp chains per trip, 2 trips unrolled
-        const double a00 = row[0][4 * k4 + t] - mx[0], a01 = row[0][4 * k4 + 4 + t] - mx[0];
-        const double a10 = row[1][4 * k4 + t] - mx[1], a11 = row[1][4 * k4 + 4 + t] - mx[1];
-        const double e00 = exp_bf(a00), e01 = exp_bf(a01), e10 = exp_bf(a10), e11 = exp_bf(a11);
-        row[0][4 * k4 + t] = e00; row[0][4 * k4 + 4 + t] = e01;
-        row[1][4 * k4 + t] = e10; row[1][4 * k4 + 4 + t] = e11;
-        sum[0] += e00; sum[0] += e01;
-        sum[1] += e10; sum[1] += e11;
-      }
-    } else {
-#pragma unroll 2
-      for (int k4 = 0; k4 < K4; k4 += 2) {   // one group per warp: 2 chains per trip, 2 trips unrolled
-        const double a0 = row[0][4 * k4 + t] - mx[0], a1 = row[0][4 * k4 + 4 + t] - mx[0];
-        const double e0 = exp_bf(a0), e1 = exp_bf(a1);
-        row[0][4 * k4 + t] = e0; row[0][4 * k4 + 4 + t] = e1;
-        sum[0] += e0; sum[0] += e1;
+    bool hard_done = false;
+    if constexpr (!SCATTER) {
+      if (A.hard) {
+        // k-means assignment (mlf_EvaluateClass, src/unsupervised/mlf_kmeans.f90:151-165): with L = I and equal constants
+        // the largest logit is the nearest centre (first minimum wins); responsibilities are the one-hot labels, so the
+        // pass-A statistics below are the cluster counts and coordinate sums of EvaluateCentres (mlf_kmeans_naive.f90:74-96)
+#pragma unroll
+        for (int grp = 0; grp < GPW; ++grp) {
+          const int64_t p = p0 + 8 * grp + g;
+          const bool valid = p < N;
+          for (int k4 = 0; k4 < K4; ++k4) row[grp][4 * k4 + t] = (valid && 4 * k4 + t == am[grp]) ? 1.0 : 0.0;
+          if (A.labels != nullptr && valid && t == 0) A.labels[p] = am[grp] + 1;
+        }
+        hard_done = true;
       }
     }
-#pragma unroll
-    for (int grp = 0; grp < GPW; ++grp) {
-      sum[grp] += shx(sum[grp], 1);
-      sum[grp] += shx(sum[grp], 2);
-      const bool v = (p0 + 8 * grp + g) < N;
-      inv[grp] = v ? (A.raw ? 1.0 : 1.0 / sum[grp]) : 0.0;
-    }
-#pragma unroll
-    for (int grp = 0; grp < GPW; ++grp) {
-      const int64_t p = p0 + 8 * grp + g;
-      const bool valid = p < N;
-      for (int k4 = 0; k4 < K4; ++k4) {
-        const int k = 4 * k4 + t;
-        const double gk = row[grp][k] * inv[grp];
-        row[grp][k] = gk;
-        if (A.gamma != nullptr && valid && k < K) A.gamma[(size_t)k * A.ldg + p] = gk;
+    if (!hard_done) {
+      if constexpr (GPW == 2) {
+  #pragma unroll 2
+        for (int k4 = 0; k4 < K4; k4 += 2) {   // K4 is even; 4 independent exp chains per trip, 2 trips unrolled
+          const double a00 = row[0][4 * k4 + t] - mx[0], a01 = row[0][4 * k4 + 4 + t] - mx[0];
+          const double a10 = row[1][4 * k4 + t] - mx[1], a11 = row[1][4 * k4 + 4 + t] - mx[1];
+          const double e00 = exp_bf(a00), e01 = exp_bf(a01), e10 = exp_bf(a10), e11 = exp_bf(a11);
+          row[0][4 * k4 + t] = e00; row[0][4 * k4 + 4 + t] = e01;
+          row[1][4 * k4 + t] = e10; row[1][4 * k4 + 4 + t] = e11;
+          sum[0] += e00; sum[0] += e01;
+          sum[1] += e10; sum[1] += e11;
+        }
+      } else {
+  #pragma unroll 2
+        for (int k4 = 0; k4 < K4; k4 += 2) {   // one group per warp: 2 chains per trip, 2 trips unrolled
+          const double a0 = row[0][4 * k4 + t] - mx[0], a1 = row[0][4 * k4 + 4 + t] - mx[0];
+          const double e0 = exp_bf(a0), e1 = exp_bf(a1);
+          row[0][4 * k4 + t] = e0; row[0][4 * k4 + 4 + t] = e1;
+          sum[0] += e0; sum[0] += e1;
+        }
       }
-      if (A.labels != nullptr && valid && t == 0) A.labels[p] = am[grp] + 1;  // MAXLOC: first maximum, 1-based
+  #pragma unroll
+      for (int grp = 0; grp < GPW; ++grp) {
+        sum[grp] += shx(sum[grp], 1);
+        sum[grp] += shx(sum[grp], 2);
+        const bool v = (p0 + 8 * grp + g) < N;
+        inv[grp] = v ? (A.raw ? 1.0 : 1.0 / sum[grp]) : 0.0;
+      }
+  #pragma unroll
+      for (int grp = 0; grp < GPW; ++grp) {
+        const int64_t p = p0 + 8 * grp + g;
+        const bool valid = p < N;
+        for (int k4 = 0; k4 < K4; ++k4) {
+          const int k = 4 * k4 + t;
+          const double gk = row[grp][k] * inv[grp];
+          row[grp][k] = gk;
+          if (A.gamma != nullptr && valid && k < K) A.gamma[(size_t)k * A.ldg + p] = gk;
+        }
+        if (A.labels != nullptr && valid && t == 0) A.labels[p] = am[grp] + 1;  // MAXLOC: first maximum, 1-based
+      }
     }
     __syncthreads();
     // ---- P3: statistics of the block tile; warp w owns component blocks w, w+8, ... ------------------------------

@@ -1026,6 +1026,33 @@ cudaError_t launch_seed_pick(const double* X, int d, const double* minDist, int6
   return cudaGetLastError();
 }
 
+// Pack of the k-means assignment for the E-pass kernels (hard mode): identity factor in fragment order (or its diagonal for
+// the compressed layout), accumulator bias -(centre - shift), constant 0; empty / dummy components get -inf.
+__global__ void k_pack_kmeans(Geom g, int PSF, int OFFB, int OFFC, int diag, const double* __restrict__ Mu,
+                              const double* __restrict__ shift, double* __restrict__ pack2) {
+  const int k = blockIdx.x, d = g.d;
+  double* p2 = pack2 + (size_t)k * PSF;
+  const bool live = k < g.K && isfinite(Mu[(size_t)(k < g.K ? k : 0) * d]);
+  if (diag) {
+    for (int n = threadIdx.x; n < 8 * g.DN; n += blockDim.x) p2[n] = (live && n < d) ? 1.0 : 0.0;
+  } else {
+    for (int i = threadIdx.x; i < g.NB * 32; i += blockDim.x) {
+      const int blk = i >> 5, l = i & 31;
+      int mb = 0;
+      while (blk_off(mb + 1) <= blk) ++mb;
+      const int nb = blk - blk_off(mb);
+      const int m = 4 * mb + (l & 3), n = 8 * nb + (l >> 2);
+      p2[i] = (live && m == n && m < d) ? 1.0 : 0.0;
+    }
+  }
+  for (int n = threadIdx.x; n < 8 * g.DN; n += blockDim.x) p2[OFFB + n] = (live && n < d) ? -(Mu[(size_t)k * d + n] - shift[n]) : 0.0;
+  if (threadIdx.x == 0) { p2[OFFC] = live ? 0.0 : -INFINITY; p2[OFFC + 1] = 0; p2[OFFC + 2] = 0; p2[OFFC + 3] = 0; }
+}
+cudaError_t launch_pack_kmeans(const Geom& g, const FusedGeom& f, const double* Mu, const double* shift, double* pack2, cudaStream_t st) {
+  k_pack_kmeans<<<g.K8 * 8, 128, 0, st>>>(g, f.PSF, f.OFFB, f.OFFC, f.diag ? 1 : 0, Mu, shift, pack2);
+  return cudaGetLastError();
+}
+
 // EvaluateCentres (src/unsupervised/mlf_kmeans_naive.f90:74-96): Mu_k = sum_k / n_k; empty clusters are flagged
 // (count 0) and given an infinite centre so that they attract no point until re-seeded by the host logic.
 __global__ void k_kmeans_centres(const double* __restrict__ sums, int K, int d, double* __restrict__ Mu,
@@ -1034,6 +1061,18 @@ __global__ void k_kmeans_centres(const double* __restrict__ sums, int K, int d, 
   const double n = sums[(size_t)k * (d + 1) + d];
   for (int a = threadIdx.x; a < d; a += blockDim.x) Mu[(size_t)k * d + a] = n > 0 ? sums[(size_t)k * (d + 1) + a] / n : INFINITY;
   if (threadIdx.x == 0) counts[k] = n;
+}
+// Same, reading the pass-A statistics layout of the E-pass kernels ([count, sum g^2, sums...] per component, stride DS).
+__global__ void k_kmeans_centres_a(const double* __restrict__ statsA, int DS, int K, int d, double* __restrict__ Mu,
+                                   double* __restrict__ counts) {
+  const int k = blockIdx.x;
+  const double n = statsA[(size_t)k * DS];
+  for (int a = threadIdx.x; a < d; a += blockDim.x) Mu[(size_t)k * d + a] = n > 0 ? statsA[(size_t)k * DS + 2 + a] / n : INFINITY;
+  if (threadIdx.x == 0) counts[k] = n;
+}
+cudaError_t launch_kmeans_centres_a(const Geom& g, const double* statsA, double* Mu, double* counts, cudaStream_t st) {
+  k_kmeans_centres_a<<<g.K, 32, 0, st>>>(statsA, g.DS, g.K, g.d, Mu, counts);
+  return cudaGetLastError();
 }
 cudaError_t launch_kmeans_centres(const double* sums, int K, int d, double* Mu, double* counts, cudaStream_t st) {
   k_kmeans_centres<<<K, 32, 0, st>>>(sums, K, d, Mu, counts);

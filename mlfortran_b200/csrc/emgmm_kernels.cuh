@@ -56,6 +56,7 @@ struct EmArgs {
   AmbEntry* amb; int amb_cap; int* amb_count;   // [grid*8][amb_cap], [grid*8]
   int accumulate;        // start from the partials / list counts already stored (chunked sweep of a streamed X)
   long long p_offset;    // index of X[0] inside the rank's shard (side-list keys)
+  int hard;              // k-means assignment: one-hot responsibilities of the largest logit (E-pass variants only)
 };
 
 constexpr int kEstepThreads = 256;      // 8 warps per persistent block
@@ -144,6 +145,9 @@ cudaError_t launch_seed_update(const double* X, int64_t N, int d, const double* 
 cudaError_t launch_seed_pick(const double* X, int d, const double* minDist, int64_t lo, int64_t hi, double target,
                              double* out, cudaStream_t st);
 cudaError_t launch_kmeans_centres(const double* sums, int K, int d, double* Mu, double* counts, cudaStream_t st);
+cudaError_t launch_kmeans_centres_a(const Geom& g, const double* statsA, double* Mu, double* counts, cudaStream_t st);
 cudaError_t launch_identity_cov(int K, int d, double* Cov, double* lambda, cudaStream_t st);
+// Pack for the k-means assignment through the E-pass kernels: L = I, bias = -(centre - shift), constant 0.
+cudaError_t launch_pack_kmeans(const Geom& g, const FusedGeom& f, const double* Mu, const double* shift, double* pack2, cudaStream_t st);
 
 }  // namespace mlfb200
