@@ -95,6 +95,10 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
     legacy_estep_ = true;  // fused pack does not fit: first-generation E-pass
   }
   fused_ = !big_ && !legacy_estep_ && fgeom_.scatter_ok;
+  {
+    const char* e16 = getenv("MLF_B200_EM16");
+    use16_ = fused_ && em16_ok(geom_, fgeom_, smem_limit_) && !(e16 && e16[0] == '0');
+  }
   n_ = n_local;
   nglob_ = n_local;
   ldg_ = ((n_ + 31) / 32) * 32;
@@ -129,10 +133,11 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   CKE(A(&dPrevCov_, (size_t)K * d * d), "cudaMalloc");
   CKE(A(&dPrevLambda_, K), "cudaMalloc");
   if (fused_) {
-    CKE(A(&dPartB2_, (size_t)sms_ * KP * fgeom_.MSF), "cudaMalloc");
-    CKE(cudaMalloc((void**)&dAmb_, (size_t)sms_ * (kEstepThreads / 32) * amb_cap_ * sizeof(AmbEntry)), "cudaMalloc side list");
-    CKE(cudaMalloc((void**)&dAmbCount_, (size_t)sms_ * (kEstepThreads / 32) * sizeof(int)), "cudaMalloc");
-    CKE(cudaMemsetAsync(dAmbCount_, 0, (size_t)sms_ * (kEstepThreads / 32) * sizeof(int), st_), "memset");
+    // the 16-warp variant writes partials per (block, half) and keeps one side list per warp
+    CKE(A(&dPartB2_, (size_t)2 * sms_ * KP * fgeom_.MSF), "cudaMalloc");
+    CKE(cudaMalloc((void**)&dAmb_, (size_t)sms_ * 16 * amb_cap_ * sizeof(AmbEntry)), "cudaMalloc side list");
+    CKE(cudaMalloc((void**)&dAmbCount_, (size_t)sms_ * 16 * sizeof(int)), "cudaMalloc");
+    CKE(cudaMemsetAsync(dAmbCount_, 0, (size_t)sms_ * 16 * sizeof(int), st_), "memset");
   }
   CKE(A(&dMu_, (size_t)K * d), "cudaMalloc");
   CKE(A(&dCov_, (size_t)K * d * d), "cudaMalloc");
@@ -144,7 +149,7 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   CKE(A(&dSumLLk_, KP), "cudaMalloc");
   CKE(A(&dStatsA_, (size_t)KP * g.DS), "cudaMalloc");
   CKE(A(&dStatsB_, (size_t)K * g.MS), "cudaMalloc");
-  CKE(A(&dPartA_, (size_t)sms_ * KP * g.DS), "cudaMalloc");
+  CKE(A(&dPartA_, (size_t)2 * sms_ * KP * g.DS), "cudaMalloc");
   CKE(A(&dPartB_, (size_t)(2 * sms_ + K + 2) * g.MS), "cudaMalloc");
   CKE(A(&dSc_, (size_t)d * d), "cudaMalloc");
   CKE(A(&dMean_, (size_t)8 * g.DN + 8), "cudaMalloc");
@@ -419,14 +424,14 @@ int EmgmmEngine::streamed_sweep(const EmArgs& base) {
   const FusedGeom& f = fgeom_;
   const int d = g.d, KP = g.K8 * 8;
   const int PM = g.MB * 64 + 8 * g.DN;
-  const int nlists = sms_ * (kEstepThreads / 32);
+  const int nlists = sms_ * 16;
   while ((int)cev_.size() < kStreamChunks + 1) {
     cudaEvent_t e;
     CKE(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
     cev_.push_back(e);
   }
-  CKE(cudaMemsetAsync(dPartA_, 0, (size_t)sms_ * KP * g.DS * sizeof(double), st_), "memset");
-  CKE(cudaMemsetAsync(dPartB2_, 0, (size_t)sms_ * KP * f.MSF * sizeof(double), st_), "memset");
+  CKE(cudaMemsetAsync(dPartA_, 0, (size_t)2 * sms_ * KP * g.DS * sizeof(double), st_), "memset");
+  CKE(cudaMemsetAsync(dPartB2_, 0, (size_t)2 * sms_ * KP * f.MSF * sizeof(double), st_), "memset");
   CKE(cudaMemsetAsync(dAmbCount_, 0, (size_t)nlists * sizeof(int), st_), "memset");
   CKE(cudaMemsetAsync(dMomPart_, 0, (size_t)sms_ * PM * sizeof(double), st_), "memset");
   // the copy may not overwrite X before everything queued so far (earlier sweeps) has read it
@@ -448,7 +453,8 @@ int EmgmmEngine::streamed_sweep(const EmArgs& base) {
     a.N = n;
     a.accumulate = 1;
     a.p_offset = off;
-    CKE(launch_em(g, f, a, true, grid, smem_limit_, st_), "em sweep (streamed chunk)");
+    if (use16_) CKE(launch_em16(g, f, a, grid, smem_limit_, st_), "em sweep (streamed chunk, 16 warps)");
+    else CKE(launch_em(g, f, a, true, grid, smem_limit_, st_), "em sweep (streamed chunk)");
     launches_ += 2;
   }
   pending_host_ = nullptr;
@@ -463,7 +469,8 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
   const Geom& g = geom_;
   const FusedGeom& f = fgeom_;
   const int K = g.K, KP = g.K8 * 8, d = g.d;
-  const int nlists = egrid_ * (kEstepThreads / 32);
+  const int nlists = egrid_ * (use16_ ? 16 : kEstepThreads / 32);
+  const int nslots = use16_ ? 2 * egrid_ : egrid_;
   const int64_t nA = (int64_t)KP * g.DS, nB = (int64_t)KP * f.MSF;
   const double minW = 1e-3 / (double)(float)nglob_;  // 1d-3/real(NX)  (src/unsupervised/mlf_gaussian.f90:50)
   double* dFlags = dAB_ + nA + nB;                    // [listed pairs, overflowing lists] ride in the same all-reduce
@@ -520,11 +527,12 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
         CKE(launch_sum_k(dSumLLk_, K, dSumLL_ + it, st_), "sum_k");
         launches_ += 2;
       } else {
-        CKE(launch_em(g, f, a, true, egrid_, smem_limit_, st_), "em sweep (fused)");
+        if (use16_) CKE(launch_em16(g, f, a, egrid_, smem_limit_, st_), "em sweep (fused, 16 warps)");
+        else CKE(launch_em(g, f, a, true, egrid_, smem_limit_, st_), "em sweep (fused)");
         ++launches_;
       }
-      CKE(launch_reduce_partials(dPartA_, egrid_, nA, dAB_, st_), "reduce statsA");
-      CKE(launch_reduce_partials(dPartB2_, egrid_, nB, dAB_ + nA, st_), "reduce statsB");
+      CKE(launch_reduce_partials(dPartA_, nslots, nA, dAB_, st_), "reduce statsA");
+      CKE(launch_reduce_partials(dPartB2_, nslots, nB, dAB_ + nA, st_), "reduce statsB");
       CKE(launch_amb_summary(dAmbCount_, nlists, amb_cap_, dFlags, st_), "amb summary");
       launches_ += 3;
       times_.sweeps += 1;

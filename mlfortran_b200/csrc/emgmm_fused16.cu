@@ -1,0 +1,370 @@
+// 16-warp variant of the fused single-sweep EM kernel (see emgmm_fused.cu for the algorithm and the threshold protocol).
+//
+// Why a second variant: the 8-warp kernel keeps the covariance-scatter accumulators (8 components x 3 blocks x 2 doubles
+// = 96 registers per thread) alive across the whole tile loop, which pins it at 255 registers and two warps per
+// scheduler; its softmax and statistics phases are latency-bound at that occupancy (profiles/ncu_r01*).  Here the
+// scatter accumulators live in TENSOR MEMORY (TMEM, 256 KB per SM, otherwise unused by an fp64 kernel -- tcgen05 has no
+// f64 MMA): each warp parks its 4 components x MB blocks in its own TMEM lane quarter and pulls one component at a time
+// into registers with tcgen05.ld while it walks that component's kept groups, then puts it back with tcgen05.st.
+// That frees the registers for 16 warps per SM (<= 128 registers each, four warps per scheduler):
+//   warp w:  P1/P2 on its own 8 points of the 128-point tile;
+//            P3a pass-A statistics of component block (w & 7) over the 4-point groups of half (w >> 3) of the tile;
+//            P3b covariance scatter of components 8*(w & 7) + 4*(w >> 3) + {0..3} over the whole tile.
+// Per-block partials are written per half: slot = 2*blockIdx.x + (w >> 3).
+#include "emgmm_kernels.cuh"
+
+#include <cmath>
+
+namespace mlfb200 {
+
+namespace {
+
+__host__ __device__ constexpr int g_blk_off(int mb) {
+  int s = 0;
+  for (int m = 0; m < mb; ++m) s += m / 2 + 1;
+  return s;
+}
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ double exp_bf(double a) {  // see emgmm_fused.cu
+  a = (a < -750.0) ? -750.0 : a;
+  a = (a > 710.0) ? 710.0 : a;
+  const double magic = 6755399441055744.0;
+  double t = fma(a, 1.4426950408889634074, magic);
+  const int n = __double2loint(t);
+  t -= magic;
+  double r = fma(t, -6.93147180369123816490e-01, a);
+  r = fma(t, -1.90821492927058770002e-10, r);
+  double p = 1.6059043836821614599e-10;
+  p = fma(p, r, 2.0876756987868098979e-09);
+  p = fma(p, r, 2.5052108385441718775e-08);
+  p = fma(p, r, 2.7557319223985890653e-07);
+  p = fma(p, r, 2.7557319223985892510e-06);
+  p = fma(p, r, 2.4801587301587301566e-05);
+  p = fma(p, r, 1.9841269841269841253e-04);
+  p = fma(p, r, 1.3888888888888889419e-03);
+  p = fma(p, r, 8.3333333333333332177e-03);
+  p = fma(p, r, 4.1666666666666664354e-02);
+  p = fma(p, r, 1.6666666666666665741e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const int n1 = n >> 1, n2 = n - n1;
+  return (p * __hiloint2double((n1 + 1023) << 20, 0)) * __hiloint2double((n2 + 1023) << 20, 0);
+}
+
+// ---- tensor memory as per-warp scratch: lane quarter (warp & 3), 4 consecutive 32-bit columns = two doubles ----------
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, double v0, double v1) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(__double2loint(v0)),
+               "r"(__double2hiint(v0)), "r"(__double2loint(v1)), "r"(__double2hiint(v1))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, double& v0, double& v1) {
+  int a, b, c, d;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+  v0 = __hiloint2double(b, a);
+  v1 = __hiloint2double(d, c);
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
+constexpr int kThreads16 = 512;
+constexpr int kTmemCols = 256;  // 4 warps per lane quarter x 4 components x 16 columns (MB <= 3 blocks x 4 columns, padded)
+
+}  // namespace
+
+size_t em16_smem_bytes(const Geom& g, const FusedGeom& f) { return f.smem + 8 * 32 + 16; }
+bool em16_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
+  return f.GPW == 2 && !f.diag && g.DN <= 2 && g.K8 <= 8 && f.scatter_ok && em16_smem_bytes(g, f) <= smem_limit;
+}
+
+template <int DM>
+__global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
+  constexpr int DN = (DM + 1) / 2;
+  constexpr int NB = g_blk_off(DM);
+  constexpr int OFFB = NB * 32, OFFC = OFFB + 8 * DN, PSF = OFFC + 4;
+  constexpr int XS = 8 * DN + 4;
+  constexpr int MB = DN * (DN + 1) / 2;
+  constexpr int DS = 8 * DN + 2;
+  constexpr int MSF = MB * 64 + 8 * DN + 2;
+  constexpr int TP = 128;
+  extern __shared__ __align__(16) double smem[];
+  const int K8 = A.K8, KP = K8 * 8, K4 = 2 * K8, S = A.S, d = A.d;
+  const int64_t N = A.N;
+  double* sp = smem;                                  // [KP][PSF]
+  double* smu = sp + (size_t)KP * PSF;                // [KP][8 DN]
+  double* xs = smu + (size_t)KP * 8 * DN;             // [128][XS]
+  double* tile = xs + (size_t)TP * XS;                // [128][S]
+  unsigned char* sact = reinterpret_cast<unsigned char*>(tile + (size_t)TP * S);  // [8][32] kept-group flags
+  uint32_t* s_taddr = reinterpret_cast<uint32_t*>(sact + 8 * 32);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int cb = warp & 7, half = warp >> 3;
+  const bool own = cb < K8;
+
+  for (int i = tid; i < KP * PSF; i += kThreads16) sp[i] = A.pack2[i];
+  for (int i = tid; i < KP * 8 * DN; i += kThreads16) smu[i] = A.muold[i];
+  double sh[DM];
+#pragma unroll
+  for (int mb = 0; mb < DM; ++mb) sh[mb] = A.shift[4 * mb + t];
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(s_taddr)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  // this warp's TMEM region: lane quarter (warp & 3), 64 columns starting at 64*(warp >> 2); component j at +16*j, block b at +4*b
+  const uint32_t tbase = *s_taddr + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * (warp >> 2));
+
+  const bool accu = A.accumulate != 0;
+  const int slot = 2 * blockIdx.x + half;
+  double* outA = A.partA + (size_t)slot * KP * DS;
+  double* outB = A.partB + (size_t)slot * KP * MSF;
+  double accA[DN][2], accK[DN][2], sg, sg2, sk, thi_r, tlo_r;
+  {
+    const bool ld = accu && own;
+    const double* o = outA + (size_t)(8 * cb + g) * DS;
+    const double* ok = outB + (size_t)(8 * cb + g) * MSF + MB * 64;
+    sg = (ld && t == 0) ? o[0] : 0.0;
+    sg2 = (ld && t == 0) ? o[1] : 0.0;
+    sk = (ld && t == 0) ? ok[8 * DN] : 0.0;
+    thi_r = own ? A.thi[8 * cb + g] : INFINITY;
+    tlo_r = own ? A.tlo[8 * cb + g] : INFINITY;
+#pragma unroll
+    for (int b = 0; b < DN; ++b) {
+      accA[b][0] = ld ? o[2 + 8 * b + 2 * t] : 0.0;
+      accA[b][1] = ld ? o[2 + 8 * b + 2 * t + 1] : 0.0;
+      accK[b][0] = ld ? ok[8 * b + 2 * t] : 0.0;
+      accK[b][1] = ld ? ok[8 * b + 2 * t + 1] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double* oq = outB + (size_t)(8 * cb + 4 * half + j) * MSF;
+#pragma unroll
+      for (int b = 0; b < MB; ++b)
+        tmem_st2(tbase + 16 * j + 4 * b, ld ? oq[b * 64 + g * 8 + 2 * t] : 0.0, ld ? oq[b * 64 + g * 8 + 2 * t + 1] : 0.0);
+    }
+    tmem_wait_st();
+  }
+  const int nlist = blockIdx.x * 16 + warp;
+  int nAmb = accu ? A.amb_count[nlist] : 0;
+  AmbEntry* ambw = A.amb + (size_t)nlist * A.amb_cap;
+
+  const int64_t ntiles = (N + TP - 1) / TP;
+  for (int64_t bt = blockIdx.x; bt < ntiles; bt += gridDim.x) {
+    const int64_t p = bt * TP + warp * 8 + g;
+    // ---- P1: logits of this warp's 8 points against every component ---------------------------------------------
+    double xa[DM];
+    {
+      double* xr = xs + (size_t)(warp * 8 + g) * XS;
+#pragma unroll
+      for (int mb = 0; mb < DM; ++mb) {
+        const int a = 4 * mb + t;
+        const double x = (p < N && a < d) ? A.X[p * d + a] : 0.0;
+        xr[a] = x;
+        xa[mb] = x - sh[mb];
+      }
+      if (8 * DN > 4 * DM) xr[4 * DM + t] = 0.0;
+    }
+    double* row = tile + (size_t)(warp * 8 + g) * S;
+    double rmax = -INFINITY;
+    for (int k4 = 0; k4 < K4; ++k4) {
+      double part[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double* pk = sp + (size_t)(4 * k4 + j) * PSF;
+        double c[DN][2];
+#pragma unroll
+        for (int nb = 0; nb < DN; ++nb) {
+          const double2 v = *reinterpret_cast<const double2*>(pk + OFFB + 8 * nb + 2 * t);
+          c[nb][0] = v.x; c[nb][1] = v.y;
+        }
+#pragma unroll
+        for (int mb = 0; mb < DM; ++mb)
+#pragma unroll
+          for (int nb = 0; nb <= mb / 2; ++nb) dmma(c[nb], xa[mb], pk[(g_blk_off(mb) + nb) * 32 + lane]);
+        double s = c[0][0] * c[0][0];
+        s = fma(c[0][1], c[0][1], s);
+#pragma unroll
+        for (int nb = 1; nb < DN; ++nb) { s = fma(c[nb][0], c[nb][0], s); s = fma(c[nb][1], c[nb][1], s); }
+        part[j] = s;
+      }
+      const double ck = sp[(size_t)(4 * k4 + t) * PSF + OFFC];
+      // transposed reduction over the quad: lane t ends with the full |u|^2 of component 4*k4+t
+      const bool hi2 = (t & 2) != 0, hi1 = (t & 1) != 0;
+      const double send0 = hi2 ? part[0] : part[2], send1 = hi2 ? part[1] : part[3];
+      const double keep0 = hi2 ? part[2] : part[0], keep1 = hi2 ? part[3] : part[1];
+      const double a0 = keep0 + shx(send0, 2), a1 = keep1 + shx(send1, 2);
+      const double maha = (hi1 ? a1 : a0) + shx(hi1 ? a0 : a1, 1);
+      const double logit = fma(-0.5, maha, ck);
+      row[4 * k4 + t] = logit;
+      rmax = fmax(rmax, logit);
+    }
+    // ---- P2: log-sum-exp over the components ---------------------------------------------------------------------
+    rmax = fmax(rmax, shx(rmax, 1));
+    rmax = fmax(rmax, shx(rmax, 2));
+    double sum = 0;
+#pragma unroll 2
+    for (int k4 = 0; k4 < K4; k4 += 2) {
+      const double e0 = exp_bf(row[4 * k4 + t] - rmax), e1 = exp_bf(row[4 * k4 + 4 + t] - rmax);
+      row[4 * k4 + t] = e0; row[4 * k4 + 4 + t] = e1;
+      sum += e0; sum += e1;
+    }
+    sum += shx(sum, 1);
+    sum += shx(sum, 2);
+    const double inv = (p < N) ? 1.0 / sum : 0.0;
+    for (int k4 = 0; k4 < K4; ++k4) row[4 * k4 + t] *= inv;
+    __syncthreads();
+    // ---- P3a: pass-A statistics of component block cb over this half's 4-point groups; kept-group flags -----------
+    if (own) {
+      const int64_t q0 = bt * TP;
+      const double* tcol = tile + 8 * cb + g;
+      unsigned act = 0;
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int pb = 16 * half + i;
+        const double a = tcol[(size_t)(4 * pb + t) * S];
+        double b[DN];
+#pragma unroll
+        for (int db = 0; db < DN; ++db) b[db] = xs[(size_t)(4 * pb + t) * XS + 8 * db + g];
+        sg += a;
+        sg2 = fma(a, a, sg2);
+#pragma unroll
+        for (int db = 0; db < DN; ++db) dmma(accA[db], a, b[db]);
+        // "If(W(i) < minW0) CYCLE" (src/mlf_matrix.f90:135); g == 0 adds nothing and is never listed
+        const bool hi = !(a < thi_r) && a != 0.0;
+        const bool mid = !hi && !(a < tlo_r) && a != 0.0;
+        const double ahi = hi ? a : 0.0;
+        sk += ahi;
+        const unsigned mh = __ballot_sync(kFull, hi);
+        const unsigned mm = __ballot_sync(kFull, mid);
+        if (mh) {
+#pragma unroll
+          for (int db = 0; db < DN; ++db) dmma(accK[db], ahi, b[db]);
+          unsigned cm = mh | (mh >> 1);
+          cm |= cm >> 2;
+          cm &= 0x11111111u;
+          cm = (cm | (cm >> 3)) & 0x03030303u;
+          cm = (cm | (cm >> 6)) & 0x000f000fu;
+          cm = (cm | (cm >> 12)) & 0xffu;
+          if (lane == i) act = cm;
+        }
+        if (mm) {
+          const int sl = nAmb + __popc(mm & ((1u << lane) - 1u));
+          if (mid && sl < A.amb_cap) {
+            AmbEntry e;
+            e.g = a;
+            e.key = (long long)(A.p_offset + q0 + 4 * pb + t) * 1024 + (8 * cb + g);
+            ambw[sl] = e;
+          }
+          nAmb += __popc(mm);
+        }
+      }
+      if (lane < 16) sact[cb * 32 + 16 * half + lane] = (unsigned char)act;
+    }
+    __syncthreads();
+    // ---- P3b: covariance scatter of this warp's 4 components over the kept groups of the whole tile ----------------
+    if (own) {
+      const unsigned flags = sact[cb * 32 + lane];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = 4 * half + j;
+        unsigned pm = __ballot_sync(kFull, (flags >> q) & 1u);
+        if (pm == 0) continue;
+        const double thq = __shfl_sync(kFull, thi_r, 4 * q);
+        const double* mq = smu + (size_t)(8 * cb + q) * 8 * DN;
+        double mu_q[DN];
+#pragma unroll
+        for (int ab = 0; ab < DN; ++ab) mu_q[ab] = mq[8 * ab + g];
+        const double* tq = tile + 8 * cb + q;
+        double acc[MB][2];
+#pragma unroll
+        for (int b = 0; b < MB; ++b) tmem_ld2(tbase + 16 * j + 4 * b, acc[b][0], acc[b][1]);
+        while (pm) {
+          const int pb = __ffs(pm) - 1;
+          pm &= pm - 1;
+          const double aq = tq[(size_t)(4 * pb + t) * S];
+          const double w = (!(aq < thq) && aq != 0.0) ? aq : 0.0;
+          double z[DN], wz[DN];
+#pragma unroll
+          for (int ab = 0; ab < DN; ++ab) {
+            z[ab] = xs[(size_t)(4 * pb + t) * XS + 8 * ab + g] - mu_q[ab];
+            wz[ab] = w * z[ab];
+          }
+#pragma unroll
+          for (int ab = 0; ab < DN; ++ab)
+#pragma unroll
+            for (int bb = 0; bb <= ab; ++bb) dmma(acc[ab * (ab + 1) / 2 + bb], wz[ab], z[bb]);
+        }
+#pragma unroll
+        for (int b = 0; b < MB; ++b) tmem_st2(tbase + 16 * j + 4 * b, acc[b][0], acc[b][1]);
+      }
+      tmem_wait_st();
+    }
+    __syncthreads();
+  }
+  // ---- per-(block, half) partials -------------------------------------------------------------------------------------
+  if (own) {
+    double a = sg, b = sg2, c = sk;
+    a += shx(a, 1); a += shx(a, 2);
+    b += shx(b, 1); b += shx(b, 2);
+    c += shx(c, 1); c += shx(c, 2);
+    double* o = outA + (size_t)(8 * cb + g) * DS;
+    double* ok = outB + (size_t)(8 * cb + g) * MSF + MB * 64;
+    if (t == 0) { o[0] = a; o[1] = b; ok[8 * DN] = c; ok[8 * DN + 1] = 0.0; }
+#pragma unroll
+    for (int db = 0; db < DN; ++db) {
+      o[2 + 8 * db + 2 * t] = accA[db][0];
+      o[2 + 8 * db + 2 * t + 1] = accA[db][1];
+      ok[8 * db + 2 * t] = accK[db][0];
+      ok[8 * db + 2 * t + 1] = accK[db][1];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double* oq = outB + (size_t)(8 * cb + 4 * half + j) * MSF;        // this half owns these scatter blocks
+      double* oz = outB + (size_t)(8 * cb + 4 * (1 - half) + j) * MSF;  // ... and contributes zero to the other half's
+#pragma unroll
+      for (int bq = 0; bq < MB; ++bq) {
+        double v0, v1;
+        tmem_ld2(tbase + 16 * j + 4 * bq, v0, v1);
+        oq[bq * 64 + g * 8 + 2 * t] = v0;
+        oq[bq * 64 + g * 8 + 2 * t + 1] = v1;
+        oz[bq * 64 + g * 8 + 2 * t] = 0.0;
+        oz[bq * 64 + g * 8 + 2 * t + 1] = 0.0;
+      }
+    }
+  }
+  if (lane == 0) A.amb_count[nlist] = nAmb;
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(*s_taddr), "n"(kTmemCols) : "memory");
+  }
+}
+
+cudaError_t launch_em16(const Geom& g, const FusedGeom& f, const EmArgs& a, int grid, size_t smem_limit, cudaStream_t st) {
+  if (!em16_ok(g, f, smem_limit)) return cudaErrorInvalidConfiguration;
+  const size_t smem = em16_smem_bytes(g, f);
+#define MLF_E16(DMv)                                                                                                   \
+  case DMv: {                                                                                                          \
+    cudaError_t e = cudaFuncSetAttribute(k_em16<DMv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+    if (e != cudaSuccess) return e;                                                                                    \
+    k_em16<DMv><<<grid, kThreads16, smem, st>>>(a);                                                                    \
+  } break;
+  switch (g.DM) {
+    MLF_E16(1) MLF_E16(2) MLF_E16(3) MLF_E16(4)
+    default: return cudaErrorInvalidConfiguration;
+  }
+#undef MLF_E16
+  return cudaGetLastError();
+}
+
+}  // namespace mlfb200

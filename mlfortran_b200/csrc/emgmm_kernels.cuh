@@ -80,6 +80,10 @@ cudaError_t launch_moments_finish(const Geom& g, const double* raw, const double
 
 // Fused sweep (scatter = true) or E-pass + pass-A statistics only (scatter = false); see emgmm_fused.cu.
 cudaError_t launch_em(const Geom& g, const FusedGeom& f, const EmArgs& a, bool scatter, int grid, size_t smem_limit, cudaStream_t st);
+// 16-warp variant with the scatter accumulators in tensor memory (emgmm_fused16.cu): partials per (block, half) -> 2*grid slots,
+// side lists per warp -> 16*grid lists.
+bool em16_ok(const Geom& g, const FusedGeom& f, size_t smem_limit);
+cudaError_t launch_em16(const Geom& g, const FusedGeom& f, const EmArgs& a, int grid, size_t smem_limit, cudaStream_t st);
 cudaError_t launch_amb_resolve(const Geom& g, const double* X, const AmbEntry* amb, int cap, const int* counts, int nlists,
                                const double* statsA, double minW, const double* muold, double* outC, cudaStream_t st);
 cudaError_t launch_amb_summary(const int* counts, int nlists, int cap, double* flags, cudaStream_t st);
