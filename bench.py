@@ -223,6 +223,7 @@ def main():
     clocks = sampler.stop(tw0, tw1) if sampler else None
     launches = em.launch_count() - l0
     times = em.times()
+    plan = em.kernel_plan()
     em.set_profile(False)
     sumll = em.sumLL
     value = N * K * args.steps / (ms * 1e-3)
@@ -258,8 +259,8 @@ def main():
     except Exception:
         pass
     roofline = {
-        "kernel": ("k_em<4,1,true> (fused sweep: whitening DMMA + log-sum-exp + pass-A statistics + thresholded covariance scatter)" if fused
-                   else "k_em/k_estep (E-pass: whitening DMMA + log-sum-exp + pass-A statistics)"), "bound": "tensor",
+        "kernel": plan + (" (whitening DMMA + log-sum-exp + pass-A statistics + thresholded covariance scatter)" if fused
+                          else " (roofline line = E-pass: whitening DMMA + log-sum-exp + pass-A statistics)"), "bound": "tensor",
         "sweeps_per_iteration": sweeps / it if fused else 1.0, "side_list_pairs": times.get("side_list_pairs", 0),
         "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None, "traffic": traffic,
         "peak_source": "fp64 DMMA (mma.sync m8n8k4.f64) measured on this pool by bench/micro/fp64_peaks.cu -> profiles/fp64_peaks_r01.json; "

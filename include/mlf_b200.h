@@ -102,6 +102,8 @@ int mlf_b200_set_seed(MLF_OBJ *obj, uint64_t seed);
 int mlf_b200_set_cov_type(MLF_OBJ *obj, int cov_type);
 int mlf_b200_refresh_x(MLF_OBJ *obj, const double *X);        /* re-copy X after the caller changed it */
 const char *mlf_b200_last_error(MLF_OBJ *obj);
+/* Which kernel generation this object's (d, K) runs through (object-owned string). */
+const char *mlf_b200_kernel_plan(MLF_OBJ *obj);
 /* sumLL of each EM iteration of the most recent mlf_step call (at most n values); returns how many exist. */
 int64_t mlf_b200_sumll_trace(MLF_OBJ *obj, double *out, int64_t n);
 /* Responsibilities (ProbaC(N,K), P[k*N+i]) and labels of the resident shard, as of the last E-pass. */

@@ -49,6 +49,7 @@ SYMBOLS = {
     "mlf_b200_set_cov_type": (C.c_int, [C.c_void_p, C.c_int]),
     "mlf_b200_refresh_x": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mlf_b200_last_error": (C.c_char_p, [C.c_void_p]),
+    "mlf_b200_kernel_plan": (C.c_char_p, [C.c_void_p]),
     "mlf_b200_sumll_trace": (C.c_int64, [C.c_void_p, c_double_p, C.c_int64]),
     "mlf_b200_resident_proba": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mlf_b200_resident_labels": (C.c_int, [C.c_void_p, C.c_void_p]),

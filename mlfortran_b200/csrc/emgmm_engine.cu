@@ -158,6 +158,23 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   return refresh_x(X, x_on_device);
 }
 
+std::string EmgmmEngine::plan() const {
+  char buf[256];
+  const Geom& g = geom_;
+  if (use16_)
+    snprintf(buf, sizeof buf, "k_em16<%d>: fused single sweep, 16 warps/SM, covariance-scatter accumulators in tensor memory", g.DM);
+  else if (fused_)
+    snprintf(buf, sizeof buf, "k_em<%d,%d,true,%d,%s>: fused single sweep, 8 warps/SM, %d-point tiles", g.DM, fgeom_.CBMAX, fgeom_.GPW,
+             fgeom_.diag ? "diag" : "full", fgeom_.TP);
+  else if (big_)
+    snprintf(buf, sizeof buf, "k_estep_big<%d,%d> + k_mstep_big<%d>: two-pass, Cholesky fragments streamed through L1", g.DM, (g.K8 + 7) / 8, g.DN);
+  else if (legacy_estep_)
+    snprintf(buf, sizeof buf, "k_estep<%d> + k_mstep<%d>: first-generation two-pass kernels", g.DM, g.DN);
+  else
+    snprintf(buf, sizeof buf, "k_em<%d,%d,false> + k_mstep<%d>: two-pass (scatter accumulators exceed the register file)", g.DM, fgeom_.CBMAX, g.DN);
+  return buf;
+}
+
 int EmgmmEngine::ensure_gamma() {
   if (dGamma_) return 0;
   CKE(cudaMalloc((void**)&dGamma_, std::max<size_t>((size_t)geom_.K * ldg_, 1) * sizeof(double)), "cudaMalloc gamma (N*K responsibilities)");

@@ -70,6 +70,8 @@ class EmgmmEngine {
   const Geom& geom() const { return geom_; }
   cudaStream_t stream() const { return st_; }
   const std::string& last_error() const { return err_; }
+  // which kernel generation this (d, K) runs through (for bench output and logs)
+  std::string plan() const;
   EngineTimes& times() { return times_; }
   void reset_times() { times_ = EngineTimes(); }
   void set_profile(bool on) { profile_ = on; }

@@ -71,7 +71,7 @@ struct EmObject : Handle {
   bool x_on_device = false;
   EmgmmEngine eng;
   std::vector<double> trace;
-  std::string err;
+  std::string err, plan;
   int rank = 0, world = 1;
   uint64_t seed = 0x9E3779B97F4A7C15ull;
 
@@ -430,6 +430,13 @@ int mlf_b200_refresh_x(MLF_OBJ* obj, const double* X) {
   if (!o) return -1;
   o->X = X;
   return o->eng.refresh_x(X, o->x_on_device);
+}
+
+const char* mlf_b200_kernel_plan(MLF_OBJ* obj) {
+  EmObject* o = as_em(obj);
+  if (!o) return "invalid handle";
+  o->plan = o->eng.plan();
+  return o->plan.c_str();
 }
 
 const char* mlf_b200_last_error(MLF_OBJ* obj) {

@@ -295,6 +295,9 @@ class mlf_algo_emgmm:
             self._lib.mlf_b200_sumll_trace(self._h, out.ctypes.data_as(_lib.c_double_p), n)
         return out
 
+    def kernel_plan(self) -> str:
+        return (self._lib.mlf_b200_kernel_plan(self._h) or b"").decode()
+
     def last_error(self) -> str:
         return (self._lib.mlf_b200_last_error(self._h) or b"").decode()
 
