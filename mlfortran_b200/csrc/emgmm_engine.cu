@@ -665,7 +665,6 @@ int EmgmmEngine::resident_labels(int32_t* labels_host) {
   CKE(cudaSetDevice(device_), "cudaSetDevice");
   if (n_ == 0) return 0;
   if (int r = ensure_moments()) return r;
-  const Geom& g = geom_;
   if (!dLabels_) CKE(cudaMalloc((void**)&dLabels_, (size_t)n_ * sizeof(int32_t)), "cudaMalloc labels");
   if (int r = do_refresh()) return r;
   if (legacy_estep_) {

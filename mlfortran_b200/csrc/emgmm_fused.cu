@@ -586,7 +586,7 @@ __global__ void k_finalize_fused(Geom g, int MSF, const double* __restrict__ sta
                                  double minProba, double* __restrict__ Mu, double* __restrict__ Cov, double* __restrict__ lambda,
                                  int cov_diag) {
   const int d = g.d;
-  __shared__ double s_mu[128], s_dl[128], s_m[128];
+  __shared__ double s_dl[128], s_m[128];
   for (int k = blockIdx.x; k < g.K; k += gridDim.x) {
     const double* sa = statsA + (size_t)k * g.DS;
     const double* sb = statsB + (size_t)k * MSF;
@@ -596,7 +596,6 @@ __global__ void k_finalize_fused(Geom g, int MSF, const double* __restrict__ sta
     const double sK = sb[g.MB * 64 + 8 * g.DN] + (sc ? sc[d * d + d] : 0.0);
     for (int a = threadIdx.x; a < d; a += blockDim.x) {
       const double mu = sa[2 + a] / s;
-      s_mu[a] = mu;
       s_dl[a] = mu - m0[a];
       s_m[a] = (sb[g.MB * 64 + a] - sb[g.MB * 64 + 8 * g.DN] * m0[a]) + (sc ? sc[d * d + a] : 0.0);
       Mu[(size_t)k * d + a] = mu;
