@@ -222,7 +222,9 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
     sum += shx(sum, 2);
     const double inv = (p < N) ? 1.0 / sum : 0.0;
     for (int k4 = 0; k4 < K4; ++k4) row[4 * k4 + t] *= inv;
-    __syncthreads();
+    // P3a of half h reads only the responsibilities and points of half h, all written by the eight warps of that half:
+    // a 256-thread named barrier per half is enough here (the full-block barrier comes at the end of the tile)
+    asm volatile("bar.sync %0, 256;\n" ::"r"(9 + half) : "memory");
     // ---- P3a: pass-A statistics of component block cb over this half's 4-point groups; kept-group flags -----------
     if (own) {
       const int64_t q0 = bt * TP;
@@ -269,8 +271,10 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
         }
       }
       if (lane < 16) sact[cb * 32 + 16 * half + lane] = (unsigned char)act;
+      // the two warps that share component block cb exchange their kept-group flags: 64-thread named barrier.  The
+      // partner passed its half's barrier before arriving here, so the other half's responsibilities are visible too.
+      asm volatile("bar.sync %0, 64;\n" ::"r"(1 + cb) : "memory");
     }
-    __syncthreads();
     // ---- P3b: covariance scatter of this warp's 4 components over the kept groups of the whole tile ----------------
     if (own) {
       const unsigned flags = sact[cb * 32 + lane];
