@@ -7,10 +7,14 @@
 // f64 MMA): each warp parks its 4 components x MB blocks in its own TMEM lane quarter and pulls one component at a time
 // into registers with tcgen05.ld while it walks that component's kept groups, then puts it back with tcgen05.st.
 // That frees the registers for 16 warps per SM (<= 128 registers each, four warps per scheduler):
-//   warp w:  P1/P2 on its own 8 points of the 128-point tile;
-//            P3a pass-A statistics of component block (w & 7) over the 4-point groups of half (w >> 3) of the tile;
-//            P3b covariance scatter of components 8*(w & 7) + 4*(w >> 3) + {0..3} over the whole tile.
-// Per-block partials are written per half: slot = 2*blockIdx.x + (w >> 3).
+// The 16 warps form TWO INDEPENDENT GROUPS of 8 (group = w >> 3), each sweeping its own 64-point tiles with its own logit
+// tile and point tile in shared memory and its own 256-thread named barrier; the groups share only the parameter pack.
+// Nothing synchronises them inside the tile loop.  (Measured: forcing the groups into antiphase with a start offset changes
+// nothing -- at four warps per scheduler the sweep is bound by the fp64 datapath's throughput, not by phase latency.)
+//   warp w of a group:  P1/P2 on its own 8 points of the group's 64-point tile;
+//                       P3a pass-A statistics of component block (w & 7) over the tile's sixteen 4-point groups;
+//                       P3b covariance scatter of the 8 components of that block over the kept groups.
+// Per-block partials are written per group: slot = 2*blockIdx.x + (w >> 3).
 #include "emgmm_kernels.cuh"
 
 #include <cmath>
@@ -75,11 +79,11 @@ __device__ __forceinline__ void tmem_ld2(uint32_t taddr, double& v0, double& v1)
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
 constexpr int kThreads16 = 512;
-constexpr int kTmemCols = 256;  // 4 warps per lane quarter x 4 components x 16 columns (MB <= 3 blocks x 4 columns, padded)
+constexpr int kTmemCols = 512;  // 4 warps per lane quarter x 8 components x 16 columns (MB <= 3 blocks x 4 columns, padded)
 
 }  // namespace
 
-size_t em16_smem_bytes(const Geom& g, const FusedGeom& f) { return f.smem + 8 * 32 + 16; }
+size_t em16_smem_bytes(const Geom& g, const FusedGeom& f) { return f.smem + 16; }
 bool em16_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
   return f.GPW == 2 && !f.diag && g.DN <= 2 && g.K8 <= 8 && f.scatter_ok && em16_smem_bytes(g, f) <= smem_limit;
 }
@@ -93,18 +97,18 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   constexpr int MB = DN * (DN + 1) / 2;
   constexpr int DS = 8 * DN + 2;
   constexpr int MSF = MB * 64 + 8 * DN + 2;
-  constexpr int TP = 128;
+  constexpr int TP = 64;   // points per group tile
   extern __shared__ __align__(16) double smem[];
   const int K8 = A.K8, KP = K8 * 8, K4 = 2 * K8, S = A.S, d = A.d;
   const int64_t N = A.N;
   double* sp = smem;                                  // [KP][PSF]
   double* smu = sp + (size_t)KP * PSF;                // [KP][8 DN]
-  double* xs = smu + (size_t)KP * 8 * DN;             // [128][XS]
-  double* tile = xs + (size_t)TP * XS;                // [128][S]
-  unsigned char* sact = reinterpret_cast<unsigned char*>(tile + (size_t)TP * S);  // [8][32] kept-group flags
-  uint32_t* s_taddr = reinterpret_cast<uint32_t*>(sact + 8 * 32);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  const int cb = warp & 7, half = warp >> 3;
+  const int cb = warp & 7, half = warp >> 3;   // half = group index
+  const int wg = warp & 7;                      // warp index inside the group
+  double* xs = smu + (size_t)KP * 8 * DN + (size_t)half * TP * XS;                    // [2][64][XS] raw points, per group
+  double* tile = smu + (size_t)KP * 8 * DN + (size_t)2 * TP * XS + (size_t)half * TP * S;  // [2][64][S] logits -> responsibilities
+  uint32_t* s_taddr = reinterpret_cast<uint32_t*>(smu + (size_t)KP * 8 * DN + (size_t)2 * TP * XS + (size_t)2 * TP * S);
   const bool own = cb < K8;
 
   for (int i = tid; i < KP * PSF; i += kThreads16) sp[i] = A.pack2[i];
@@ -121,8 +125,8 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  // this warp's TMEM region: lane quarter (warp & 3), 64 columns starting at 64*(warp >> 2); component j at +16*j, block b at +4*b
-  const uint32_t tbase = *s_taddr + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * (warp >> 2));
+  // this warp's TMEM region: lane quarter (warp & 3), 128 columns starting at 128*(warp >> 2); component q at +16*q, block b at +4*b
+  const uint32_t tbase = *s_taddr + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(128 * (warp >> 2));
 
   const bool accu = A.accumulate != 0;
   const int slot = 2 * blockIdx.x + half;
@@ -146,11 +150,11 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
       accK[b][1] = ld ? ok[8 * b + 2 * t + 1] : 0.0;
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const double* oq = outB + (size_t)(8 * cb + 4 * half + j) * MSF;
+    for (int q = 0; q < 8; ++q) {
+      const double* oq = outB + (size_t)(8 * cb + q) * MSF;
 #pragma unroll
       for (int b = 0; b < MB; ++b)
-        tmem_st2(tbase + 16 * j + 4 * b, ld ? oq[b * 64 + g * 8 + 2 * t] : 0.0, ld ? oq[b * 64 + g * 8 + 2 * t + 1] : 0.0);
+        tmem_st2(tbase + 16 * q + 4 * b, ld ? oq[b * 64 + g * 8 + 2 * t] : 0.0, ld ? oq[b * 64 + g * 8 + 2 * t + 1] : 0.0);
     }
     tmem_wait_st();
   }
@@ -159,12 +163,12 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   AmbEntry* ambw = A.amb + (size_t)nlist * A.amb_cap;
 
   const int64_t ntiles = (N + TP - 1) / TP;
-  for (int64_t bt = blockIdx.x; bt < ntiles; bt += gridDim.x) {
-    const int64_t p = bt * TP + warp * 8 + g;
+  for (int64_t bt = 2 * (int64_t)blockIdx.x + half; bt < ntiles; bt += 2 * (int64_t)gridDim.x) {
+    const int64_t p = bt * TP + wg * 8 + g;
     // ---- P1: logits of this warp's 8 points against every component ---------------------------------------------
     double xa[DM];
     {
-      double* xr = xs + (size_t)(warp * 8 + g) * XS;
+      double* xr = xs + (size_t)(wg * 8 + g) * XS;
 #pragma unroll
       for (int mb = 0; mb < DM; ++mb) {
         const int a = 4 * mb + t;
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
       }
       if (8 * DN > 4 * DM) xr[4 * DM + t] = 0.0;
     }
-    double* row = tile + (size_t)(warp * 8 + g) * S;
+    double* row = tile + (size_t)(wg * 8 + g) * S;
     double rmax = -INFINITY;
     for (int k4 = 0; k4 < K4; ++k4) {
       double part[4];
@@ -222,17 +226,16 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
     sum += shx(sum, 2);
     const double inv = (p < N) ? 1.0 / sum : 0.0;
     for (int k4 = 0; k4 < K4; ++k4) row[4 * k4 + t] *= inv;
-    // P3a of half h reads only the responsibilities and points of half h, all written by the eight warps of that half:
-    // a 256-thread named barrier per half is enough here (the full-block barrier comes at the end of the tile)
-    asm volatile("bar.sync %0, 256;\n" ::"r"(9 + half) : "memory");
-    // ---- P3a: pass-A statistics of component block cb over this half's 4-point groups; kept-group flags -----------
+    // the group's responsibilities and points are complete: 256-thread named barrier of this group only
+    asm volatile("bar.sync %0, 256;\n" ::"r"(1 + half) : "memory");
+    unsigned act = 0;   // lane pb: bit q set <=> component 8*cb+q keeps some point of 4-point group pb
+    // ---- P3a: pass-A statistics of component block cb over the tile's 4-point groups; kept-group flags ---------------
     if (own) {
       const int64_t q0 = bt * TP;
       const double* tcol = tile + 8 * cb + g;
-      unsigned act = 0;
 #pragma unroll 4
       for (int i = 0; i < 16; ++i) {
-        const int pb = 16 * half + i;
+        const int pb = i;
         const double a = tcol[(size_t)(4 * pb + t) * S];
         double b[DN];
 #pragma unroll
@@ -270,18 +273,12 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
           nAmb += __popc(mm);
         }
       }
-      if (lane < 16) sact[cb * 32 + 16 * half + lane] = (unsigned char)act;
-      // the two warps that share component block cb exchange their kept-group flags: 64-thread named barrier.  The
-      // partner passed its half's barrier before arriving here, so the other half's responsibilities are visible too.
-      asm volatile("bar.sync %0, 64;\n" ::"r"(1 + cb) : "memory");
     }
-    // ---- P3b: covariance scatter of this warp's 4 components over the kept groups of the whole tile ----------------
+    // ---- P3b: covariance scatter of this block's 8 components over the kept groups of the tile ----------------------
     if (own) {
-      const unsigned flags = sact[cb * 32 + lane];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int q = 4 * half + j;
-        unsigned pm = __ballot_sync(kFull, (flags >> q) & 1u);
+      for (int q = 0; q < 8; ++q) {
+        unsigned pm = __ballot_sync(kFull, (act >> q) & 1u);
         if (pm == 0) continue;
         const double thq = __shfl_sync(kFull, thi_r, 4 * q);
         const double* mq = smu + (size_t)(8 * cb + q) * 8 * DN;
@@ -291,7 +288,7 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
         const double* tq = tile + 8 * cb + q;
         double acc[MB][2];
 #pragma unroll
-        for (int b = 0; b < MB; ++b) tmem_ld2(tbase + 16 * j + 4 * b, acc[b][0], acc[b][1]);
+        for (int b = 0; b < MB; ++b) tmem_ld2(tbase + 16 * q + 4 * b, acc[b][0], acc[b][1]);
         while (pm) {
           const int pb = __ffs(pm) - 1;
           pm &= pm - 1;
@@ -309,11 +306,12 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
             for (int bb = 0; bb <= ab; ++bb) dmma(acc[ab * (ab + 1) / 2 + bb], wz[ab], z[bb]);
         }
 #pragma unroll
-        for (int b = 0; b < MB; ++b) tmem_st2(tbase + 16 * j + 4 * b, acc[b][0], acc[b][1]);
+        for (int b = 0; b < MB; ++b) tmem_st2(tbase + 16 * q + 4 * b, acc[b][0], acc[b][1]);
       }
       tmem_wait_st();
     }
-    __syncthreads();
+    // the group's tiles may be overwritten only after every warp of the group is done with them
+    asm volatile("bar.sync %0, 256;\n" ::"r"(1 + half) : "memory");
   }
   // ---- per-(block, half) partials -------------------------------------------------------------------------------------
   if (own) {
@@ -332,17 +330,14 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
       ok[8 * db + 2 * t + 1] = accK[db][1];
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      double* oq = outB + (size_t)(8 * cb + 4 * half + j) * MSF;        // this half owns these scatter blocks
-      double* oz = outB + (size_t)(8 * cb + 4 * (1 - half) + j) * MSF;  // ... and contributes zero to the other half's
+    for (int q = 0; q < 8; ++q) {
+      double* oq = outB + (size_t)(8 * cb + q) * MSF;
 #pragma unroll
       for (int bq = 0; bq < MB; ++bq) {
         double v0, v1;
-        tmem_ld2(tbase + 16 * j + 4 * bq, v0, v1);
+        tmem_ld2(tbase + 16 * q + 4 * bq, v0, v1);
         oq[bq * 64 + g * 8 + 2 * t] = v0;
         oq[bq * 64 + g * 8 + 2 * t + 1] = v1;
-        oz[bq * 64 + g * 8 + 2 * t] = 0.0;
-        oz[bq * 64 + g * 8 + 2 * t + 1] = 0.0;
       }
     }
   }
