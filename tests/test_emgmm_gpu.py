@@ -242,6 +242,7 @@ def test_fused_sweep_band_and_side_list(oracle):
     assert rel(em.Mu, oMu) <= PAR_RTOL and rel(em.Cov, oCov) <= PAR_RTOL and np.abs(em.lambda_ - olam).max() <= PAR_RTOL
     assert abs(em.sumLL - otr[-1]) <= LL_RTOL * abs(otr[-1])
     assert np.abs(em.ProbaC - oP).max() <= 1e-9     # re-evaluated on demand with the parameters of the last E-step
+    assert "k_em16" in em.kernel_plan()           # default plan for d <= 16, K <= 64
     assert t["sweeps"] >= iters                      # counters are live (fused path) ...
     assert t["sweeps"] < 2 * iters                   # ... and the band held in at least one iteration
     em.finalize()
@@ -301,6 +302,24 @@ def test_large_shapes_match_oracle(case, oracle):
     bad = cl != oracle.get_class(Pn)
     if bad.any():
         assert near_tie_mask(oracle, X[:300], em.Mu, em.Cov, em.lambda_)[bad].all()
+    em.finalize()
+
+
+@pytest.mark.parametrize("env", [{"MLF_B200_EM16": "0"}, {"MLF_B200_LEGACY": "1"}], ids=["k_em_8warps", "first_generation"])
+def test_alternative_kernel_generations_agree(env, oracle, monkeypatch):
+    """The 8-warp fused kernel (MLF_B200_EM16=0) and the first-generation two-pass kernels (MLF_B200_LEGACY=1) stay in the
+    build for A/B measurements: they must give the oracle's numbers too."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    data = synth.make_mixture(16, 24, 300, 6.0, 1.0, 171)
+    X = data["X"]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 171)
+    oMu, oCov, olam, otr, oP = oracle.em_iterations(X, Mu0, Cov0, lam0, 0.0, 4, return_proba=True)
+    em = make_em(X, 24, 0.0, Mu0, Cov0, lam0)
+    assert ("k_em16" not in em.kernel_plan())
+    assert em.step(4)[0] == 0, em.last_error()
+    check_against(em, oMu, oCov, olam, otr)
+    assert np.abs(em.ProbaC - oP).max() <= 1e-9
     em.finalize()
 
 
