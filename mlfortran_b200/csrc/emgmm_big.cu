@@ -77,18 +77,23 @@ bool estep_big_ok(const Geom& g, size_t smem_limit) {
 }
 
 // pack2 layout per component (FusedGeom): [NB*32 L fragments | 8*DN bias -L^T(mu-m) | log(lambda)-lnDet, pad]
-template <int DM, int CB>
+// GPW: 8-point groups per warp.  GPW = 2 (128-point tiles, large d) halves the fragment traffic per DMMA; its output
+// coordinates are then processed in H = 2 halves so that the accumulators (GPW x DN/H x 2 doubles) stay in registers.
+template <int DM, int CB, int GPW>
 __global__ void __launch_bounds__(256, 1) k_estep_big(EmArgs A) {
   constexpr int DN = (DM + 1) / 2;
   constexpr int NB = b_blk_off(DM);
   constexpr int OFFB = NB * 32, OFFC = OFFB + 8 * DN, PSF = OFFC + 4;
   constexpr int XS = 8 * DN + 4;
   constexpr int DS = 8 * DN + 2;
+  constexpr int TP = 64 * GPW;
+  constexpr int H = (GPW * DN > 16) ? 2 : 1;
+  constexpr int DH = (DN + H - 1) / H;   // output blocks per half
   extern __shared__ __align__(16) double smem[];
   const int K8 = A.K8, KP = K8 * 8, S = A.S, d = A.d, K = A.K;
   const int64_t N = A.N;
-  double* xs = smem;                          // [64][XS] raw points of the tile
-  double* tile = xs + (size_t)kBigTile * XS;  // [64][S]  logits -> responsibilities
+  double* xs = smem;                    // [TP][XS] raw points of the tile
+  double* tile = xs + (size_t)TP * XS;  // [TP][S]  logits -> responsibilities
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
 
   double accA[CB][DN][2], sg[CB], sg2[CB];
@@ -98,70 +103,101 @@ __global__ void __launch_bounds__(256, 1) k_estep_big(EmArgs A) {
 #pragma unroll
     for (int b = 0; b < DN; ++b) { accA[c][b][0] = 0; accA[c][b][1] = 0; }
   }
-  const int64_t ntiles = (N + kBigTile - 1) / kBigTile;
+  const int64_t ntiles = (N + TP - 1) / TP;
   for (int64_t bt = blockIdx.x; bt < ntiles; bt += gridDim.x) {
-    const int64_t p = bt * kBigTile + warp * 8 + g;
-    // ---- P1: logits of this warp's 8 points against every component -------------------------------------------
-    double xa[DM];
-    {
-      double* xr = xs + (size_t)(warp * 8 + g) * XS;
+    const int64_t p0 = bt * TP + warp * 8 * GPW + g;
+    // ---- P1: logits of this warp's points against every component ---------------------------------------------
+    double xa[GPW][DM];
+#pragma unroll
+    for (int grp = 0; grp < GPW; ++grp) {
+      const int64_t p = p0 + 8 * grp;
+      double* xr = xs + (size_t)(warp * 8 * GPW + 8 * grp + g) * XS;
 #pragma unroll
       for (int mb = 0; mb < DM; ++mb) {
         const int a = 4 * mb + t;
         const double x = (p < N && a < d) ? A.X[p * d + a] : 0.0;
         xr[a] = x;
-        xa[mb] = x - A.shift[a];
+        xa[grp][mb] = x - A.shift[a];
       }
       if (8 * DN > 4 * DM) xr[4 * DM + t] = 0.0;
     }
-    double* row = tile + (size_t)(warp * 8 + g) * S;
-    double rmax = -INFINITY;
-    int rarg = 0;
+    double* row[GPW];
+    double rmax[GPW];
+    int rarg[GPW];
+#pragma unroll
+    for (int grp = 0; grp < GPW; ++grp) { row[grp] = tile + (size_t)(warp * 8 * GPW + 8 * grp + g) * S; rmax[grp] = -INFINITY; rarg[grp] = 0; }
     for (int k = 0; k < KP; ++k) {
       const double* pk = A.pack2 + (size_t)k * PSF;
-      double c[DN][2];
+      double s[GPW];
 #pragma unroll
-      for (int nb = 0; nb < DN; ++nb) {
-        const double2 v = *reinterpret_cast<const double2*>(pk + OFFB + 8 * nb + 2 * t);
-        c[nb][0] = v.x; c[nb][1] = v.y;
+      for (int grp = 0; grp < GPW; ++grp) s[grp] = 0;
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int lo = h * DH;
+        double c[GPW][DH][2];
+#pragma unroll
+        for (int nb = 0; nb < DH; ++nb) {
+          double2 v = make_double2(0.0, 0.0);
+          if (lo + nb < DN) v = *reinterpret_cast<const double2*>(pk + OFFB + 8 * (lo + nb) + 2 * t);
+#pragma unroll
+          for (int grp = 0; grp < GPW; ++grp) { c[grp][nb][0] = v.x; c[grp][nb][1] = v.y; }
+        }
+#pragma unroll
+        for (int mb = 0; mb < DM; ++mb)
+#pragma unroll
+          for (int nb = 0; nb < DH; ++nb)
+            if (lo + nb < DN && lo + nb <= mb / 2) {
+              const double Lf = __ldg(pk + (b_blk_off(mb) + lo + nb) * 32 + lane);
+#pragma unroll
+              for (int grp = 0; grp < GPW; ++grp) dmma(c[grp][nb], xa[grp][mb], Lf);
+            }
+#pragma unroll
+        for (int grp = 0; grp < GPW; ++grp)
+#pragma unroll
+          for (int nb = 0; nb < DH; ++nb) { s[grp] = fma(c[grp][nb][0], c[grp][nb][0], s[grp]); s[grp] = fma(c[grp][nb][1], c[grp][nb][1], s[grp]); }
       }
+      const double ck = pk[OFFC];
 #pragma unroll
-      for (int mb = 0; mb < DM; ++mb)
-#pragma unroll
-        for (int nb = 0; nb <= mb / 2; ++nb) dmma(c[nb], xa[mb], __ldg(pk + (b_blk_off(mb) + nb) * 32 + lane));
-      double s = 0;
-#pragma unroll
-      for (int nb = 0; nb < DN; ++nb) { s = fma(c[nb][0], c[nb][0], s); s = fma(c[nb][1], c[nb][1], s); }
-      s += shx(s, 1);
-      s += shx(s, 2);
-      const double logit = fma(-0.5, s, pk[OFFC]);
-      if (t == 0) row[k] = logit;
-      if (logit > rmax) { rmax = logit; rarg = k; }  // k ascending: first maximum wins (MAXLOC)
+      for (int grp = 0; grp < GPW; ++grp) {
+        double v = s[grp];
+        v += shx(v, 1);
+        v += shx(v, 2);
+        const double logit = fma(-0.5, v, ck);
+        if (t == 0) row[grp][k] = logit;
+        if (logit > rmax[grp]) { rmax[grp] = logit; rarg[grp] = k; }  // k ascending: first maximum wins (MAXLOC)
+      }
     }
     __syncwarp();
     // ---- P2: log-sum-exp over the components; lane t handles components t, t+4, ... ----------------------------
-    const bool valid = p < N;
-    if (A.hard) {  // k-means assignment: one-hot of the nearest centre (see emgmm_fused.cu)
-      for (int k = t; k < KP; k += 4) row[k] = (valid && k == rarg) ? 1.0 : 0.0;
-    } else {
-      const double mx = A.raw ? 0.0 : rmax;
-      double sum = 0;
+#pragma unroll
+    for (int grp = 0; grp < GPW; ++grp) {
+      const int64_t p = p0 + 8 * grp;
+      const bool valid = p < N;
+      double* rw = row[grp];
+      if (A.hard) {  // k-means assignment: one-hot of the nearest centre (see emgmm_fused.cu)
+        for (int k = t; k < KP; k += 4) rw[k] = (valid && k == rarg[grp]) ? 1.0 : 0.0;
+      } else {
+        const double mx = A.raw ? 0.0 : rmax[grp];
+        double sum = 0;
 #pragma unroll 4
-      for (int k = t; k < KP; k += 4) {
-        const double e = exp_bf(row[k] - mx);
-        row[k] = e;
-        sum += e;
+        for (int k = t; k < KP; k += 4) {
+          const double e = exp_bf(rw[k] - mx);
+          rw[k] = e;
+          sum += e;
+        }
+        sum += shx(sum, 1);
+        sum += shx(sum, 2);
+        const double inv = valid ? (A.raw ? 1.0 : 1.0 / sum) : 0.0;
+        for (int k = t; k < KP; k += 4) {
+          const double gk = rw[k] * inv;
+          rw[k] = gk;
+          if (A.gamma != nullptr && valid && k < K) A.gamma[(size_t)k * A.ldg + p] = gk;
+        }
       }
-      sum += shx(sum, 1);
-      sum += shx(sum, 2);
-      const double inv = valid ? (A.raw ? 1.0 : 1.0 / sum) : 0.0;
-      for (int k = t; k < KP; k += 4) {
-        const double gk = row[k] * inv;
-        row[k] = gk;
-        if (A.gamma != nullptr && valid && k < K) A.gamma[(size_t)k * A.ldg + p] = gk;
-      }
+      if (A.labels != nullptr && valid && t == 0) A.labels[p] = rarg[grp] + 1;
     }
-    if (A.labels != nullptr && valid && t == 0) A.labels[p] = rarg + 1;
     __syncthreads();
     // ---- P3: pass-A statistics; warp w owns component blocks w, w+8, ... -----------------------------------------
 #pragma unroll
@@ -169,7 +205,7 @@ __global__ void __launch_bounds__(256, 1) k_estep_big(EmArgs A) {
       const int cb = warp + 8 * ci;
       if (cb < K8) {
 #pragma unroll 2
-        for (int pb = 0; pb < kBigTile / 4; ++pb) {
+        for (int pb = 0; pb < TP / 4; ++pb) {
           const double a = tile[(size_t)(4 * pb + t) * S + 8 * cb + g];
           sg[ci] += a;
           sg2[ci] = fma(a, a, sg2[ci]);
@@ -199,39 +235,49 @@ __global__ void __launch_bounds__(256, 1) k_estep_big(EmArgs A) {
   }
 }
 
-template <int DM, int CB>
+// 128-point tiles (two groups per warp) where d is large and the tiles fit shared memory; 64-point tiles otherwise
+int estep_big_gpw(const Geom& g, size_t smem_limit) {
+  const int XS = 8 * g.DN + 4;
+  const int S = ((g.K8 * 8 + 15) / 16) * 16 + 4;
+  const size_t need2 = ((size_t)128 * XS + (size_t)128 * S) * sizeof(double);
+  return (g.DM >= 16 && estep_big_cb(g) == 1 && need2 <= smem_limit) ? 2 : 1;
+}
+
+template <int DM, int CB, int GPW>
 static cudaError_t launch_big_t(const EmArgs& a, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(k_estep_big<DM, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_estep_big<DM, CB, GPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_estep_big<DM, CB><<<grid, 256, smem, st>>>(a);
+  k_estep_big<DM, CB, GPW><<<grid, 256, smem, st>>>(a);
   return cudaGetLastError();
 }
 template <int DM>
-static cudaError_t launch_big_dm(const EmArgs& a, int cb, int grid, size_t smem, cudaStream_t st) {
+static cudaError_t launch_big_dm(const EmArgs& a, int cb, int gpw, int grid, size_t smem, cudaStream_t st) {
   constexpr int DN = (DM + 1) / 2;
-  if constexpr (1 * DN <= 16) { if (cb == 1) return launch_big_t<DM, 1>(a, grid, smem, st); }
-  if constexpr (2 * DN <= 16) { if (cb == 2) return launch_big_t<DM, 2>(a, grid, smem, st); }
-  if constexpr (4 * DN <= 16) { if (cb == 4) return launch_big_t<DM, 4>(a, grid, smem, st); }
+  if constexpr (DM >= 16) { if (gpw == 2 && cb == 1) return launch_big_t<DM, 1, 2>(a, grid, smem, st); }
+  if constexpr (1 * DN <= 16) { if (cb == 1) return launch_big_t<DM, 1, 1>(a, grid, smem, st); }
+  if constexpr (2 * DN <= 16) { if (cb == 2) return launch_big_t<DM, 2, 1>(a, grid, smem, st); }
+  if constexpr (4 * DN <= 16) { if (cb == 4) return launch_big_t<DM, 4, 1>(a, grid, smem, st); }
   return cudaErrorInvalidConfiguration;
 }
 cudaError_t launch_estep_big(const Geom& g, EmArgs a, int grid, size_t smem_limit, cudaStream_t st) {
   if (!estep_big_ok(g, smem_limit)) return cudaErrorInvalidConfiguration;
-  const size_t smem = estep_big_smem(g);
+  const int gpw = estep_big_gpw(g, smem_limit);
   a.S = ((g.K8 * 8 + 15) / 16) * 16 + 4;
+  const size_t smem = ((size_t)64 * gpw * (8 * g.DN + 4) + (size_t)64 * gpw * a.S) * sizeof(double);
   const int cb = estep_big_cb(g);
   switch (g.DM) {
-    case 1: return launch_big_dm<1>(a, cb, grid, smem, st);
-    case 2: return launch_big_dm<2>(a, cb, grid, smem, st);
-    case 4: return launch_big_dm<4>(a, cb, grid, smem, st);
-    case 8: return launch_big_dm<8>(a, cb, grid, smem, st);
-    case 12: return launch_big_dm<12>(a, cb, grid, smem, st);
-    case 16: return launch_big_dm<16>(a, cb, grid, smem, st);
-    case 24: return launch_big_dm<24>(a, cb, grid, smem, st);
-    case 32: return launch_big_dm<32>(a, cb, grid, smem, st);
+    case 1: return launch_big_dm<1>(a, cb, gpw, grid, smem, st);
+    case 2: return launch_big_dm<2>(a, cb, gpw, grid, smem, st);
+    case 4: return launch_big_dm<4>(a, cb, gpw, grid, smem, st);
+    case 8: return launch_big_dm<8>(a, cb, gpw, grid, smem, st);
+    case 12: return launch_big_dm<12>(a, cb, gpw, grid, smem, st);
+    case 16: return launch_big_dm<16>(a, cb, gpw, grid, smem, st);
+    case 24: return launch_big_dm<24>(a, cb, gpw, grid, smem, st);
+    case 32: return launch_big_dm<32>(a, cb, gpw, grid, smem, st);
     default: return cudaErrorInvalidConfiguration;
   }
 }
-int estep_big_tile() { return kBigTile; }
+int estep_big_tile(const Geom& g, size_t smem_limit) { return 64 * estep_big_gpw(g, smem_limit); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // M-pass for large d.  grid = (point chunks, components); block = 8 warps; warp w owns the lower-triangular 8x8 output

@@ -112,7 +112,7 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   egrid_ = (int)std::max<int64_t>(1, std::min<int64_t>(sms_, etiles));
   mstep_grid(g, sms_, n_, &mgx_, &mgy_);
   if (big_) {
-    egrid_ = (int)std::max<int64_t>(1, std::min<int64_t>(sms_, (n_ + estep_big_tile() - 1) / estep_big_tile()));
+    egrid_ = (int)std::max<int64_t>(1, std::min<int64_t>(sms_, (n_ + estep_big_tile(geom_, smem_limit_) - 1) / estep_big_tile(geom_, smem_limit_)));
     mstep_big_grid(g, sms_, n_, &mgx_, &mchunk_);
   }
   auto A = [&](double** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(double)); };
@@ -333,7 +333,7 @@ int EmgmmEngine::run_estep(const double* X, int64_t n, double* gamma, int64_t ld
     a.X = X; a.N = n; a.d = g.d; a.K = g.K; a.K8 = g.K8; a.S = g.S;
     a.pack2 = dPack2_; a.shift = dShift_; a.gamma = gamma; a.ldg = ldg; a.labels = labels; a.raw = raw ? 1 : 0; a.partA = dPartA_;
     a.hard = hard ? 1 : 0;
-    const int bgrid = (int)std::max<int64_t>(1, std::min<int64_t>(sms_, (n + estep_big_tile() - 1) / estep_big_tile()));
+    const int bgrid = (int)std::max<int64_t>(1, std::min<int64_t>(sms_, (n + estep_big_tile(geom_, smem_limit_) - 1) / estep_big_tile(geom_, smem_limit_)));
     CKE(launch_estep_big(g, a, bgrid, smem_limit_, st_), "estep (large shape)");
     ++launches_;
     if (want_stats) {

@@ -94,7 +94,7 @@ cudaError_t launch_finalize_fused(const Geom& g, const FusedGeom& f, const doubl
 // Large-shape path (emgmm_big.cu): 32 < d <= 128, or packs that do not fit shared memory.
 size_t estep_big_smem(const Geom& g);
 bool estep_big_ok(const Geom& g, size_t smem_limit);
-int estep_big_tile();
+int estep_big_tile(const Geom& g, size_t smem_limit);
 cudaError_t launch_estep_big(const Geom& g, EmArgs a, int grid, size_t smem_limit, cudaStream_t st);
 void mstep_big_grid(const Geom& g, int sms, int64_t N, int* gx, int64_t* chunk);
 cudaError_t launch_mstep_big(const Geom& g, const double* X, int64_t N, const double* gamma, int64_t ldg, const double* mupad,
