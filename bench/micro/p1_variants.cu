@@ -236,6 +236,39 @@ static void runw(const double* dpack, const double* dX, int tiles, double* dout,
   printf("{\"variant\": \"%s\", \"ms\": %.4f, \"ns_per_pair\": %.5f, \"dmma_tflops\": %.3f, \"frac_of_37.16\": %.3f}\n", name, best, best * 1e6 / pairs, tf, tf / 37.16);
 }
 
+// DMMA stream whose operands differ per instruction (NA distinct A registers, NBR distinct B registers, 8 accumulator chains):
+// does operand variety (register-file bandwidth / bank conflicts) lower the DMMA rate below the same-operand peak?
+template <int NA, int NBR>
+__global__ void __launch_bounds__(256, 1) k_dmma_var(int iters, const double* __restrict__ src, double* out) {
+  double a[NA], b[NBR], c[8][2];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) a[i] = src[threadIdx.x + 256 * i];
+#pragma unroll
+  for (int i = 0; i < NBR; ++i) b[i] = src[threadIdx.x + 256 * (NA + i)];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { c[j][0] = j; c[j][1] = threadIdx.x * 1e-9; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 6; ++u)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dmma_v(c[j], a[(u * 8 + j) % NA], b[(u * 3 + j) % NBR]);
+  }
+  double s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += c[j][0] + c[j][1];
+  if (s == 1.2345e-300) out[0] = s;
+}
+template <int NA, int NBR>
+static void run_var(const double* dsrc, double* dout, const char* name) {
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const int iters = 20000;
+  k_dmma_var<NA, NBR><<<148, 256>>>(iters, dsrc, dout); CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(e0)); k_dmma_var<NA, NBR><<<148, 256>>>(iters, dsrc, dout); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+  float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+  const double tf = 148.0 * 8 * iters * 48 * 512 / (ms * 1e-3) * 1e-12;
+  printf("{\"variant\": \"%s\", \"ms\": %.4f, \"dmma_tflops\": %.3f}\n", name, ms, tf);
+}
+
 int main() {
   const int tiles = 200;
   std::vector<double> hp((size_t)K * PSF), hx((size_t)148 * tiles * 128 * 16);
@@ -265,5 +298,8 @@ int main() {
     const double tf = 148.0 * 8 * iters * 48 * 512 / (ms * 1e-3) * 1e-12;
     printf("{\"variant\": \"pure DMMA, 8 warps/SM, 4 chains\", \"ms\": %.4f, \"dmma_tflops\": %.3f}\n", ms, tf);
   }
+  run_var<1, 1>(dx, dout, "DMMA 8 chains, 1 A x 1 B operand register");
+  run_var<8, 6>(dx, dout, "DMMA 8 chains, 8 A x 6 B operand registers (as the whitening loop)");
+  run_var<16, 12>(dx, dout, "DMMA 8 chains, 16 A x 12 B operand registers");
   return 0;
 }
