@@ -150,7 +150,9 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   CKE(A(&dStatsA_, (size_t)KP * g.DS), "cudaMalloc");
   CKE(A(&dStatsB_, (size_t)K * g.MS), "cudaMalloc");
   CKE(A(&dPartA_, (size_t)2 * sms_ * KP * g.DS), "cudaMalloc");
-  CKE(A(&dPartB_, (size_t)(2 * sms_ + K + 2) * g.MS), "cudaMalloc");
+  // pass-B partials: [mgx_][K][MS] (two-pass kernels, mgx_ <= sms_; large-shape kernels, mgx_*K <= 2*sms_+K), and the
+  // unit-weight moments run of the large-shape M-pass ([<= 2*sms_][1][MS])
+  CKE(A(&dPartB_, (size_t)std::max<int64_t>((int64_t)mgx_ * K, 2 * (int64_t)sms_ + K + 2) * g.MS), "cudaMalloc");
   CKE(A(&dSc_, (size_t)d * d), "cudaMalloc");
   CKE(A(&dMean_, (size_t)8 * g.DN + 8), "cudaMalloc");
   CKE(A(&dNglob_, 8), "cudaMalloc");
