@@ -85,6 +85,28 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(gpu_index: int) -> str:
+    """Pin this rank's host threads (and therefore its pinned staging buffer, placed at first touch / pin time) to the CPU
+    cores NVML reports as local to its GPU.  Without it the eight ranks' host buffers tend to land on one NUMA node and the
+    per-step H2D of the e2e path shares that node's memory and PCIe root."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n)
+        cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1]
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"bound to {len(cpus)} cores local to GPU {gpu_index}"
+        return "no local cores reported"
+    except Exception as exc:  # noqa: BLE001 -- affinity is an optimisation, never a failure
+        return f"not bound ({type(exc).__name__})"
+
+
 def cpu_oracle_rate(d, K, n_cpu, min_proba, steps, warmup, threads=None):
     """Times the CPU restatement of the reference algorithm (oracle/, kind "port") on a bounded sample."""
     from mlfortran_b200 import synth
@@ -167,6 +189,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device (mlfortran_b200 has no CPU fallback)")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa_note = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank: no binding"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -305,7 +328,7 @@ def main():
         barrier()
         pbytes = 8 * (K * d + K * d * d + K)
         e2e = {"value": N * K * e_steps / el, "unit": UNIT, "h2d_bytes_per_step": int(8 * n_loc * d + pbytes), "d2h_bytes_per_step": int(pbytes + 8),
-               "steps": e_steps, "ms_per_step": el / e_steps * 1e3, "em_iter_per_s": e_steps / el,
+               "steps": e_steps, "ms_per_step": el / e_steps * 1e3, "em_iter_per_s": e_steps / el, "host_affinity": numa_note,
                "note": "per rank and step: mlf_b200_refresh_x(pinned host X) + mlf_step(1) + parameters/sumLL back; the X upload is "
                        "chunked underneath the step's sweep, so the step is PCIe-bound (h2d_bytes / ms_per_step = achieved H2D GB/s)",
                "h2d_gbs": (8 * n_loc * d + pbytes) / (el / e_steps) * 1e-9}
