@@ -292,9 +292,9 @@ __global__ void __launch_bounds__(256) k_mstep_big(const double* __restrict__ X,
   constexpr int MB = DN * (DN + 1) / 2;
   constexpr int OWN = (MB + 7) / 8;
   constexpr int ZS = 8 * DN + 4;
-  __shared__ double zs[32][ZS];     // (x - mu) of up to 8 kept 4-point groups, compacted across strips
-  __shared__ double ws[32];         // kept weight of each staged point (0 if dropped)
-  __shared__ long long pidx[32];    // global index of each staged point (-1: none)
+  extern __shared__ __align__(16) double zdyn[];       // [2][32][ZS]: (x - mu) of up to 8 kept 4-point groups, double-buffered
+  __shared__ double ws[2][32];         // kept weight of each staged point (0 if dropped)
+  __shared__ long long pidx[2][32];    // global index of each staged point
   __shared__ double smu[8 * DN];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int k = blockIdx.y;
@@ -313,65 +313,107 @@ __global__ void __launch_bounds__(256) k_mstep_big(const double* __restrict__ X,
     ob[o] = blk - ab * (ab + 1) / 2;
   }
   double sg2 = 0;
-  int cnt = 0;  // staged groups; every warp evaluates the same ballots, so cnt is uniform over the block
-  __syncthreads();
   const int64_t lo = (int64_t)blockIdx.x * chunk;
   const int64_t hi = (lo + chunk < N) ? lo + chunk : N;
-  auto flush = [&]() {
-    __syncthreads();  // pidx / ws of this batch are written
-    // 32 * 8*DN / 256 = DN loads per thread, all issued before the first is used
-    double xv[DN];
+  // scan state: every warp evaluates the same strips and ballots, so all of it is uniform over the block.  The
+  // responsibilities are fetched eight 32-point strips at a time (eight loads in flight per lane): the scan used to wait
+  // for one load per strip, which was a third of the kernel's stall samples (profiles/ncu_r01h_big_d128.md).
+  constexpr int SB = 8;
+  int64_t ib = lo - 32 * SB;   // first point of the current batch of strips
+  int us = SB;                 // next strip of the batch to look at
+  int64_t i0 = lo;
+  double gvb[SB];
+  unsigned gm = 0;        // 4-point groups of the current strip that hold a kept point and are not listed yet
+  double gvk = 0;         // this lane's kept weight in the current strip (0 if dropped)
+  // list up to 8 kept groups (compacted across strips) into buffer `buf`; returns how many
+  auto fill = [&](int buf) -> int {
+    int c = 0;
+    while (c < 8) {
+      if (gm == 0) {
+        if (us == SB) {
+          ib += 32 * SB;
+          if (ib >= hi) break;
+#pragma unroll
+          for (int u = 0; u < SB; ++u) {
+            const int64_t pl = ib + 32 * u + lane;
+            gvb[u] = (pl < hi) ? (gk ? gk[pl] : 1.0) : 0.0;
+          }
+          us = 0;
+        }
+        double gv = 0;
+#pragma unroll
+        for (int u = 0; u < SB; ++u) gv = (u == us) ? gvb[u] : gv;   // register select: us is uniform
+        i0 = ib + 32 * us;
+        ++us;
+        if (i0 >= hi) { us = SB; continue; }
+        const int64_t pl = i0 + lane;
+        if (warp == 0) sg2 = fma(gv, gv, sg2);                  // SUM(W*W) runs over all points (src/mlf_matrix.f90:119)
+        const bool kept = !(gv < th) && pl < hi && gv != 0.0;   // "If(W(i) < minW0) CYCLE" (:135)
+        gvk = kept ? gv : 0.0;
+        unsigned m = __ballot_sync(kFull, kept);
+        m |= m >> 1;
+        m |= m >> 2;
+        gm = m & 0x11111111u;  // bit 4q: 4-point group q holds a kept point
+        continue;
+      }
+      const int q = (__ffs(gm) - 1) >> 2;
+      gm &= gm - 1;
+      const double wq = __shfl_sync(kFull, gvk, 4 * q + (lane & 3));
+      if (warp == 0 && lane < 4) {
+        ws[buf][4 * c + lane] = wq;
+        pidx[buf][4 * c + lane] = i0 + 4 * q + lane;
+      }
+      ++c;
+    }
+    return c;
+  };
+  // gather the listed points' rows into registers (DN loads per thread in flight), store them centred
+  auto gather = [&](int buf, int cnt, double (&xv)[DN]) {
 #pragma unroll
     for (int u = 0; u < DN; ++u) {
       const int i = tid + 256 * u;
       const int pt = i / (8 * DN), a = i % (8 * DN);
-      const long long pp = pt < 4 * cnt ? pidx[pt] : -1;
-      xv[u] = (pp >= 0 && pp < hi && a < d) ? X[pp * d + a] : 0.0;
+      const long long pp = pt < 4 * cnt ? pidx[buf][pt] : -1;
+      xv[u] = (pp >= 0 && pp < hi && a < d) ? X[pp * d + a] - smu[a] : 0.0;
     }
+  };
+  auto store = [&](int buf, const double (&xv)[DN]) {
+    double* zb = zdyn + (size_t)buf * 32 * ZS;
 #pragma unroll
     for (int u = 0; u < DN; ++u) {
       const int i = tid + 256 * u;
-      const int pt = i / (8 * DN), a = i % (8 * DN);
-      const long long pp = pt < 4 * cnt ? pidx[pt] : -1;
-      zs[pt][a] = (pp >= 0 && pp < hi && a < d) ? xv[u] - smu[a] : 0.0;
+      zb[(size_t)(i / (8 * DN)) * ZS + i % (8 * DN)] = xv[u];
     }
+  };
+  __syncthreads();
+  int cur = 0;
+  int cc = fill(0);
+  double xv[DN];
+  __syncthreads();
+  gather(0, cc, xv);
+  store(0, xv);
+  __syncthreads();
+  while (cc > 0) {
+    const int cn = fill(cur ^ 1);   // list the next batch ...
     __syncthreads();
-    for (int q = 0; q < cnt; ++q) {
-      const double w = ws[4 * q + t];
+    gather(cur ^ 1, cn, xv);        // ... and start fetching its rows: they land while this batch is multiplied
+    const double* zb = zdyn + (size_t)cur * 32 * ZS;
+    for (int q = 0; q < cc; ++q) {
+      const double w = ws[cur][4 * q + t];
 #pragma unroll
       for (int o = 0; o < OWN; ++o) {
         if (warp + 8 * o < MB) {
-          const double za = zs[4 * q + t][8 * oa[o] + g];
-          const double zb = zs[4 * q + t][8 * ob[o] + g];
-          dmma(acc[o], w * za, zb);
+          const double za = zb[(size_t)(4 * q + t) * ZS + 8 * oa[o] + g];
+          const double zc = zb[(size_t)(4 * q + t) * ZS + 8 * ob[o] + g];
+          dmma(acc[o], w * za, zc);
         }
       }
     }
-    __syncthreads();  // batch consumed before the next one is listed
-    cnt = 0;
-  };
-  for (int64_t i0 = lo; i0 < hi; i0 += 32) {
-    const int64_t pl = i0 + lane;
-    const double gv = (pl < hi) ? (gk ? gk[pl] : 1.0) : 0.0;
-    if (warp == 0) sg2 = fma(gv, gv, sg2);               // SUM(W*W) runs over all points (src/mlf_matrix.f90:119)
-    const bool kept = !(gv < th) && pl < hi && gv != 0.0;  // "If(W(i) < minW0) CYCLE" (:135)
-    const unsigned mask = __ballot_sync(kFull, kept);
-    if (mask == 0) continue;
-    unsigned gm = mask | (mask >> 1);
-    gm |= gm >> 2;
-    gm &= 0x11111111u;  // bit 4q: 4-point group q holds a kept point
-    while (gm) {
-      const int q = (__ffs(gm) - 1) >> 2;
-      gm &= gm - 1;
-      const double wq = __shfl_sync(kFull, kept ? gv : 0.0, 4 * q + (lane & 3));
-      if (warp == 0 && lane < 4) {
-        ws[4 * cnt + lane] = wq;
-        pidx[4 * cnt + lane] = i0 + 4 * q + lane;
-      }
-      if (++cnt == 8) flush();
-    }
+    store(cur ^ 1, xv);
+    __syncthreads();                // next batch staged; this batch's lists and rows are free again
+    cur ^= 1;
+    cc = cn;
   }
-  if (cnt) flush();
   double* out = partial + ((size_t)blockIdx.x * K + k) * MS;
 #pragma unroll
   for (int o = 0; o < OWN; ++o) {
@@ -404,8 +446,13 @@ void mstep_big_grid(const Geom& g, int sms, int64_t N, int* gx, int64_t* chunk) 
 cudaError_t launch_mstep_big(const Geom& g, const double* X, int64_t N, const double* gamma, int64_t ldg, const double* mupad,
                              const double* thr, double* partial, int gx, int64_t chunk, cudaStream_t st) {
   const dim3 grid(gx, g.K);
-#define MLF_MB(DNv) \
-  case DNv: k_mstep_big<DNv><<<grid, 256, 0, st>>>(X, N, g.d, g.K, gamma, ldg, mupad, thr, partial, g.MS, chunk); break;
+#define MLF_MB(DNv)                                                                                                        \
+  case DNv: {                                                                                                              \
+    const size_t dyn = (size_t)2 * 32 * (8 * DNv + 4) * sizeof(double);                                                    \
+    cudaError_t e = cudaFuncSetAttribute(k_mstep_big<DNv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);         \
+    if (e != cudaSuccess) return e;                                                                                        \
+    k_mstep_big<DNv><<<grid, 256, dyn, st>>>(X, N, g.d, g.K, gamma, ldg, mupad, thr, partial, g.MS, chunk);               \
+  } break;
   switch (g.DN) {
     MLF_MB(1) MLF_MB(2) MLF_MB(4) MLF_MB(6) MLF_MB(8) MLF_MB(12) MLF_MB(16)
     default: return cudaErrorInvalidConfiguration;

@@ -187,7 +187,8 @@ int EmgmmEngine::ensure_gamma() {
 // InverseSymMatrix eigen branch + packing for both kernel generations (k_refresh).
 int EmgmmEngine::do_refresh(bool with_sumll) {
   CKE(launch_refresh(geom_, dMu_, dCov_, dLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_, dPack2_, dMuOld_,
-                     dShift_, with_sumll ? 1 : 0, cov_diag_ ? 1 : 0, &fgeom_), "refresh");
+                     dShift_, with_sumll ? 1 : 0, cov_diag_ ? 1 : 0, &fgeom_, (refresh_count_ % 8 != 0) ? 1 : 0), "refresh");
+  ++refresh_count_;  // every 8th refresh restarts the eigenvectors from the identity (bounds their orthogonality drift)
   ++launches_;
   return 0;
 }
@@ -640,7 +641,8 @@ int EmgmmEngine::materialize_gamma() {
   if (!prev_valid_ || n_ == 0) return 0;  // no E-step yet: ProbaC = 0 (src/unsupervised/mlf_emgmm.f90:119)
   if (int r = ensure_moments()) return r;
   CKE(launch_refresh(geom_, dPrevMu_, dPrevCov_, dPrevLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_,
-                     dPack2_, dMuOld_, dShift_, 1, cov_diag_ ? 1 : 0, &fgeom_), "refresh");
+                     dPack2_, dMuOld_, dShift_, 1, cov_diag_ ? 1 : 0, &fgeom_, 0), "refresh");
+  refresh_count_ = 0;  // scratch now holds the eigenvectors of the previous parameters: next refresh starts cold
   ++launches_;
   if (int r = run_estep(dX_, n_, dGamma_, ldg_, nullptr, false)) return r;
   gamma_current_ = true;

@@ -104,6 +104,7 @@ class EmgmmEngine {
   bool legacy_estep_ = false; // MLF_B200_LEGACY=1: first-generation kernels (A/B comparisons)
   bool big_ = false;          // large-shape kernels (d > 32 or pack too large for shared memory; MLF_B200_BIG=1 forces them)
   int64_t mchunk_ = 0;
+  int64_t refresh_count_ = 0;  // warm-started Jacobi refresh at large d (see k_refresh)
   int device_ = 0, sms_ = 148;
   size_t smem_limit_ = 0;
   cudaStream_t st_ = nullptr;

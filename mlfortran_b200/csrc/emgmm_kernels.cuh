@@ -69,7 +69,7 @@ constexpr int kMstepTilePts = 2048;     // points per block tile of the M-pass s
 cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, const double* lambda, const double* Sc,
                            const double* mean, double Nglob, double* scratch, double* pack, double* sumLLk, int* info,
                            cudaStream_t st, double* pack2 = nullptr, double* muold = nullptr, const double* shift = nullptr,
-                           int do_sumll = 1, int cov_diag = 0, const FusedGeom* fg = nullptr);
+                           int do_sumll = 1, int cov_diag = 0, const FusedGeom* fg = nullptr, int warm = 0);
 cudaError_t launch_sumll(const Geom& g, const double* Mu, const double* Sc, const double* mean, double Nglob, const double* scratch,
                          const double* pack, double* sumLLk, cudaStream_t st);
 // Global moments about `shift`: partial[grid][MB*64 + 8*DN]; finish turns the all-reduced sums into mean and centred scatter.
