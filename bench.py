@@ -292,8 +292,8 @@ def main():
         "hbm": {"achieved_gbs": (8.0 * n_loc * d + (0.0 if fused else 8.0 * n_loc * K)) / (e_ms * 1e-3) * 1e-9 if e_ms > 0 else 0.0, "peak_gbs": hbm_peak,
                 "peak_source": hbm_src, "note": ("fused sweep reads X once and writes nothing per point" if fused else
                                                  "E-pass reads X once and writes the responsibilities once") + "; fp64-bound, not HBM-bound"},
-        "mstep": {"ms_per_launch": m_ms, "algorithmic_bytes": 8.0 * n_loc * K + 8.0 * n_loc * d,
-                  "achieved_gbs": (8.0 * n_loc * K + 8.0 * n_loc * d) / (m_ms * 1e-3) * 1e-9 if m_ms > 0 else 0.0},
+        "mstep": (None if fused else {"ms_per_launch": m_ms, "algorithmic_bytes": 8.0 * n_loc * K + 8.0 * n_loc * d,
+                                      "achieved_gbs": (8.0 * n_loc * K + 8.0 * n_loc * d) / (m_ms * 1e-3) * 1e-9 if m_ms > 0 else 0.0}),
         "per_iteration_ms": {k: v / it for k, v in times.items() if k != "iters"},
     }
 
