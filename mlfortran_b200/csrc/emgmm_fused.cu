@@ -562,18 +562,29 @@ cudaError_t launch_amb_resolve(const Geom& g, const double* X, const AmbEntry* a
 }
 
 // flags[0] = listed pairs on this rank, flags[1] = lists that overflowed their capacity (both all-reduced as doubles)
-__global__ void k_amb_summary(const int* __restrict__ counts, int nlists, int cap, double* __restrict__ flags) {
+__global__ void __launch_bounds__(256) k_amb_summary(const int* __restrict__ counts, int nlists, int cap, double* __restrict__ flags) {
+  __shared__ long long s_tot[256];
+  __shared__ int s_over[256];
   long long tot = 0;
   int over = 0;
-  for (int l = 0; l < nlists; ++l) {
+  for (int l = threadIdx.x; l < nlists; l += 256) {
     tot += counts[l];
     over += counts[l] > cap;
   }
-  flags[0] = (double)tot;
-  flags[1] = (double)over;
+  s_tot[threadIdx.x] = tot;
+  s_over[threadIdx.x] = over;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { s_tot[threadIdx.x] += s_tot[threadIdx.x + s]; s_over[threadIdx.x] += s_over[threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    flags[0] = (double)s_tot[0];
+    flags[1] = (double)s_over[0];
+  }
 }
 cudaError_t launch_amb_summary(const int* counts, int nlists, int cap, double* flags, cudaStream_t st) {
-  k_amb_summary<<<1, 1, 0, st>>>(counts, nlists, cap, flags);
+  k_amb_summary<<<1, 256, 0, st>>>(counts, nlists, cap, flags);
   return cudaGetLastError();
 }
 
