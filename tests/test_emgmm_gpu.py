@@ -273,6 +273,37 @@ def test_streamed_refresh_of_x(oracle):
     em.finalize()
 
 
+# ---- randomized sweep over small shapes (every kernel plan that serves d <= 32) ----------------------------------------
+def _random_cases(n_cases, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n_cases):
+        d = int(rng.integers(1, 21))
+        K = int(rng.integers(1, 41))
+        npc = int(rng.integers(max(2 * d + 2, 8), 120))
+        sc = float(rng.choice([1.0, 2.5, 6.0]))          # from heavily overlapping to well separated
+        mp = float(rng.choice([0.0, 0.2, 1.0]))
+        out.append((d, K, npc, sc, 1000 + i, mp, int(rng.integers(1, 5))))
+    return out
+
+
+@pytest.mark.parametrize("case", _random_cases(36, 2024), ids=lambda c: f"d{c[0]}_K{c[1]}_n{c[2]}_sc{c[3]}_mp{c[5]}_it{c[6]}")
+def test_randomized_small_shapes(case, oracle):
+    d, K, npc, sc, seed, mp, iters = case
+    data = synth.make_mixture(d, K, npc, sc, 1.0, seed)
+    X = data["X"]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], seed)
+    oMu, oCov, olam, otr, oP = oracle.em_iterations(X, Mu0, Cov0, lam0, mp, iters, return_proba=True)
+    if not (np.isfinite(oCov).all() and np.isfinite(otr).all()):
+        pytest.skip("the reference iteration itself degenerates on this draw (NaN), nothing to compare")
+    em = make_em(X, K, mp, Mu0, Cov0, lam0)
+    info, _ = em.step(iters)
+    assert info == 0, em.last_error()
+    check_against(em, oMu, oCov, olam, otr)
+    assert np.abs(em.ProbaC - oP).max() <= 1e-9, em.kernel_plan()
+    em.finalize()
+
+
 # ---- large shapes: d up to 128 (BASELINE configs[3] shape) and packs too large for shared memory ---------------------
 BIG_CASES = [
     # d, K, n_per_comp, sigma_c, seed, minProba, iters
