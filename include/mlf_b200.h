@@ -88,6 +88,14 @@ MLF_OBJ *mlf_emgmm_c(double *X, int nX, int nY, int nC, double minProba, MLF_OBJ
 /* As mlf_emgmm_c with 64-bit point count, device selection (-1 = current) and flags. */
 MLF_OBJ *mlf_b200_emgmm_create(const double *X, int64_t nX, int nY, int nC, double minProba, MLF_OBJ *handler, int device, unsigned flags);
 
+/* Single-process multi-GPU object: the points are sharded in contiguous blocks over `devices` (ndevices <= 0: every visible
+ * device), one engine and one host thread per shard, and the statistics all-reduce is done by the library itself over peer
+ * memory (NVLink P2P loads, summed in rank order so that all shards hold bit-identical parameters).  This is how a plain
+ * one-process caller of the reference's API (Fortran `init(X, nC)` / `step`) gets every GPU of the box.  X must be a host
+ * array.  The handle behaves like any other EM handle (mlf_step, mlf_getrsc, mlf_pushState, mlf_getClass, ...). */
+MLF_OBJ *mlf_b200_emgmm_create_multi(const double *X, int64_t nX, int nY, int nC, double minProba, MLF_OBJ *handler,
+                                     const int *devices, int ndevices, unsigned flags);
+
 /* Sharded operation (one process per GPU): install an in-place sum all-reduce over `count` doubles at device
  * pointer buf, enqueued on CUDA stream `stream`.  The object then treats its X as one shard of the global data. */
 typedef int (*mlf_b200_allreduce_fn)(void *ctx, double *buf, int64_t count, void *stream);

@@ -14,9 +14,11 @@
 
 #include "../../include/mlf_b200.h"
 #include "emgmm_engine.h"
+#include "emgmm_multi.h"
 #include "mlf_hdf5_min.h"
 
 using mlfb200::EmgmmEngine;
+using mlfb200::MultiEngine;
 
 namespace {
 
@@ -69,7 +71,15 @@ struct EmObject : Handle {
   bool initialized = false;
   const double* X = nullptr;
   bool x_on_device = false;
-  EmgmmEngine eng;
+  EmgmmEngine eng;                     // single-GPU object (or one shard of a one-process-per-GPU job)
+  std::unique_ptr<MultiEngine> multi;  // single-process multi-GPU object: one engine per device, peer-memory all-reduce
+  // dispatch to whichever of the two this object is
+  int e_upload() { return multi ? multi->upload_params(Mu.data(), Cov.data(), lambda.data()) : eng.upload_params(Mu.data(), Cov.data(), lambda.data()); }
+  int e_download() { return multi ? multi->download_params(Mu.data(), Cov.data(), lambda.data()) : eng.download_params(Mu.data(), Cov.data(), lambda.data()); }
+  int e_kmeans(int nkm, uint64_t sd) { return multi ? multi->kmeans_init(nkm, sd) : eng.kmeans_init(nkm, sd); }
+  int e_iterate(int64_t n, double mp, double* ll, double* tr) { return multi ? multi->iterate(n, mp, ll, tr) : eng.iterate(n, mp, ll, tr); }
+  int e_expect(const double* Xq, int64_t nq, double* P, int32_t* cl) { return multi ? multi->expectation(Xq, nq, P, cl) : eng.expectation(Xq, false, nq, P, cl); }
+  std::string e_error() { return multi ? multi->last_error() : eng.last_error(); }
   std::vector<double> trace;
   std::string err, plan;
   int rank = 0, world = 1;
@@ -135,24 +145,24 @@ int em_stepF(EmObject* o, int64_t niter) {
   int64_t em_iters = niter;
   if (!o->initialized) {
     // first iteration of a fresh object: k-means (nkm = 16), Cov = I, lambda = 1/K  (:135-145)
-    int r = o->eng.kmeans_init(16, o->seed);
-    if (r < 0) { o->err = o->eng.last_error(); return r; }
-    r = o->eng.download_params(o->Mu.data(), o->Cov.data(), o->lambda.data());
+    int r = o->e_kmeans(16, o->seed);
+    if (r < 0) { o->err = o->e_error(); return r; }
+    r = o->e_download();
     if (r < 0) return r;
     o->initialized = true;
     em_iters = niter - 1;
   } else {
     // host mirrors are the source of truth between steps: callers hold direct pointers (mlf_getrsc) and may
     // write them, and mlf_updatersc memcpy's into them
-    int r = o->eng.upload_params(o->Mu.data(), o->Cov.data(), o->lambda.data());
-    if (r < 0) { o->err = o->eng.last_error(); return r; }
+    int r = o->e_upload();
+    if (r < 0) { o->err = o->e_error(); return r; }
   }
   if (em_iters > 0) {
     o->trace.assign((size_t)em_iters, 0.0);
-    int r = o->eng.iterate(em_iters, o->minProba(), &o->sumLL(), o->trace.data());
-    if (r < 0) { o->err = o->eng.last_error(); return r; }
-    r = o->eng.download_params(o->Mu.data(), o->Cov.data(), o->lambda.data());
-    if (r < 0) { o->err = o->eng.last_error(); return r; }
+    int r = o->e_iterate(em_iters, o->minProba(), &o->sumLL(), o->trace.data());
+    if (r < 0) { o->err = o->e_error(); return r; }
+    r = o->e_download();
+    if (r < 0) { o->err = o->e_error(); return r; }
   } else {
     o->trace.clear();
   }
@@ -186,7 +196,8 @@ bool restore_from(Hdf5Handle* h, EmObject* o, int d, int& K) {
          rd("rVar", mlfh5::F64, o->rVar, 3);
 }
 
-MLF_OBJ* em_create(const double* X, int64_t nX, int nY, int nC, double minProba, MLF_OBJ* handler, int device, unsigned flags) {
+MLF_OBJ* em_create(const double* X, int64_t nX, int nY, int nC, double minProba, MLF_OBJ* handler, int device, unsigned flags,
+                   const std::vector<int>* devices = nullptr) {
   if (!X && nX > 0) return nullptr;
   if (nX < 0 || nY < 1) return nullptr;
   std::unique_ptr<EmObject> o(new EmObject());
@@ -217,14 +228,21 @@ MLF_OBJ* em_create(const double* X, int64_t nX, int nY, int nC, double minProba,
     if (cudaGetDevice(&cur) != cudaSuccess) cur = 0;
     device = cur;
   }
-  if (o->eng.init(X, o->x_on_device, nX, nY, K, device, (flags & MLF_B200_COV_DIAG) != 0) < 0) {
+  if (devices) {
+    if (o->x_on_device) { fprintf(stderr, "mlf_b200_emgmm_create_multi: X must be a host array\n"); return nullptr; }
+    o->multi.reset(new MultiEngine());
+    if (o->multi->init(X, nX, nY, K, *devices, (flags & MLF_B200_COV_DIAG) != 0) < 0) {
+      fprintf(stderr, "mlf_b200_emgmm_create_multi: %s\n", o->multi->last_error().c_str());
+      return nullptr;
+    }
+  } else if (o->eng.init(X, o->x_on_device, nX, nY, K, device, (flags & MLF_B200_COV_DIAG) != 0) < 0) {
     fprintf(stderr, "mlf_emgmm_c: %s\n", o->eng.last_error().c_str());
     return nullptr;
   }
   if (h5) {
     o->minProba() = minProba;  // not part of the checkpoint (see rPar note above)
     o->initialized = true;     // src/unsupervised/mlf_emgmm.f90:106-107
-    if (o->eng.upload_params(o->Mu.data(), o->Cov.data(), o->lambda.data()) < 0) return nullptr;
+    if (o->e_upload() < 0) return nullptr;
   } else {
     o->reinit();  // :109
     o->minProba() = minProba;  // InitOrDefault(this%minProba, 0d0, minProba) (:105)
@@ -342,9 +360,9 @@ int mlf_getNumClasses(MLF_OBJ* obj) {
 static int em_expect(EmObject* o, const double* X, int nX, int nIn, double* P, int* Cl) {
   if (!o->initialized) return mlf_UNINIT;  // src/unsupervised/mlf_emgmm.f90:166-169
   if (nX != o->d || nIn < 0) return -1;
-  int r = o->eng.upload_params(o->Mu.data(), o->Cov.data(), o->lambda.data());
+  int r = o->e_upload();
   if (r < 0) return r;
-  return o->eng.expectation(X, false, nIn, P, Cl);
+  return o->e_expect(X, nIn, P, Cl);
 }
 
 int mlf_getClass(MLF_OBJ* obj, const double* X, int* Cl, int nX, int nIn) {
@@ -391,9 +409,26 @@ MLF_OBJ* mlf_b200_emgmm_create(const double* X, int64_t nX, int nY, int nC, doub
   return em_create(X, nX, nY, nC, minProba, handler, device, flags);
 }
 
+MLF_OBJ* mlf_b200_emgmm_create_multi(const double* X, int64_t nX, int nY, int nC, double minProba, MLF_OBJ* handler, const int* devices,
+                                     int ndevices, unsigned flags) {
+  std::vector<int> dv;
+  if (ndevices <= 0 || !devices) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+      fprintf(stderr, "mlf_b200_emgmm_create_multi: no CUDA device visible; mlfortran_b200 has no CPU fallback\n");
+      return nullptr;
+    }
+    for (int i = 0; i < n; ++i) dv.push_back(i);
+  } else {
+    dv.assign(devices, devices + ndevices);
+  }
+  return em_create(X, nX, nY, nC, minProba, handler, -1, flags, &dv);
+}
+
 int mlf_b200_set_allreduce(MLF_OBJ* obj, mlf_b200_allreduce_fn fn, void* ctx, int rank, int world) {
   EmObject* o = as_em(obj);
   if (!o) return -1;
+  if (o->multi) return -1;  // a single-process multi-GPU object does its own all-reduce
   o->eng.set_allreduce(fn, ctx, rank, world);
   o->rank = rank;
   o->world = world;
@@ -414,7 +449,8 @@ int mlf_b200_get_initialized(MLF_OBJ* obj) {
 int mlf_b200_set_cov_type(MLF_OBJ* obj, int cov_type) {
   EmObject* o = as_em(obj);
   if (!o || (cov_type != 0 && cov_type != 1)) return -1;
-  o->eng.set_cov_diag(cov_type == 1);
+  if (o->multi) o->multi->set_cov_diag(cov_type == 1);
+  else o->eng.set_cov_diag(cov_type == 1);
   return 0;
 }
 
@@ -429,20 +465,21 @@ int mlf_b200_refresh_x(MLF_OBJ* obj, const double* X) {
   EmObject* o = as_em(obj);
   if (!o) return -1;
   o->X = X;
-  return o->eng.refresh_x(X, o->x_on_device);
+  return o->multi ? o->multi->refresh_x(X) : o->eng.refresh_x(X, o->x_on_device);
 }
 
 const char* mlf_b200_kernel_plan(MLF_OBJ* obj) {
   EmObject* o = as_em(obj);
   if (!o) return "invalid handle";
-  o->plan = o->eng.plan();
+  o->plan = o->multi ? o->multi->plan() : o->eng.plan();
   return o->plan.c_str();
 }
 
 const char* mlf_b200_last_error(MLF_OBJ* obj) {
   EmObject* o = as_em(obj);
   if (!o) return "invalid handle";
-  return o->err.empty() ? o->eng.last_error().c_str() : o->err.c_str();
+  if (o->err.empty()) o->err = o->e_error();
+  return o->err.c_str();
 }
 
 int64_t mlf_b200_sumll_trace(MLF_OBJ* obj, double* out, int64_t n) {
@@ -457,12 +494,13 @@ int64_t mlf_b200_sumll_trace(MLF_OBJ* obj, double* out, int64_t n) {
 int mlf_b200_resident_proba(MLF_OBJ* obj, double* P) {
   EmObject* o = as_em(obj);
   if (!o || !P) return -1;
-  return o->eng.resident_proba(P);
+  return o->multi ? o->multi->resident_proba(P) : o->eng.resident_proba(P);
 }
 
 const double* mlf_b200_resident_proba_device(MLF_OBJ* obj, int64_t* ld) {
   EmObject* o = as_em(obj);
   if (!o) return nullptr;
+  if (o->multi) return nullptr;  // sharded over several devices: use mlf_b200_resident_proba
   if (ld) *ld = o->eng.gamma_ld();
   return o->eng.gamma_device();
 }
@@ -471,37 +509,37 @@ int mlf_b200_resident_labels(MLF_OBJ* obj, int* Cl) {
   EmObject* o = as_em(obj);
   if (!o || !Cl) return -1;
   if (!o->initialized) return mlf_UNINIT;
-  int r = o->eng.upload_params(o->Mu.data(), o->Cov.data(), o->lambda.data());
+  int r = o->e_upload();
   if (r < 0) return r;
-  return o->eng.resident_labels(Cl);
+  return o->multi ? o->multi->resident_labels(Cl) : o->eng.resident_labels(Cl);
 }
 
 int mlf_b200_set_profile(MLF_OBJ* obj, int on) {
   EmObject* o = as_em(obj);
   if (!o) return -1;
-  o->eng.set_profile(on != 0);
-  o->eng.reset_times();
+  if (o->multi) { o->multi->set_profile(on != 0); o->multi->reset_times(); }
+  else { o->eng.set_profile(on != 0); o->eng.reset_times(); }
   return 0;
 }
 int mlf_b200_get_times(MLF_OBJ* obj, double out[8]) {
   EmObject* o = as_em(obj);
   if (!o || !out) return -1;
-  const mlfb200::EngineTimes& t = o->eng.times();
+  const mlfb200::EngineTimes t = o->multi ? o->multi->times() : o->eng.times();
   out[0] = t.refresh; out[1] = t.estep; out[2] = t.mid; out[3] = t.mstep; out[4] = t.fin; out[5] = (double)t.iters;
   out[6] = (double)t.sweeps; out[7] = (double)t.amb_pairs;
   return 0;
 }
 int64_t mlf_b200_launch_count(MLF_OBJ* obj) {
   EmObject* o = as_em(obj);
-  return o ? o->eng.launches() : -1;
+  return o ? (o->multi ? o->multi->launches() : o->eng.launches()) : -1;
 }
 void* mlf_b200_stream(MLF_OBJ* obj) {
   EmObject* o = as_em(obj);
-  return o ? (void*)o->eng.stream() : nullptr;
+  return (o && !o->multi) ? (void*)o->eng.stream() : nullptr;
 }
 int64_t mlf_b200_global_points(MLF_OBJ* obj) {
   EmObject* o = as_em(obj);
-  return o ? o->eng.n_global() : -1;
+  return o ? (o->multi ? o->multi->n_global() : o->eng.n_global()) : -1;
 }
 
 int mlf_b200_h5_put(MLF_OBJ* handler, const char* name, int dtype, int rank, const int64_t* dims, const void* data, int override_) {

@@ -102,7 +102,7 @@ class mlf_algo_emgmm:
 
     # -- init / lifetime ------------------------------------------------------------------------------------------
     def init(self, X, nC: int, minProba: float | None = None, data_handler: mlf_hdf5_file | None = None,
-             device: int = -1, cov_type: str = "full") -> int:
+             device: int = -1, cov_type: str = "full", devices=None) -> int:
         """info = this%init(X, nC, minProba, data_handler) (src/unsupervised/mlf_emgmm.f90:76-112).
 
         X: NumPy (N,d) float64 C-contiguous (borrowed, copied once to HBM) or a CUDA torch tensor of that shape
@@ -124,7 +124,13 @@ class mlf_algo_emgmm:
         self._X = X
         n, d = int(X.shape[0]), int(X.shape[1])
         h = data_handler._h if data_handler is not None else None
-        self._h = lib.mlf_b200_emgmm_create(ptr, n, d, int(nC), 0.0 if minProba is None else float(minProba), h, device, flags)
+        if devices is not None:   # single-process multi-GPU object: one shard per listed device ([] = every visible device)
+            if flags & X_ON_DEVICE:
+                return mlf_OTHERERROR
+            dv = (C.c_int * max(len(devices), 1))(*devices)
+            self._h = lib.mlf_b200_emgmm_create_multi(ptr, n, d, int(nC), 0.0 if minProba is None else float(minProba), h, dv, len(devices), flags)
+        else:
+            self._h = lib.mlf_b200_emgmm_create(ptr, n, d, int(nC), 0.0 if minProba is None else float(minProba), h, device, flags)
         if not self._h:
             return mlf_OTHERERROR
         self._bind()

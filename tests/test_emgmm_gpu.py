@@ -753,6 +753,42 @@ def test_two_shards_kmeans_initialiser(oracle):
     assert (dist.min(axis=0) < 0.5).all()
 
 
+# ---- single-process multi-GPU object (peer-memory all-reduce); on a one-GPU box the shards share the device ----------
+@pytest.mark.parametrize("devices", [[0, 0], [0, 0, 0], []], ids=["2_shards", "3_shards", "all_visible_devices"])
+def test_single_process_multi_gpu_object(devices, oracle):
+    import torch
+
+    if devices == [] and torch.cuda.device_count() > 1:
+        devices = list(range(torch.cuda.device_count()))
+    data = synth.make_mixture(6, 7, 500, 4.0, 1.0, 181)
+    X = data["X"]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 181)
+    oMu, oCov, olam, otr, oP = oracle.em_iterations(X, Mu0, Cov0, lam0, 0.0, 5, return_proba=True)
+    em = mlf_algo_emgmm()
+    assert em.init(X, 7, 0.0, devices=devices) == 0
+    if devices:
+        assert f"{len(devices)} shards" in em.kernel_plan()
+    em.inject(Mu0, Cov0, lam0)
+    assert em.step(5)[0] == 0, em.last_error()
+    check_against(em, oMu, oCov, olam, otr)
+    assert em.global_points() == X.shape[0]
+    assert np.abs(em.ProbaC - oP).max() <= 1e-9          # gathered from the shards
+    info, cl = em.getClass(X)
+    _, Pn, _ = oracle.exp_step(X, em.Mu, em.Cov, em.lambda_)
+    bad = cl != oracle.get_class(Pn)
+    if bad.any():
+        assert near_tie_mask(oracle, X, em.Mu, em.Cov, em.lambda_)[bad].all()
+    np.testing.assert_array_equal(em.labels(), cl)
+    em.finalize()
+    # fresh object: the k-means initialiser draws from the global data through the same peer all-reduce
+    em = mlf_algo_emgmm()
+    assert em.init(X, 7, 1.0, devices=devices) == 0
+    em.set_seed(5)
+    assert em.step(3)[0] == 0, em.last_error()
+    assert np.isfinite(em.Mu).all() and em.niter == 3
+    em.finalize()
+
+
 # ---- full-size properties (BASELINE configs[2] shape on one GPU) ----------------------------------------------------
 def test_full_size_properties_and_sample_parity(oracle):
     """N=1e8 (or what fits), d=16, K=64: size-independent invariants plus oracle parity on a 20 000-point sample."""
