@@ -30,6 +30,10 @@ Module mlf_emgmm_b200
 
   Integer(c_int), Parameter :: nkm_default = 16   ! hard-coded in the reference (src/unsupervised/mlf_emgmm.f90:131)
 
+  ! .TRUE.: objects initialised from now on shard their points over every visible GPU inside this process (peer-memory
+  ! all-reduce, mlf_b200_engine_create_multi); .FALSE.: the current CUDA device only.
+  Logical, Public, Save :: mlf_b200_use_all_gpus = .FALSE.
+
   Type, Public, Extends(mlf_step_obj) :: mlf_algo_emgmm_b200
     real(c_double), pointer :: X(:,:), Mu(:,:), Cov(:,:,:), lambda(:)
     real(c_double), pointer :: sumLL, minProba
@@ -60,6 +64,14 @@ Module mlf_emgmm_b200
       integer(c_int), value :: nY, nC, device, flags
       type(c_ptr) :: eng
     End Function c_engine_create
+    Function c_engine_create_multi(X, nX, nY, nC, devices, ndevices, flags) Result(eng) bind(C, name="mlf_b200_engine_create_multi")
+      Import :: c_ptr, c_double, c_int64_t, c_int
+      real(c_double), intent(in) :: X(*)
+      integer(c_int64_t), value :: nX
+      integer(c_int), value :: nY, nC, ndevices, flags
+      type(c_ptr), value :: devices        ! C_NULL_PTR with ndevices = 0: every visible device
+      type(c_ptr) :: eng
+    End Function c_engine_create_multi
     Subroutine c_engine_destroy(eng) bind(C, name="mlf_b200_engine_destroy")
       Import :: c_ptr
       type(c_ptr), value :: eng
@@ -125,7 +137,12 @@ Contains
     CALL this%addRVar(nf, this%sumLL, "sumLL")
     CALL this%addRPar(nf, this%minProba, "minProba")
     CALL InitOrDefault(this%minProba, 0.0d0, minProba)
-    this%engine = c_engine_create(X, INT(SIZE(X,2), c_int64_t), INT(SIZE(X,1), c_int), INT(nC, c_int), this%device, 0_c_int)
+    If(mlf_b200_use_all_gpus) Then
+      this%engine = c_engine_create_multi(X, INT(SIZE(X,2), c_int64_t), INT(SIZE(X,1), c_int), INT(nC, c_int), &
+        C_NULL_PTR, 0_c_int, 0_c_int)
+    Else
+      this%engine = c_engine_create(X, INT(SIZE(X,2), c_int64_t), INT(SIZE(X,1), c_int), INT(nC, c_int), this%device, 0_c_int)
+    Endif
     If(.NOT. C_ASSOCIATED(this%engine)) Then
       info = mlf_OTHERERROR                                   ! no GPU / no library: there is no CPU fallback
       RETURN

@@ -137,6 +137,8 @@ const char *mlf_b200_version(void);
  * its end), replacing ExpStep/MaxStep of src/unsupervised/mlf_emgmm.f90:174-207. */
 typedef void MLF_B200_ENGINE;
 MLF_B200_ENGINE *mlf_b200_engine_create(const double *X, int64_t nX, int nY, int nC, int device, unsigned flags);
+/* As above, sharded over `devices` inside this process (ndevices <= 0: every visible device); see mlf_b200_emgmm_create_multi. */
+MLF_B200_ENGINE *mlf_b200_engine_create_multi(const double *X, int64_t nX, int nY, int nC, const int *devices, int ndevices, unsigned flags);
 void mlf_b200_engine_destroy(MLF_B200_ENGINE *eng);
 /* niter x (ExpStep + MaxStep) from the caller's current Mu/Cov/lambda; sumLL of the last iteration. 0 or negative. */
 int mlf_b200_engine_step(MLF_B200_ENGINE *eng, int64_t niter, double minProba, double *Mu, double *Cov, double *lambda, double *sumLL);

@@ -62,6 +62,7 @@ SYMBOLS = {
     "mlf_b200_global_points": (C.c_int64, [C.c_void_p]),
     "mlf_b200_version": (C.c_char_p, []),
     "mlf_b200_engine_create": (C.c_void_p, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint]),
+    "mlf_b200_engine_create_multi": (C.c_void_p, [C.c_void_p, C.c_int64, C.c_int, C.c_int, c_int_p, C.c_int, C.c_uint]),
     "mlf_b200_engine_destroy": (None, [C.c_void_p]),
     "mlf_b200_engine_step": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, c_double_p]),
     "mlf_b200_engine_kmeans_init": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),

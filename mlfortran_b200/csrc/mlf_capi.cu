@@ -589,55 +589,85 @@ const char* mlf_b200_h5_name(MLF_OBJ* handler, int idx) {
 }
 
 // ---- engine-level entry points (bound by fortran/mlf_emgmm_b200.f90) ---------------------------------------------
+namespace {
+struct EngHandle {  // one device, or every listed device of the box inside this process
+  std::unique_ptr<EmgmmEngine> single;
+  std::unique_ptr<MultiEngine> multi;
+  std::string err;
+};
+EngHandle* as_eng(MLF_B200_ENGINE* p) { return static_cast<EngHandle*>(p); }
+}  // namespace
+
 MLF_B200_ENGINE* mlf_b200_engine_create(const double* X, int64_t nX, int nY, int nC, int device, unsigned flags) {
   if ((!X && nX > 0) || nX < 0 || nY < 1 || nC < 1) return nullptr;
-  std::unique_ptr<EmgmmEngine> e(new EmgmmEngine());
+  std::unique_ptr<EngHandle> h(new EngHandle());
+  h->single.reset(new EmgmmEngine());
   if (device < 0 && cudaGetDevice(&device) != cudaSuccess) device = 0;
-  if (e->init(X, (flags & MLF_B200_X_ON_DEVICE) != 0, nX, nY, nC, device, (flags & MLF_B200_COV_DIAG) != 0) < 0) {
-    fprintf(stderr, "mlf_b200_engine_create: %s\n", e->last_error().c_str());
+  if (h->single->init(X, (flags & MLF_B200_X_ON_DEVICE) != 0, nX, nY, nC, device, (flags & MLF_B200_COV_DIAG) != 0) < 0) {
+    fprintf(stderr, "mlf_b200_engine_create: %s\n", h->single->last_error().c_str());
     return nullptr;
   }
-  return e.release();
+  return h.release();
 }
-void mlf_b200_engine_destroy(MLF_B200_ENGINE* eng) { delete static_cast<EmgmmEngine*>(eng); }
+MLF_B200_ENGINE* mlf_b200_engine_create_multi(const double* X, int64_t nX, int nY, int nC, const int* devices, int ndevices, unsigned flags) {
+  if ((!X && nX > 0) || nX < 0 || nY < 1 || nC < 1 || (flags & MLF_B200_X_ON_DEVICE)) return nullptr;
+  std::vector<int> dv;
+  if (ndevices <= 0 || !devices) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { fprintf(stderr, "mlf_b200_engine_create_multi: no CUDA device\n"); return nullptr; }
+    for (int i = 0; i < n; ++i) dv.push_back(i);
+  } else {
+    dv.assign(devices, devices + ndevices);
+  }
+  std::unique_ptr<EngHandle> h(new EngHandle());
+  h->multi.reset(new MultiEngine());
+  if (h->multi->init(X, nX, nY, nC, dv, (flags & MLF_B200_COV_DIAG) != 0) < 0) {
+    fprintf(stderr, "mlf_b200_engine_create_multi: %s\n", h->multi->last_error().c_str());
+    return nullptr;
+  }
+  return h.release();
+}
+void mlf_b200_engine_destroy(MLF_B200_ENGINE* eng) { delete as_eng(eng); }
 int mlf_b200_engine_step(MLF_B200_ENGINE* eng, int64_t niter, double minProba, double* Mu, double* Cov, double* lambda, double* sumLL) {
-  EmgmmEngine* e = static_cast<EmgmmEngine*>(eng);
+  EngHandle* e = as_eng(eng);
   if (!e || !Mu || !Cov || !lambda) return -1;
   if (niter <= 0) return 0;
-  int r = e->upload_params(Mu, Cov, lambda);
-  if (r == 0) r = e->iterate(niter, minProba, sumLL, nullptr);
-  if (r == 0) r = e->download_params(Mu, Cov, lambda);
+  int r = e->multi ? e->multi->upload_params(Mu, Cov, lambda) : e->single->upload_params(Mu, Cov, lambda);
+  if (r == 0) r = e->multi ? e->multi->iterate(niter, minProba, sumLL, nullptr) : e->single->iterate(niter, minProba, sumLL, nullptr);
+  if (r == 0) r = e->multi ? e->multi->download_params(Mu, Cov, lambda) : e->single->download_params(Mu, Cov, lambda);
   return r;
 }
 int mlf_b200_engine_kmeans_init(MLF_B200_ENGINE* eng, int nkm, uint64_t seed, double* Mu, double* Cov, double* lambda) {
-  EmgmmEngine* e = static_cast<EmgmmEngine*>(eng);
+  EngHandle* e = as_eng(eng);
   if (!e || !Mu || !Cov || !lambda) return -1;
-  int r = e->kmeans_init(nkm, seed);
-  if (r == 0) r = e->download_params(Mu, Cov, lambda);
+  int r = e->multi ? e->multi->kmeans_init(nkm, seed) : e->single->kmeans_init(nkm, seed);
+  if (r == 0) r = e->multi ? e->multi->download_params(Mu, Cov, lambda) : e->single->download_params(Mu, Cov, lambda);
   return r;
 }
 int mlf_b200_engine_expectation(MLF_B200_ENGINE* eng, const double* Mu, const double* Cov, const double* lambda, const double* Xq,
                                 int64_t nIn, double* P, int* Cl) {
-  EmgmmEngine* e = static_cast<EmgmmEngine*>(eng);
+  EngHandle* e = as_eng(eng);
   if (!e || !Mu || !Cov || !lambda || nIn < 0 || (!Xq && nIn > 0)) return -1;
-  int r = e->upload_params(Mu, Cov, lambda);
-  if (r == 0) r = e->expectation(Xq, false, nIn, P, Cl);
+  int r = e->multi ? e->multi->upload_params(Mu, Cov, lambda) : e->single->upload_params(Mu, Cov, lambda);
+  if (r == 0) r = e->multi ? e->multi->expectation(Xq, nIn, P, Cl) : e->single->expectation(Xq, false, nIn, P, Cl);
   return r;
 }
 int mlf_b200_engine_proba(MLF_B200_ENGINE* eng, double* ProbaC) {
-  EmgmmEngine* e = static_cast<EmgmmEngine*>(eng);
+  EngHandle* e = as_eng(eng);
   if (!e || !ProbaC) return -1;
-  return e->resident_proba(ProbaC);
+  return e->multi ? e->multi->resident_proba(ProbaC) : e->single->resident_proba(ProbaC);
 }
 int mlf_b200_engine_set_allreduce(MLF_B200_ENGINE* eng, mlf_b200_allreduce_fn fn, void* ctx, int rank, int world) {
-  EmgmmEngine* e = static_cast<EmgmmEngine*>(eng);
-  if (!e) return -1;
-  e->set_allreduce(fn, ctx, rank, world);
+  EngHandle* e = as_eng(eng);
+  if (!e || e->multi) return -1;
+  e->single->set_allreduce(fn, ctx, rank, world);
   return 0;
 }
 const char* mlf_b200_engine_last_error(MLF_B200_ENGINE* eng) {
-  EmgmmEngine* e = static_cast<EmgmmEngine*>(eng);
-  return e ? e->last_error().c_str() : "invalid engine";
+  EngHandle* e = as_eng(eng);
+  if (!e) return "invalid engine";
+  e->err = e->multi ? e->multi->last_error() : e->single->last_error();
+  return e->err.c_str();
 }
 
 // Single-component entry points (src/unsupervised/mlf_gaussian.f90:53-59,81-88): a temporary K = 1 engine over the

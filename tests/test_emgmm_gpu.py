@@ -637,6 +637,16 @@ def test_engine_level_abi_matches_handle_level(oracle):
     assert lib.mlf_b200_engine_kmeans_init(eng, 16, 7, Mk.ctypes.data, Ck.ctypes.data, lk.ctypes.data) == 0
     assert np.isfinite(Mk).all() and (Ck == np.eye(d)).all() and (lk == 1.0 / K).all()
     lib.mlf_b200_engine_destroy(eng)
+    # the same calls on an engine sharded inside this process (what the Fortran shim binds when mlf_b200_use_all_gpus is set)
+    dv = (C.c_int * 2)(0, 0)
+    eng = lib.mlf_b200_engine_create_multi(X.ctypes.data, n, d, K, dv, 2, 0)
+    assert eng
+    Mu, Cov, lam = Mu0.copy(), Cov0.copy(), lam0.copy()
+    assert lib.mlf_b200_engine_step(eng, 4, 0.0, Mu.ctypes.data, Cov.ctypes.data, lam.ctypes.data, C.byref(ll)) == 0
+    assert abs(ll.value - otr[-1]) <= LL_RTOL * abs(otr[-1])
+    assert rel(Mu, oMu) <= PAR_RTOL and rel(Cov, oCov) <= PAR_RTOL and np.abs(lam - olam).max() <= PAR_RTOL
+    assert lib.mlf_b200_engine_proba(eng, P.ctypes.data) == 0 and np.abs(P - oP).max() <= 1e-9
+    lib.mlf_b200_engine_destroy(eng)
 
 
 # ---- sharded protocol on one GPU: two objects, each with half the points, host-side all-reduce between them ---------
