@@ -98,6 +98,8 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   {
     const char* e16 = getenv("MLF_B200_EM16");
     use16_ = fused_ && em16_ok(geom_, fgeom_, smem_limit_) && !(e16 && e16[0] == '0');
+    const char* ed = getenv("MLF_B200_EMD");
+    used_ = fused_ && cov_diag_ && emd_ok(geom_, fgeom_, smem_limit_) && !(ed && ed[0] == '0');
   }
   n_ = n_local;
   nglob_ = n_local;
@@ -165,6 +167,8 @@ std::string EmgmmEngine::plan() const {
   const Geom& g = geom_;
   if (use16_)
     snprintf(buf, sizeof buf, "k_em16<%d>: fused single sweep, 16 warps/SM, covariance-scatter accumulators in tensor memory", g.DM);
+  else if (used_)
+    snprintf(buf, sizeof buf, "k_emd: fused single sweep for diagonal covariances on the fp64 CUDA cores (lane = component)");
   else if (fused_)
     snprintf(buf, sizeof buf, "k_em<%d,%d,true,%d,%s>: fused single sweep, 8 warps/SM, %d-point tiles", g.DM, fgeom_.CBMAX, fgeom_.GPW,
              fgeom_.diag ? "diag" : "full", fgeom_.TP);
@@ -474,6 +478,7 @@ int EmgmmEngine::streamed_sweep(const EmArgs& base) {
     a.accumulate = 1;
     a.p_offset = off;
     if (use16_) CKE(launch_em16(g, f, a, grid, smem_limit_, st_), "em sweep (streamed chunk, 16 warps)");
+    else if (used_) CKE(launch_emd(g, f, a, grid, smem_limit_, st_), "em sweep (streamed chunk, diagonal)");
     else CKE(launch_em(g, f, a, true, grid, smem_limit_, st_), "em sweep (streamed chunk)");
     launches_ += 2;
   }
@@ -548,6 +553,7 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
         launches_ += 2;
       } else {
         if (use16_) CKE(launch_em16(g, f, a, egrid_, smem_limit_, st_), "em sweep (fused, 16 warps)");
+        else if (used_) CKE(launch_emd(g, f, a, egrid_, smem_limit_, st_), "em sweep (fused, diagonal)");
         else CKE(launch_em(g, f, a, true, egrid_, smem_limit_, st_), "em sweep (fused)");
         ++launches_;
       }

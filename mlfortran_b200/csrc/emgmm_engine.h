@@ -100,6 +100,7 @@ class EmgmmEngine {
   Geom geom_{};
   FusedGeom fgeom_{};
   bool fused_ = false;        // single-sweep path available for this (d, K)
+  bool used_ = false;         // diagonal fused sweep on the CUDA cores (emgmm_diag.cu; MLF_B200_EMD=0 disables)
   bool use16_ = false;        // 16-warp fused sweep with the scatter accumulators in tensor memory (MLF_B200_EM16=0 disables)
   bool legacy_estep_ = false; // MLF_B200_LEGACY=1: first-generation kernels (A/B comparisons)
   bool big_ = false;          // large-shape kernels (d > 32 or pack too large for shared memory; MLF_B200_BIG=1 forces them)

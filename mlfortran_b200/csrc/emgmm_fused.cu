@@ -94,6 +94,9 @@ FusedGeom make_fused_geom(const Geom& g, bool cov_diag, size_t smem_limit) {
   };
   // preference: 128-point tiles with the full pack; 64-point tiles for large K at d <= 8; the diagonal-compressed
   // pack (extension) when the caller asked for diagonal covariances and nothing else fits
+  // diagonal covariances at d <= 8 with >= 128 components: the lane-per-component CUDA-core kernel (emgmm_diag.cu) wants
+  // the compressed pack
+  if (cov_diag && g.DN == 1 && g.K8 * 8 >= 128 && plan(1, true)) return f;
   if (plan(2, false)) return f;
   const bool small = (g.DM <= 2) && (f.CBMAX == 2 || f.CBMAX == 4);
   if (small && plan(1, false)) return f;

@@ -84,6 +84,9 @@ cudaError_t launch_em(const Geom& g, const FusedGeom& f, const EmArgs& a, bool s
 // side lists per warp -> 16*grid lists.
 bool em16_ok(const Geom& g, const FusedGeom& f, size_t smem_limit);
 cudaError_t launch_em16(const Geom& g, const FusedGeom& f, const EmArgs& a, int grid, size_t smem_limit, cudaStream_t st);
+// Diagonal-covariance extension at small d / large K on the fp64 CUDA cores (emgmm_diag.cu): lane = component.
+bool emd_ok(const Geom& g, const FusedGeom& f, size_t smem_limit);
+cudaError_t launch_emd(const Geom& g, const FusedGeom& f, EmArgs a, int grid, size_t smem_limit, cudaStream_t st);
 cudaError_t launch_amb_resolve(const Geom& g, const double* X, const AmbEntry* amb, int cap, const int* counts, int nlists,
                                const double* statsA, double minW, const double* muold, double* outC, cudaStream_t st);
 cudaError_t launch_amb_summary(const int* counts, int nlists, int cap, double* flags, cudaStream_t st);

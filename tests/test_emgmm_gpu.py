@@ -416,6 +416,83 @@ def test_config5_shape_runs_through_the_single_sweep_kernel(oracle):
     em.finalize()
 
 
+def _diag_oracle(oracle, fn, *a, **kw):
+    oracle.set_cov_diag(True)
+    try:
+        return fn(*a, **kw)
+    finally:
+        oracle.set_cov_diag(False)
+
+
+EMD_CASES = [
+    # d, K, n_per_comp, sigma_c, seed, minProba, iters
+    (8, 256, 30, 6.0, 181, 1.0, 3),
+    (5, 130, 40, 5.0, 182, 0.0, 4),      # KP = 136: the last warp owns 8 components, 24 idle lanes
+    (3, 160, 50, 2.0, 183, 0.0, 6),      # heavy overlap: threshold band + side list traffic
+    (8, 128, 35, 4.0, 184, 0.5, 3),
+    (1, 129, 25, 40.0, 185, 1.0, 3),
+]
+
+
+@pytest.mark.parametrize("case", EMD_CASES, ids=[f"d{c[0]}_K{c[1]}" for c in EMD_CASES])
+def test_diagonal_cuda_core_kernel_matches_oracle(case, oracle):
+    """k_emd (lane = component, fp64 FMA on the CUDA cores; the plan for diagonal covariances at d <= 8, K >= 128)."""
+    d, K, npc, sc, seed, mp, iters = case
+    data = synth.make_mixture(d, K, npc, sc, 1.0, seed)
+    X = data["X"]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], seed)
+    oMu, oCov, olam, otr, oP = _diag_oracle(oracle, oracle.em_iterations, X, Mu0, Cov0, lam0, mp, iters, return_proba=True)
+    em = mlf_algo_emgmm()
+    assert em.init(X, K, mp, cov_type="diag") == 0
+    em.inject(Mu0, Cov0, lam0)
+    assert "k_emd" in em.kernel_plan(), em.kernel_plan()
+    for _ in range(iters):
+        assert em.step(1)[0] == 0, em.last_error()
+    assert rel(em.Mu, oMu) <= PAR_RTOL and rel(em.Cov, oCov) <= PAR_RTOL and np.abs(em.lambda_ - olam).max() <= PAR_RTOL
+    assert abs(em.sumLL - otr[-1]) <= LL_RTOL * abs(otr[-1])
+    assert np.abs(em.ProbaC - oP).max() <= 1e-9
+    lab = em.labels()                       # classes under the CURRENT parameters (reference getClass semantics)
+    _, Pn, _ = _diag_oracle(oracle, oracle.exp_step, X, em.Mu, em.Cov, em.lambda_)
+    bad = lab != oracle.get_class(Pn)
+    if bad.any():
+        top2 = np.sort(Pn, axis=0)[-2:]
+        assert ((top2[1] - top2[0]) <= 1e-9 * top2[1])[bad].all()
+    assert em.times()["sweeps"] >= iters
+    em.finalize()
+
+
+def test_diagonal_cuda_core_kernel_streamed_chunks_and_ab(oracle, monkeypatch):
+    """refresh_x + step streams X in chunks under k_emd (partials accumulate in place across launches); and the tensor-core
+    diagonal kernel (MLF_B200_EMD=0) gives the same numbers on the same inputs."""
+    d, K = 6, 128
+    data = synth.make_mixture(d, K, 700, 5.0, 1.0, 186)        # 89 600 points >= the streaming threshold
+    X1 = data["X"]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 186)
+    em = mlf_algo_emgmm()
+    assert em.init(X1, K, 0.0, cov_type="diag") == 0
+    em.inject(Mu0, Cov0, lam0)
+    assert "k_emd" in em.kernel_plan()
+    assert em.step(2)[0] == 0, em.last_error()
+    rng = np.random.default_rng(187)
+    X2 = np.ascontiguousarray(X1 + 0.05 * rng.standard_normal(X1.shape) + 0.2)
+    Mu1, Cov1, lam1 = em.Mu.copy(), em.Cov.copy(), em.lambda_.copy()
+    assert em.refresh_x(X2) == 0
+    assert em.step(2)[0] == 0, em.last_error()
+    oMu, oCov, olam, otr = _diag_oracle(oracle, oracle.em_iterations, X2, Mu1, Cov1, lam1, 0.0, 2)
+    check_against(em, oMu, oCov, olam, otr)
+    res = (em.Mu.copy(), em.Cov.copy(), em.lambda_.copy(), em.sumLL)
+    em.finalize()
+    monkeypatch.setenv("MLF_B200_EMD", "0")
+    em2 = mlf_algo_emgmm()
+    assert em2.init(X2, K, 0.0, cov_type="diag") == 0
+    em2.inject(Mu1, Cov1, lam1)
+    assert "k_emd" not in em2.kernel_plan()
+    assert em2.step(2)[0] == 0, em2.last_error()
+    assert rel(em2.Mu, res[0]) <= 1e-11 and rel(em2.Cov, res[1]) <= 1e-11 and np.abs(em2.lambda_ - res[2]).max() <= 1e-12
+    assert abs(em2.sumLL - res[3]) <= 1e-11 * abs(res[3])
+    em2.finalize()
+
+
 def test_64_point_tiles_full_covariance_large_k(oracle):
     # d=8, K=128 full covariances: the pack fits shared memory only with 64-point tiles (one 8-point group per warp)
     data = synth.make_mixture(8, 128, 60, 6.0, 1.0, 152)
