@@ -12,6 +12,7 @@
 //       sum g (x-mu)^2, sum g (x-mu), sum g, all in registers; undecided pairs go to the per-warp side list.
 // Partial layouts, threshold band and side list are those of emgmm_fused.cu, so the engine's protocol is unchanged.
 #include "emgmm_kernels.cuh"
+#include "exp_tab.cuh"
 
 #include <cmath>
 
@@ -22,39 +23,12 @@ namespace {
 __device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 constexpr unsigned kFull = 0xffffffffu;
 
-__device__ __forceinline__ double exp_bf(double a) {  // see emgmm_fused.cu
-  a = (a < -750.0) ? -750.0 : a;
-  a = (a > 710.0) ? 710.0 : a;
-  const double magic = 6755399441055744.0;
-  double t = fma(a, 1.4426950408889634074, magic);
-  const int n = __double2loint(t);
-  t -= magic;
-  double r = fma(t, -6.93147180369123816490e-01, a);
-  r = fma(t, -1.90821492927058770002e-10, r);
-  double p = 1.6059043836821614599e-10;
-  p = fma(p, r, 2.0876756987868098979e-09);
-  p = fma(p, r, 2.5052108385441718775e-08);
-  p = fma(p, r, 2.7557319223985890653e-07);
-  p = fma(p, r, 2.7557319223985892510e-06);
-  p = fma(p, r, 2.4801587301587301566e-05);
-  p = fma(p, r, 1.9841269841269841253e-04);
-  p = fma(p, r, 1.3888888888888889419e-03);
-  p = fma(p, r, 8.3333333333333332177e-03);
-  p = fma(p, r, 4.1666666666666664354e-02);
-  p = fma(p, r, 1.6666666666666665741e-01);
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  const int n1 = n >> 1, n2 = n - n1;
-  return (p * __hiloint2double((n1 + 1023) << 20, 0)) * __hiloint2double((n2 + 1023) << 20, 0);
-}
-
 constexpr int kTP = 64;   // points per block tile
 constexpr int kD = 8;     // dimensions held in registers (d <= 8; padding dimensions are zero)
 
 }  // namespace
 
-size_t emd_smem_bytes(const Geom& g) { return ((size_t)kTP * 12 + (size_t)kTP * g.S) * sizeof(double); }
+size_t emd_smem_bytes(const Geom& g) { return ((size_t)kTP * 12 + (size_t)kTP * g.S + 8 * kTP + 128) * sizeof(double); }
 bool emd_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
   return f.diag && g.DN == 1 && g.K8 * 8 <= 256 && emd_smem_bytes(g) <= smem_limit;
 }
@@ -65,8 +39,10 @@ __global__ void __launch_bounds__(256, 1) k_emd(EmArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int K8 = A.K8, KP = K8 * 8, K4 = 2 * K8, S = A.S, d = A.d;
   const int64_t N = A.N;
-  double* xs = smem;                       // [64][12]: x' = x - shift in columns 0..7 (zero padded), raw x not needed separately
-  double* tile = xs + (size_t)kTP * XS;    // [64][S] logits -> responsibilities
+  double* xs = smem;                       // [64][12]: x' = x - shift in columns 0..7 (zero padded), 1/sum of the point in column 8
+  double* tile = xs + (size_t)kTP * XS;    // [64][S] logits -> softmax numerators
+  double* wmax = tile + (size_t)kTP * S;   // [8 warps][64] largest logit of the warp's 32 components, per point
+  double* etab = wmax + 8 * kTP;           // [128] 2^(j/128)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int comp = 32 * warp + lane;       // the component this lane owns in P1 / P3
   const bool own = comp < KP;
@@ -99,6 +75,12 @@ __global__ void __launch_bounds__(256, 1) k_emd(EmArgs A) {
   int nAmb = accu ? A.amb_count[nlist] : 0;
   AmbEntry* ambw = A.amb + (size_t)nlist * A.amb_cap;
 
+  if (tid < 128) etab[tid] = kExpTab128[tid];
+  if (!wact)
+    for (int i = lane; i < kTP; i += 32) wmax[warp * kTP + i] = -INFINITY;   // never written again
+  const int amb_cap = A.amb_cap;
+  const long long key0 = (long long)A.p_offset * 1024 + comp;
+
   const int64_t ntiles = (N + kTP - 1) / kTP;
   for (int64_t bt = blockIdx.x; bt < ntiles; bt += gridDim.x) {
     const int64_t q0 = bt * kTP;
@@ -109,91 +91,142 @@ __global__ void __launch_bounds__(256, 1) k_emd(EmArgs A) {
       xs[pt * XS + a] = (p < N && a < d) ? A.X[p * d + a] - A.shift[a] : 0.0;
     }
     __syncthreads();
-    // ---- P1: lane = component; logits of every point of the tile -----------------------------------------------------
-    if (own) {
-#pragma unroll 4
-      for (int pt = 0; pt < kTP; ++pt) {
-        const double2* xr = reinterpret_cast<const double2*>(xs + pt * XS);
-        double s = 0;
+    // ---- P1: lane = component; logits of 8 points at a time (8 independent chains), and the warp's maximum per point ----
+    if (wact) {
+#pragma unroll 1
+      for (int pt0 = 0; pt0 < kTP; pt0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.0;
 #pragma unroll
         for (int a2 = 0; a2 < kD / 2; ++a2) {
-          const double2 x = xr[a2];   // broadcast load: every lane reads the same point
-          const double u0 = fma(l[2 * a2], x.x, b[2 * a2]);
-          const double u1 = fma(l[2 * a2 + 1], x.y, b[2 * a2 + 1]);
-          s = fma(u0, u0, s);
-          s = fma(u1, u1, s);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const double2 x = *reinterpret_cast<const double2*>(xs + (pt0 + j) * XS + 2 * a2);   // broadcast load
+            const double u0 = fma(l[2 * a2], x.x, b[2 * a2]);
+            const double u1 = fma(l[2 * a2 + 1], x.y, b[2 * a2 + 1]);
+            v[j] = fma(u0, u0, v[j]);
+            v[j] = fma(u1, u1, v[j]);
+          }
         }
-        tile[(size_t)pt * S + comp] = fma(-0.5, s, ck);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = fma(-0.5, v[j], ck);                  // lanes without a component: -inf
+          if (own) tile[(size_t)(pt0 + j) * S + comp] = v[j];
+        }
+        // warp maximum of 8 values with 9 exchanges: halve the number of values a lane carries at each of the first 3 steps
+        double w4[4], w2[2], w1;
+        {
+          const bool up = lane & 16;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const double send = up ? v[i] : v[4 + i], keep = up ? v[4 + i] : v[i];
+            w4[i] = fmax(keep, shx(send, 16));
+          }
+        }
+        {
+          const bool up = lane & 8;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const double send = up ? w4[i] : w4[2 + i], keep = up ? w4[2 + i] : w4[i];
+            w2[i] = fmax(keep, shx(send, 8));
+          }
+        }
+        {
+          const bool up = lane & 4;
+          const double send = up ? w2[0] : w2[1], keep = up ? w2[1] : w2[0];
+          w1 = fmax(keep, shx(send, 4));
+        }
+        w1 = fmax(w1, shx(w1, 2));
+        w1 = fmax(w1, shx(w1, 1));
+        if ((lane & 3) == 0) wmax[warp * kTP + pt0 + (lane >> 2)] = w1;   // lane bits 4,3,2 = point bits 2,1,0
       }
     }
     __syncthreads();
-    // ---- P2: warp = 8 points, lane (g, t) = point g, components == t (mod 4): log-sum-exp over the components ----------
+    // ---- P2: warp = 8 points, lane (g, t) = point g, components == t (mod 4): softmax numerators and 1/sum --------------
     {
-      const int64_t p = q0 + warp * 8 + g;
-      double* row = tile + (size_t)(warp * 8 + g) * S;
-      double m = -INFINITY;
-      int am = 0;
-      for (int k4 = 0; k4 < K4; ++k4) {
-        const double v = row[4 * k4 + t];
-        if (v > m) { m = v; am = 4 * k4 + t; }
+      const int pl = warp * 8 + g;
+      const int64_t p = q0 + pl;
+      double* row = tile + (size_t)pl * S;
+      double m = fmax(wmax[(2 * t) * kTP + pl], wmax[(2 * t + 1) * kTP + pl]);
+      m = fmax(m, shx(m, 1));
+      m = fmax(m, shx(m, 2));
+      if (A.labels != nullptr) {   // getClass: lowest index among the largest (only the label queries ask for it)
+        int am = 1 << 30;
+        for (int k4 = K4 - 1; k4 >= 0; --k4)
+          if (row[4 * k4 + t] == m) am = 4 * k4 + t;
+        am = min(am, __shfl_xor_sync(kFull, am, 1));
+        am = min(am, __shfl_xor_sync(kFull, am, 2));
+        if (p < N && t == 0) A.labels[p] = am + 1;
       }
-#pragma unroll
-      for (int s2 = 1; s2 <= 2; s2 <<= 1) {
-        const double om = shx(m, s2);
-        const int oa = __shfl_xor_sync(kFull, am, s2);
-        if (om > m || (om == m && oa < am)) { m = om; am = oa; }
-      }
-      double sum = 0;
+      double sum0 = 0, sum1 = 0;
 #pragma unroll 4
       for (int k4 = 0; k4 < K4; k4 += 2) {
-        const double e0 = exp_bf(row[4 * k4 + t] - m), e1 = exp_bf(row[4 * k4 + 4 + t] - m);
+        const double e0 = exp_tab(row[4 * k4 + t] - m, etab), e1 = exp_tab(row[4 * k4 + 4 + t] - m, etab);
         row[4 * k4 + t] = e0; row[4 * k4 + 4 + t] = e1;
-        sum += e0; sum += e1;
+        sum0 += e0; sum1 += e1;
       }
+      double sum = sum0 + sum1;
       sum += shx(sum, 1);
       sum += shx(sum, 2);
-      const double inv = (p < N) ? 1.0 / sum : 0.0;
-      for (int k4 = 0; k4 < K4; ++k4) row[4 * k4 + t] *= inv;
-      if (A.labels != nullptr && p < N && t == 0) A.labels[p] = am + 1;
+      if (t == 0) xs[pl * XS + 8] = (p < N) ? 1.0 / sum : 0.0;
     }
     __syncthreads();
-    // ---- P3: lane = component; statistics of the tile ---------------------------------------------------------------------
-    if (wact) {   // warp-uniform branch (ballots inside); lanes without a component carry g = 0
-#pragma unroll 2
-      for (int pt = 0; pt < kTP; ++pt) {
-        const double a = own ? tile[(size_t)pt * S + comp] : 0.0;
-        const double2* xr = reinterpret_cast<const double2*>(xs + pt * XS);
-        double x[kD];
+    // ---- P3: lane = component; statistics of the tile, 4 points at a time -------------------------------------------------
+    if (wact) {   // warp-uniform branch (votes inside); lanes without a component carry g = 0
+#pragma unroll 1
+      for (int pt0 = 0; pt0 < kTP; pt0 += 4) {
+        double a[4];
+        bool cand = false;
 #pragma unroll
-        for (int a2 = 0; a2 < kD / 2; ++a2) { const double2 v = xr[a2]; x[2 * a2] = v.x; x[2 * a2 + 1] = v.y; }
-        sg += a;
-        sg2 = fma(a, a, sg2);
+        for (int j = 0; j < 4; ++j) {
+          const double e = own ? tile[(size_t)(pt0 + j) * S + comp] : 0.0;
+          a[j] = e * xs[(pt0 + j) * XS + 8];
+          // "If(W(i) < minW0) CYCLE" (src/mlf_matrix.f90:135): candidates for the kept set reach the lower band edge;
+          // g == 0 adds nothing and is never listed
+          cand |= !(a[j] < tlo) && ((__double2hiint(a[j]) | __double2loint(a[j])) != 0);
+        }
 #pragma unroll
-        for (int c = 0; c < kD; ++c) sgx[c] = fma(a, x[c], sgx[c]);   // about the shift; the shift is added back at the end
-        // "If(W(i) < minW0) CYCLE" (src/mlf_matrix.f90:135); g == 0 adds nothing and is never listed
-        const bool hi = !(a < thi) && a != 0.0;
-        const bool mid = !hi && !(a < tlo) && a != 0.0;
-        if (__any_sync(kFull, hi)) {
-          const double ah = hi ? a : 0.0;
-          sk += ah;
+        for (int j = 0; j < 4; ++j) {
+          sg += a[j];
+          sg2 = fma(a[j], a[j], sg2);
 #pragma unroll
-          for (int c = 0; c < kD; ++c) {
-            const double z = x[c] - mu[c];
-            const double az = ah * z;
-            skx[c] += az;
-            skz2[c] = fma(az, z, skz2[c]);
+          for (int c2 = 0; c2 < kD / 2; ++c2) {
+            const double2 x = *reinterpret_cast<const double2*>(xs + (pt0 + j) * XS + 2 * c2);
+            sgx[2 * c2] = fma(a[j], x.x, sgx[2 * c2]);        // about the shift; the shift is added back at the end
+            sgx[2 * c2 + 1] = fma(a[j], x.y, sgx[2 * c2 + 1]);
           }
         }
-        const unsigned mm = __ballot_sync(kFull, mid);
-        if (mm) {  // undecided until s_k is final: side list, settled by k_amb_resolve
-          const int sl = nAmb + __popc(mm & ((1u << lane) - 1u));
-          if (mid && sl < A.amb_cap) {
-            AmbEntry e;
-            e.g = a;
-            e.key = (long long)(A.p_offset + q0 + pt) * 1024 + comp;
-            ambw[sl] = e;
+        if (__any_sync(kFull, cand)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const double aj = a[j];
+            const bool nz = (__double2hiint(aj) | __double2loint(aj)) != 0;
+            const bool hi = !(aj < thi) && nz;
+            const bool mid = !hi && !(aj < tlo) && nz;
+            if (__any_sync(kFull, hi)) {
+              const double ah = hi ? aj : 0.0;
+              sk += ah;
+#pragma unroll
+              for (int c = 0; c < kD; ++c) {
+                const double z = xs[(pt0 + j) * XS + c] - mu[c];
+                const double az = ah * z;
+                skx[c] += az;
+                skz2[c] = fma(az, z, skz2[c]);
+              }
+            }
+            const unsigned mm = __ballot_sync(kFull, mid);
+            if (mm) {  // undecided until s_k is final: side list, settled by k_amb_resolve
+              const int sl = nAmb + __popc(mm & ((1u << lane) - 1u));
+              if (mid && sl < amb_cap) {
+                AmbEntry e;
+                e.g = aj;
+                e.key = key0 + (long long)(q0 + pt0 + j) * 1024;
+                ambw[sl] = e;
+              }
+              nAmb += __popc(mm);
+            }
           }
-          nAmb += __popc(mm);
         }
       }
     }
