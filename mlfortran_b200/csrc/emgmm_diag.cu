@@ -14,6 +14,7 @@
 #include "emgmm_kernels.cuh"
 #include "exp_tab.cuh"
 
+#include <climits>
 #include <cmath>
 
 namespace mlfb200 {
@@ -28,7 +29,7 @@ constexpr int kD = 8;     // dimensions held in registers (d <= 8; padding dimen
 
 }  // namespace
 
-size_t emd_smem_bytes(const Geom& g) { return ((size_t)kTP * 12 + (size_t)kTP * g.S + 8 * kTP + 128) * sizeof(double); }
+size_t emd_smem_bytes(const Geom& g) { return ((size_t)kTP * 12 + (size_t)kTP * g.S + 128) * sizeof(double) + 8 * kTP * sizeof(int); }
 bool emd_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
   return f.diag && g.DN == 1 && g.K8 * 8 <= 256 && emd_smem_bytes(g) <= smem_limit;
 }
@@ -41,8 +42,8 @@ __global__ void __launch_bounds__(256, 1) k_emd(EmArgs A) {
   const int64_t N = A.N;
   double* xs = smem;                       // [64][12]: x' = x - shift in columns 0..7 (zero padded), 1/sum of the point in column 8
   double* tile = xs + (size_t)kTP * XS;    // [64][S] logits -> softmax numerators
-  double* wmax = tile + (size_t)kTP * S;   // [8 warps][64] largest logit of the warp's 32 components, per point
-  double* etab = wmax + 8 * kTP;           // [128] 2^(j/128)
+  double* etab = tile + (size_t)kTP * S;   // [128] 2^(j/128)
+  int* wmax = reinterpret_cast<int*>(etab + 128);   // [8 warps][64] ordered key of the warp's largest logit (high word), per point
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int comp = 32 * warp + lane;       // the component this lane owns in P1 / P3
   const bool own = comp < KP;
@@ -77,18 +78,29 @@ __global__ void __launch_bounds__(256, 1) k_emd(EmArgs A) {
 
   if (tid < 128) etab[tid] = kExpTab128[tid];
   if (!wact)
-    for (int i = lane; i < kTP; i += 32) wmax[warp * kTP + i] = -INFINITY;   // never written again
+    for (int i = lane; i < kTP; i += 32) wmax[warp * kTP + i] = INT_MIN;   // never written again
   const int amb_cap = A.amb_cap;
   const long long key0 = (long long)A.p_offset * 1024 + comp;
 
   const int64_t ntiles = (N + kTP - 1) / kTP;
+  const int spt = tid >> 3, sa = tid & 7;   // staging role: points spt and spt + 32, dimension sa
+  const double ssh = (sa < d) ? A.shift[sa] : 0.0;
+  double nx0, nx1;
+  {
+    const int64_t qn = (int64_t)blockIdx.x * kTP;
+    nx0 = (qn + spt < N && sa < d) ? A.X[(qn + spt) * d + sa] - ssh : 0.0;
+    nx1 = (qn + spt + 32 < N && sa < d) ? A.X[(qn + spt + 32) * d + sa] - ssh : 0.0;
+  }
   for (int64_t bt = blockIdx.x; bt < ntiles; bt += gridDim.x) {
     const int64_t q0 = bt * kTP;
-    // ---- stage the tile: x' = x - shift, zero padded to 8 dimensions; rows beyond N are zero ---------------------
-    for (int i = tid; i < kTP * 8; i += 256) {
-      const int pt = i >> 3, a = i & 7;
-      const int64_t p = q0 + pt;
-      xs[pt * XS + a] = (p < N && a < d) ? A.X[p * d + a] - A.shift[a] : 0.0;
+    // ---- stage the tile: x' = x - shift, zero padded to 8 dimensions; rows beyond N are zero.  The values were fetched
+    //      into registers one tile ahead, so the global-memory latency hides under the previous tile's arithmetic ------
+    xs[spt * XS + sa] = nx0;
+    xs[(spt + 32) * XS + sa] = nx1;
+    {
+      const int64_t qn = (bt + gridDim.x) * kTP;
+      nx0 = (qn + spt < N && sa < d) ? A.X[(qn + spt) * d + sa] - ssh : 0.0;
+      nx1 = (qn + spt + 32 < N && sa < d) ? A.X[(qn + spt + 32) * d + sa] - ssh : 0.0;
     }
     __syncthreads();
     // ---- P1: lane = component; logits of 8 points at a time (8 independent chains), and the warp's maximum per point ----
@@ -114,32 +126,16 @@ __global__ void __launch_bounds__(256, 1) k_emd(EmArgs A) {
           v[j] = fma(-0.5, v[j], ck);                  // lanes without a component: -inf
           if (own) tile[(size_t)(pt0 + j) * S + comp] = v[j];
         }
-        // warp maximum of 8 values with 9 exchanges: halve the number of values a lane carries at each of the first 3 steps
-        double w4[4], w2[2], w1;
-        {
-          const bool up = lane & 16;
+        // the warp's largest logit per point, to 2^-20 relative: one integer REDUX on the order-preserving image of the
+        // high word (the softmax only needs the offset to be within a few hundred of the true maximum; see P2)
+        int mk = INT_MIN;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const double send = up ? v[i] : v[4 + i], keep = up ? v[4 + i] : v[i];
-            w4[i] = fmax(keep, shx(send, 16));
-          }
+        for (int j = 0; j < 8; ++j) {
+          const int hi = __double2hiint(v[j]);
+          const int r = __reduce_max_sync(kFull, hi ^ ((hi >> 31) & 0x7fffffff));
+          mk = (lane == j) ? r : mk;
         }
-        {
-          const bool up = lane & 8;
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const double send = up ? w4[i] : w4[2 + i], keep = up ? w4[2 + i] : w4[i];
-            w2[i] = fmax(keep, shx(send, 8));
-          }
-        }
-        {
-          const bool up = lane & 4;
-          const double send = up ? w2[0] : w2[1], keep = up ? w2[1] : w2[0];
-          w1 = fmax(keep, shx(send, 4));
-        }
-        w1 = fmax(w1, shx(w1, 2));
-        w1 = fmax(w1, shx(w1, 1));
-        if ((lane & 3) == 0) wmax[warp * kTP + pt0 + (lane >> 2)] = w1;   // lane bits 4,3,2 = point bits 2,1,0
+        if (lane < 8) wmax[warp * kTP + pt0 + lane] = mk;
       }
     }
     __syncthreads();
@@ -148,16 +144,27 @@ __global__ void __launch_bounds__(256, 1) k_emd(EmArgs A) {
       const int pl = warp * 8 + g;
       const int64_t p = q0 + pl;
       double* row = tile + (size_t)pl * S;
-      double m = fmax(wmax[(2 * t) * kTP + pl], wmax[(2 * t + 1) * kTP + pl]);
-      m = fmax(m, shx(m, 1));
-      m = fmax(m, shx(m, 2));
-      if (A.labels != nullptr) {   // getClass: lowest index among the largest (only the label queries ask for it)
-        int am = 1 << 30;
-        for (int k4 = K4 - 1; k4 >= 0; --k4)
-          if (row[4 * k4 + t] == m) am = 4 * k4 + t;
-        am = min(am, __shfl_xor_sync(kFull, am, 1));
-        am = min(am, __shfl_xor_sync(kFull, am, 2));
-        if (p < N && t == 0) A.labels[p] = am + 1;
+      int mk = max(wmax[(2 * t) * kTP + pl], wmax[(2 * t + 1) * kTP + pl]);
+      mk = max(mk, __shfl_xor_sync(kFull, mk, 1));
+      mk = max(mk, __shfl_xor_sync(kFull, mk, 2));
+      // softmax offset: the largest logit with its low word dropped (|m - max| <= 2^-20 |max|); exact for |max| < 2^27 in the
+      // sense that exp(v - m) neither overflows nor loses the leading terms.  Beyond that, and for label queries, scan.
+      double m = __hiloint2double(mk ^ ((mk >> 31) & 0x7fffffff), 0);
+      if (__any_sync(kFull, A.labels != nullptr || !(fabs(m) < 134217728.0))) {
+        double mx = -INFINITY;
+        int am = 0;
+        for (int k4 = 0; k4 < K4; ++k4) {
+          const double v = row[4 * k4 + t];
+          if (v > mx) { mx = v; am = 4 * k4 + t; }
+        }
+#pragma unroll
+        for (int s2 = 1; s2 <= 2; s2 <<= 1) {
+          const double om = shx(mx, s2);
+          const int oa = __shfl_xor_sync(kFull, am, s2);
+          if (om > mx || (om == mx && oa < am)) { mx = om; am = oa; }
+        }
+        m = mx;
+        if (A.labels != nullptr && p < N && t == 0) A.labels[p] = am + 1;   // getClass: lowest index among the largest
       }
       double sum0 = 0, sum1 = 0;
 #pragma unroll 4
@@ -174,17 +181,23 @@ __global__ void __launch_bounds__(256, 1) k_emd(EmArgs A) {
     __syncthreads();
     // ---- P3: lane = component; statistics of the tile, 4 points at a time -------------------------------------------------
     if (wact) {   // warp-uniform branch (votes inside); lanes without a component carry g = 0
+      double en[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) en[j] = own ? tile[(size_t)j * S + comp] : 0.0;
 #pragma unroll 1
       for (int pt0 = 0; pt0 < kTP; pt0 += 4) {
         double a[4];
         bool cand = false;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const double e = own ? tile[(size_t)(pt0 + j) * S + comp] : 0.0;
-          a[j] = e * xs[(pt0 + j) * XS + 8];
+          a[j] = en[j] * xs[(pt0 + j) * XS + 8];
           // "If(W(i) < minW0) CYCLE" (src/mlf_matrix.f90:135): candidates for the kept set reach the lower band edge;
           // g == 0 adds nothing and is never listed
           cand |= !(a[j] < tlo) && ((__double2hiint(a[j]) | __double2loint(a[j])) != 0);
+        }
+        if (pt0 + 4 < kTP) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) en[j] = own ? tile[(size_t)(pt0 + 4 + j) * S + comp] : 0.0;   // next group, ahead of the votes
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
