@@ -16,6 +16,7 @@
 
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 
 namespace mlfb200 {
 
@@ -24,39 +25,51 @@ namespace {
 __device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 constexpr unsigned kFull = 0xffffffffu;
 
-constexpr int kTP = 64;   // points per block tile
 constexpr int kD = 8;     // dimensions held in registers (d <= 8; padding dimensions are zero)
+constexpr int kXS = 12;   // row stride of the staged points: 8 coordinates, 1/sum, padding
+
+// row stride of the logit tile: the P2 access (TP/8 rows per warp, 32/(TP/8) lanes of 8 bytes each) must spread over the banks
+int emd_stride(int KP, int tp) { return ((KP + 15) / 16) * 16 + (tp == 64 ? 4 : 8); }
+size_t emd_smem(int KP, int tp) {
+  return ((size_t)tp * kXS + (size_t)tp * emd_stride(KP, tp) + 128 + 8 * (size_t)KP) * sizeof(double) + 8 * (size_t)tp * sizeof(int);
+}
 
 }  // namespace
 
-size_t emd_smem_bytes(const Geom& g) { return ((size_t)kTP * 12 + (size_t)kTP * g.S + 128) * sizeof(double) + 8 * kTP * sizeof(int); }
 bool emd_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
-  return f.diag && g.DN == 1 && g.K8 * 8 <= 256 && emd_smem_bytes(g) <= smem_limit;
+  return f.diag && g.DN == 1 && g.K8 * 8 <= 256 && emd_smem(g.K8 * 8, 64) <= smem_limit;
 }
 
-// pack2: diagonal-compressed layout of FusedGeom (DN = 1): [8 diag(L) | 8 bias | const, pad3] = 20 doubles per component
-__global__ void __launch_bounds__(256, 1) k_emd(EmArgs A) {
-  constexpr int PSF = 20, XS = 12, DS = 10, MSF = 74;
+// pack2: diagonal-compressed layout of FusedGeom (DN = 1): [8 diag(L) | 8 bias | const, pad3] = 20 doubles per component.
+// 8 warps, one lane per component, 238 registers per thread: two warps per scheduler hide the fp64 latencies through the
+// 8-point / 4-point blocking below.  Measured alternatives (config-5 shard, 185 ms with this kernel): TP = 32 with two blocks
+// per SM spills at 128 registers (457 ms); 16 warps with a pair of lanes per component (half the dimensions each, 128
+// registers, no spills) doubles the shuffle / REDUX / shared-memory instructions per pair and lands at 210 ms.
+template <int TP>
+__global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
+  constexpr int PSF = 20, XS = kXS, DS = 10, MSF = 74;
+  constexpr int GP = TP / 8;       // points per warp in P2
+  constexpr int TT = 32 / GP;      // lanes per point in P2
   extern __shared__ __align__(16) double smem[];
-  const int K8 = A.K8, KP = K8 * 8, K4 = 2 * K8, S = A.S, d = A.d;
+  const int K8 = A.K8, KP = K8 * 8, S = A.S, d = A.d;
   const int64_t N = A.N;
-  double* xs = smem;                       // [64][12]: x' = x - shift in columns 0..7 (zero padded), 1/sum of the point in column 8
-  double* tile = xs + (size_t)kTP * XS;    // [64][S] logits -> softmax numerators
-  double* etab = tile + (size_t)kTP * S;   // [128] 2^(j/128)
-  int* wmax = reinterpret_cast<int*>(etab + 128);   // [8 warps][64] ordered key of the warp's largest logit (high word), per point
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  double* xs = smem;                       // [TP][12]: x' = x - shift in columns 0..7 (zero padded), 1/sum of the point in column 8
+  double* tile = xs + (size_t)TP * XS;     // [TP][S] logits -> softmax numerators
+  double* etab = tile + (size_t)TP * S;    // [128] 2^(j/128)
+  double* mus = etab + 128;                // [8][KP] scatter centres mu_old - shift, dimension-major
+  int* wmax = reinterpret_cast<int*>(mus + 8 * (size_t)KP);   // [8 warps][TP] ordered key of the warp's largest logit, per point
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane / TT, t = lane % TT;
   const int comp = 32 * warp + lane;       // the component this lane owns in P1 / P3
   const bool own = comp < KP;
   const bool wact = 32 * warp < KP;        // warp-uniform: this warp owns at least one component
 
   // component parameters and statistics live in registers for the whole sweep
-  double l[kD], b[kD], mu[kD], sh[kD], ck = -INFINITY, thi = INFINITY, tlo = INFINITY;
+  double l[kD], b[kD], ck = -INFINITY, thi = INFINITY, tlo = INFINITY;
 #pragma unroll
   for (int a = 0; a < kD; ++a) {
-    sh[a] = A.shift[a];
     l[a] = own ? A.pack2[(size_t)comp * PSF + a] : 0.0;
     b[a] = own ? A.pack2[(size_t)comp * PSF + 8 + a] : 0.0;
-    mu[a] = own ? A.muold[(size_t)comp * 8 + a] - sh[a] : 0.0;   // scatter centre in shifted coordinates
+    if (own) mus[a * KP + comp] = A.muold[(size_t)comp * 8 + a] - A.shift[a];
   }
   if (own) { ck = A.pack2[(size_t)comp * PSF + 16]; thi = A.thi[comp]; tlo = A.tlo[comp]; }
   const bool accu = A.accumulate != 0;
@@ -65,10 +78,10 @@ __global__ void __launch_bounds__(256, 1) k_emd(EmArgs A) {
   double sg = 0, sg2 = 0, sk = 0, sgx[kD], skx[kD], skz2[kD];
 #pragma unroll
   for (int a = 0; a < kD; ++a) {
-    const bool ld = accu && own;
+    const bool ld = accu && own && a < d;
     // the partial slots hold raw sums (see the end of the kernel): back to the shifted / centred accumulators
-    sgx[a] = (ld && a < d) ? oA[2 + a] - sh[a] * oA[0] : 0.0;
-    skx[a] = (ld && a < d) ? oB[64 + a] - (mu[a] + sh[a]) * oB[72] : 0.0;
+    sgx[a] = ld ? oA[2 + a] - A.shift[a] * oA[0] : 0.0;
+    skx[a] = ld ? oB[64 + a] - A.muold[(size_t)comp * 8 + a] * oB[72] : 0.0;
     skz2[a] = ld ? oB[a * 9] : 0.0;   // diagonal entry (a, a) of the 8x8 scatter block
   }
   if (accu && own) { sg = oA[0]; sg2 = oA[1]; sk = oB[72]; }
@@ -78,42 +91,43 @@ __global__ void __launch_bounds__(256, 1) k_emd(EmArgs A) {
 
   if (tid < 128) etab[tid] = kExpTab128[tid];
   if (!wact)
-    for (int i = lane; i < kTP; i += 32) wmax[warp * kTP + i] = INT_MIN;   // never written again
+    for (int i = lane; i < TP; i += 32) wmax[warp * TP + i] = INT_MIN;   // never written again
   const int amb_cap = A.amb_cap;
   const long long key0 = (long long)A.p_offset * 1024 + comp;
 
-  const int64_t ntiles = (N + kTP - 1) / kTP;
-  const int spt = tid >> 3, sa = tid & 7;   // staging role: points spt and spt + 32, dimension sa
+  const int64_t ntiles = (N + TP - 1) / TP;
+  const int spt = tid >> 3, sa = tid & 7;   // staging role: point spt (and spt + 32), dimension sa
   const double ssh = (sa < d) ? A.shift[sa] : 0.0;
-  double nx0, nx1;
+  double nx0, nx1 = 0.0;
   {
-    const int64_t qn = (int64_t)blockIdx.x * kTP;
+    const int64_t qn = (int64_t)blockIdx.x * TP;
     nx0 = (qn + spt < N && sa < d) ? A.X[(qn + spt) * d + sa] - ssh : 0.0;
-    nx1 = (qn + spt + 32 < N && sa < d) ? A.X[(qn + spt + 32) * d + sa] - ssh : 0.0;
+    if (TP == 64) nx1 = (qn + spt + 32 < N && sa < d) ? A.X[(qn + spt + 32) * d + sa] - ssh : 0.0;
   }
   for (int64_t bt = blockIdx.x; bt < ntiles; bt += gridDim.x) {
-    const int64_t q0 = bt * kTP;
+    const int64_t q0 = bt * TP;
     // ---- stage the tile: x' = x - shift, zero padded to 8 dimensions; rows beyond N are zero.  The values were fetched
     //      into registers one tile ahead, so the global-memory latency hides under the previous tile's arithmetic ------
     xs[spt * XS + sa] = nx0;
-    xs[(spt + 32) * XS + sa] = nx1;
+    if (TP == 64) xs[(spt + 32) * XS + sa] = nx1;
     {
-      const int64_t qn = (bt + gridDim.x) * kTP;
+      const int64_t qn = (bt + gridDim.x) * TP;
       nx0 = (qn + spt < N && sa < d) ? A.X[(qn + spt) * d + sa] - ssh : 0.0;
-      nx1 = (qn + spt + 32 < N && sa < d) ? A.X[(qn + spt + 32) * d + sa] - ssh : 0.0;
+      if (TP == 64) nx1 = (qn + spt + 32 < N && sa < d) ? A.X[(qn + spt + 32) * d + sa] - ssh : 0.0;
     }
     __syncthreads();
-    // ---- P1: lane = component; logits of 8 points at a time (8 independent chains), and the warp's maximum per point ----
+    // ---- P1: lane = component; logits of PB points at a time (PB independent chains), and the warp's maximum per point ----
     if (wact) {
+      constexpr int PB = (TP == 64) ? 8 : 4;
 #pragma unroll 1
-      for (int pt0 = 0; pt0 < kTP; pt0 += 8) {
-        double v[8];
+      for (int pt0 = 0; pt0 < TP; pt0 += PB) {
+        double v[PB];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = 0.0;
+        for (int j = 0; j < PB; ++j) v[j] = 0.0;
 #pragma unroll
         for (int a2 = 0; a2 < kD / 2; ++a2) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < PB; ++j) {
             const double2 x = *reinterpret_cast<const double2*>(xs + (pt0 + j) * XS + 2 * a2);   // broadcast load
             const double u0 = fma(l[2 * a2], x.x, b[2 * a2]);
             const double u1 = fma(l[2 * a2 + 1], x.y, b[2 * a2 + 1]);
@@ -121,44 +135,44 @@ __global__ void __launch_bounds__(256, 1) k_emd(EmArgs A) {
             v[j] = fma(u1, u1, v[j]);
           }
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          v[j] = fma(-0.5, v[j], ck);                  // lanes without a component: -inf
-          if (own) tile[(size_t)(pt0 + j) * S + comp] = v[j];
-        }
         // the warp's largest logit per point, to 2^-20 relative: one integer REDUX on the order-preserving image of the
         // high word (the softmax only needs the offset to be within a few hundred of the true maximum; see P2)
         int mk = INT_MIN;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < PB; ++j) {
+          v[j] = fma(-0.5, v[j], ck);                  // lanes without a component: -inf
+          if (own) tile[(size_t)(pt0 + j) * S + comp] = v[j];
           const int hi = __double2hiint(v[j]);
           const int r = __reduce_max_sync(kFull, hi ^ ((hi >> 31) & 0x7fffffff));
           mk = (lane == j) ? r : mk;
         }
-        if (lane < 8) wmax[warp * kTP + pt0 + lane] = mk;
+        if (lane < PB) wmax[warp * TP + pt0 + lane] = mk;
       }
     }
     __syncthreads();
-    // ---- P2: warp = 8 points, lane (g, t) = point g, components == t (mod 4): softmax numerators and 1/sum --------------
+    // ---- P2: warp = GP points, lane (g, t) = point g, components == t (mod TT): softmax numerators and 1/sum ------------
     {
-      const int pl = warp * 8 + g;
+      const int pl = warp * GP + g;
       const int64_t p = q0 + pl;
       double* row = tile + (size_t)pl * S;
-      int mk = max(wmax[(2 * t) * kTP + pl], wmax[(2 * t + 1) * kTP + pl]);
-      mk = max(mk, __shfl_xor_sync(kFull, mk, 1));
-      mk = max(mk, __shfl_xor_sync(kFull, mk, 2));
-      // softmax offset: the largest logit with its low word dropped (|m - max| <= 2^-20 |max|); exact for |max| < 2^27 in the
-      // sense that exp(v - m) neither overflows nor loses the leading terms.  Beyond that, and for label queries, scan.
+      const int cnt = KP / TT;
+      int mk = INT_MIN;
+#pragma unroll
+      for (int w = t; w < 8; w += TT) mk = max(mk, wmax[w * TP + pl]);
+#pragma unroll
+      for (int s2 = 1; s2 < TT; s2 <<= 1) mk = max(mk, __shfl_xor_sync(kFull, mk, s2));
+      // softmax offset: the largest logit with its low word dropped (|m - max| <= 2^-20 |max|): below 2^27 the numerators
+      // neither overflow nor lose their leading terms.  Beyond that, and for label queries, scan for the exact maximum.
       double m = __hiloint2double(mk ^ ((mk >> 31) & 0x7fffffff), 0);
       if (__any_sync(kFull, A.labels != nullptr || !(fabs(m) < 134217728.0))) {
         double mx = -INFINITY;
         int am = 0;
-        for (int k4 = 0; k4 < K4; ++k4) {
-          const double v = row[4 * k4 + t];
-          if (v > mx) { mx = v; am = 4 * k4 + t; }
+        for (int k = 0; k < cnt; ++k) {
+          const double v = row[TT * k + t];
+          if (v > mx) { mx = v; am = TT * k + t; }
         }
 #pragma unroll
-        for (int s2 = 1; s2 <= 2; s2 <<= 1) {
+        for (int s2 = 1; s2 < TT; s2 <<= 1) {
           const double om = shx(mx, s2);
           const int oa = __shfl_xor_sync(kFull, am, s2);
           if (om > mx || (om == mx && oa < am)) { mx = om; am = oa; }
@@ -167,15 +181,21 @@ __global__ void __launch_bounds__(256, 1) k_emd(EmArgs A) {
         if (A.labels != nullptr && p < N && t == 0) A.labels[p] = am + 1;   // getClass: lowest index among the largest
       }
       double sum0 = 0, sum1 = 0;
-#pragma unroll 4
-      for (int k4 = 0; k4 < K4; k4 += 2) {
-        const double e0 = exp_tab(row[4 * k4 + t] - m, etab), e1 = exp_tab(row[4 * k4 + 4 + t] - m, etab);
-        row[4 * k4 + t] = e0; row[4 * k4 + 4 + t] = e1;
+      int k = 0;
+#pragma unroll (TP == 64 ? 4 : 1)
+      for (; k + 1 < cnt; k += 2) {
+        const double e0 = exp_tab(row[TT * k + t] - m, etab), e1 = exp_tab(row[TT * k + TT + t] - m, etab);
+        row[TT * k + t] = e0; row[TT * k + TT + t] = e1;
         sum0 += e0; sum1 += e1;
       }
+      if (k < cnt) {
+        const double e0 = exp_tab(row[TT * k + t] - m, etab);
+        row[TT * k + t] = e0;
+        sum0 += e0;
+      }
       double sum = sum0 + sum1;
-      sum += shx(sum, 1);
-      sum += shx(sum, 2);
+#pragma unroll
+      for (int s2 = 1; s2 < TT; s2 <<= 1) sum += shx(sum, s2);
       if (t == 0) xs[pl * XS + 8] = (p < N) ? 1.0 / sum : 0.0;
     }
     __syncthreads();
@@ -185,7 +205,7 @@ __global__ void __launch_bounds__(256, 1) k_emd(EmArgs A) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) en[j] = own ? tile[(size_t)j * S + comp] : 0.0;
 #pragma unroll 1
-      for (int pt0 = 0; pt0 < kTP; pt0 += 4) {
+      for (int pt0 = 0; pt0 < TP; pt0 += 4) {
         double a[4];
         bool cand = false;
 #pragma unroll
@@ -195,7 +215,7 @@ __global__ void __launch_bounds__(256, 1) k_emd(EmArgs A) {
           // g == 0 adds nothing and is never listed
           cand |= !(a[j] < tlo) && ((__double2hiint(a[j]) | __double2loint(a[j])) != 0);
         }
-        if (pt0 + 4 < kTP) {
+        if (pt0 + 4 < TP) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) en[j] = own ? tile[(size_t)(pt0 + 4 + j) * S + comp] : 0.0;   // next group, ahead of the votes
         }
@@ -222,7 +242,7 @@ __global__ void __launch_bounds__(256, 1) k_emd(EmArgs A) {
               sk += ah;
 #pragma unroll
               for (int c = 0; c < kD; ++c) {
-                const double z = xs[(pt0 + j) * XS + c] - mu[c];
+                const double z = xs[(pt0 + j) * XS + c] - (own ? mus[c * KP + comp] : 0.0);
                 const double az = ah * z;
                 skx[c] += az;
                 skz2[c] = fma(az, z, skz2[c]);
@@ -249,11 +269,11 @@ __global__ void __launch_bounds__(256, 1) k_emd(EmArgs A) {
   if (own) {
     oA[0] = sg;
     oA[1] = sg2;
-    // sum g x = sum g x' + shift * sum g;  sum_kept g x = sum_kept g (z + mu') + shift * sum_kept g
+    // sum g x = sum g x' + shift * sum g;  sum_kept g x = sum_kept g z + mu_old * sum_kept g
 #pragma unroll
     for (int a = 0; a < kD; ++a) {
-      oA[2 + a] = (a < d) ? fma(sh[a], sg, sgx[a]) : 0.0;
-      oB[64 + a] = (a < d) ? skx[a] + (mu[a] + sh[a]) * sk : 0.0;
+      oA[2 + a] = (a < d) ? fma(A.shift[a], sg, sgx[a]) : 0.0;
+      oB[64 + a] = (a < d) ? skx[a] + A.muold[(size_t)comp * 8 + a] * sk : 0.0;
     }
     for (int i = 0; i < 64; ++i) oB[i] = 0.0;
 #pragma unroll
@@ -264,14 +284,20 @@ __global__ void __launch_bounds__(256, 1) k_emd(EmArgs A) {
   if (lane == 0) A.amb_count[nlist] = nAmb;
 }
 
+template <int TP>
+static cudaError_t launch_emd_t(const Geom& g, EmArgs a, int grid, cudaStream_t st) {
+  const int KP = g.K8 * 8;
+  const size_t smem = emd_smem(KP, TP);
+  cudaError_t e = cudaFuncSetAttribute(k_emd<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  a.S = emd_stride(KP, TP);
+  k_emd<TP><<<grid, 256, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_emd(const Geom& g, const FusedGeom& f, EmArgs a, int grid, size_t smem_limit, cudaStream_t st) {
   if (!emd_ok(g, f, smem_limit)) return cudaErrorInvalidConfiguration;
-  const size_t smem = emd_smem_bytes(g);
-  cudaError_t e = cudaFuncSetAttribute(k_emd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  a.S = g.S;
-  k_emd<<<grid, 256, smem, st>>>(a);
-  return cudaGetLastError();
+  return launch_emd_t<64>(g, a, grid, st);
 }
 
 }  // namespace mlfb200

@@ -461,6 +461,30 @@ def test_diagonal_cuda_core_kernel_matches_oracle(case, oracle):
     em.finalize()
 
 
+def test_diagonal_cuda_core_kernel_far_outliers(monkeypatch):
+    """Points 1e5 sigma away: |logit| > 2^27, where k_emd's approximate softmax offset (high word of the largest logit) is
+    replaced by the exact scan.  The reference itself has no answer here (it exponentiates without an offset: 0/0), so
+    the check is against the tensor-core diagonal kernel, which always scans for the exact maximum."""
+    d, K = 4, 128
+    data = synth.make_mixture(d, K, 30, 5.0, 1.0, 188)
+    X = data["X"].copy()
+    X[::97] += 1.0e5 * np.sign(X[::97] - X.mean(0))
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 188)
+    res = []
+    for emd in ("1", "0"):
+        monkeypatch.setenv("MLF_B200_EMD", emd)
+        em = mlf_algo_emgmm()
+        assert em.init(X, K, 0.0, cov_type="diag") == 0
+        em.inject(Mu0, Cov0, lam0)
+        assert ("k_emd" in em.kernel_plan()) == (emd == "1")
+        assert em.step(2)[0] == 0, em.last_error()
+        assert np.isfinite(em.Mu).all() and np.isfinite(em.Cov).all() and np.isfinite(em.sumLL)
+        res.append((em.Mu.copy(), em.Cov.copy(), em.lambda_.copy(), em.sumLL))
+        em.finalize()
+    assert rel(res[0][0], res[1][0]) <= 1e-11 and rel(res[0][1], res[1][1]) <= 1e-11
+    assert np.abs(res[0][2] - res[1][2]).max() <= 1e-12 and abs(res[0][3] - res[1][3]) <= 1e-11 * abs(res[1][3])
+
+
 def test_diagonal_cuda_core_kernel_streamed_chunks_and_ab(oracle, monkeypatch):
     """refresh_x + step streams X in chunks under k_emd (partials accumulate in place across launches); and the tensor-core
     diagonal kernel (MLF_B200_EMD=0) gives the same numbers on the same inputs."""
