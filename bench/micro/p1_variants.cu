@@ -236,6 +236,157 @@ static void runw(const double* dpack, const double* dX, int tiles, double* dout,
   printf("{\"variant\": \"%s\", \"ms\": %.4f, \"ns_per_pair\": %.5f, \"dmma_tflops\": %.3f, \"frac_of_37.16\": %.3f}\n", name, best, best * 1e6 / pairs, tf, tf / 37.16);
 }
 
+// Warp pairs: NW warps, warp (pi, ch) takes the 16 points of pair pi against half ch of the components (tile = NW*8 points):
+// the work per warp and the shared-memory footprint of "NW warps x 8 points", with each fragment load feeding two DMMAs.
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1) k_p1h(const double* __restrict__ pack, const double* __restrict__ X, int tiles, double* __restrict__ out) {
+  extern __shared__ __align__(16) double smem[];
+  double* sp = smem;
+  double* tile = smem + K * PSF;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int pi = warp >> 1, ch = warp & 1;
+  for (int i = tid; i < K * PSF; i += NW * 32) sp[i] = pack[i];
+  __syncthreads();
+  constexpr int TP = NW * 8;
+  double acc = 0;
+  for (int bt = 0; bt < tiles; ++bt) {
+    double xa[2][DM];
+#pragma unroll
+    for (int grp = 0; grp < 2; ++grp)
+#pragma unroll
+      for (int mb = 0; mb < DM; ++mb) xa[grp][mb] = X[(((size_t)(blockIdx.x * tiles + bt) * TP + pi * 16 + 8 * grp + g) % (148u * 200u * 128u)) * 16 + 4 * mb + t];
+    double* row[2];
+    double rmax[2];
+    int rarg[2];
+#pragma unroll
+    for (int grp = 0; grp < 2; ++grp) { row[grp] = tile + (size_t)(pi * 16 + 8 * grp + g) * S; rmax[grp] = -1e300; rarg[grp] = 0; }
+    for (int k4 = ch * (K4 / 2); k4 < (ch + 1) * (K4 / 2); ++k4) {
+      double part[2][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) comp_pair<true>(sp + (size_t)(4 * k4 + j) * PSF, lane, t, xa, part[0][j], part[1][j]);
+      const double ck = sp[(size_t)(4 * k4 + t) * PSF + OFFC];
+      reduce_store(part[0], ck, row[0], k4, t, rmax[0], rarg[0]);
+      reduce_store(part[1], ck, row[1], k4, t, rmax[1], rarg[1]);
+    }
+    acc += rmax[0] + rmax[1] + rarg[0] + rarg[1];
+  }
+  if (acc == 1.2345e-300) out[0] = acc + tile[tid];
+}
+template <int NW>
+static void runh(const double* dpack, const double* dX, int tiles, double* dout, const char* name) {
+  const size_t smem = ((size_t)K * PSF + (size_t)NW * 8 * S) * 8;
+  CK(cudaFuncSetAttribute(k_p1h<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  k_p1h<NW><<<148, NW * 32, smem>>>(dpack, dX, tiles, dout);
+  CK(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int r = 0; r < 3; ++r) {
+    CK(cudaEventRecord(e0));
+    k_p1h<NW><<<148, NW * 32, smem>>>(dpack, dX, tiles, dout);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  const double pairs = 148.0 * tiles * NW * 8 * K;
+  const double tf = pairs * 6 / 8 * 512 / (best * 1e-3) * 1e-12;
+  printf("{\"variant\": \"%s\", \"ms\": %.4f, \"ns_per_pair\": %.5f, \"dmma_tflops\": %.3f, \"frac_of_37.16\": %.3f}\n", name, best, best * 1e6 / pairs, tf, tf / 37.16);
+}
+
+// Ablations of k_p1w: NOLDS keeps one component's fragments in registers (no shared-memory loads in the loop); NOTAIL drops
+// the quad reduction / logit store.  Where do the 23% between the whitening loop and the pure DMMA stream go?
+template <int NW, int GPW, bool NOLDS, bool NOTAIL>
+__global__ void __launch_bounds__(NW * 32, 1) k_p1x(const double* __restrict__ pack, const double* __restrict__ X, int tiles, double* __restrict__ out) {
+  extern __shared__ __align__(16) double smem[];
+  double* sp = smem;
+  double* tile = smem + K * PSF;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < K * PSF; i += NW * 32) sp[i] = pack[i];
+  __syncthreads();
+  constexpr int TP = NW * 8 * GPW;
+  double acc = 0;
+  for (int bt = 0; bt < tiles; ++bt) {
+    double xa[GPW][DM];
+#pragma unroll
+    for (int grp = 0; grp < GPW; ++grp)
+#pragma unroll
+      for (int mb = 0; mb < DM; ++mb) xa[grp][mb] = X[(((size_t)(blockIdx.x * tiles + bt) * TP + warp * 8 * GPW + 8 * grp + g) % (148u * 200u * 128u)) * 16 + 4 * mb + t];
+    double* row[GPW];
+    double rmax[GPW];
+    int rarg[GPW];
+#pragma unroll
+    for (int grp = 0; grp < GPW; ++grp) { row[grp] = tile + (size_t)(warp * 8 * GPW + 8 * grp + g) * S; rmax[grp] = -1e300; rarg[grp] = 0; }
+    double Lr[NB];
+    double2 nr2[DN];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) Lr[b] = sp[b * 32 + lane];
+#pragma unroll
+    for (int nb = 0; nb < DN; ++nb) nr2[nb] = *reinterpret_cast<const double2*>(sp + OFFB + 8 * nb + 2 * t);
+    for (int k4 = 0; k4 < K4; ++k4) {
+      double part[GPW][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double* pk = sp + (size_t)(4 * k4 + j) * PSF;
+        double Lf[NB];
+        double2 nb2[DN];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) Lf[b] = NOLDS ? __hiloint2double(__double2hiint(Lr[b]), __double2loint(Lr[b]) ^ (4 * k4 + j)) : pk[b * 32 + lane];
+#pragma unroll
+        for (int nb = 0; nb < DN; ++nb) nb2[nb] = NOLDS ? nr2[nb] : *reinterpret_cast<const double2*>(pk + OFFB + 8 * nb + 2 * t);
+#pragma unroll
+        for (int grp = 0; grp < GPW; ++grp) {
+          double c[DN][2];
+#pragma unroll
+          for (int nb = 0; nb < DN; ++nb) { c[nb][0] = nb2[nb].x; c[nb][1] = nb2[nb].y; }
+#pragma unroll
+          for (int mb = 0; mb < DM; ++mb)
+#pragma unroll
+            for (int nb = 0; nb <= mb / 2; ++nb) dmma_v(c[nb], xa[grp][mb], Lf[blk_off(mb) + nb]);
+          double s2 = c[0][0] * c[0][0];
+          s2 = fma(c[0][1], c[0][1], s2);
+#pragma unroll
+          for (int nb = 1; nb < DN; ++nb) { s2 = fma(c[nb][0], c[nb][0], s2); s2 = fma(c[nb][1], c[nb][1], s2); }
+          part[grp][j] = s2;
+        }
+      }
+      if (NOTAIL) {
+#pragma unroll
+        for (int grp = 0; grp < GPW; ++grp) rmax[grp] += (part[grp][0] + part[grp][1]) + (part[grp][2] + part[grp][3]);
+      } else {
+        const double ck = sp[(size_t)(4 * k4 + t) * PSF + OFFC];
+#pragma unroll
+        for (int grp = 0; grp < GPW; ++grp) reduce_store(part[grp], ck, row[grp], k4, t, rmax[grp], rarg[grp]);
+      }
+    }
+#pragma unroll
+    for (int grp = 0; grp < GPW; ++grp) acc += rmax[grp] + rarg[grp];
+  }
+  if (acc == 1.2345e-300) out[0] = acc + tile[tid];
+}
+
+template <int NW, int GPW, bool NOLDS, bool NOTAIL>
+static void runx(const double* dpack, const double* dX, int tiles, double* dout, const char* name) {
+  const size_t smem = ((size_t)K * PSF + (size_t)NW * 8 * GPW * S) * 8;
+  CK(cudaFuncSetAttribute(k_p1x<NW, GPW, NOLDS, NOTAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  k_p1x<NW, GPW, NOLDS, NOTAIL><<<148, NW * 32, smem>>>(dpack, dX, tiles, dout);
+  CK(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int r = 0; r < 3; ++r) {
+    CK(cudaEventRecord(e0));
+    k_p1x<NW, GPW, NOLDS, NOTAIL><<<148, NW * 32, smem>>>(dpack, dX, tiles, dout);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  const double pairs = 148.0 * tiles * NW * 8 * GPW * K;
+  const double tf = pairs * 6 / 8 * 512 / (best * 1e-3) * 1e-12;
+  printf("{\"variant\": \"%s\", \"ms\": %.4f, \"ns_per_pair\": %.5f, \"dmma_tflops\": %.3f, \"frac_of_37.16\": %.3f}\n", name, best, best * 1e6 / pairs, tf, tf / 37.16);
+}
+
 // DMMA stream whose operands differ per instruction (NA distinct A registers, NBR distinct B registers, 8 accumulator chains):
 // does operand variety (register-file bandwidth / bank conflicts) lower the DMMA rate below the same-operand peak?
 template <int NA, int NBR>
@@ -289,6 +440,14 @@ int main() {
   runw<12, 2>(dp, dx, tiles, dout, "12 warps x 16 points");
   runw<12, 1>(dp, dx, tiles, dout, "12 warps x 8 points");
   runw<8, 1>(dp, dx, tiles, dout, "8 warps x 8 points");
+  runh<16>(dp, dx, tiles, dout, "16 warps as 8 pairs: 16 points x half the components per warp");
+  runh<12>(dp, dx, tiles, dout, "12 warps as 6 pairs: 16 points x half the components per warp");
+  runx<16, 1, true, false>(dp, dx, tiles, dout, "16 warps x 8 points, fragments in registers (no LDS)");
+  runx<16, 1, false, true>(dp, dx, tiles, dout, "16 warps x 8 points, no quad reduction / store");
+  runx<16, 1, true, true>(dp, dx, tiles, dout, "16 warps x 8 points, no LDS, no reduction");
+  runx<12, 2, true, false>(dp, dx, tiles, dout, "12 warps x 16 points, fragments in registers (no LDS)");
+  runx<12, 2, false, true>(dp, dx, tiles, dout, "12 warps x 16 points, no quad reduction / store");
+  runx<12, 2, true, true>(dp, dx, tiles, dout, "12 warps x 16 points, no LDS, no reduction");
   {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     const int iters = 20000;

@@ -16,6 +16,7 @@
 //                       P3b covariance scatter of the 8 components of that block over the kept groups.
 // Per-block partials are written per group: slot = 2*blockIdx.x + (w >> 3).
 #include "emgmm_kernels.cuh"
+#include "exp_tab.cuh"
 
 #include <cmath>
 
@@ -83,7 +84,7 @@ constexpr int kTmemCols = 512;  // 4 warps per lane quarter x 8 components x 16 
 
 }  // namespace
 
-size_t em16_smem_bytes(const Geom& g, const FusedGeom& f) { return f.smem + 16; }
+size_t em16_smem_bytes(const Geom& g, const FusedGeom& f) { return f.smem + 128 * sizeof(double) + 16; }
 bool em16_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
   return f.GPW == 2 && !f.diag && g.DN <= 2 && g.K8 <= 8 && f.scatter_ok && em16_smem_bytes(g, f) <= smem_limit;
 }
@@ -108,8 +109,10 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   const int wg = warp & 7;                      // warp index inside the group
   double* xs = smu + (size_t)KP * 8 * DN + (size_t)half * TP * XS;                    // [2][64][XS] raw points, per group
   double* tile = smu + (size_t)KP * 8 * DN + (size_t)2 * TP * XS + (size_t)half * TP * S;  // [2][64][S] logits -> responsibilities
-  uint32_t* s_taddr = reinterpret_cast<uint32_t*>(smu + (size_t)KP * 8 * DN + (size_t)2 * TP * XS + (size_t)2 * TP * S);
+  double* etab = smu + (size_t)KP * 8 * DN + (size_t)2 * TP * XS + (size_t)2 * TP * S;   // [128] 2^(j/128) (exp_tab.cuh)
+  uint32_t* s_taddr = reinterpret_cast<uint32_t*>(etab + 128);
   const bool own = cb < K8;
+  if (tid < 128) etab[tid] = kExpTab128[tid];
 
   for (int i = tid; i < KP * PSF; i += kThreads16) sp[i] = A.pack2[i];
   for (int i = tid; i < KP * 8 * DN; i += kThreads16) smu[i] = A.muold[i];
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
     double sum = 0;
 #pragma unroll 2
     for (int k4 = 0; k4 < K4; k4 += 2) {
-      const double e0 = exp_bf(row[4 * k4 + t] - rmax), e1 = exp_bf(row[4 * k4 + 4 + t] - rmax);
+      const double e0 = exp_tab(row[4 * k4 + t] - rmax, etab), e1 = exp_tab(row[4 * k4 + 4 + t] - rmax, etab);
       row[4 * k4 + t] = e0; row[4 * k4 + 4 + t] = e1;
       sum += e0; sum += e1;
     }
