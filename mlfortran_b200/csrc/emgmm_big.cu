@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(256) k_mstep_big(const double* __restrict__ X,
   constexpr int MB = DN * (DN + 1) / 2;
   constexpr int OWN = (MB + 7) / 8;
   constexpr int ZS = 8 * DN + 4;
-  extern __shared__ __align__(16) double zdyn[];       // [2][32][ZS]: (x - mu) of up to 8 kept 4-point groups, double-buffered
+  extern __shared__ __align__(16) double zdyn[];       // [2][32][ZS]: (x - mu) of up to 32 kept points, double-buffered
   __shared__ double ws[2][32];         // kept weight of each staged point (0 if dropped)
   __shared__ long long pidx[2][32];    // global index of each staged point
   __shared__ double smu[8 * DN];
@@ -315,56 +315,66 @@ __global__ void __launch_bounds__(256) k_mstep_big(const double* __restrict__ X,
   double sg2 = 0;
   const int64_t lo = (int64_t)blockIdx.x * chunk;
   const int64_t hi = (lo + chunk < N) ? lo + chunk : N;
-  // scan state: every warp evaluates the same strips and ballots, so all of it is uniform over the block.  The
-  // responsibilities are fetched eight 32-point strips at a time (eight loads in flight per lane): the scan used to wait
-  // for one load per strip, which was a third of the kernel's stall samples (profiles/ncu_r01h_big_d128.md).
-  constexpr int SB = 8;
-  int64_t ib = lo - 32 * SB;   // first point of the current batch of strips
-  int us = SB;                 // next strip of the batch to look at
+  // scan state.  The responsibilities of the chunk are looked at in rounds of 64 strips of 32 points: warp w fetches strips
+  // 8w..8w+7 (eight loads in flight per lane, 2048 points per round trip to memory), leaves the kept weights and the
+  // kept-group masks in shared memory, and every warp then walks the masks in strip order -- uniform over the block, and
+  // the order of the kept points is the point order (deterministic).  One warp looking at one strip at a time waited a full
+  // memory latency per ~1 kept point at K = 32 (profiles/ncu_r01h_big_d128.md: the scan, not the scatter, bounded the pass).
+  constexpr int SR = 64;
+  __shared__ double wr[SR][32];   // kept weight of every point of the round (0 if dropped)
+  __shared__ unsigned mr[SR];     // kept points of strip s
+  int64_t ib = lo - 32 * SR;      // first point of the current round
+  int us = SR;                    // next strip of the round to look at
+  int sc = 0;                     // strip the groups in gm belong to
   int64_t i0 = lo;
-  double gvb[SB];
-  unsigned gm = 0;        // 4-point groups of the current strip that hold a kept point and are not listed yet
-  double gvk = 0;         // this lane's kept weight in the current strip (0 if dropped)
-  // list up to 8 kept groups (compacted across strips) into buffer `buf`; returns how many
+  unsigned gm = 0;        // kept points of the current strip that are not listed yet
+  // list up to 32 kept points (compacted across strips, in point order) into buffer `buf`; returns how many
   auto fill = [&](int buf) -> int {
     int c = 0;
-    while (c < 8) {
+    while (c < 32) {
       if (gm == 0) {
-        if (us == SB) {
-          ib += 32 * SB;
+        if (us == SR) {
+          ib += 32 * SR;
           if (ib >= hi) break;
+          __syncthreads();   // the previous round's weights have been copied out by every warp that needed them
+          double gv[8];
 #pragma unroll
-          for (int u = 0; u < SB; ++u) {
-            const int64_t pl = ib + 32 * u + lane;
-            gvb[u] = (pl < hi) ? (gk ? gk[pl] : 1.0) : 0.0;
+          for (int u = 0; u < 8; ++u) {
+            const int64_t pl = ib + 32 * (8 * warp + u) + lane;
+            gv[u] = (pl < hi) ? (gk ? gk[pl] : 1.0) : 0.0;
           }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int64_t pl = ib + 32 * (8 * warp + u) + lane;
+            sg2 = fma(gv[u], gv[u], sg2);                                  // SUM(W*W) runs over all points (src/mlf_matrix.f90:119)
+            const bool kept = !(gv[u] < th) && pl < hi && gv[u] != 0.0;    // "If(W(i) < minW0) CYCLE" (:135)
+            wr[8 * warp + u][lane] = kept ? gv[u] : 0.0;
+            const unsigned m = __ballot_sync(kFull, kept);
+            if (lane == 0) mr[8 * warp + u] = m;
+          }
+          __syncthreads();
           us = 0;
         }
-        double gv = 0;
-#pragma unroll
-        for (int u = 0; u < SB; ++u) gv = (u == us) ? gvb[u] : gv;   // register select: us is uniform
+        sc = us;
         i0 = ib + 32 * us;
         ++us;
-        if (i0 >= hi) { us = SB; continue; }
-        const int64_t pl = i0 + lane;
-        if (warp == 0) sg2 = fma(gv, gv, sg2);                  // SUM(W*W) runs over all points (src/mlf_matrix.f90:119)
-        const bool kept = !(gv < th) && pl < hi && gv != 0.0;   // "If(W(i) < minW0) CYCLE" (:135)
-        gvk = kept ? gv : 0.0;
-        unsigned m = __ballot_sync(kFull, kept);
-        m |= m >> 1;
-        m |= m >> 2;
-        gm = m & 0x11111111u;  // bit 4q: 4-point group q holds a kept point
+        if (i0 >= hi) { us = SR; continue; }
+        gm = mr[sc];
         continue;
       }
-      const int q = (__ffs(gm) - 1) >> 2;
-      gm &= gm - 1;
-      const double wq = __shfl_sync(kFull, gvk, 4 * q + (lane & 3));
-      if (warp == 0 && lane < 4) {
-        ws[buf][4 * c + lane] = wq;
-        pidx[buf][4 * c + lane] = i0 + 4 * q + lane;
+      // take the strip's kept points (lowest first) until the batch of 32 is full
+      const int n = __popc(gm), take = n < 32 - c ? n : 32 - c;
+      if (warp == 0 && lane < take) {
+        const int bit = __fns(gm, 0, lane + 1);
+        ws[buf][c + lane] = wr[sc][bit];
+        pidx[buf][c + lane] = i0 + bit;
       }
-      ++c;
+      if (take == n) gm = 0;
+      else
+        for (int r = 0; r < take; ++r) gm &= gm - 1;
+      c += take;
     }
+    if (warp == 0 && lane >= c) ws[buf][lane] = 0.0;   // unused slots of the last group weigh nothing
     return c;
   };
   // gather the listed points' rows into registers (DN loads per thread in flight), store them centred
@@ -373,7 +383,7 @@ __global__ void __launch_bounds__(256) k_mstep_big(const double* __restrict__ X,
     for (int u = 0; u < DN; ++u) {
       const int i = tid + 256 * u;
       const int pt = i / (8 * DN), a = i % (8 * DN);
-      const long long pp = pt < 4 * cnt ? pidx[buf][pt] : -1;
+      const long long pp = pt < cnt ? pidx[buf][pt] : -1;
       xv[u] = (pp >= 0 && pp < hi && a < d) ? X[pp * d + a] - smu[a] : 0.0;
     }
   };
@@ -398,7 +408,7 @@ __global__ void __launch_bounds__(256) k_mstep_big(const double* __restrict__ X,
     __syncthreads();
     gather(cur ^ 1, cn, xv);        // ... and start fetching its rows: they land while this batch is multiplied
     const double* zb = zdyn + (size_t)cur * 32 * ZS;
-    for (int q = 0; q < cc; ++q) {
+    for (int q = 0; q < (cc + 3) / 4; ++q) {
       const double w = ws[cur][4 * q + t];
 #pragma unroll
       for (int o = 0; o < OWN; ++o) {
@@ -423,11 +433,19 @@ __global__ void __launch_bounds__(256) k_mstep_big(const double* __restrict__ X,
       out[(size_t)blk * 64 + g * 8 + 2 * t + 1] = acc[o][1];
     }
   }
-  if (warp == 0) {
+  {
+    __shared__ double sg2w[8];
     double s = sg2;
 #pragma unroll
     for (int sh = 16; sh > 0; sh >>= 1) s += shx(s, sh);
-    if (lane == 0) { out[(size_t)MB * 64] = s; out[(size_t)MB * 64 + 1] = 0.0; }
+    if (lane == 0) sg2w[warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+      double tot = 0;
+      for (int w = 0; w < 8; ++w) tot += sg2w[w];   // fixed order
+      out[(size_t)MB * 64] = tot;
+      out[(size_t)MB * 64 + 1] = 0.0;
+    }
   }
 }
 
