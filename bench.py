@@ -189,7 +189,10 @@ def main():
         raise SystemExit("bench.py: no CUDA device (mlfortran_b200 has no CPU fallback)")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    numa_note = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank: no binding"
+    # the single rank is bound too (its pinned staging buffer should sit on the GPU's NUMA node); the CPU-baseline leg
+    # gets the full affinity mask back
+    full_affinity = os.sched_getaffinity(0)
+    numa_note = bind_to_gpu_numa_node(local_rank) if (world > 1 or os.environ.get("MLF_BENCH_NO_BIND") != "1") else "not bound (MLF_BENCH_NO_BIND=1)"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -345,6 +348,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        os.sched_setaffinity(0, full_affinity)
         r = cpu_oracle_rate(d, K, args.cpu_points, args.min_proba, 3, 1)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
                "sample": f"oracle (C restatement of the reference, OpenMP over components) on N_cpu={r['n']} points of the same d={d}, K={K} mixture, "

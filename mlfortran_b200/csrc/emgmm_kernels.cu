@@ -107,7 +107,6 @@ __global__ void __launch_bounds__(256) k_refresh(Geom g, const double* __restric
   const double* Ck = Cov + (size_t)k * d * d;
   __shared__ double s_c[64], s_s[64], s_red[256], s_f[128];
   __shared__ int s_p[64], s_q[64];
-  __shared__ int s_flag;
 
   // dsytrd 'U' reads the upper triangle only (src/mlf_matrix.f90:269)
   auto csym = [&](int a, int b) -> double {
