@@ -128,6 +128,9 @@ int64_t mlf_b200_launch_count(MLF_OBJ *obj);
 void *mlf_b200_stream(MLF_OBJ *obj);
 int64_t mlf_b200_global_points(MLF_OBJ *obj);
 const char *mlf_b200_version(void);
+/* Self-test hook: the device exp of the softmax (exp_tab.cuh: table-driven, arguments <= 0) evaluated on n host values on
+ * device `device`; out[i] = exp(in[i]).  Exists so that the tests can pin the kernel's transcendental against libm. */
+int mlf_b200_selftest_exp(const double *in, double *out, int64_t n, int device);
 
 /* ---- engine-level entry points: what a Fortran extension type binds with iso_c_binding --------------------------
  * Deliverable form (A) of INTEGRATION.md: fortran/mlf_emgmm_b200.f90 declares a type extending the reference's

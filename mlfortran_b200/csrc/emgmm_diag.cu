@@ -295,6 +295,20 @@ static cudaError_t launch_emd_t(const Geom& g, EmArgs a, int grid, cudaStream_t 
   return cudaGetLastError();
 }
 
+namespace {
+__global__ void k_selftest_exp(const double* __restrict__ in, double* __restrict__ out, int64_t n) {
+  __shared__ double etab[128];
+  if (threadIdx.x < 128) etab[threadIdx.x] = kExpTab128[threadIdx.x];
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = exp_tab(in[i], etab);
+}
+}  // namespace
+
+cudaError_t launch_selftest_exp(const double* in, double* out, int64_t n, cudaStream_t st) {
+  k_selftest_exp<<<148, 256, 0, st>>>(in, out, n);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_emd(const Geom& g, const FusedGeom& f, EmArgs a, int grid, size_t smem_limit, cudaStream_t st) {
   if (!emd_ok(g, f, smem_limit)) return cudaErrorInvalidConfiguration;
   return launch_emd_t<64>(g, a, grid, st);

@@ -37,33 +37,6 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 __device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 constexpr unsigned kFull = 0xffffffffu;
 
-__device__ __forceinline__ double exp_bf(double a) {  // see emgmm_fused.cu
-  a = (a < -750.0) ? -750.0 : a;
-  a = (a > 710.0) ? 710.0 : a;
-  const double magic = 6755399441055744.0;
-  double t = fma(a, 1.4426950408889634074, magic);
-  const int n = __double2loint(t);
-  t -= magic;
-  double r = fma(t, -6.93147180369123816490e-01, a);
-  r = fma(t, -1.90821492927058770002e-10, r);
-  double p = 1.6059043836821614599e-10;
-  p = fma(p, r, 2.0876756987868098979e-09);
-  p = fma(p, r, 2.5052108385441718775e-08);
-  p = fma(p, r, 2.7557319223985890653e-07);
-  p = fma(p, r, 2.7557319223985892510e-06);
-  p = fma(p, r, 2.4801587301587301566e-05);
-  p = fma(p, r, 1.9841269841269841253e-04);
-  p = fma(p, r, 1.3888888888888889419e-03);
-  p = fma(p, r, 8.3333333333333332177e-03);
-  p = fma(p, r, 4.1666666666666664354e-02);
-  p = fma(p, r, 1.6666666666666665741e-01);
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  const int n1 = n >> 1, n2 = n - n1;
-  return (p * __hiloint2double((n1 + 1023) << 20, 0)) * __hiloint2double((n2 + 1023) << 20, 0);
-}
-
 // ---- tensor memory as per-warp scratch: lane quarter (warp & 3), 4 consecutive 32-bit columns = two doubles ----------
 __device__ __forceinline__ void tmem_st2(uint32_t taddr, double v0, double v1) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(__double2loint(v0)),

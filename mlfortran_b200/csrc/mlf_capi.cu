@@ -256,6 +256,24 @@ extern "C" {
 
 const char* mlf_b200_version(void) { return "mlfortran_b200 0.1 (sm_100a, fp64 DMMA EM-GMM)"; }
 
+int mlf_b200_selftest_exp(const double* in, double* out, int64_t n, int device) {
+  if (!in || !out || n < 0) return -1;
+  if (n == 0) return 0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return -7;   // no CPU fallback
+  if (cudaSetDevice(device) != cudaSuccess) return -7;
+  double *di = nullptr, *dout = nullptr;
+  int rc = -7;
+  if (cudaMalloc((void**)&di, (size_t)n * sizeof(double)) == cudaSuccess && cudaMalloc((void**)&dout, (size_t)n * sizeof(double)) == cudaSuccess &&
+      cudaMemcpy(di, in, (size_t)n * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
+      mlfb200::launch_selftest_exp(di, dout, n, 0) == cudaSuccess &&
+      cudaMemcpy(out, dout, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess)
+    rc = 0;
+  cudaFree(di);
+  cudaFree(dout);
+  return rc;
+}
+
 int mlf_init(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {

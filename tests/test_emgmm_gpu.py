@@ -48,6 +48,25 @@ def check_against(em, oMu, oCov, olam, otr):
     assert em.sumLL == tr[-1]
 
 
+# ---- the kernel's transcendental ------------------------------------------------------------------------------------
+def test_device_exp_against_libm():
+    """exp_tab (the softmax's exp in k_em16 / k_emd): <= 1 ulp-level agreement with libm over the whole range of softmax
+    arguments, exact 1 at 0, exact 0 below -708 (where fp64 exp leaves the normal range) and at -inf."""
+    rng = np.random.default_rng(7)
+    x = np.concatenate([-707.0 * rng.random(400000), -40.0 * rng.random(400000), -1.0 * rng.random(200000),
+                        -np.logspace(-300, 2.8, 2000), np.array([0.0, -0.0, -707.0, -1e-320])])
+    out = np.empty_like(x)
+    lib = _lib.load()
+    assert lib.mlf_b200_selftest_exp(x.ctypes.data_as(C.POINTER(C.c_double)), out.ctypes.data_as(C.POINTER(C.c_double)), x.size, 0) == 0
+    ref = np.exp(x.astype(np.longdouble)).astype(np.float64)
+    assert (np.abs(out - ref) <= 2.3e-16 * ref).all(), np.abs(out / ref - 1).max()
+    assert out[-4] == 1.0 and out[-3] == 1.0
+    z = np.array([-708.5, -745.0, -1e4, -1e300, -np.inf])
+    oz = np.ones_like(z)
+    assert lib.mlf_b200_selftest_exp(z.ctypes.data_as(C.POINTER(C.c_double)), oz.ctypes.data_as(C.POINTER(C.c_double)), z.size, 0) == 0
+    assert (oz == 0.0).all()
+
+
 # ---- golden fixtures -------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
 def test_golden_trajectories(path, oracle):
