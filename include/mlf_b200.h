@@ -106,7 +106,9 @@ int mlf_b200_get_initialized(MLF_OBJ *obj);
 /* Seed of the k-means initialiser's random stream (the reference uses an unseeded RANDOM_NUMBER, src/mlf_rand.f90:173-182). */
 int mlf_b200_set_seed(MLF_OBJ *obj, uint64_t seed);
 /* EXTENSION (the reference has full covariances only): cov_type 0 = full (default, reference behaviour), 1 = diagonal --
- * the E-step reads diag(C_k) only and the M-step keeps the diagonal of the reference's C_k (BASELINE config 5). */
+ * the E-step reads diag(C_k) only and the M-step keeps the diagonal of the reference's C_k (BASELINE config 5).
+ * Returns -7 (mlf_OTHERERROR) when asked for full covariances on an object constructed with MLF_B200_COV_DIAG whose
+ * kernels were planned around the diagonal-compressed parameter pack (d <= 8 with K >= 128): construct a new object. */
 int mlf_b200_set_cov_type(MLF_OBJ *obj, int cov_type);
 int mlf_b200_refresh_x(MLF_OBJ *obj, const double *X);        /* re-copy X after the caller changed it */
 const char *mlf_b200_last_error(MLF_OBJ *obj);

@@ -77,7 +77,13 @@ class EmgmmEngine {
   void set_profile(bool on) { profile_ = on; }
   // EXTENSION (no reference semantics): diagonal covariances -- the E-step reads diag(C_k) only and the
   // M-step keeps the diagonal of the reference's C_k.  Default: full covariances (reference behaviour).
-  void set_cov_diag(bool on) { cov_diag_ = on; }
+  // false when the object was planned around the diagonal-compressed pack (diagonal covariances at construction, K >= 128
+  // at d <= 8): its kernels cannot represent full covariances, a new object is needed for that
+  bool set_cov_diag(bool on) {
+    if (!on && fgeom_.diag) { err_ = "object planned for diagonal covariances: construct a new one for full covariances"; return false; }
+    cov_diag_ = on;
+    return true;
+  }
   bool cov_diag() const { return cov_diag_; }
   int64_t launches() const { return launches_; }
 

@@ -206,8 +206,11 @@ std::string MultiEngine::plan() const {
   snprintf(buf, sizeof buf, "%d shards in one process (peer-memory all-reduce) x ", (int)w_.size());
   return std::string(buf) + w_[0].eng->plan();
 }
-void MultiEngine::set_cov_diag(bool on) {
-  for (auto& w : w_) w.eng->set_cov_diag(on);
+bool MultiEngine::set_cov_diag(bool on) {
+  bool ok = true;
+  for (auto& w : w_)
+    if (!w.eng->set_cov_diag(on)) { ok = false; err_ = w.eng->last_error(); }
+  return ok;
 }
 
 }  // namespace mlfb200

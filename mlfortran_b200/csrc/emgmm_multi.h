@@ -40,7 +40,7 @@ class MultiEngine {
   int world() const { return (int)w_.size(); }
   std::string plan() const;
   const std::string& last_error() const { return err_; }
-  void set_cov_diag(bool on);
+  bool set_cov_diag(bool on);
 
  private:
   struct Worker {

@@ -467,9 +467,8 @@ int mlf_b200_get_initialized(MLF_OBJ* obj) {
 int mlf_b200_set_cov_type(MLF_OBJ* obj, int cov_type) {
   EmObject* o = as_em(obj);
   if (!o || (cov_type != 0 && cov_type != 1)) return -1;
-  if (o->multi) o->multi->set_cov_diag(cov_type == 1);
-  else o->eng.set_cov_diag(cov_type == 1);
-  return 0;
+  const bool ok = o->multi ? o->multi->set_cov_diag(cov_type == 1) : o->eng.set_cov_diag(cov_type == 1);
+  return ok ? 0 : -7;   // mlf_OTHERERROR: see mlf_b200_last_error
 }
 
 int mlf_b200_set_seed(MLF_OBJ* obj, uint64_t seed) {

@@ -480,6 +480,22 @@ def test_diagonal_cuda_core_kernel_matches_oracle(case, oracle):
     em.finalize()
 
 
+def test_diag_planned_object_refuses_full_covariances():
+    """An object built around the diagonal-compressed pack (K >= 128 at d <= 8, cov_type fixed at construction) cannot
+    represent full covariances: switching back must fail loudly, not compute with the wrong pack."""
+    data = synth.make_mixture(4, 128, 20, 5.0, 1.0, 189)
+    em = mlf_algo_emgmm()
+    assert em.init(data["X"], 128, 1.0, cov_type="diag") == 0
+    assert em.set_cov_type("diag") == 0
+    assert em.set_cov_type("full") == -7
+    assert "diagonal" in em.last_error()
+    em.finalize()
+    em2 = mlf_algo_emgmm()          # a small-K object keeps the full pack and may switch either way
+    assert em2.init(data["X"], 8, 1.0, cov_type="diag") == 0
+    assert em2.set_cov_type("full") == 0 and em2.set_cov_type("diag") == 0
+    em2.finalize()
+
+
 def test_diagonal_cuda_core_kernel_far_outliers(monkeypatch):
     """Points 1e5 sigma away: |logit| > 2^27, where k_emd's approximate softmax offset (high word of the largest logit) is
     replaced by the exact scan.  The reference itself has no answer here (it exponentiates without an offset: 0/0), so
