@@ -14,6 +14,8 @@
 #include "emgmm_kernels.cuh"
 
 #include <cmath>
+#include <cstdint>
+#include <cstdlib>
 
 namespace mlfb200 {
 
@@ -79,7 +81,10 @@ bool estep_big_ok(const Geom& g, size_t smem_limit) {
 // pack2 layout per component (FusedGeom): [NB*32 L fragments | 8*DN bias -L^T(mu-m) | log(lambda)-lnDet, pad]
 // GPW: 8-point groups per warp.  GPW = 2 (128-point tiles, large d) halves the fragment traffic per DMMA; its output
 // coordinates are then processed in H = 2 halves so that the accumulators (GPW x DN/H x 2 doubles) stay in registers.
-template <int DM, int CB, int GPW>
+// STAGE: the component's pack is copied into shared memory with cp.async one component ahead of the DMMAs (two buffers, one
+// block barrier per component) instead of being read through L1 by every warp; the raw points are then not kept in shared
+// memory (the pass-A statistics re-read them from L2), which is what makes room for the two buffers at d = 128.
+template <int DM, int CB, int GPW, bool STAGE>
 __global__ void __launch_bounds__(256, 1) k_estep_big(EmArgs A) {
   constexpr int DN = (DM + 1) / 2;
   constexpr int NB = b_blk_off(DM);
@@ -92,9 +97,17 @@ __global__ void __launch_bounds__(256, 1) k_estep_big(EmArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int K8 = A.K8, KP = K8 * 8, S = A.S, d = A.d, K = A.K;
   const int64_t N = A.N;
-  double* xs = smem;                    // [TP][XS] raw points of the tile
-  double* tile = xs + (size_t)TP * XS;  // [TP][S]  logits -> responsibilities
+  double* xs = smem;                                           // [TP][XS] raw points of the tile (not with STAGE)
+  double* tile = STAGE ? smem : xs + (size_t)TP * XS;          // [TP][S]  logits -> responsibilities
+  double* fbuf = tile + (size_t)TP * S;                        // STAGE: [2][PSF] pack of the current / next component
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  auto stage = [&](int k) {   // all threads: 16-byte chunks of component k's pack into buffer k & 1
+    const char* src = reinterpret_cast<const char*>(A.pack2 + (size_t)k * PSF);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(fbuf + (size_t)(k & 1) * PSF);
+    for (int i = tid; i < PSF / 2; i += 256)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 16u * (uint32_t)i), "l"(src + 16 * (size_t)i) : "memory");
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
 
   double accA[CB][DN][2], sg[CB], sg2[CB];
 #pragma unroll
@@ -116,18 +129,25 @@ __global__ void __launch_bounds__(256, 1) k_estep_big(EmArgs A) {
       for (int mb = 0; mb < DM; ++mb) {
         const int a = 4 * mb + t;
         const double x = (p < N && a < d) ? A.X[p * d + a] : 0.0;
-        xr[a] = x;
+        if (!STAGE) xr[a] = x;
         xa[grp][mb] = x - A.shift[a];
       }
-      if (8 * DN > 4 * DM) xr[4 * DM + t] = 0.0;
+      if (!STAGE && 8 * DN > 4 * DM) xr[4 * DM + t] = 0.0;
     }
     double* row[GPW];
     double rmax[GPW];
     int rarg[GPW];
 #pragma unroll
     for (int grp = 0; grp < GPW; ++grp) { row[grp] = tile + (size_t)(warp * 8 * GPW + 8 * grp + g) * S; rmax[grp] = -INFINITY; rarg[grp] = 0; }
+    if (STAGE) stage(0);   // the previous tile ended with a block barrier: both buffers are free
     for (int k = 0; k < KP; ++k) {
       const double* pk = A.pack2 + (size_t)k * PSF;
+      if (STAGE) {
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();   // component k has landed for every thread, and every warp is done with component k - 1
+        if (k + 1 < KP) stage(k + 1);
+        pk = fbuf + (size_t)(k & 1) * PSF;
+      }
       double s[GPW];
 #pragma unroll
       for (int grp = 0; grp < GPW; ++grp) s[grp] = 0;
@@ -149,7 +169,7 @@ __global__ void __launch_bounds__(256, 1) k_estep_big(EmArgs A) {
 #pragma unroll
           for (int nb = 0; nb < DH; ++nb)
             if (lo + nb < DN && lo + nb <= mb / 2) {
-              const double Lf = __ldg(pk + (b_blk_off(mb) + lo + nb) * 32 + lane);
+              const double Lf = STAGE ? pk[(b_blk_off(mb) + lo + nb) * 32 + lane] : __ldg(pk + (b_blk_off(mb) + lo + nb) * 32 + lane);
 #pragma unroll
               for (int grp = 0; grp < GPW; ++grp) dmma(c[grp][nb], xa[grp][mb], Lf);
             }
@@ -210,7 +230,16 @@ __global__ void __launch_bounds__(256, 1) k_estep_big(EmArgs A) {
           sg[ci] += a;
           sg2[ci] = fma(a, a, sg2[ci]);
 #pragma unroll
-          for (int db = 0; db < DN; ++db) dmma(accA[ci][db], a, xs[(size_t)(4 * pb + t) * XS + 8 * db + g]);
+          for (int db = 0; db < DN; ++db) {
+            double xv;
+            if (STAGE) {   // rows of the tile that lie beyond N carry a = 0
+              const int64_t pp = bt * TP + 4 * pb + t;
+              xv = (pp < N && 8 * db + g < d) ? A.X[pp * d + 8 * db + g] : 0.0;
+            } else {
+              xv = xs[(size_t)(4 * pb + t) * XS + 8 * db + g];
+            }
+            dmma(accA[ci][db], a, xv);
+          }
         }
       }
     }
@@ -243,17 +272,31 @@ int estep_big_gpw(const Geom& g, size_t smem_limit) {
   return (g.DM >= 16 && estep_big_cb(g) == 1 && need2 <= smem_limit) ? 2 : 1;
 }
 
-template <int DM, int CB, int GPW>
+template <int DM, int CB, int GPW, bool STAGE = false>
 static cudaError_t launch_big_t(const EmArgs& a, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(k_estep_big<DM, CB, GPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_estep_big<DM, CB, GPW, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_estep_big<DM, CB, GPW><<<grid, 256, smem, st>>>(a);
+  k_estep_big<DM, CB, GPW, STAGE><<<grid, 256, smem, st>>>(a);
   return cudaGetLastError();
 }
+// staged variant: 128-point logit tile + two pack buffers
+size_t estep_big_stage_smem(const Geom& g) {
+  const int S = ((g.K8 * 8 + 15) / 16) * 16 + 4;
+  const int PSF = g.NB * 32 + 8 * g.DN + 4;
+  return ((size_t)128 * S + (size_t)2 * PSF) * sizeof(double);
+}
+bool estep_big_stage(const Geom& g, size_t smem_limit) {
+  const char* e = getenv("MLF_B200_BIG_STAGE");   // read per call: the tests flip it inside one process
+  const bool off = e && e[0] == '0';
+  return !off && estep_big_gpw(g, smem_limit) == 2 && estep_big_stage_smem(g) <= smem_limit;
+}
 template <int DM>
-static cudaError_t launch_big_dm(const EmArgs& a, int cb, int gpw, int grid, size_t smem, cudaStream_t st) {
+static cudaError_t launch_big_dm(const EmArgs& a, int cb, int gpw, bool stage, int grid, size_t smem, cudaStream_t st) {
   constexpr int DN = (DM + 1) / 2;
-  if constexpr (DM >= 16) { if (gpw == 2 && cb == 1) return launch_big_t<DM, 1, 2>(a, grid, smem, st); }
+  if constexpr (DM >= 16) {
+    if (gpw == 2 && cb == 1 && stage) return launch_big_t<DM, 1, 2, true>(a, grid, smem, st);
+    if (gpw == 2 && cb == 1) return launch_big_t<DM, 1, 2>(a, grid, smem, st);
+  }
   if constexpr (1 * DN <= 16) { if (cb == 1) return launch_big_t<DM, 1, 1>(a, grid, smem, st); }
   if constexpr (2 * DN <= 16) { if (cb == 2) return launch_big_t<DM, 2, 1>(a, grid, smem, st); }
   if constexpr (4 * DN <= 16) { if (cb == 4) return launch_big_t<DM, 4, 1>(a, grid, smem, st); }
@@ -263,17 +306,18 @@ cudaError_t launch_estep_big(const Geom& g, EmArgs a, int grid, size_t smem_limi
   if (!estep_big_ok(g, smem_limit)) return cudaErrorInvalidConfiguration;
   const int gpw = estep_big_gpw(g, smem_limit);
   a.S = ((g.K8 * 8 + 15) / 16) * 16 + 4;
-  const size_t smem = ((size_t)64 * gpw * (8 * g.DN + 4) + (size_t)64 * gpw * a.S) * sizeof(double);
+  const bool stage = estep_big_stage(g, smem_limit);
+  const size_t smem = stage ? estep_big_stage_smem(g) : ((size_t)64 * gpw * (8 * g.DN + 4) + (size_t)64 * gpw * a.S) * sizeof(double);
   const int cb = estep_big_cb(g);
   switch (g.DM) {
-    case 1: return launch_big_dm<1>(a, cb, gpw, grid, smem, st);
-    case 2: return launch_big_dm<2>(a, cb, gpw, grid, smem, st);
-    case 4: return launch_big_dm<4>(a, cb, gpw, grid, smem, st);
-    case 8: return launch_big_dm<8>(a, cb, gpw, grid, smem, st);
-    case 12: return launch_big_dm<12>(a, cb, gpw, grid, smem, st);
-    case 16: return launch_big_dm<16>(a, cb, gpw, grid, smem, st);
-    case 24: return launch_big_dm<24>(a, cb, gpw, grid, smem, st);
-    case 32: return launch_big_dm<32>(a, cb, gpw, grid, smem, st);
+    case 1: return launch_big_dm<1>(a, cb, gpw, stage, grid, smem, st);
+    case 2: return launch_big_dm<2>(a, cb, gpw, stage, grid, smem, st);
+    case 4: return launch_big_dm<4>(a, cb, gpw, stage, grid, smem, st);
+    case 8: return launch_big_dm<8>(a, cb, gpw, stage, grid, smem, st);
+    case 12: return launch_big_dm<12>(a, cb, gpw, stage, grid, smem, st);
+    case 16: return launch_big_dm<16>(a, cb, gpw, stage, grid, smem, st);
+    case 24: return launch_big_dm<24>(a, cb, gpw, stage, grid, smem, st);
+    case 32: return launch_big_dm<32>(a, cb, gpw, stage, grid, smem, st);
     default: return cudaErrorInvalidConfiguration;
   }
 }

@@ -173,7 +173,8 @@ std::string EmgmmEngine::plan() const {
     snprintf(buf, sizeof buf, "k_em<%d,%d,true,%d,%s>: fused single sweep, 8 warps/SM, %d-point tiles", g.DM, fgeom_.CBMAX, fgeom_.GPW,
              fgeom_.diag ? "diag" : "full", fgeom_.TP);
   else if (big_)
-    snprintf(buf, sizeof buf, "k_estep_big<%d,%d> + k_mstep_big<%d>: two-pass, Cholesky fragments streamed through L1", g.DM, (g.K8 + 7) / 8, g.DN);
+    snprintf(buf, sizeof buf, "k_estep_big<%d,%d> + k_mstep_big<%d>: two-pass, Cholesky fragments %s", g.DM, (g.K8 + 7) / 8, g.DN,
+             estep_big_stage(g, smem_limit_) ? "staged in shared memory one component ahead (cp.async, two buffers)" : "streamed through L1");
   else if (legacy_estep_)
     snprintf(buf, sizeof buf, "k_estep<%d> + k_mstep<%d>: first-generation two-pass kernels", g.DM, g.DN);
   else

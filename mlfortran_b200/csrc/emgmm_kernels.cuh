@@ -99,6 +99,7 @@ cudaError_t launch_finalize_fused(const Geom& g, const FusedGeom& f, const doubl
 size_t estep_big_smem(const Geom& g);
 bool estep_big_ok(const Geom& g, size_t smem_limit);
 int estep_big_tile(const Geom& g, size_t smem_limit);
+bool estep_big_stage(const Geom& g, size_t smem_limit);   // pack staged in shared memory with cp.async (MLF_B200_BIG_STAGE=0 disables)
 cudaError_t launch_estep_big(const Geom& g, EmArgs a, int grid, size_t smem_limit, cudaStream_t st);
 void mstep_big_grid(const Geom& g, int sms, int64_t N, int* gx, int64_t* chunk);
 cudaError_t launch_mstep_big(const Geom& g, const double* X, int64_t N, const double* gamma, int64_t ldg, const double* mupad,

@@ -373,6 +373,24 @@ def test_alternative_kernel_generations_agree(env, oracle, monkeypatch):
     em.finalize()
 
 
+@pytest.mark.parametrize("stage", ["1", "0"], ids=["cp_async_staged", "through_L1"])
+def test_large_d_estep_staged_and_streamed_agree_with_oracle(stage, oracle, monkeypatch):
+    """d = 64 and d = 128 with few components take the 128-point-tile E-pass; its pack is either staged in shared memory
+    one component ahead (default) or read through L1 (MLF_B200_BIG_STAGE=0): same numbers either way."""
+    monkeypatch.setenv("MLF_B200_BIG_STAGE", stage)
+    for d, K, npc, seed in ((128, 5, 300, 127), (64, 7, 250, 128)):
+        data = synth.make_mixture(d, K, npc, 3.0, 1.0, seed)
+        X = data["X"]
+        Mu0, Cov0, lam0 = synth.injected_init(data["centres"], seed)
+        oMu, oCov, olam, otr, oP = oracle.em_iterations(X, Mu0, Cov0, lam0, 1.0, 2, return_proba=True)
+        em = make_em(X, K, 1.0, Mu0, Cov0, lam0)
+        assert ("staged" in em.kernel_plan()) == (stage == "1"), em.kernel_plan()
+        assert em.step(2)[0] == 0, em.last_error()
+        check_against(em, oMu, oCov, olam, otr)
+        assert np.abs(em.ProbaC - oP).max() <= 1e-9
+        em.finalize()
+
+
 def test_large_shape_kernels_forced_on_a_small_shape(oracle, monkeypatch):
     """MLF_B200_BIG=1 routes a shape the fused sweep normally handles through the large-shape kernels: same numbers."""
     monkeypatch.setenv("MLF_B200_BIG", "1")
