@@ -323,6 +323,47 @@ cudaError_t launch_estep_big(const Geom& g, EmArgs a, int grid, size_t smem_limi
 }
 int estep_big_tile(const Geom& g, size_t smem_limit) { return 64 * estep_big_gpw(g, smem_limit); }
 
+// Row / column of lower-triangular block number blk (row-major over the triangle: 0 -> (0,0), 1 -> (1,0), 2 -> (1,1), ...).
+__host__ __device__ constexpr int tri_row(int blk) {
+  int ab = 0;
+  while ((ab + 1) * (ab + 2) / 2 <= blk) ++ab;
+  return ab;
+}
+// Scatter of `ng` staged 4-point groups into warp W's output blocks W, W + 8, ...: the 8-coordinate blocks of (x - mu) that
+// those output blocks touch are loaded once per group (compile-time set, <= DN loads) and reused by every DMMA; the
+// weighted copy w * z feeds the row operand (same product as the reference's W(i) * (X - Mu) outer product).
+template <int DN, int W>
+__device__ __forceinline__ void mb_scatter(double (&acc)[(DN * (DN + 1) / 2 + 7) / 8][2], const double* __restrict__ zb,
+                                           const double* __restrict__ wsb, int ng, int g, int t) {
+  constexpr int MB = DN * (DN + 1) / 2;
+  constexpr int OWN = (MB + 7) / 8;
+  constexpr int ZS = 8 * DN + 4;
+  for (int q = 0; q < ng; ++q) {
+    const double w = wsb[4 * q + t];
+    const double* zr = zb + (size_t)(4 * q + t) * ZS + g;
+    double z[DN], wz[DN];
+#pragma unroll
+    for (int b = 0; b < DN; ++b) {
+      bool need = false;   // does any of this warp's blocks use coordinate block b?
+#pragma unroll
+      for (int o = 0; o < OWN; ++o) {
+        const int blk = W + 8 * o;
+        if (blk < MB) { const int ab = tri_row(blk), bb = blk - ab * (ab + 1) / 2; need = need || ab == b || bb == b; }
+      }
+      z[b] = need ? zr[8 * b] : 0.0;
+      wz[b] = w * z[b];
+    }
+#pragma unroll
+    for (int o = 0; o < OWN; ++o) {
+      const int blk = W + 8 * o;
+      if (blk < MB) {
+        const int ab = tri_row(blk), bb = blk - ab * (ab + 1) / 2;
+        dmma(acc[o], wz[ab], z[bb]);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // M-pass for large d.  grid = (point chunks, components); block = 8 warps; warp w owns the lower-triangular 8x8 output
 // blocks w, w+8, ... of the scatter matrix (<= 17 at d = 128).  partial[chunk][K][MS] as k_mstep.
@@ -346,76 +387,77 @@ __global__ void __launch_bounds__(256) k_mstep_big(const double* __restrict__ X,
   const double th = thr[k];
   const double* gk = gamma ? gamma + (size_t)k * ldg : nullptr;
   double acc[OWN][2];
-  int oa[OWN], ob[OWN];
 #pragma unroll
-  for (int o = 0; o < OWN; ++o) {
-    acc[o][0] = 0; acc[o][1] = 0;
-    const int blk = warp + 8 * o;
-    int ab = 0;
-    while ((ab + 1) * (ab + 2) / 2 <= blk) ++ab;
-    oa[o] = ab;
-    ob[o] = blk - ab * (ab + 1) / 2;
-  }
+  for (int o = 0; o < OWN; ++o) { acc[o][0] = 0; acc[o][1] = 0; }
   double sg2 = 0;
   const int64_t lo = (int64_t)blockIdx.x * chunk;
   const int64_t hi = (lo + chunk < N) ? lo + chunk : N;
   // scan state.  The responsibilities of the chunk are looked at in rounds of 64 strips of 32 points: warp w fetches strips
   // 8w..8w+7 (eight loads in flight per lane, 2048 points per round trip to memory), leaves the kept weights and the
-  // kept-group masks in shared memory, and every warp then walks the masks in strip order -- uniform over the block, and
-  // the order of the kept points is the point order (deterministic).  One warp looking at one strip at a time waited a full
+  // kept-point masks in shared memory; warp 0 turns the masks into prefix counts -- everything that follows is uniform over
+  // the block, and the order of the kept points is the point order (deterministic).  One warp looking at one strip at a time waited a full
   // memory latency per ~1 kept point at K = 32 (profiles/ncu_r01h_big_d128.md: the scan, not the scatter, bounded the pass).
   constexpr int SR = 64;
   __shared__ double wr[SR][32];   // kept weight of every point of the round (0 if dropped)
   __shared__ unsigned mr[SR];     // kept points of strip s
+  __shared__ int pre[SR + 1];     // kept points of the round before strip s (pre[SR]: all of them)
   int64_t ib = lo - 32 * SR;      // first point of the current round
-  int us = SR;                    // next strip of the round to look at
-  int sc = 0;                     // strip the groups in gm belong to
-  int64_t i0 = lo;
-  unsigned gm = 0;        // kept points of the current strip that are not listed yet
-  // list up to 32 kept points (compacted across strips, in point order) into buffer `buf`; returns how many
+  int used = 0, total = 0;        // kept points of the round already listed / in all
+  // list up to 32 kept points (compacted across strips and rounds, in point order) into buffer `buf`; returns how many.
+  // The r-th kept point of a round is found by a binary search of the per-strip prefix counts and a find-n-th-set-bit on
+  // the strip's mask: 32 lanes place 32 points at once, nothing walks the strips one by one.
   auto fill = [&](int buf) -> int {
     int c = 0;
     while (c < 32) {
-      if (gm == 0) {
-        if (us == SR) {
-          ib += 32 * SR;
-          if (ib >= hi) break;
-          __syncthreads();   // the previous round's weights have been copied out by every warp that needed them
-          double gv[8];
+      if (used == total) {
+        ib += 32 * SR;
+        if (ib >= hi) break;
+        __syncthreads();   // the previous round's weights have been copied out by every warp that needed them
+        double gv[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int64_t pl = ib + 32 * (8 * warp + u) + lane;
-            gv[u] = (pl < hi) ? (gk ? gk[pl] : 1.0) : 0.0;
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int64_t pl = ib + 32 * (8 * warp + u) + lane;
-            sg2 = fma(gv[u], gv[u], sg2);                                  // SUM(W*W) runs over all points (src/mlf_matrix.f90:119)
-            const bool kept = !(gv[u] < th) && pl < hi && gv[u] != 0.0;    // "If(W(i) < minW0) CYCLE" (:135)
-            wr[8 * warp + u][lane] = kept ? gv[u] : 0.0;
-            const unsigned m = __ballot_sync(kFull, kept);
-            if (lane == 0) mr[8 * warp + u] = m;
-          }
-          __syncthreads();
-          us = 0;
+        for (int u = 0; u < 8; ++u) {
+          const int64_t pl = ib + 32 * (8 * warp + u) + lane;
+          gv[u] = (pl < hi) ? (gk ? gk[pl] : 1.0) : 0.0;
         }
-        sc = us;
-        i0 = ib + 32 * us;
-        ++us;
-        if (i0 >= hi) { us = SR; continue; }
-        gm = mr[sc];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int64_t pl = ib + 32 * (8 * warp + u) + lane;
+          sg2 = fma(gv[u], gv[u], sg2);                                  // SUM(W*W) runs over all points (src/mlf_matrix.f90:119)
+          const bool kept = !(gv[u] < th) && pl < hi && gv[u] != 0.0;    // "If(W(i) < minW0) CYCLE" (:135)
+          wr[8 * warp + u][lane] = kept ? gv[u] : 0.0;
+          const unsigned m = __ballot_sync(kFull, kept);
+          if (lane == 0) mr[8 * warp + u] = m;
+        }
+        __syncthreads();
+        if (warp == 0) {   // exclusive prefix counts of the 64 strips
+          const int c0 = __popc(mr[2 * lane]), c1 = __popc(mr[2 * lane + 1]);
+          int inc = c0 + c1;
+#pragma unroll
+          for (int sh = 1; sh < 32; sh <<= 1) {
+            const int o = __shfl_up_sync(kFull, inc, sh);
+            if (lane >= sh) inc += o;
+          }
+          pre[2 * lane] = inc - c0 - c1;
+          pre[2 * lane + 1] = inc - c1;
+          if (lane == 31) pre[SR] = inc;
+        }
+        __syncthreads();
+        used = 0;
+        total = pre[SR];
         continue;
       }
-      // take the strip's kept points (lowest first) until the batch of 32 is full
-      const int n = __popc(gm), take = n < 32 - c ? n : 32 - c;
+      const int take = (total - used < 32 - c) ? total - used : 32 - c;
       if (warp == 0 && lane < take) {
-        const int bit = __fns(gm, 0, lane + 1);
-        ws[buf][c + lane] = wr[sc][bit];
-        pidx[buf][c + lane] = i0 + bit;
+        const int r = used + lane;
+        int s0 = 0;   // last strip with pre[s0] <= r
+#pragma unroll
+        for (int step = SR / 2; step > 0; step >>= 1)
+          if (pre[s0 + step] <= r) s0 += step;
+        const int bit = __fns(mr[s0], 0, r - pre[s0] + 1);
+        ws[buf][c + lane] = wr[s0][bit];
+        pidx[buf][c + lane] = ib + 32 * s0 + bit;
       }
-      if (take == n) gm = 0;
-      else
-        for (int r = 0; r < take; ++r) gm &= gm - 1;
+      used += take;
       c += take;
     }
     if (warp == 0 && lane >= c) ws[buf][lane] = 0.0;   // unused slots of the last group weigh nothing
@@ -452,16 +494,15 @@ __global__ void __launch_bounds__(256) k_mstep_big(const double* __restrict__ X,
     __syncthreads();
     gather(cur ^ 1, cn, xv);        // ... and start fetching its rows: they land while this batch is multiplied
     const double* zb = zdyn + (size_t)cur * 32 * ZS;
-    for (int q = 0; q < (cc + 3) / 4; ++q) {
-      const double w = ws[cur][4 * q + t];
-#pragma unroll
-      for (int o = 0; o < OWN; ++o) {
-        if (warp + 8 * o < MB) {
-          const double za = zb[(size_t)(4 * q + t) * ZS + 8 * oa[o] + g];
-          const double zc = zb[(size_t)(4 * q + t) * ZS + 8 * ob[o] + g];
-          dmma(acc[o], w * za, zc);
-        }
-      }
+    switch (warp) {   // compile-time block map per warp: every shared-memory offset is an immediate
+      case 0: mb_scatter<DN, 0>(acc, zb, ws[cur], (cc + 3) / 4, g, t); break;
+      case 1: mb_scatter<DN, 1>(acc, zb, ws[cur], (cc + 3) / 4, g, t); break;
+      case 2: mb_scatter<DN, 2>(acc, zb, ws[cur], (cc + 3) / 4, g, t); break;
+      case 3: mb_scatter<DN, 3>(acc, zb, ws[cur], (cc + 3) / 4, g, t); break;
+      case 4: mb_scatter<DN, 4>(acc, zb, ws[cur], (cc + 3) / 4, g, t); break;
+      case 5: mb_scatter<DN, 5>(acc, zb, ws[cur], (cc + 3) / 4, g, t); break;
+      case 6: mb_scatter<DN, 6>(acc, zb, ws[cur], (cc + 3) / 4, g, t); break;
+      default: mb_scatter<DN, 7>(acc, zb, ws[cur], (cc + 3) / 4, g, t); break;
     }
     store(cur ^ 1, xv);
     __syncthreads();                // next batch staged; this batch's lists and rows are free again
