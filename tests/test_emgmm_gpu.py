@@ -953,6 +953,24 @@ def test_single_process_multi_gpu_object(devices, oracle):
     em.finalize()
 
 
+def test_diagonal_cuda_core_kernel_sharded(oracle):
+    """Config-5 style job in miniature: diagonal covariances, K = 128, the points in two shards whose statistics (and side
+    lists' thresholds) meet in the all-reduce; the result must be the single-object / oracle result."""
+    d, K = 6, 128
+    data = synth.make_mixture(d, K, 45, 3.0, 1.0, 190)
+    X = data["X"]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 190)
+    oMu, oCov, olam, otr = _diag_oracle(oracle, oracle.em_iterations, X, Mu0, Cov0, lam0, 0.0, 4)
+    em = mlf_algo_emgmm()
+    assert em.init(X, K, 0.0, cov_type="diag", devices=[0, 0]) == 0
+    assert "2 shards" in em.kernel_plan() and "k_emd" in em.kernel_plan(), em.kernel_plan()
+    em.inject(Mu0, Cov0, lam0)
+    assert em.step(4)[0] == 0, em.last_error()
+    check_against(em, oMu, oCov, olam, otr)
+    assert em.global_points() == X.shape[0]
+    em.finalize()
+
+
 # ---- full-size properties (BASELINE configs[2] shape on one GPU) ----------------------------------------------------
 def test_full_size_properties_and_sample_parity(oracle):
     """N=1e8 (or what fits), d=16, K=64: size-independent invariants plus oracle parity on a 20 000-point sample."""
