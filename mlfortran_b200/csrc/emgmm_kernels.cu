@@ -77,7 +77,7 @@ __device__ double block_sum(double v, double* red) {
 // One block (128 threads) per component.  Matrices are column-major M(a,b) = M[b*d + a] in global scratch.
 // Follows InverseSymMatrix(C, invC, lnDet, .TRUE.)  (src/mlf_matrix.f90:256-298) with a cyclic Jacobi
 // eigensolver in place of dsytrd/dorgtr/dsteqr (only invC and lnDet enter the result, not the eigenvectors).
-__global__ void __launch_bounds__(256) k_refresh(Geom g, const double* __restrict__ Mu, const double* __restrict__ Cov,
+__global__ void __launch_bounds__(1024) k_refresh(Geom g, const double* __restrict__ Mu, const double* __restrict__ Cov,
                                                  const double* __restrict__ lambda, const double* __restrict__ Sc,
                                                  const double* __restrict__ mean, double Nglob, double* __restrict__ scratch,
                                                  double* __restrict__ pack, double* __restrict__ sumLLk,
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) k_refresh(Geom g, const double* __restric
   double* V = scratch + (size_t)k * 3 * d * d + (size_t)d * d;
   double* W = V + (size_t)d * d;
   const double* Ck = Cov + (size_t)k * d * d;
-  __shared__ double s_c[64], s_s[64], s_red[256], s_f[128];
+  __shared__ double s_c[64], s_s[64], s_red[1024], s_f[128];
   __shared__ int s_p[64], s_q[64];
 
   // dsytrd 'U' reads the upper triangle only (src/mlf_matrix.f90:269)
@@ -304,7 +304,9 @@ cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, c
     cudaError_t e = cudaFuncSetAttribute(k_refresh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
   }
-  k_refresh<<<g.K8 * 8, large ? 256 : 128, dyn, st>>>(g, Mu, Cov, lambda, Sc, mean, Nglob, scratch, pack, sumLLk, info, pack2, muold,
+  // d > 64: the eigenvector updates go to global scratch (A and V do not both fit shared memory at d = 128) and are bound by
+  // loads in flight, so the block is as large as the register file allows
+  k_refresh<<<g.K8 * 8, g.d > 64 ? 1024 : (large ? 256 : 128), dyn, st>>>(g, Mu, Cov, lambda, Sc, mean, Nglob, scratch, pack, sumLLk, info, pack2, muold,
                                                      f.PSF, f.OFFB, f.OFFC, shift ? shift : mean, do_sumll, large ? 1 : 0, cov_diag, f.diag ? 1 : 0,
                                                      (large && warm) ? 1 : 0);
   return cudaGetLastError();
