@@ -73,9 +73,14 @@ size_t estep_big_smem(const Geom& g) {
 }
 int estep_big_cb(const Geom& g) { return (g.K8 + 7) / 8; }
 bool estep_big_ok(const Geom& g, size_t smem_limit) {
-  const int cb = estep_big_cb(g);
   const bool inst = (g.DM == 1 || g.DM == 2 || g.DM == 4 || g.DM == 8 || g.DM == 12 || g.DM == 16 || g.DM == 24 || g.DM == 32);
-  return inst && cb * g.DN <= 16 && (cb == 1 || cb == 2 || cb == 4) && estep_big_smem(g) <= smem_limit;
+  return inst && g.K8 * 8 <= 256 && estep_big_smem(g) <= smem_limit;
+}
+// component blocks per warp whose pass-A accumulators stay in registers for the whole sweep (1, 2 or 4), or 0: the generic
+// variant, which accumulates one component block at a time and adds it to the block's partial slot after every tile
+static int estep_big_cbt(const Geom& g) {
+  const int cb = estep_big_cb(g);
+  return (cb * g.DN <= 16 && (cb == 1 || cb == 2 || cb == 4)) ? cb : 0;
 }
 
 // pack2 layout per component (FusedGeom): [NB*32 L fragments | 8*DN bias -L^T(mu-m) | log(lambda)-lnDet, pad]
@@ -109,12 +114,22 @@ __global__ void __launch_bounds__(256, 1) k_estep_big(EmArgs A) {
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   };
 
-  double accA[CB][DN][2], sg[CB], sg2[CB];
+  constexpr int CBX = CB > 0 ? CB : 1;
+  double accA[CBX][DN][2], sg[CBX], sg2[CBX];
 #pragma unroll
-  for (int c = 0; c < CB; ++c) {
+  for (int c = 0; c < CBX; ++c) {
     sg[c] = 0; sg2[c] = 0;
 #pragma unroll
     for (int b = 0; b < DN; ++b) { accA[c][b][0] = 0; accA[c][b][1] = 0; }
+  }
+  double* outA = A.partA + (size_t)blockIdx.x * KP * DS;
+  if (CB == 0) {   // generic variant: this warp's component blocks start from zero in the block's partial slot
+    for (int cb = warp; cb < K8; cb += 8) {
+      double* o = outA + (size_t)(8 * cb + g) * DS;
+      if (t == 0) { o[0] = 0.0; o[1] = 0.0; }
+#pragma unroll
+      for (int db = 0; db < DN; ++db) { o[2 + 8 * db + 2 * t] = 0.0; o[2 + 8 * db + 2 * t + 1] = 0.0; }
+    }
   }
   const int64_t ntiles = (N + TP - 1) / TP;
   for (int64_t bt = blockIdx.x; bt < ntiles; bt += gridDim.x) {
@@ -220,6 +235,32 @@ __global__ void __launch_bounds__(256, 1) k_estep_big(EmArgs A) {
     }
     __syncthreads();
     // ---- P3: pass-A statistics; warp w owns component blocks w, w+8, ... -----------------------------------------
+    if (CB == 0) {
+      // any number of component blocks: one block's accumulators at a time, added to the block's own partial slot after
+      // the tile (plain read-modify-write by the owning warp; at these shapes one tile's P1 takes milliseconds)
+      for (int cb = warp; cb < K8; cb += 8) {
+        double a1 = 0, a2 = 0, acc[DN][2];
+#pragma unroll
+        for (int db = 0; db < DN; ++db) { acc[db][0] = 0; acc[db][1] = 0; }
+#pragma unroll 2
+        for (int pb = 0; pb < TP / 4; ++pb) {
+          const double a = tile[(size_t)(4 * pb + t) * S + 8 * cb + g];
+          a1 += a;
+          a2 = fma(a, a, a2);
+#pragma unroll
+          for (int db = 0; db < DN; ++db) dmma(acc[db], a, xs[(size_t)(4 * pb + t) * XS + 8 * db + g]);
+        }
+        a1 += shx(a1, 1); a1 += shx(a1, 2);
+        a2 += shx(a2, 1); a2 += shx(a2, 2);
+        double* o = outA + (size_t)(8 * cb + g) * DS;
+        if (t == 0) { o[0] += a1; o[1] += a2; }
+#pragma unroll
+        for (int db = 0; db < DN; ++db) {
+          o[2 + 8 * db + 2 * t] += acc[db][0];
+          o[2 + 8 * db + 2 * t + 1] += acc[db][1];
+        }
+      }
+    }
 #pragma unroll
     for (int ci = 0; ci < CB; ++ci) {
       const int cb = warp + 8 * ci;
@@ -245,7 +286,6 @@ __global__ void __launch_bounds__(256, 1) k_estep_big(EmArgs A) {
     }
     __syncthreads();
   }
-  double* outA = A.partA + (size_t)blockIdx.x * KP * DS;
 #pragma unroll
   for (int ci = 0; ci < CB; ++ci) {
     const int cb = warp + 8 * ci;
@@ -269,7 +309,7 @@ int estep_big_gpw(const Geom& g, size_t smem_limit) {
   const int XS = 8 * g.DN + 4;
   const int S = ((g.K8 * 8 + 15) / 16) * 16 + 4;
   const size_t need2 = ((size_t)128 * XS + (size_t)128 * S) * sizeof(double);
-  return (g.DM >= 16 && estep_big_cb(g) == 1 && need2 <= smem_limit) ? 2 : 1;
+  return (g.DM >= 16 && estep_big_cbt(g) == 1 && need2 <= smem_limit) ? 2 : 1;
 }
 
 template <int DM, int CB, int GPW, bool STAGE = false>
@@ -300,6 +340,7 @@ static cudaError_t launch_big_dm(const EmArgs& a, int cb, int gpw, bool stage, i
   if constexpr (1 * DN <= 16) { if (cb == 1) return launch_big_t<DM, 1, 1>(a, grid, smem, st); }
   if constexpr (2 * DN <= 16) { if (cb == 2) return launch_big_t<DM, 2, 1>(a, grid, smem, st); }
   if constexpr (4 * DN <= 16) { if (cb == 4) return launch_big_t<DM, 4, 1>(a, grid, smem, st); }
+  if (cb == 0) return launch_big_t<DM, 0, 1>(a, grid, smem, st);
   return cudaErrorInvalidConfiguration;
 }
 cudaError_t launch_estep_big(const Geom& g, EmArgs a, int grid, size_t smem_limit, cudaStream_t st) {
@@ -308,7 +349,7 @@ cudaError_t launch_estep_big(const Geom& g, EmArgs a, int grid, size_t smem_limi
   a.S = ((g.K8 * 8 + 15) / 16) * 16 + 4;
   const bool stage = estep_big_stage(g, smem_limit);
   const size_t smem = stage ? estep_big_stage_smem(g) : ((size_t)64 * gpw * (8 * g.DN + 4) + (size_t)64 * gpw * a.S) * sizeof(double);
-  const int cb = estep_big_cb(g);
+  const int cb = estep_big_cbt(g);
   switch (g.DM) {
     case 1: return launch_big_dm<1>(a, cb, gpw, stage, grid, smem, st);
     case 2: return launch_big_dm<2>(a, cb, gpw, stage, grid, smem, st);

@@ -87,7 +87,7 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
     geom_ = make_geom(d, K, true);
     fgeom_ = make_fused_geom(geom_, false, smem_limit_);
     if (!estep_big_ok(geom_, smem_limit_)) {
-      err_ = "this (d, K) is outside the shapes the large-shape kernels are built for (K <= 256 at d <= 32, K*d <= 8192 beyond)";
+      err_ = "this (d, K) is outside the shapes the large-shape kernels are built for (d <= 128, K <= 256)";
       return -7;
     }
     legacy_estep_ = false;

@@ -332,6 +332,8 @@ BIG_CASES = [
     (64, 9, 300, 4.0, 124, 0.5, 3),
     (8, 256, 60, 6.0, 125, 1.0, 2),       # config-5 shape (as full covariances): K*d^2 pack + logit tile exceed shared memory
     (32, 40, 200, 5.0, 126, 0.0, 2),
+    (40, 200, 90, 4.0, 129, 1.0, 2),      # 25 component blocks: pass-A accumulators flushed per tile (generic variant)
+    (72, 72, 150, 4.0, 130, 0.0, 2),      # 2 component blocks per warp x 12 coordinate blocks exceed the register budget: generic
 ]
 
 
