@@ -1,0 +1,82 @@
+"""One-off stress of the API paths around the iteration on random shapes: fresh object (k-means initialiser, then EM from its
+result), getProba / getClass on new points, two shards in one process; everything against the oracle.
+Usage (GPU box): python scripts/fuzz_api.py [n_cases] [seed]"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from mlfortran_b200 import mlf_algo_emgmm, synth
+from oracle.emgmm_oracle import get
+
+LL_RTOL, PAR_RTOL = 1e-10, 1e-9
+rel = lambda a, b: np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300)
+n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 3)
+orc = get()
+bad = 0
+checked = {'em_after_kmeans': 0, 'getProba': 0, 'getClass': 0, 'two_shards': 0}
+t0 = time.time()
+for i in range(n_cases):
+    d = int(rng.choice([rng.integers(1, 9), rng.integers(9, 17), rng.integers(17, 41)]))
+    K = int(rng.choice([rng.integers(1, 9), rng.integers(9, 49)]))
+    npc = int(rng.integers(max(2 * d + 2, 8), max(2 * d + 3, 80)))
+    sc, mp, seed = float(rng.choice([3.0, 8.0])), float(rng.choice([0.0, 1.0])), 9000 + i
+    data = synth.make_mixture(d, K, npc, sc, 1.0, seed)
+    X = data["X"]
+    tag = dict(d=d, K=K, N=X.shape[0], sc=sc, mp=mp, seed=seed)
+    def fail(what, **kw):
+        global bad
+        bad += 1
+        print("FAIL", what, tag, kw, flush=True)
+    # (a) fresh object: initialiser, then one EM iteration from whatever it produced
+    em = mlf_algo_emgmm()
+    if em.init(X, K, mp) != 0:
+        fail("init"); continue
+    em.set_seed(seed)
+    if em.step(1)[0] != 0:
+        fail("kmeans step", err=em.last_error()); em.finalize(); continue
+    Mu1, Cov1, lam1 = em.Mu.copy(), em.Cov.copy(), em.lambda_.copy()
+    if not (np.isfinite(Mu1).all() and np.isfinite(Cov1).all() and abs(lam1.sum() - 1) < 1e-12):
+        fail("kmeans result not finite / lambda not normalised")
+    oMu, oCov, olam, otr = orc.em_iterations(X, Mu1, Cov1, lam1, mp, 1)
+    if np.isfinite(oCov).all() and np.isfinite(otr).all():
+        checked['em_after_kmeans'] += 1
+        if em.step(1)[0] != 0:
+            fail("em step", err=em.last_error())
+        elif not (abs(em.sumLL - otr[-1]) <= LL_RTOL * abs(otr[-1]) and rel(em.Mu, oMu) <= PAR_RTOL and rel(em.Cov, oCov) <= PAR_RTOL
+                  and np.abs(em.lambda_ - olam).max() <= PAR_RTOL):
+            fail("em after kmeans", ll=abs(em.sumLL - otr[-1]) / abs(otr[-1]), mu=rel(em.Mu, oMu), cov=rel(em.Cov, oCov))
+        # (b) inference on new points
+        Q = np.ascontiguousarray(X[rng.permutation(X.shape[0])[: min(257, X.shape[0])]] + 0.1 * rng.standard_normal((min(257, X.shape[0]), d)))
+        info, P = em.getProba(Q)
+        _, Po, _ = orc.exp_step(Q, em.Mu, em.Cov, em.lambda_)
+        checked['getProba'] += int(np.isfinite(Po).all())
+        if info != 0 or not np.isfinite(Po).all() or np.abs(P - Po).max() > 1e-9:
+            if np.isfinite(Po).all():
+                fail("getProba", info=info, err=float(np.abs(P - Po).max()))
+        info, cl = em.getClass(Q)
+        if np.isfinite(Po).all():
+            checked['getClass'] += 1
+            ocl = orc.get_class(Po)
+            top2 = np.sort(Po, axis=0)[-2:]
+            tie = (top2[1] - top2[0]) <= 1e-9 * top2[1] if Po.shape[0] > 1 else np.zeros(Po.shape[1], bool)
+            if info != 0 or not ((cl == ocl) | tie).all():
+                fail("getClass", info=info, n=int(((cl != ocl) & ~tie).sum()))
+    em.finalize()
+    # (c) two shards in one process, injected parameters
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], seed)
+    oMu, oCov, olam, otr = orc.em_iterations(X, Mu0, Cov0, lam0, mp, 2)
+    if np.isfinite(oCov).all() and np.isfinite(otr).all() and X.shape[0] >= 4:
+        em = mlf_algo_emgmm()
+        if em.init(X, K, mp, devices=[0, 0]) != 0:
+            fail("multi init"); continue
+        em.inject(Mu0, Cov0, lam0)
+        checked['two_shards'] += 1
+        if em.step(2)[0] != 0:
+            fail("multi step", err=em.last_error())
+        else:
+            tr = em.sumLL_trace()
+            if not (np.abs((tr - otr) / otr).max() <= LL_RTOL and rel(em.Mu, oMu) <= PAR_RTOL and rel(em.Cov, oCov) <= PAR_RTOL):
+                fail("two shards", ll=float(np.abs((tr - otr) / otr).max()), mu=rel(em.Mu, oMu), cov=rel(em.Cov, oCov))
+        em.finalize()
+print(f"fuzz_api: {n_cases} cases, {bad} failures, checks done {checked}, {time.time() - t0:.0f} s")
+sys.exit(1 if bad else 0)
