@@ -13,7 +13,7 @@ n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 3)
 orc = get()
 bad = 0
-checked = {'em_after_kmeans': 0, 'getProba': 0, 'getClass': 0, 'two_shards': 0}
+checked = {'em_after_kmeans': 0, 'getProba': 0, 'getClass': 0, 'two_shards': 0, 'streamed_refresh': 0}
 t0 = time.time()
 for i in range(n_cases):
     d = int(rng.choice([rng.integers(1, 9), rng.integers(9, 17), rng.integers(17, 41)]))
@@ -78,5 +78,35 @@ for i in range(n_cases):
             if not (np.abs((tr - otr) / otr).max() <= LL_RTOL and rel(em.Mu, oMu) <= PAR_RTOL and rel(em.Cov, oCov) <= PAR_RTOL):
                 fail("two shards", ll=float(np.abs((tr - otr) / otr).max()), mu=rel(em.Mu, oMu), cov=rel(em.Cov, oCov))
         em.finalize()
+# (d) refresh_x + step: the upload is chunked underneath the sweep (ragged sizes around the chunk boundaries), full and diagonal
+for i in range(max(n_cases // 10, 4)):
+    d, K = int(rng.integers(1, 17)), int(rng.integers(2, 33))
+    diag = bool(rng.random() < 0.3)
+    if diag and rng.random() < 0.5:
+        d, K = int(rng.integers(1, 9)), int(rng.integers(128, 200))
+    n = int(rng.integers(70000, 260000))
+    data = synth.make_mixture(d, K, n // K + 1, 6.0, 1.0, 9500 + i)
+    X1 = np.ascontiguousarray(data["X"][:n])
+    X2 = np.ascontiguousarray(X1 + 0.03 * rng.standard_normal(X1.shape) + 0.1)
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 9500 + i)
+    tag = dict(d=d, K=K, N=n, diag=diag)
+    em = mlf_algo_emgmm()
+    assert em.init(X1, K, 1.0, cov_type="diag" if diag else "full") == 0
+    em.inject(Mu0, Cov0, lam0)
+    assert em.step(1)[0] == 0
+    Mu1, Cov1, lam1 = em.Mu.copy(), em.Cov.copy(), em.lambda_.copy()
+    assert em.refresh_x(X2) == 0
+    info, _ = em.step(2)
+    orc.set_cov_diag(diag)
+    try:
+        oMu, oCov, olam, otr = orc.em_iterations(X2, Mu1, Cov1, lam1, 1.0, 2)
+    finally:
+        orc.set_cov_diag(False)
+    checked['streamed_refresh'] += 1
+    tr = em.sumLL_trace()
+    if info != 0 or not (np.abs((tr - otr) / otr).max() <= LL_RTOL and rel(em.Mu, oMu) <= PAR_RTOL and rel(em.Cov, oCov) <= PAR_RTOL):
+        bad += 1
+        print("FAIL streamed refresh", tag, em.kernel_plan()[:40], float(np.abs((tr - otr) / otr).max()), rel(em.Mu, oMu), rel(em.Cov, oCov), flush=True)
+    em.finalize()
 print(f"fuzz_api: {n_cases} cases, {bad} failures, checks done {checked}, {time.time() - t0:.0f} s")
 sys.exit(1 if bad else 0)
