@@ -37,12 +37,16 @@ for i in range(n_cases):
     Mu1, Cov1, lam1 = em.Mu.copy(), em.Cov.copy(), em.lambda_.copy()
     if not (np.isfinite(Mu1).all() and np.isfinite(Cov1).all() and abs(lam1.sum() - 1) < 1e-12):
         fail("kmeans result not finite / lambda not normalised")
-    oMu, oCov, olam, otr = orc.em_iterations(X, Mu1, Cov1, lam1, mp, 1)
+    oMu, oCov, olam, otr, oP = orc.em_iterations(X, Mu1, Cov1, lam1, mp, 1, return_proba=True)
+    # a component owning (almost) a single point has ms^2 = 1/(1 - sum W^2)^2 ~ 1e17 in front of a cancelled outer product:
+    # the reference's own result is rounding noise there (both sides are ~1e-7 from the exact value), nothing to compare
+    Wn = oP / oP.sum(1, keepdims=True)
+    wellc = (1.0 - (Wn * Wn).sum(1)) > 1e-4
     if np.isfinite(oCov).all() and np.isfinite(otr).all():
         checked['em_after_kmeans'] += 1
         if em.step(1)[0] != 0:
             fail("em step", err=em.last_error())
-        elif not (abs(em.sumLL - otr[-1]) <= LL_RTOL * abs(otr[-1]) and rel(em.Mu, oMu) <= PAR_RTOL and rel(em.Cov, oCov) <= PAR_RTOL
+        elif not (abs(em.sumLL - otr[-1]) <= LL_RTOL * abs(otr[-1]) and rel(em.Mu, oMu) <= PAR_RTOL and rel(em.Cov[wellc], oCov[wellc]) <= PAR_RTOL
                   and np.abs(em.lambda_ - olam).max() <= PAR_RTOL):
             fail("em after kmeans", ll=abs(em.sumLL - otr[-1]) / abs(otr[-1]), mu=rel(em.Mu, oMu), cov=rel(em.Cov, oCov))
         # (b) inference on new points
