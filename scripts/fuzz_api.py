@@ -13,7 +13,7 @@ n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 3)
 orc = get()
 bad = 0
-checked = {'em_after_kmeans': 0, 'getProba': 0, 'getClass': 0, 'two_shards': 0, 'streamed_refresh': 0}
+checked = {'em_after_kmeans': 0, 'getProba': 0, 'getClass': 0, 'two_shards': 0, 'streamed_refresh': 0, 'single_component': 0}
 t0 = time.time()
 for i in range(n_cases):
     d = int(rng.choice([rng.integers(1, 9), rng.integers(9, 17), rng.integers(17, 41)]))
@@ -112,5 +112,27 @@ for i in range(max(n_cases // 10, 4)):
         bad += 1
         print("FAIL streamed refresh", tag, em.kernel_plan()[:40], float(np.abs((tr - otr) / otr).max()), rel(em.Mu, oMu), rel(em.Cov, oCov), flush=True)
     em.finalize()
+# (e) single-component entry points over all supported dimensions
+from mlfortran_b200 import mlf_evalGaussian, mlf_maxGaussian
+for i in range(max(n_cases // 4, 10)):
+    d = int(rng.choice([rng.integers(1, 17), rng.integers(17, 129)]))
+    n = int(rng.integers(2 * d + 3, 3000))
+    A_ = rng.standard_normal((d, d))
+    Cm = A_ @ A_.T / d + 0.3 * np.eye(d)
+    mu = rng.standard_normal(d) * 3
+    Xs = np.ascontiguousarray(rng.standard_normal((n, d)) @ np.linalg.cholesky(Cm).T + mu)
+    lam = float(rng.random() + 0.05)
+    info, P, ll = mlf_evalGaussian(Xs, mu, Cm, lam)
+    oinfo, oP, oll = orc.eval_gaussian(Xs, mu, Cm, lam)
+    checked['single_component'] += 1
+    if info != 0 or oinfo != 0 or not np.allclose(P, oP, rtol=1e-10, atol=1e-300) or abs(ll - oll) > LL_RTOL * abs(oll):
+        bad += 1
+        print("FAIL evalGaussian", dict(d=d, n=n), info, float(np.abs(P / oP - 1).max()), abs(ll - oll) / abs(oll), flush=True)
+    w = rng.random(n) ** int(rng.integers(1, 10))
+    s_, m_, C_ = mlf_maxGaussian(Xs, w)
+    os_, om, oC = orc.max_gaussian(Xs, w)
+    if abs(s_ - os_) > 1e-12 * os_ or np.abs(m_ - om).max() > PAR_RTOL * np.abs(om).max() or np.abs(C_ - oC).max() > PAR_RTOL * np.abs(oC).max():
+        bad += 1
+        print("FAIL maxGaussian", dict(d=d, n=n), abs(s_ - os_) / os_, np.abs(m_ - om).max() / np.abs(om).max(), np.abs(C_ - oC).max() / np.abs(oC).max(), flush=True)
 print(f"fuzz_api: {n_cases} cases, {bad} failures, checks done {checked}, {time.time() - t0:.0f} s")
 sys.exit(1 if bad else 0)
