@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(1024) k_refresh(Geom g, const double* __restri
     return (cov_diag && a != b) ? 0.0 : Ck[(size_t)hi * d + lo];  // cov_diag: extension, diagonal of C only
   };
   if (warm) {
-    // warm start (large d): the eigenvectors V of the previous EM iteration are still in scratch and nearly diagonalise the
+    // warm start: the eigenvectors V of the previous EM iteration are still in scratch and nearly diagonalise the
     // new covariance, so the sweeps start from A = V^T C V (two d^3 products) and converge in 2-3 sweeps instead of ~9
     for (int i = tid; i < d * d; i += nt) {   // W = C V
       const int a = i % d, b = i / d;
@@ -308,7 +308,7 @@ cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, c
   // loads in flight, so the block is as large as the register file allows
   k_refresh<<<g.K8 * 8, g.d > 64 ? 1024 : (large ? 256 : 128), dyn, st>>>(g, Mu, Cov, lambda, Sc, mean, Nglob, scratch, pack, sumLLk, info, pack2, muold,
                                                      f.PSF, f.OFFB, f.OFFC, shift ? shift : mean, do_sumll, large ? 1 : 0, cov_diag, f.diag ? 1 : 0,
-                                                     (large && warm) ? 1 : 0);
+                                                     warm ? 1 : 0);
   return cudaGetLastError();
 }
 
