@@ -213,8 +213,9 @@ def main():
     d, K, N = args.dims, args.comps, args.points
     lo, hi = parallel.shard_bounds(N, rank, world)
     n_loc = hi - lo
-    # same mixture on every rank (seed), rank-specific sample stream
-    X, centres, _ = synth.make_mixture_torch(d, K, n_loc, SIGMA_C, SIGMA_X, SEED, dev, stream_seed=SEED + 1000 * rank)
+    # the library's own device generator (mlf_b200_synth_gmm, recipe of tests/test_emgmm.f90:105-124): every point is a pure
+    # function of (seed, global index), so the N-point data set is the same whatever the number of ranks
+    X, centres, _ = synth.make_mixture_device(d, K, n_loc, lo, N, SIGMA_C, SIGMA_X, SEED, dev)
     Mu0, Cov0, lam0 = synth.injected_init(centres, SEED)
 
     em = mlf_algo_emgmm()

@@ -134,6 +134,18 @@ const char *mlf_b200_version(void);
  * device `device`; out[i] = exp(in[i]).  Exists so that the tests can pin the kernel's transcendental against libm. */
 int mlf_b200_selftest_exp(const double *in, double *out, int64_t n, int device);
 
+/* Workload generator of the reference's own EM test program (tests/test_emgmm.f90:105-124, testGMM) run on the device:
+ * centres = sigmaC N(0,I) (RandN, src/mlf_rand.f90:241-257), C12_k = O_k diag(w), O_k Haar orthogonal (randOrthogonal,
+ * src/mlf_matrix.f90:153-180), w_i = sqrt(sigmaX (1/i) / mean_j(1/j)), x = c_k + C12_k N(0,I), points shuffled (randPerm).
+ * Points [n0, n0 + nX) of a job of nTotal points are written to X (nY x nX, i.e. [nX][nY] in memory; a device pointer with
+ * MLF_B200_X_ON_DEVICE in flags, else a host array).  Every value is a pure function of (seed, global point index) --
+ * counter-based Philox4x32-10 + Box-Muller, keyed Feistel permutation -- so shards generated on different GPUs form the same
+ * data set as one call with n0 = 0, nX = nTotal.  The component of output point i is pi(i) mod nC.  The reference's RNG is
+ * gfortran's unseeded RANDOM_NUMBER: the distribution is reproduced, not its bits.  centres (nY x nC) and C12 (nY x nY x nC,
+ * Fortran order) are host outputs, nullable.  nX = 0 only computes those (no device needed).  0, or a negative MLF_ERRORTYPE. */
+int mlf_b200_synth_gmm(double *X, int64_t n0, int64_t nX, int64_t nTotal, int nY, int nC, double sigmaC, double sigmaX, uint64_t seed,
+                       int device, unsigned flags, double *centres, double *C12);
+
 /* ---- engine-level entry points: what a Fortran extension type binds with iso_c_binding --------------------------
  * Deliverable form (A) of INTEGRATION.md: fortran/mlf_emgmm_b200.f90 declares a type extending the reference's
  * mlf_step_obj whose init/reinit/stepF forward here, so that the reference's generic handle functions, HDF5

@@ -80,3 +80,39 @@ def make_mixture_torch(d: int, K: int, N: int, sigma_c: float, sigma_x: float, s
             cc = comp[t:t + step]
             out[t:t + step] = tXC[cc] + torch.bmm(z[t:t + step].unsqueeze(1), tC12T[cc]).squeeze(1)
     return X, XC, C12
+
+
+def make_mixture_device(d: int, K: int, n_local: int, n0: int, n_total: int, sigma_c: float, sigma_x: float, seed: int, device):
+    """The library's own device generator (`mlf_b200_synth_gmm`, csrc/mlf_synth.cu): points [n0, n0 + n_local) of the
+    n_total-point job written by one CUDA kernel into a torch-allocated HBM buffer (torch is only the allocator here).
+    Every value is a pure function of (seed, global point index), so the shards of any number of ranks form the same data set.
+    Returns (X [n_local, d] float64 on device, centres [K, d] numpy, C12 [K, d, d] numpy with C12[k] = O_k diag(w))."""
+    import torch
+
+    from . import _lib
+
+    lib = _lib.load()
+    dev = torch.device(device)
+    X = torch.empty((n_local, d), dtype=torch.float64, device=dev)
+    centres = np.empty((K, d))
+    C12f = np.empty((K, d, d))  # Fortran C12(a, b, k): C12f[k, b, a]
+    torch.cuda.synchronize(dev)
+    rc = lib.mlf_b200_synth_gmm(X.data_ptr(), n0, n_local, n_total, d, K, float(sigma_c), float(sigma_x), int(seed),
+                                dev.index if dev.index is not None else torch.cuda.current_device(), 1,  # MLF_B200_X_ON_DEVICE
+                                centres.ctypes.data, C12f.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"mlf_b200_synth_gmm failed with {rc}")
+    return X, centres, np.ascontiguousarray(C12f.transpose(0, 2, 1))
+
+
+def mixture_params(d: int, K: int, sigma_c: float, sigma_x: float, seed: int):
+    """centres and C12 of the device generator's mixture (host part of `mlf_b200_synth_gmm`, no GPU needed)."""
+    from . import _lib
+
+    centres = np.empty((K, d))
+    C12f = np.empty((K, d, d))
+    rc = _lib.load().mlf_b200_synth_gmm(None, 0, 0, 1, d, K, float(sigma_c), float(sigma_x), int(seed), 0, 0,
+                                        centres.ctypes.data, C12f.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"mlf_b200_synth_gmm failed with {rc}")
+    return centres, np.ascontiguousarray(C12f.transpose(0, 2, 1))
