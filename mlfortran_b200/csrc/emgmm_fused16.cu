@@ -19,6 +19,7 @@
 #include "exp_tab.cuh"
 
 #include <cmath>
+#include <cstdlib>
 
 namespace mlfb200 {
 
@@ -57,13 +58,25 @@ constexpr int kTmemCols = 512;  // 4 warps per lane quarter x 8 components x 16 
 
 }  // namespace
 
-size_t em16_smem_bytes(const Geom& g, const FusedGeom& f) { return f.smem + 128 * sizeof(double) + 16; }
+size_t em16_smem_bytes(const Geom& g, const FusedGeom& f) { return f.smem + (128 + 128) * sizeof(double) + 16; }
 bool em16_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
   return f.GPW == 2 && !f.diag && g.DN <= 2 && g.K8 <= 8 && f.scatter_ok && em16_smem_bytes(g, f) <= smem_limit;
 }
 
-template <int DM>
+// VAR (MLF_B200_EM16_VAR, default 5; every variant produces the same bits):
+//   bit 0      the 1/sum of a point is kept beside the tile and applied where the responsibilities are consumed (P3) instead of
+//              in a third pass over the logit row (same product);
+//   bits 1-2   0: quad reduction of a component group right after its DMMAs; 1: software-pipelined -- the reduction of group
+//              k4-1 is issued after the DMMAs of group k4, so its shuffles run under them; 2: the same, unrolled twice
+//              (ping-pong partial sums, no register moves).
+// Measured at N=1e8, d=16, K=64 (ms per sweep): 0: 123.5, 1: 121.9, 2: 119.7, 4: 121.0, 5: 119.4.  Also measured, no gain:
+// issuing the DMMA chains of 2 or 4 components interleaved (119.5 / 120.5: the loop is not bound by dependent-issue latency),
+// parking the pass-A accumulators in spare tensor-memory columns to free registers for fragment prefetch (+2 ms),
+// unconditional kept-sum DMMAs in P3a (+3 ms), skipping 4-point groups whose responsibilities are all exactly 0 (+-0).
+template <int DM, int VAR>
 __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
+  constexpr bool FOLD = (VAR & 1) != 0;
+  constexpr int PIPE = (VAR >> 1) & 3;
   constexpr int DN = (DM + 1) / 2;
   constexpr int NB = g_blk_off(DM);
   constexpr int OFFB = NB * 32, OFFC = OFFB + 8 * DN, PSF = OFFC + 4;
@@ -83,7 +96,8 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   double* xs = smu + (size_t)KP * 8 * DN + (size_t)half * TP * XS;                    // [2][64][XS] raw points, per group
   double* tile = smu + (size_t)KP * 8 * DN + (size_t)2 * TP * XS + (size_t)half * TP * S;  // [2][64][S] logits -> responsibilities
   double* etab = smu + (size_t)KP * 8 * DN + (size_t)2 * TP * XS + (size_t)2 * TP * S;   // [128] 2^(j/128) (exp_tab.cuh)
-  uint32_t* s_taddr = reinterpret_cast<uint32_t*>(etab + 128);
+  double* invs = etab + 128 + half * TP;                                                 // [2][64] 1/sum per point (FOLD)
+  uint32_t* s_taddr = reinterpret_cast<uint32_t*>(etab + 128 + 2 * TP);
   const bool own = cb < K8;
   if (tid < 128) etab[tid] = kExpTab128[tid];
 
@@ -156,8 +170,8 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
     }
     double* row = tile + (size_t)(wg * 8 + g) * S;
     double rmax = -INFINITY;
-    for (int k4 = 0; k4 < K4; ++k4) {
-      double part[4];
+    // |u|^2 of the four components of group k4 for this thread's output columns
+    auto comp4 = [&](int k4, double (&part)[4]) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const double* pk = sp + (size_t)(4 * k4 + j) * PSF;
@@ -177,8 +191,10 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
         for (int nb = 1; nb < DN; ++nb) { s = fma(c[nb][0], c[nb][0], s); s = fma(c[nb][1], c[nb][1], s); }
         part[j] = s;
       }
+    };
+    // transposed reduction over the quad: lane t ends with the full |u|^2 of component 4*k4+t
+    auto reduce4 = [&](int k4, const double (&part)[4]) {
       const double ck = sp[(size_t)(4 * k4 + t) * PSF + OFFC];
-      // transposed reduction over the quad: lane t ends with the full |u|^2 of component 4*k4+t
       const bool hi2 = (t & 2) != 0, hi1 = (t & 1) != 0;
       const double send0 = hi2 ? part[0] : part[2], send1 = hi2 ? part[1] : part[3];
       const double keep0 = hi2 ? part[2] : part[0], keep1 = hi2 ? part[3] : part[1];
@@ -187,6 +203,36 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
       const double logit = fma(-0.5, maha, ck);
       row[4 * k4 + t] = logit;
       rmax = fmax(rmax, logit);
+    };
+    if (PIPE == 0) {
+      for (int k4 = 0; k4 < K4; ++k4) {
+        double part[4];
+        comp4(k4, part);
+        reduce4(k4, part);
+      }
+    } else if (PIPE == 1) {
+      double prev[4];
+      comp4(0, prev);
+      for (int k4 = 1; k4 < K4; ++k4) {
+        double part[4];
+        comp4(k4, part);
+        reduce4(k4 - 1, prev);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) prev[j] = part[j];
+      }
+      reduce4(K4 - 1, prev);
+    } else {   // K4 = 2 K8 is even
+      double pa[4], pb[4];
+      comp4(0, pa);
+      for (int k4 = 1; k4 + 1 < K4; k4 += 2) {
+        comp4(k4, pb);
+        reduce4(k4 - 1, pa);
+        comp4(k4 + 1, pa);
+        reduce4(k4, pb);
+      }
+      comp4(K4 - 1, pb);
+      reduce4(K4 - 2, pa);
+      reduce4(K4 - 1, pb);
     }
     // ---- P2: log-sum-exp over the components ---------------------------------------------------------------------
     rmax = fmax(rmax, shx(rmax, 1));
@@ -201,7 +247,11 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
     sum += shx(sum, 1);
     sum += shx(sum, 2);
     const double inv = (p < N) ? 1.0 / sum : 0.0;
-    for (int k4 = 0; k4 < K4; ++k4) row[4 * k4 + t] *= inv;
+    if (FOLD) {
+      if (t == 0) invs[wg * 8 + g] = inv;
+    } else {
+      for (int k4 = 0; k4 < K4; ++k4) row[4 * k4 + t] *= inv;
+    }
     // the group's responsibilities and points are complete: 256-thread named barrier of this group only
     asm volatile("bar.sync %0, 256;\n" ::"r"(1 + half) : "memory");
     unsigned act = 0;   // lane pb: bit q set <=> component 8*cb+q keeps some point of 4-point group pb
@@ -212,7 +262,7 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
 #pragma unroll 4
       for (int i = 0; i < 16; ++i) {
         const int pb = i;
-        const double a = tcol[(size_t)(4 * pb + t) * S];
+        const double a = FOLD ? tcol[(size_t)(4 * pb + t) * S] * invs[4 * pb + t] : tcol[(size_t)(4 * pb + t) * S];
         double b[DN];
 #pragma unroll
         for (int db = 0; db < DN; ++db) b[db] = xs[(size_t)(4 * pb + t) * XS + 8 * db + g];
@@ -268,7 +318,7 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
         while (pm) {
           const int pb = __ffs(pm) - 1;
           pm &= pm - 1;
-          const double aq = tq[(size_t)(4 * pb + t) * S];
+          const double aq = FOLD ? tq[(size_t)(4 * pb + t) * S] * invs[4 * pb + t] : tq[(size_t)(4 * pb + t) * S];
           const double w = (!(aq < thq) && aq != 0.0) ? aq : 0.0;
           double z[DN], wz[DN];
 #pragma unroll
@@ -328,16 +378,19 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
 cudaError_t launch_em16(const Geom& g, const FusedGeom& f, const EmArgs& a, int grid, size_t smem_limit, cudaStream_t st) {
   if (!em16_ok(g, f, smem_limit)) return cudaErrorInvalidConfiguration;
   const size_t smem = em16_smem_bytes(g, f);
-#define MLF_E16(DMv)                                                                                                   \
-  case DMv: {                                                                                                          \
-    cudaError_t e = cudaFuncSetAttribute(k_em16<DMv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+  static const int var = [] { const char* e = getenv("MLF_B200_EM16_VAR"); return e ? atoi(e) : 5; }();
+#define MLF_E16V(DMv, V)                                                                                               \
+  case 8 * DMv + V: {                                                                                                  \
+    cudaError_t e = cudaFuncSetAttribute(k_em16<DMv, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
     if (e != cudaSuccess) return e;                                                                                    \
-    k_em16<DMv><<<grid, kThreads16, smem, st>>>(a);                                                                    \
+    k_em16<DMv, V><<<grid, kThreads16, smem, st>>>(a);                                                                 \
   } break;
-  switch (g.DM) {
+#define MLF_E16(DMv) MLF_E16V(DMv, 0) MLF_E16V(DMv, 2) MLF_E16V(DMv, 5)
+  switch (8 * g.DM + (var & 7)) {
     MLF_E16(1) MLF_E16(2) MLF_E16(3) MLF_E16(4)
     default: return cudaErrorInvalidConfiguration;
   }
+#undef MLF_E16V
 #undef MLF_E16
   return cudaGetLastError();
 }
