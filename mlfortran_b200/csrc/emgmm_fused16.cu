@@ -58,25 +58,32 @@ constexpr int kTmemCols = 512;  // 4 warps per lane quarter x 8 components x 16 
 
 }  // namespace
 
-size_t em16_smem_bytes(const Geom& g, const FusedGeom& f) { return f.smem + (128 + 128) * sizeof(double) + 16; }
+size_t em16_smem_bytes(const Geom& g, const FusedGeom& f) { return f.smem + (128 + 128) * sizeof(double) + 32; }
 bool em16_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
   return f.GPW == 2 && !f.diag && g.DN <= 2 && g.K8 <= 8 && f.scatter_ok && em16_smem_bytes(g, f) <= smem_limit;
 }
 
-// VAR (MLF_B200_EM16_VAR, default 5; every variant produces the same bits):
+// VAR (MLF_B200_EM16_VAR, default 53; every variant produces the same bits):
 //   bit 0      the 1/sum of a point is kept beside the tile and applied where the responsibilities are consumed (P3) instead of
 //              in a third pass over the logit row (same product);
 //   bits 1-2   0: quad reduction of a component group right after its DMMAs; 1: software-pipelined -- the reduction of group
 //              k4-1 is issued after the DMMAs of group k4, so its shuffles run under them; 2: the same, unrolled twice
-//              (ping-pong partial sums, no register moves).
-// Measured at N=1e8, d=16, K=64 (ms per sweep): 0: 123.5, 1: 121.9, 2: 119.7, 4: 121.0, 5: 119.4.  Also measured, no gain:
-// issuing the DMMA chains of 2 or 4 components interleaved (119.5 / 120.5: the loop is not bound by dependent-issue latency),
-// parking the pass-A accumulators in spare tensor-memory columns to free registers for fragment prefetch (+2 ms),
-// unconditional kept-sum DMMAs in P3a (+3 ms), skipping 4-point groups whose responsibilities are all exactly 0 (+-0).
+//              (ping-pong partial sums, no register moves);
+//   bits 3-4   the barrier that protects the group's tiles from being overwritten by the next tile is split (mbarrier): a warp
+//              arrives when its statistics are done and waits only where it first writes shared memory -- 1: after the next
+//              tile's points have been requested, 2: after the first group of DMMAs of the next tile, 3: after the second;
+//   bit 5      the next tile's points are fetched into registers before the statistics phase.
+// Measured at N=1e8, d=16, K=64 (ms per sweep): 0: 123.5, 1: 121.9, 2: 119.7, 4: 121.0, 5: 119.4, 13: 118.2, 21: 117.6,
+// 29: 117.4 (4-byte spill), 53: 117.0, 61: 116.9 (4-byte spill).  Also measured, no gain: issuing the DMMA chains of 2 or 4
+// components interleaved (119.5 / 120.5: the loop is not bound by dependent-issue latency), parking the pass-A accumulators in
+// spare tensor-memory columns to free registers for fragment prefetch (+2 ms), unconditional kept-sum DMMAs in P3a (+3 ms),
+// skipping 4-point groups whose responsibilities are all exactly 0 (+-0).
 template <int DM, int VAR>
 __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   constexpr bool FOLD = (VAR & 1) != 0;
   constexpr int PIPE = (VAR >> 1) & 3;
+  constexpr int SPLIT = (VAR >> 3) & 3;   // trailing group barrier as a split mbarrier: 1 wait after the X loads are issued, 2 after the first DMMA group, 3 after the second
+  constexpr bool PREF = (VAR & 32) != 0;  // the next tile's points are fetched into registers before the statistics phase
   constexpr int DN = (DM + 1) / 2;
   constexpr int NB = g_blk_off(DM);
   constexpr int OFFB = NB * 32, OFFC = OFFB + 8 * DN, PSF = OFFC + 4;
@@ -99,6 +106,12 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   double* invs = etab + 128 + half * TP;                                                 // [2][64] 1/sum per point (FOLD)
   uint32_t* s_taddr = reinterpret_cast<uint32_t*>(etab + 128 + 2 * TP);
   const bool own = cb < K8;
+  const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(etab + 128 + 2 * TP + 2 + half);   // one 8-byte mbarrier per group
+  if (SPLIT && tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;\n" ::"r"(mbar) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;\n" ::"r"(mbar + 8) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
   if (tid < 128) etab[tid] = kExpTab128[tid];
 
   for (int i = tid; i < KP * PSF; i += kThreads16) sp[i] = A.pack2[i];
@@ -153,21 +166,40 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   AmbEntry* ambw = A.amb + (size_t)nlist * A.amb_cap;
 
   const int64_t ntiles = (N + TP - 1) / TP;
+  bool first = true;
+  uint32_t phase = 0;
+  double xraw[DM];
   for (int64_t bt = 2 * (int64_t)blockIdx.x + half; bt < ntiles; bt += 2 * (int64_t)gridDim.x) {
     const int64_t p = bt * TP + wg * 8 + g;
     // ---- P1: logits of this warp's 8 points against every component ---------------------------------------------
     double xa[DM];
-    {
-      double* xr = xs + (size_t)(wg * 8 + g) * XS;
+    double* xr = xs + (size_t)(wg * 8 + g) * XS;
+    if (!PREF || first) {
 #pragma unroll
       for (int mb = 0; mb < DM; ++mb) {
         const int a = 4 * mb + t;
-        const double x = (p < N && a < d) ? A.X[p * d + a] : 0.0;
-        xr[a] = x;
-        xa[mb] = x - sh[mb];
+        xraw[mb] = (p < N && a < d) ? A.X[p * d + a] : 0.0;
       }
-      if (8 * DN > 4 * DM) xr[4 * DM + t] = 0.0;
     }
+    // the previous tile's buffers may be overwritten only after every warp of the group is done with them
+    auto wait_prev = [&]() {
+      if (SPLIT && !first) {
+        uint32_t done;
+        do {
+          asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }\n"
+                       : "=r"(done) : "r"(mbar), "r"(phase) : "memory");
+        } while (!done);
+        phase ^= 1u;
+      }
+    };
+    auto stage_x = [&]() {
+#pragma unroll
+      for (int mb = 0; mb < DM; ++mb) xr[4 * mb + t] = xraw[mb];
+      if (8 * DN > 4 * DM) xr[4 * DM + t] = 0.0;
+    };
+    if (SPLIT < 2) { wait_prev(); stage_x(); }
+#pragma unroll
+    for (int mb = 0; mb < DM; ++mb) xa[mb] = xraw[mb] - sh[mb];
     double* row = tile + (size_t)(wg * 8 + g) * S;
     double rmax = -INFINITY;
     // |u|^2 of the four components of group k4 for this thread's output columns
@@ -221,9 +253,10 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
         for (int j = 0; j < 4; ++j) prev[j] = part[j];
       }
       reduce4(K4 - 1, prev);
-    } else {   // K4 = 2 K8 is even
+    } else if (SPLIT < 3) {   // K4 = 2 K8 is even
       double pa[4], pb[4];
       comp4(0, pa);
+      if (SPLIT == 2) { wait_prev(); stage_x(); }
       for (int k4 = 1; k4 + 1 < K4; k4 += 2) {
         comp4(k4, pb);
         reduce4(k4 - 1, pa);
@@ -232,6 +265,20 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
       }
       comp4(K4 - 1, pb);
       reduce4(K4 - 2, pa);
+      reduce4(K4 - 1, pb);
+    } else {
+      double pa[4], pb[4];
+      comp4(0, pa);
+      comp4(1, pb);
+      wait_prev();
+      stage_x();
+      reduce4(0, pa);
+      for (int k4 = 2; k4 + 1 < K4; k4 += 2) {
+        comp4(k4, pa);
+        reduce4(k4 - 1, pb);
+        comp4(k4 + 1, pb);
+        reduce4(k4, pa);
+      }
       reduce4(K4 - 1, pb);
     }
     // ---- P2: log-sum-exp over the components ---------------------------------------------------------------------
@@ -254,6 +301,14 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
     }
     // the group's responsibilities and points are complete: 256-thread named barrier of this group only
     asm volatile("bar.sync %0, 256;\n" ::"r"(1 + half) : "memory");
+    if (PREF) {
+      const int64_t pn = p + 2 * (int64_t)gridDim.x * TP;
+#pragma unroll
+      for (int mb = 0; mb < DM; ++mb) {
+        const int a = 4 * mb + t;
+        xraw[mb] = (pn < N && a < d) ? A.X[pn * d + a] : 0.0;
+      }
+    }
     unsigned act = 0;   // lane pb: bit q set <=> component 8*cb+q keeps some point of 4-point group pb
     // ---- P3a: pass-A statistics of component block cb over the tile's 4-point groups; kept-group flags ---------------
     if (own) {
@@ -337,7 +392,13 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
       tmem_wait_st();
     }
     // the group's tiles may be overwritten only after every warp of the group is done with them
-    asm volatile("bar.sync %0, 256;\n" ::"r"(1 + half) : "memory");
+    if (SPLIT) {
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(mbar) : "memory");
+    } else {
+      asm volatile("bar.sync %0, 256;\n" ::"r"(1 + half) : "memory");
+    }
+    first = false;
   }
   // ---- per-(block, half) partials -------------------------------------------------------------------------------------
   if (own) {
@@ -378,15 +439,15 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
 cudaError_t launch_em16(const Geom& g, const FusedGeom& f, const EmArgs& a, int grid, size_t smem_limit, cudaStream_t st) {
   if (!em16_ok(g, f, smem_limit)) return cudaErrorInvalidConfiguration;
   const size_t smem = em16_smem_bytes(g, f);
-  static const int var = [] { const char* e = getenv("MLF_B200_EM16_VAR"); return e ? atoi(e) : 5; }();
+  static const int var = [] { const char* e = getenv("MLF_B200_EM16_VAR"); return e ? atoi(e) : 53; }();
 #define MLF_E16V(DMv, V)                                                                                               \
-  case 8 * DMv + V: {                                                                                                  \
+  case 64 * DMv + V: {                                                                                                  \
     cudaError_t e = cudaFuncSetAttribute(k_em16<DMv, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
     if (e != cudaSuccess) return e;                                                                                    \
     k_em16<DMv, V><<<grid, kThreads16, smem, st>>>(a);                                                                 \
   } break;
-#define MLF_E16(DMv) MLF_E16V(DMv, 0) MLF_E16V(DMv, 2) MLF_E16V(DMv, 5)
-  switch (8 * g.DM + (var & 7)) {
+#define MLF_E16(DMv) MLF_E16V(DMv, 0) MLF_E16V(DMv, 5) MLF_E16V(DMv, 21) MLF_E16V(DMv, 53)
+  switch (64 * g.DM + (var & 63)) {
     MLF_E16(1) MLF_E16(2) MLF_E16(3) MLF_E16(4)
     default: return cudaErrorInvalidConfiguration;
   }

@@ -3,7 +3,7 @@
 [ -n "$SKIP_PYTEST" ] || { python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_v.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu_v.log; }
 [ -n "$SKIP_PYTEST" ] || tail -5 gpurun_out/pytest_gpu_v.log
 for v in ${VARS:-0 1 2 3}; do
-  MLF_B200_EM16_VAR=$v python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_var$v.json 2> gpurun_out/bench_var$v.err
+  MLF_B200_EM16_VAR=$v timeout -s KILL ${BTO:-120} python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_var$v.json 2> gpurun_out/bench_var$v.err
 done
 python - <<'PY'
 import json, glob
