@@ -78,7 +78,8 @@ bool em16_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
 // components interleaved (119.5 / 120.5: the loop is not bound by dependent-issue latency), parking the pass-A accumulators in
 // spare tensor-memory columns to free registers for fragment prefetch (+2 ms), unconditional kept-sum DMMAs in P3a (+3 ms),
 // skipping 4-point groups whose responsibilities are all exactly 0 (+-0), a two-stage P3a (branch-free pass-A sweep that records
-// which 4-point groups hold kept / undecided pairs, then those groups only: +1.4 ms).
+// which 4-point groups hold kept / undecided pairs, then those groups only: +1.4 ms), shift and thresholds re-read from shared
+// memory per tile instead of living in registers (+0.5 ms), eight instead of four exps in flight in P2 (+-0).
 template <int DM, int VAR>
 __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   constexpr bool FOLD = (VAR & 1) != 0;
@@ -442,13 +443,13 @@ cudaError_t launch_em16(const Geom& g, const FusedGeom& f, const EmArgs& a, int 
   const size_t smem = em16_smem_bytes(g, f);
   static const int var = [] { const char* e = getenv("MLF_B200_EM16_VAR"); return e ? atoi(e) : 53; }();
 #define MLF_E16V(DMv, V)                                                                                               \
-  case 128 * DMv + V: {                                                                                                  \
+  case 64 * DMv + V: {                                                                                                  \
     cudaError_t e = cudaFuncSetAttribute(k_em16<DMv, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
     if (e != cudaSuccess) return e;                                                                                    \
     k_em16<DMv, V><<<grid, kThreads16, smem, st>>>(a);                                                                 \
   } break;
 #define MLF_E16(DMv) MLF_E16V(DMv, 0) MLF_E16V(DMv, 5) MLF_E16V(DMv, 21) MLF_E16V(DMv, 53)
-  switch (128 * g.DM + (var & 127)) {
+  switch (64 * g.DM + (var & 63)) {
     MLF_E16(1) MLF_E16(2) MLF_E16(3) MLF_E16(4)
     default: return cudaErrorInvalidConfiguration;
   }
