@@ -79,7 +79,9 @@ bool em16_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
 // spare tensor-memory columns to free registers for fragment prefetch (+2 ms), unconditional kept-sum DMMAs in P3a (+3 ms),
 // skipping 4-point groups whose responsibilities are all exactly 0 (+-0), a two-stage P3a (branch-free pass-A sweep that records
 // which 4-point groups hold kept / undecided pairs, then those groups only: +1.4 ms), shift and thresholds re-read from shared
-// memory per tile instead of living in registers (+0.5 ms), eight instead of four exps in flight in P2 (+-0).
+// memory per tile instead of living in registers (+0.5 ms), eight instead of four exps in flight in P2 (+-0),
+// requesting the next component's scatter accumulators from tensor memory while the current one is updated (dynamic component
+// index instead of the unrolled loop: +1.4 ms).
 template <int DM, int VAR>
 __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   constexpr bool FOLD = (VAR & 1) != 0;
