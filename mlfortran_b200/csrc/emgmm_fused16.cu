@@ -443,7 +443,8 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
 cudaError_t launch_em16(const Geom& g, const FusedGeom& f, const EmArgs& a, int grid, size_t smem_limit, cudaStream_t st) {
   if (!em16_ok(g, f, smem_limit)) return cudaErrorInvalidConfiguration;
   const size_t smem = em16_smem_bytes(g, f);
-  static const int var = [] { const char* e = getenv("MLF_B200_EM16_VAR"); return e ? atoi(e) : 53; }();
+  const char* ev = getenv("MLF_B200_EM16_VAR");   // A/B switch, read per launch (tests flip it inside one process)
+  const int var = ev ? atoi(ev) : 53;
 #define MLF_E16V(DMv, V)                                                                                               \
   case 64 * DMv + V: {                                                                                                  \
     cudaError_t e = cudaFuncSetAttribute(k_em16<DMv, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \

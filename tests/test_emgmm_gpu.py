@@ -357,6 +357,32 @@ def test_large_shapes_match_oracle(case, oracle):
     em.finalize()
 
 
+def test_em16_scheduling_variants_are_bit_identical(oracle, monkeypatch):
+    """k_em16's scheduling variants (MLF_B200_EM16_VAR: pipelined quad reduction, 1/sum applied at the consumer, split
+    tile-reuse barrier, register prefetch) only move instructions: parameters, sumLL and labels must agree to the last bit with
+    the unpipelined kernel, on a ragged N that exercises the tail tile and several tiles per group."""
+    d, K = 16, 24
+    data = synth.make_mixture(d, K, 1237, 5.0, 1.0, 173)
+    X = data["X"][: 29_003]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 173)
+    ref = None
+    for var in ("0", "5", "21", "53"):
+        monkeypatch.setenv("MLF_B200_EM16_VAR", var)
+        em = make_em(X, K, 1.0, Mu0, Cov0, lam0)
+        assert "k_em16" in em.kernel_plan()
+        info, _ = em.step(4)
+        assert info == 0, em.last_error()
+        got = (em.Mu.copy(), em.Cov.copy(), em.lambda_.copy(), em.sumLL_trace().copy(), em.getClass(X)[1].copy())
+        em.finalize()
+        if ref is None:
+            ref = got
+            oMu, oCov, olam, otr = oracle.em_iterations(X, Mu0, Cov0, lam0, 1.0, 4)
+            assert np.abs((got[3] - otr) / otr).max() <= LL_RTOL and rel(got[0], oMu) <= PAR_RTOL and rel(got[1], oCov) <= PAR_RTOL
+        else:
+            for a, b in zip(got, ref):
+                assert np.array_equal(a, b), f"variant {var} differs from variant 0"
+
+
 @pytest.mark.parametrize("env", [{"MLF_B200_EM16": "0"}, {"MLF_B200_LEGACY": "1"}], ids=["k_em_8warps", "first_generation"])
 def test_alternative_kernel_generations_agree(env, oracle, monkeypatch):
     """The 8-warp fused kernel (MLF_B200_EM16=0) and the first-generation two-pass kernels (MLF_B200_LEGACY=1) stay in the
