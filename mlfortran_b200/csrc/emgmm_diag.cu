@@ -72,6 +72,9 @@ __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
     if (own) mus[a * KP + comp] = A.muold[(size_t)comp * 8 + a] - A.shift[a];
   }
   if (own) { ck = A.pack2[(size_t)comp * PSF + 16]; thi = A.thi[comp]; tlo = A.tlo[comp]; }
+  // "not below the threshold and not zero" as one comparison: responsibilities are >= 0 (or NaN), so
+  // !(a < t) && a != 0  <=>  !(a < max(t, smallest subnormal)); NaN stays a candidate as before
+  const double tlo_e = fmax(tlo, 4.9406564584124654e-324), thi_e = fmax(thi, 4.9406564584124654e-324);
   const bool accu = A.accumulate != 0;
   double* oA = A.partA + ((size_t)blockIdx.x * KP + (own ? comp : 0)) * DS;
   double* oB = A.partB + ((size_t)blockIdx.x * KP + (own ? comp : 0)) * MSF;
@@ -202,8 +205,9 @@ __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
     // ---- P3: lane = component; statistics of the tile, 4 points at a time -------------------------------------------------
     if (wact) {   // warp-uniform branch (votes inside); lanes without a component carry g = 0
       double en[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) en[j] = own ? tile[(size_t)j * S + comp] : 0.0;
+      const double* tcol = tile + (own ? comp : 0);   // lanes without a component read a valid column and discard it
+      const int S2 = 2 * S, S3 = 3 * S, S4 = 4 * S;
+      en[0] = own ? tcol[0] : 0.0; en[1] = own ? tcol[S] : 0.0; en[2] = own ? tcol[S2] : 0.0; en[3] = own ? tcol[S3] : 0.0;
 #pragma unroll 1
       for (int pt0 = 0; pt0 < TP; pt0 += 4) {
         double a[4];
@@ -213,11 +217,11 @@ __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
           a[j] = en[j] * xs[(pt0 + j) * XS + 8];
           // "If(W(i) < minW0) CYCLE" (src/mlf_matrix.f90:135): candidates for the kept set reach the lower band edge;
           // g == 0 adds nothing and is never listed
-          cand |= !(a[j] < tlo) && ((__double2hiint(a[j]) | __double2loint(a[j])) != 0);
+          cand = cand || !(a[j] < tlo_e);
         }
-        if (pt0 + 4 < TP) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) en[j] = own ? tile[(size_t)(pt0 + 4 + j) * S + comp] : 0.0;   // next group, ahead of the votes
+        if (pt0 + 4 < TP) {   // next group, ahead of the votes
+          tcol += S4;
+          en[0] = own ? tcol[0] : 0.0; en[1] = own ? tcol[S] : 0.0; en[2] = own ? tcol[S2] : 0.0; en[3] = own ? tcol[S3] : 0.0;
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -234,9 +238,8 @@ __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const double aj = a[j];
-            const bool nz = (__double2hiint(aj) | __double2loint(aj)) != 0;
-            const bool hi = !(aj < thi) && nz;
-            const bool mid = !hi && !(aj < tlo) && nz;
+            const bool hi = !(aj < thi_e);
+            const bool mid = !hi && !(aj < tlo_e);
             if (__any_sync(kFull, hi)) {
               const double ah = hi ? aj : 0.0;
               sk += ah;

@@ -166,7 +166,7 @@ std::string EmgmmEngine::plan() const {
   char buf[256];
   const Geom& g = geom_;
   if (use16_)
-    snprintf(buf, sizeof buf, "k_em16<%d>: fused single sweep, 16 warps/SM, covariance-scatter accumulators in tensor memory", g.DM);
+    snprintf(buf, sizeof buf, "k_em16<%d>: fused single sweep, 16 warps/SM, software-pipelined whitening reduction, split tile barrier, covariance-scatter accumulators in tensor memory", g.DM);
   else if (used_)
     snprintf(buf, sizeof buf, "k_emd: fused single sweep for diagonal covariances on the fp64 CUDA cores (lane = component)");
   else if (fused_)

@@ -147,8 +147,10 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
     sg = (ld && t == 0) ? o[0] : 0.0;
     sg2 = (ld && t == 0) ? o[1] : 0.0;
     sk = (ld && t == 0) ? ok[8 * DN] : 0.0;
-    thi_r = own ? A.thi[8 * cb + g] : INFINITY;
-    tlo_r = own ? A.tlo[8 * cb + g] : INFINITY;
+    // "not below the threshold and not zero" as one comparison: responsibilities are >= 0 (or NaN), so
+    // !(a < t) && a != 0  <=>  !(a < max(t, smallest subnormal))
+    thi_r = own ? fmax(A.thi[8 * cb + g], 4.9406564584124654e-324) : INFINITY;
+    tlo_r = own ? fmax(A.tlo[8 * cb + g], 4.9406564584124654e-324) : INFINITY;
 #pragma unroll
     for (int b = 0; b < DN; ++b) {
       accA[b][0] = ld ? o[2 + 8 * b + 2 * t] : 0.0;
@@ -330,8 +332,8 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
 #pragma unroll
         for (int db = 0; db < DN; ++db) dmma(accA[db], a, b[db]);
         // "If(W(i) < minW0) CYCLE" (src/mlf_matrix.f90:135); g == 0 adds nothing and is never listed
-        const bool hi = !(a < thi_r) && a != 0.0;
-        const bool mid = !hi && !(a < tlo_r) && a != 0.0;
+        const bool hi = !(a < thi_r);
+        const bool mid = !hi && !(a < tlo_r);
         const double ahi = hi ? a : 0.0;
         sk += ahi;
         const unsigned mh = __ballot_sync(kFull, hi);
@@ -378,7 +380,7 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
           const int pb = __ffs(pm) - 1;
           pm &= pm - 1;
           const double aq = FOLD ? tq[(size_t)(4 * pb + t) * S] * invs[4 * pb + t] : tq[(size_t)(4 * pb + t) * S];
-          const double w = (!(aq < thq) && aq != 0.0) ? aq : 0.0;
+          const double w = !(aq < thq) ? aq : 0.0;
           double z[DN], wz[DN];
 #pragma unroll
           for (int ab = 0; ab < DN; ++ab) {
