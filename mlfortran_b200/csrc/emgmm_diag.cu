@@ -24,6 +24,9 @@ namespace {
 
 __device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 constexpr unsigned kFull = 0xffffffffu;
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
 
 constexpr int kD = 8;     // dimensions held in registers (d <= 8; padding dimensions are zero)
 constexpr int kXS = 12;   // row stride of the staged points: 8 coordinates, 1/sum, padding
@@ -45,7 +48,7 @@ bool emd_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
 // 8-point / 4-point blocking below.  Measured alternatives (config-5 shard, 185 ms with this kernel): TP = 32 with two blocks
 // per SM spills at 128 registers (457 ms); 16 warps with a pair of lanes per component (half the dimensions each, 128
 // registers, no spills) doubles the shuffle / REDUX / shared-memory instructions per pair and lands at 210 ms.
-template <int TP>
+template <int TP, bool XMMA>
 __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
   constexpr int PSF = 20, XS = kXS, DS = 10, MSF = 74;
   constexpr int GP = TP / 8;       // points per warp in P2
@@ -79,15 +82,28 @@ __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
   double* oA = A.partA + ((size_t)blockIdx.x * KP + (own ? comp : 0)) * DS;
   double* oB = A.partB + ((size_t)blockIdx.x * KP + (own ? comp : 0)) * MSF;
   double sg = 0, sg2 = 0, sk = 0, sgx[kD], skx[kD], skz2[kD];
+  // XMMA: sum g x' as DMMA tiles [8 components x 4 points].[4 points x 8 dims], one per 8-component block of the warp; lane
+  // (gq, tq) holds dims 2 tq, 2 tq + 1 of component 32 warp + 8 b + gq.  One shared-memory load per block instead of the four
+  // broadcast LDS.128 per point of the lane = component form (the P3 loop is bound by shared-memory instruction issue).
+  const int gq = lane >> 2, tq = lane & 3;
+  double accX[4][2];
 #pragma unroll
   for (int a = 0; a < kD; ++a) {
     const bool ld = accu && own && a < d;
     // the partial slots hold raw sums (see the end of the kernel): back to the shifted / centred accumulators
-    sgx[a] = ld ? oA[2 + a] - A.shift[a] * oA[0] : 0.0;
+    sgx[a] = (ld && !XMMA) ? oA[2 + a] - A.shift[a] * oA[0] : 0.0;
     skx[a] = ld ? oB[64 + a] - A.muold[(size_t)comp * 8 + a] * oB[72] : 0.0;
     skz2[a] = ld ? oB[a * 9] : 0.0;   // diagonal entry (a, a) of the 8x8 scatter block
   }
   if (accu && own) { sg = oA[0]; sg2 = oA[1]; sk = oB[72]; }
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int c = 32 * warp + 8 * b + gq;
+    const double* oc = A.partA + ((size_t)blockIdx.x * KP + (c < KP ? c : 0)) * DS;
+    const bool ld = XMMA && accu && c < KP;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) accX[b][i] = (ld && 2 * tq + i < d) ? oc[2 + 2 * tq + i] - A.shift[2 * tq + i] * oc[0] : 0.0;
+  }
   const int nlist = blockIdx.x * 8 + warp;
   int nAmb = accu ? A.amb_count[nlist] : 0;
   AmbEntry* ambw = A.amb + (size_t)nlist * A.amb_cap;
@@ -223,12 +239,19 @@ __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
           tcol += S4;
           en[0] = own ? tcol[0] : 0.0; en[1] = own ? tcol[S] : 0.0; en[2] = own ? tcol[S2] : 0.0; en[3] = own ? tcol[S3] : 0.0;
         }
+        if (XMMA) {
+          const double invq = xs[(pt0 + tq) * XS + 8], xq = xs[(pt0 + tq) * XS + gq];
+          const double* tq_p = tile + (size_t)(pt0 + tq) * S + 32 * warp + gq;
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            if (32 * warp + 8 * b < KP) dmma(accX[b], tq_p[8 * b] * invq, xq);   // warp-uniform guard: whole blocks exist or not
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           sg += a[j];
           sg2 = fma(a[j], a[j], sg2);
 #pragma unroll
-          for (int c2 = 0; c2 < kD / 2; ++c2) {
+          for (int c2 = 0; c2 < (XMMA ? 0 : kD / 2); ++c2) {
             const double2 x = *reinterpret_cast<const double2*>(xs + (pt0 + j) * XS + 2 * c2);
             sgx[2 * c2] = fma(a[j], x.x, sgx[2 * c2]);        // about the shift; the shift is added back at the end
             sgx[2 * c2 + 1] = fma(a[j], x.y, sgx[2 * c2 + 1]);
@@ -275,7 +298,7 @@ __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
     // sum g x = sum g x' + shift * sum g;  sum_kept g x = sum_kept g z + mu_old * sum_kept g
 #pragma unroll
     for (int a = 0; a < kD; ++a) {
-      oA[2 + a] = (a < d) ? fma(A.shift[a], sg, sgx[a]) : 0.0;
+      if (!XMMA) oA[2 + a] = (a < d) ? fma(A.shift[a], sg, sgx[a]) : 0.0;
       oB[64 + a] = (a < d) ? skx[a] + A.muold[(size_t)comp * 8 + a] * sk : 0.0;
     }
     for (int i = 0; i < 64; ++i) oB[i] = 0.0;
@@ -284,6 +307,18 @@ __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
     oB[72] = sk;
     oB[73] = 0.0;
   }
+  if (XMMA && wact) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int c = 32 * warp + 8 * b + gq;
+      const double sgc = __shfl_sync(kFull, sg, 8 * b + gq);
+      if (c < KP) {
+        double* oc = A.partA + ((size_t)blockIdx.x * KP + c) * DS;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) oc[2 + 2 * tq + i] = (2 * tq + i < d) ? fma(A.shift[2 * tq + i], sgc, accX[b][i]) : 0.0;
+      }
+    }
+  }
   if (lane == 0) A.amb_count[nlist] = nAmb;
 }
 
@@ -291,10 +326,13 @@ template <int TP>
 static cudaError_t launch_emd_t(const Geom& g, EmArgs a, int grid, cudaStream_t st) {
   const int KP = g.K8 * 8;
   const size_t smem = emd_smem(KP, TP);
-  cudaError_t e = cudaFuncSetAttribute(k_emd<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const char* ev = getenv("MLF_B200_EMD_XMMA");   // A/B switch: 0 = sum g x on the CUDA cores (lane = component)
+  const bool xmma = !(ev && ev[0] == '0');
+  cudaError_t e = cudaFuncSetAttribute(xmma ? k_emd<TP, true> : k_emd<TP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   a.S = emd_stride(KP, TP);
-  k_emd<TP><<<grid, 256, smem, st>>>(a);
+  if (xmma) k_emd<TP, true><<<grid, 256, smem, st>>>(a);
+  else k_emd<TP, false><<<grid, 256, smem, st>>>(a);
   return cudaGetLastError();
 }
 
