@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
   // (gq, tq) holds dims 2 tq, 2 tq + 1 of component 32 warp + 8 b + gq.  One shared-memory load per block instead of the four
   // broadcast LDS.128 per point of the lane = component form (the P3 loop is bound by shared-memory instruction issue).
   const int gq = lane >> 2, tq = lane & 3;
-  double accX[4][2];
+  double accX[4][2], sgq[4], sg2q[4], tloq[4];   // sum g and sum g^2 ride along in the same layout (per lane: its point column)
 #pragma unroll
   for (int a = 0; a < kD; ++a) {
     const bool ld = accu && own && a < d;
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
     skx[a] = ld ? oB[64 + a] - A.muold[(size_t)comp * 8 + a] * oB[72] : 0.0;
     skz2[a] = ld ? oB[a * 9] : 0.0;   // diagonal entry (a, a) of the 8x8 scatter block
   }
-  if (accu && own) { sg = oA[0]; sg2 = oA[1]; sk = oB[72]; }
+  if (accu && own) { sg = oA[0]; sg2 = oA[1]; sk = oB[72]; }   // (sg, sg2: lane = component form only)
 #pragma unroll
   for (int b = 0; b < 4; ++b) {
     const int c = 32 * warp + 8 * b + gq;
@@ -103,6 +103,9 @@ __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
     const bool ld = XMMA && accu && c < KP;
 #pragma unroll
     for (int i = 0; i < 2; ++i) accX[b][i] = (ld && 2 * tq + i < d) ? oc[2 + 2 * tq + i] - A.shift[2 * tq + i] * oc[0] : 0.0;
+    sgq[b] = (ld && tq == 0) ? oc[0] : 0.0;
+    sg2q[b] = (ld && tq == 0) ? oc[1] : 0.0;
+    tloq[b] = (c < KP) ? fmax(A.tlo[c], 4.9406564584124654e-324) : INFINITY;
   }
   const int nlist = blockIdx.x * 8 + warp;
   int nAmb = accu ? A.amb_count[nlist] : 0;
@@ -218,8 +221,66 @@ __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
       if (t == 0) xs[pl * XS + 8] = (p < N) ? 1.0 / sum : 0.0;
     }
     __syncthreads();
-    // ---- P3: lane = component; statistics of the tile, 4 points at a time -------------------------------------------------
-    if (wact) {   // warp-uniform branch (votes inside); lanes without a component carry g = 0
+    // ---- P3: statistics of the tile, 4 points at a time ---------------------------------------------------------------------
+    // kept-set sums and side list of one 4-point group, lane = component; a[j] = responsibility of (this lane's component, point j)
+    auto kept_and_listed = [&](int pt0, const double (&a)[4]) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double aj = a[j];
+        const bool hi = !(aj < thi_e);
+        const bool mid = !hi && !(aj < tlo_e);
+        if (__any_sync(kFull, hi)) {
+          const double ah = hi ? aj : 0.0;
+          sk += ah;
+#pragma unroll
+          for (int c = 0; c < kD; ++c) {
+            const double z = xs[(pt0 + j) * XS + c] - (own ? mus[c * KP + comp] : 0.0);
+            const double az = ah * z;
+            skx[c] += az;
+            skz2[c] = fma(az, z, skz2[c]);
+          }
+        }
+        const unsigned mm = __ballot_sync(kFull, mid);
+        if (mm) {  // undecided until s_k is final: side list, settled by k_amb_resolve
+          const int sl = nAmb + __popc(mm & ((1u << lane) - 1u));
+          if (mid && sl < amb_cap) {
+            AmbEntry e;
+            e.g = aj;
+            e.key = key0 + (long long)(q0 + pt0 + j) * 1024;
+            ambw[sl] = e;
+          }
+          nAmb += __popc(mm);
+        }
+      }
+    };
+    if (wact && XMMA) {
+      // main path in DMMA fragment layout: lane (gq, tq) reads the responsibility of (component 32 warp + 8 b + gq, point pt0 + tq)
+      // for the four 8-component blocks b of the warp: sum g, sum g^2, sum g x' and the candidate test need one shared-memory
+      // load per block; the lane = component form is rebuilt only for groups that hold a candidate of the kept set
+#pragma unroll 1
+      for (int pt0 = 0; pt0 < TP; pt0 += 4) {
+        const double invq = xs[(pt0 + tq) * XS + 8], xq = xs[(pt0 + tq) * XS + gq];
+        const double* tq_p = tile + (size_t)(pt0 + tq) * S + 32 * warp + gq;
+        bool cand = false;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (32 * warp + 8 * b < KP) {   // warp-uniform: whole blocks exist or not
+            const double af = tq_p[8 * b] * invq;
+            dmma(accX[b], af, xq);
+            sgq[b] += af;
+            sg2q[b] = fma(af, af, sg2q[b]);
+            // "If(W(i) < minW0) CYCLE" (src/mlf_matrix.f90:135): candidates for the kept set reach the lower band edge
+            cand = cand || !(af < tloq[b]);
+          }
+        if (__any_sync(kFull, cand)) {
+          double a[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a[j] = own ? tile[(size_t)(pt0 + j) * S + comp] * xs[(pt0 + j) * XS + 8] : 0.0;
+          kept_and_listed(pt0, a);
+        }
+      }
+    }
+    if (wact && !XMMA) {   // lane = component throughout; lanes without a component carry g = 0
       double en[4];
       const double* tcol = tile + (own ? comp : 0);   // lanes without a component read a valid column and discard it
       const int S2 = 2 * S, S3 = 3 * S, S4 = 4 * S;
@@ -231,70 +292,31 @@ __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           a[j] = en[j] * xs[(pt0 + j) * XS + 8];
-          // "If(W(i) < minW0) CYCLE" (src/mlf_matrix.f90:135): candidates for the kept set reach the lower band edge;
-          // g == 0 adds nothing and is never listed
-          cand = cand || !(a[j] < tlo_e);
+          cand = cand || !(a[j] < tlo_e);   // g == 0 adds nothing and is never listed
         }
         if (pt0 + 4 < TP) {   // next group, ahead of the votes
           tcol += S4;
           en[0] = own ? tcol[0] : 0.0; en[1] = own ? tcol[S] : 0.0; en[2] = own ? tcol[S2] : 0.0; en[3] = own ? tcol[S3] : 0.0;
-        }
-        if (XMMA) {
-          const double invq = xs[(pt0 + tq) * XS + 8], xq = xs[(pt0 + tq) * XS + gq];
-          const double* tq_p = tile + (size_t)(pt0 + tq) * S + 32 * warp + gq;
-#pragma unroll
-          for (int b = 0; b < 4; ++b)
-            if (32 * warp + 8 * b < KP) dmma(accX[b], tq_p[8 * b] * invq, xq);   // warp-uniform guard: whole blocks exist or not
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           sg += a[j];
           sg2 = fma(a[j], a[j], sg2);
 #pragma unroll
-          for (int c2 = 0; c2 < (XMMA ? 0 : kD / 2); ++c2) {
+          for (int c2 = 0; c2 < kD / 2; ++c2) {
             const double2 x = *reinterpret_cast<const double2*>(xs + (pt0 + j) * XS + 2 * c2);
             sgx[2 * c2] = fma(a[j], x.x, sgx[2 * c2]);        // about the shift; the shift is added back at the end
             sgx[2 * c2 + 1] = fma(a[j], x.y, sgx[2 * c2 + 1]);
           }
         }
-        if (__any_sync(kFull, cand)) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const double aj = a[j];
-            const bool hi = !(aj < thi_e);
-            const bool mid = !hi && !(aj < tlo_e);
-            if (__any_sync(kFull, hi)) {
-              const double ah = hi ? aj : 0.0;
-              sk += ah;
-#pragma unroll
-              for (int c = 0; c < kD; ++c) {
-                const double z = xs[(pt0 + j) * XS + c] - (own ? mus[c * KP + comp] : 0.0);
-                const double az = ah * z;
-                skx[c] += az;
-                skz2[c] = fma(az, z, skz2[c]);
-              }
-            }
-            const unsigned mm = __ballot_sync(kFull, mid);
-            if (mm) {  // undecided until s_k is final: side list, settled by k_amb_resolve
-              const int sl = nAmb + __popc(mm & ((1u << lane) - 1u));
-              if (mid && sl < amb_cap) {
-                AmbEntry e;
-                e.g = aj;
-                e.key = key0 + (long long)(q0 + pt0 + j) * 1024;
-                ambw[sl] = e;
-              }
-              nAmb += __popc(mm);
-            }
-          }
-        }
+        if (__any_sync(kFull, cand)) kept_and_listed(pt0, a);
       }
     }
     __syncthreads();
   }
   // ---- per-block partials in the layouts of the fused kernels ---------------------------------------------------------------
   if (own) {
-    oA[0] = sg;
-    oA[1] = sg2;
+    if (!XMMA) { oA[0] = sg; oA[1] = sg2; }
     // sum g x = sum g x' + shift * sum g;  sum_kept g x = sum_kept g z + mu_old * sum_kept g
 #pragma unroll
     for (int a = 0; a < kD; ++a) {
@@ -311,9 +333,12 @@ __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const int c = 32 * warp + 8 * b + gq;
-      const double sgc = __shfl_sync(kFull, sg, 8 * b + gq);
+      double sgc = sgq[b], sg2c = sg2q[b];
+      sgc += shx(sgc, 1); sgc += shx(sgc, 2);
+      sg2c += shx(sg2c, 1); sg2c += shx(sg2c, 2);
       if (c < KP) {
         double* oc = A.partA + ((size_t)blockIdx.x * KP + c) * DS;
+        if (tq == 0) { oc[0] = sgc; oc[1] = sg2c; }
 #pragma unroll
         for (int i = 0; i < 2; ++i) oc[2 + 2 * tq + i] = (2 * tq + i < d) ? fma(A.shift[2 * tq + i], sgc, accX[b][i]) : 0.0;
       }
