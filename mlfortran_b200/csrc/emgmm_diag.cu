@@ -48,6 +48,10 @@ bool emd_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
 // 8-point / 4-point blocking below.  Measured alternatives (config-5 shard, 185 ms with this kernel): TP = 32 with two blocks
 // per SM spills at 128 registers (457 ms); 16 warps with a pair of lanes per component (half the dimensions each, 128
 // registers, no spills) doubles the shuffle / REDUX / shared-memory instructions per pair and lands at 210 ms.
+// The statistics loop is bound by instruction issue (shared-memory loads first), not by the fp64 pipe: threshold tests as one
+// comparison and strength-reduced addressing took 185 -> 174 ms, sum g x' as DMMA tiles 174 -> 166, the whole main path of P3 in
+// the DMMA fragment layout 166 -> 160 (MLF_B200_EMD_XMMA=0 keeps the lane = component form).  No gain: driving the kept /
+// listed branches from one warp-wide OR of per-point flags, computed in the main path (177 ms) or inside the rare path (161 ms).
 template <int TP, bool XMMA>
 __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
   constexpr int PSF = 20, XS = kXS, DS = 10, MSF = 74;
