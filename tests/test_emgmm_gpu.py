@@ -598,6 +598,30 @@ def test_diagonal_cuda_core_kernel_streamed_chunks_and_ab(oracle, monkeypatch):
     em2.finalize()
 
 
+def test_diagonal_cuda_core_kernel_statistics_layouts_agree(oracle, monkeypatch):
+    """k_emd's statistics phase in the DMMA fragment layout (default) and in the lane = component form (MLF_B200_EMD_XMMA=0):
+    both match the oracle, and each other far inside the parity budget (the sums are taken in a different order), with K not a
+    multiple of 32 (a warp whose last 8-component blocks do not exist) and a ragged N."""
+    d, K = 7, 200
+    data = synth.make_mixture(d, K, 45, 5.0, 1.0, 191)
+    X = data["X"][: 8_991]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 191)
+    oMu, oCov, olam, otr = _diag_oracle(oracle, oracle.em_iterations, X, Mu0, Cov0, lam0, 0.3, 3)
+    res = []
+    for xmma in ("1", "0"):
+        monkeypatch.setenv("MLF_B200_EMD_XMMA", xmma)
+        em = mlf_algo_emgmm()
+        assert em.init(X, K, 0.3, cov_type="diag") == 0
+        em.inject(Mu0, Cov0, lam0)
+        assert "k_emd" in em.kernel_plan()
+        assert em.step(3)[0] == 0, em.last_error()
+        check_against(em, oMu, oCov, olam, otr)
+        res.append((em.Mu.copy(), em.Cov.copy(), em.lambda_.copy(), em.sumLL))
+        em.finalize()
+    assert rel(res[0][0], res[1][0]) <= 1e-12 and rel(res[0][1], res[1][1]) <= 1e-11
+    assert np.abs(res[0][2] - res[1][2]).max() <= 1e-13 and abs(res[0][3] - res[1][3]) <= 1e-12 * abs(res[1][3])
+
+
 def test_64_point_tiles_full_covariance_large_k(oracle):
     # d=8, K=128 full covariances: the pack fits shared memory only with 64-point tiles (one 8-point group per warp)
     data = synth.make_mixture(8, 128, 60, 6.0, 1.0, 152)
