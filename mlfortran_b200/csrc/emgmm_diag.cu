@@ -124,22 +124,23 @@ __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
   const int64_t ntiles = (N + TP - 1) / TP;
   const int spt = tid >> 3, sa = tid & 7;   // staging role: point spt (and spt + 32), dimension sa
   const double ssh = (sa < d) ? A.shift[sa] : 0.0;
-  double nx0, nx1 = 0.0;
+  double nx0, nx1 = 0.0;   // raw prefetched coordinates (the shift itself where there is no point: x - shift = 0); the shift is
+                           // subtracted when the tile is staged, so that nothing waits on the loads before then
   {
     const int64_t qn = (int64_t)blockIdx.x * TP;
-    nx0 = (qn + spt < N && sa < d) ? A.X[(qn + spt) * d + sa] - ssh : 0.0;
-    if (TP == 64) nx1 = (qn + spt + 32 < N && sa < d) ? A.X[(qn + spt + 32) * d + sa] - ssh : 0.0;
+    nx0 = (qn + spt < N && sa < d) ? A.X[(qn + spt) * d + sa] : ssh;
+    if (TP == 64) nx1 = (qn + spt + 32 < N && sa < d) ? A.X[(qn + spt + 32) * d + sa] : ssh;
   }
   for (int64_t bt = blockIdx.x; bt < ntiles; bt += gridDim.x) {
     const int64_t q0 = bt * TP;
     // ---- stage the tile: x' = x - shift, zero padded to 8 dimensions; rows beyond N are zero.  The values were fetched
     //      into registers one tile ahead, so the global-memory latency hides under the previous tile's arithmetic ------
-    xs[spt * XS + sa] = nx0;
-    if (TP == 64) xs[(spt + 32) * XS + sa] = nx1;
+    xs[spt * XS + sa] = nx0 - ssh;
+    if (TP == 64) xs[(spt + 32) * XS + sa] = nx1 - ssh;
     {
       const int64_t qn = (bt + gridDim.x) * TP;
-      nx0 = (qn + spt < N && sa < d) ? A.X[(qn + spt) * d + sa] - ssh : 0.0;
-      if (TP == 64) nx1 = (qn + spt + 32 < N && sa < d) ? A.X[(qn + spt + 32) * d + sa] - ssh : 0.0;
+      nx0 = (qn + spt < N && sa < d) ? A.X[(qn + spt) * d + sa] : ssh;
+      if (TP == 64) nx1 = (qn + spt + 32 < N && sa < d) ? A.X[(qn + spt + 32) * d + sa] : ssh;
     }
     __syncthreads();
     // ---- P1: lane = component; logits of PB points at a time (PB independent chains), and the warp's maximum per point ----
