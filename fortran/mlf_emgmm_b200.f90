@@ -103,6 +103,17 @@ Module mlf_emgmm_b200
       type(c_ptr), value :: eng
       real(c_double), intent(out) :: ProbaC(*)
     End Function c_engine_proba
+    ! Workload generator of tests/test_emgmm.f90:105-124 (RandN centres, randOrthogonal(C12, weight), RandN(X, X0, C12), randPerm)
+    ! on the device: points n0+1 .. n0+nX of an nTotal-point job into X(nY, nX) (host array with flags = 0); XC(nY, nC) and
+    ! C12(nY, nY, nC) come back as the test program's own arrays would.  Replaces the generation loop of testGMM at scale.
+    Integer(c_int) Function c_synth_gmm(X, n0, nX, nTotal, nY, nC, sigmaC, sigmaX, seed, device, flags, XC, C12) &
+        bind(C, name="mlf_b200_synth_gmm")
+      Import :: c_double, c_int64_t, c_int
+      real(c_double), intent(out) :: X(*), XC(*), C12(*)
+      integer(c_int64_t), value :: n0, nX, nTotal, seed
+      integer(c_int), value :: nY, nC, device, flags
+      real(c_double), value :: sigmaC, sigmaX
+    End Function c_synth_gmm
   End Interface
 
 Contains

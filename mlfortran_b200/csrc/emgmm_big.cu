@@ -168,8 +168,6 @@ __global__ void __launch_bounds__(256, 1) k_estep_big(EmArgs A) {
       for (int grp = 0; grp < GPW; ++grp) s[grp] = 0;
 #pragma unroll
       for (int h = 0; h < H; ++h) {
-        constexpr int dummy = 0;
-        (void)dummy;
         const int lo = h * DH;
         double c[GPW][DH][2];
 #pragma unroll
