@@ -130,9 +130,11 @@ int64_t mlf_b200_launch_count(MLF_OBJ *obj);
 void *mlf_b200_stream(MLF_OBJ *obj);
 int64_t mlf_b200_global_points(MLF_OBJ *obj);
 const char *mlf_b200_version(void);
-/* Self-test hook: the device exp of the softmax (exp_tab.cuh: table-driven, arguments <= 0) evaluated on n host values on
+/* Self-test hook: the device exp of the softmax (exp_tab.cuh: table-driven, 256 entries, arguments <= 0; k_em16) evaluated on n host values on
  * device `device`; out[i] = exp(in[i]).  Exists so that the tests can pin the kernel's transcendental against libm. */
 int mlf_b200_selftest_exp(const double *in, double *out, int64_t n, int device);
+/* The same for the 128-entry form of the table-driven exp that k_emd (diagonal covariances) keeps. */
+int mlf_b200_selftest_exp128(const double *in, double *out, int64_t n, int device);
 
 /* Workload generator of the reference's own EM test program (tests/test_emgmm.f90:105-124, testGMM) run on the device:
  * centres = sigmaC N(0,I) (RandN, src/mlf_rand.f90:241-257), C12_k = O_k diag(w), O_k Haar orthogonal (randOrthogonal,

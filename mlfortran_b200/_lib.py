@@ -62,6 +62,7 @@ SYMBOLS = {
     "mlf_b200_global_points": (C.c_int64, [C.c_void_p]),
     "mlf_b200_version": (C.c_char_p, []),
     "mlf_b200_selftest_exp": (C.c_int, [c_double_p, c_double_p, C.c_int64, C.c_int]),
+    "mlf_b200_selftest_exp128": (C.c_int, [c_double_p, c_double_p, C.c_int64, C.c_int]),
     "mlf_b200_synth_gmm": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double, C.c_uint64,
                                      C.c_int, C.c_uint, C.c_void_p, C.c_void_p]),
     "mlf_b200_engine_create": (C.c_void_p, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint]),

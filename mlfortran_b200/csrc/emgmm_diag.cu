@@ -211,12 +211,12 @@ __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
       int k = 0;
 #pragma unroll (TP == 64 ? 4 : 1)
       for (; k + 1 < cnt; k += 2) {
-        const double e0 = exp_tab(row[TT * k + t] - m, etab), e1 = exp_tab(row[TT * k + TT + t] - m, etab);
+        const double e0 = exp_tab128(row[TT * k + t] - m, etab), e1 = exp_tab128(row[TT * k + TT + t] - m, etab);
         row[TT * k + t] = e0; row[TT * k + TT + t] = e1;
         sum0 += e0; sum1 += e1;
       }
       if (k < cnt) {
-        const double e0 = exp_tab(row[TT * k + t] - m, etab);
+        const double e0 = exp_tab128(row[TT * k + t] - m, etab);
         row[TT * k + t] = e0;
         sum0 += e0;
       }
@@ -367,16 +367,20 @@ static cudaError_t launch_emd_t(const Geom& g, EmArgs a, int grid, cudaStream_t 
 }
 
 namespace {
+template <bool T256>
 __global__ void k_selftest_exp(const double* __restrict__ in, double* __restrict__ out, int64_t n) {
-  __shared__ double etab[128];
-  if (threadIdx.x < 128) etab[threadIdx.x] = kExpTab128[threadIdx.x];
+  __shared__ double etab[kExpTabN];
+  for (int i = threadIdx.x; i < (T256 ? kExpTabN : 128); i += blockDim.x) etab[i] = T256 ? kExpTab[i] : kExpTab128[i];
   __syncthreads();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = exp_tab(in[i], etab);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = T256 ? exp_tab(in[i], etab) : exp_tab128(in[i], etab);
 }
 }  // namespace
 
-cudaError_t launch_selftest_exp(const double* in, double* out, int64_t n, cudaStream_t st) {
-  k_selftest_exp<<<148, 256, 0, st>>>(in, out, n);
+// which: 0 = exp_tab (256 entries, k_em16), 1 = exp_tab128 (k_emd)
+cudaError_t launch_selftest_exp(const double* in, double* out, int64_t n, int which, cudaStream_t st) {
+  if (which == 0) k_selftest_exp<true><<<148, 256, 0, st>>>(in, out, n);
+  else k_selftest_exp<false><<<148, 256, 0, st>>>(in, out, n);
   return cudaGetLastError();
 }
 

@@ -58,7 +58,7 @@ constexpr int kTmemCols = 512;  // 4 warps per lane quarter x 8 components x 16 
 
 }  // namespace
 
-size_t em16_smem_bytes(const Geom& g, const FusedGeom& f) { return f.smem + (128 + 128) * sizeof(double) + 32; }
+size_t em16_smem_bytes(const Geom& g, const FusedGeom& f) { return f.smem + (kExpTabN + 128) * sizeof(double) + 32; }
 bool em16_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
   return f.GPW == 2 && !f.diag && g.DN <= 2 && g.K8 <= 8 && f.scatter_ok && em16_smem_bytes(g, f) <= smem_limit;
 }
@@ -74,7 +74,8 @@ bool em16_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
 //              tile's points have been requested, 2: after the first group of DMMAs of the next tile, 3: after the second;
 //   bit 5      the next tile's points are fetched into registers before the statistics phase.
 // Measured at N=1e8, d=16, K=64 (ms per sweep): 0: 123.5, 1: 121.9, 2: 119.7, 4: 121.0, 5: 119.4, 13: 118.2, 21: 117.6,
-// 29: 117.4 (4-byte spill), 53: 117.0, 61: 116.9 (4-byte spill).  Also measured, no gain: issuing the DMMA chains of 2 or 4
+// 29: 117.4 (4-byte spill), 53: 117.0, 61: 116.9 (4-byte spill).  (Later in the round, on top of variant 53: one-comparison threshold
+// tests 116.1, 256-entry exp table 115.7.)  Also measured, no gain: issuing the DMMA chains of 2 or 4
 // components interleaved (119.5 / 120.5: the loop is not bound by dependent-issue latency), parking the pass-A accumulators in
 // spare tensor-memory columns to free registers for fragment prefetch (+2 ms), unconditional kept-sum DMMAs in P3a (+3 ms),
 // skipping 4-point groups whose responsibilities are all exactly 0 (+-0), a two-stage P3a (branch-free pass-A sweep that records
@@ -106,17 +107,17 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   const int wg = warp & 7;                      // warp index inside the group
   double* xs = smu + (size_t)KP * 8 * DN + (size_t)half * TP * XS;                    // [2][64][XS] raw points, per group
   double* tile = smu + (size_t)KP * 8 * DN + (size_t)2 * TP * XS + (size_t)half * TP * S;  // [2][64][S] logits -> responsibilities
-  double* etab = smu + (size_t)KP * 8 * DN + (size_t)2 * TP * XS + (size_t)2 * TP * S;   // [128] 2^(j/128) (exp_tab.cuh)
-  double* invs = etab + 128 + half * TP;                                                 // [2][64] 1/sum per point (FOLD)
-  uint32_t* s_taddr = reinterpret_cast<uint32_t*>(etab + 128 + 2 * TP);
+  double* etab = smu + (size_t)KP * 8 * DN + (size_t)2 * TP * XS + (size_t)2 * TP * S;   // [kExpTabN] 2^(j/256) (exp_tab.cuh)
+  double* invs = etab + kExpTabN + half * TP;                                                 // [2][64] 1/sum per point (FOLD)
+  uint32_t* s_taddr = reinterpret_cast<uint32_t*>(etab + kExpTabN + 2 * TP);
   const bool own = cb < K8;
-  const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(etab + 128 + 2 * TP + 2 + half);   // one 8-byte mbarrier per group
+  const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(etab + kExpTabN + 2 * TP + 2 + half);   // one 8-byte mbarrier per group
   if (SPLIT && tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;\n" ::"r"(mbar) : "memory");
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;\n" ::"r"(mbar + 8) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (tid < 128) etab[tid] = kExpTab128[tid];
+  if (tid < kExpTabN) etab[tid] = kExpTab[tid];
 
   for (int i = tid; i < KP * PSF; i += kThreads16) sp[i] = A.pack2[i];
   for (int i = tid; i < KP * 8 * DN; i += kThreads16) smu[i] = A.muold[i];

@@ -86,7 +86,7 @@ bool em16_ok(const Geom& g, const FusedGeom& f, size_t smem_limit);
 cudaError_t launch_em16(const Geom& g, const FusedGeom& f, const EmArgs& a, int grid, size_t smem_limit, cudaStream_t st);
 // Diagonal-covariance extension at small d / large K on the fp64 CUDA cores (emgmm_diag.cu): lane = component.
 bool emd_ok(const Geom& g, const FusedGeom& f, size_t smem_limit);
-cudaError_t launch_selftest_exp(const double* in, double* out, int64_t n, cudaStream_t st);   // exp_tab on n device values
+cudaError_t launch_selftest_exp(const double* in, double* out, int64_t n, int which, cudaStream_t st);   // exp_tab (which = 0) / exp_tab128 (1) on n device values
 cudaError_t launch_emd(const Geom& g, const FusedGeom& f, EmArgs a, int grid, size_t smem_limit, cudaStream_t st);
 cudaError_t launch_amb_resolve(const Geom& g, const double* X, const AmbEntry* amb, int cap, const int* counts, int nlists,
                                const double* statsA, double minW, const double* muold, double* outC, cudaStream_t st);

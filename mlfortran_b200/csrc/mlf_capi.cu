@@ -256,7 +256,7 @@ extern "C" {
 
 const char* mlf_b200_version(void) { return "mlfortran_b200 0.1 (sm_100a, fp64 DMMA EM-GMM)"; }
 
-int mlf_b200_selftest_exp(const double* in, double* out, int64_t n, int device) {
+static int selftest_exp_impl(const double* in, double* out, int64_t n, int device, int which) {
   if (!in || !out || n < 0) return -1;
   if (n == 0) return 0;
   int ndev = 0;
@@ -266,13 +266,15 @@ int mlf_b200_selftest_exp(const double* in, double* out, int64_t n, int device) 
   int rc = -7;
   if (cudaMalloc((void**)&di, (size_t)n * sizeof(double)) == cudaSuccess && cudaMalloc((void**)&dout, (size_t)n * sizeof(double)) == cudaSuccess &&
       cudaMemcpy(di, in, (size_t)n * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
-      mlfb200::launch_selftest_exp(di, dout, n, 0) == cudaSuccess &&
+      mlfb200::launch_selftest_exp(di, dout, n, which, 0) == cudaSuccess &&
       cudaMemcpy(out, dout, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess)
     rc = 0;
   cudaFree(di);
   cudaFree(dout);
   return rc;
 }
+int mlf_b200_selftest_exp(const double* in, double* out, int64_t n, int device) { return selftest_exp_impl(in, out, n, device, 0); }
+int mlf_b200_selftest_exp128(const double* in, double* out, int64_t n, int device) { return selftest_exp_impl(in, out, n, device, 1); }
 
 int mlf_init(void) {
   int n = 0;
