@@ -214,3 +214,25 @@ def test_diagonal_extension_c_vs_numpy(oracle):
     assert (off == 0).all()
     fMu, fCov, flam, ftr = oracle.em_iterations(X, Mu0, Cov0, lam0, 0.0, 5)
     assert np.abs(fCov - Cov).max() > 1e-3      # the full-covariance reference path is a different computation
+
+
+@pytest.mark.parametrize("d,K,npc,sc,min_proba,seed", [(2, 3, 25, 3.0, 1.0, 11), (3, 3, 20, 2.0, 0.0, 5), (5, 2, 30, 1.0, 0.3, 7), (1, 4, 15, 4.0, 0.0, 9)])
+def test_oracle_rounding_error_against_50_digit_arithmetic(oracle, d, K, npc, sc, min_proba, seed):
+    """The fp64 oracle against the same formulas evaluated with 50 significant digits (oracle/emgmm_mp.py), iteration by
+    iteration from the oracle's own fp64 state: sumLL to 1e-13 relative, parameters to 1e-12 -- the oracle's rounding error is
+    three orders of magnitude inside the 1e-10 / 1e-9 budget the CUDA path is compared with."""
+    from oracle import emgmm_mp
+
+    data = synth.make_mixture(d, K, npc, sc, 1.0, seed)
+    X = data["X"]
+    Mu, Cov, lam = synth.injected_init(data["centres"], seed)
+    for _ in range(3):
+        mMu, mCov, mLam, mLL, _ = emgmm_mp.em_iteration(X, Mu, Cov, lam, min_proba)
+        Mu, Cov, lam, tr = oracle.em_iterations(X, Mu, Cov, lam, min_proba, 1)
+        eMu = np.array([[float(v) for v in r] for r in mMu])
+        eCov = np.array([[[float(v) for v in r] for r in C] for C in mCov])
+        eLam = np.array([float(v) for v in mLam])
+        assert abs(float(mLL) - tr[0]) <= 1e-13 * abs(tr[0])
+        assert np.abs(eMu - Mu).max() <= 1e-12 * max(1.0, np.abs(Mu).max())
+        assert np.abs(eCov - Cov).max() <= 1e-12 * max(1.0, np.abs(Cov).max())
+        assert np.abs(eLam - lam).max() <= 1e-13
