@@ -69,6 +69,27 @@ def test_device_exp_against_libm(entry):
     assert (oz == 0.0).all()
 
 
+# ---- the CUDA path against exact arithmetic -------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,K,npc,sc,min_proba,seed", [(2, 3, 25, 3.0, 1.0, 11), (3, 3, 20, 2.0, 0.0, 5), (5, 2, 30, 1.0, 0.3, 7)])
+def test_cuda_iteration_against_50_digit_arithmetic(d, K, npc, sc, min_proba, seed):
+    """One EM iteration on the GPU against the reference's formulas evaluated with 50 significant digits (oracle/emgmm_mp.py):
+    the CUDA path's own rounding error, with no fp64 oracle in between, is orders of magnitude inside the parity budget."""
+    from oracle import emgmm_mp
+
+    data = synth.make_mixture(d, K, npc, sc, 1.0, seed)
+    X = data["X"]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], seed)
+    mMu, mCov, mLam, mLL, _ = emgmm_mp.em_iteration(X, Mu0, Cov0, lam0, min_proba)
+    em = make_em(X, K, min_proba, Mu0, Cov0, lam0)
+    assert em.step(1)[0] == 0, em.last_error()
+    eMu = np.array([[float(v) for v in r] for r in mMu])
+    eCov = np.array([[[float(v) for v in r] for r in Cm] for Cm in mCov])
+    eLam = np.array([float(v) for v in mLam])
+    assert abs(em.sumLL - float(mLL)) <= 1e-11 * abs(float(mLL))
+    assert rel(em.Mu, eMu) <= 1e-11 and rel(em.Cov, eCov) <= 1e-11 and np.abs(em.lambda_ - eLam).max() <= 1e-12
+    em.finalize()
+
+
 # ---- golden fixtures -------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
 def test_golden_trajectories(path, oracle):
