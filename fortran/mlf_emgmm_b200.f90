@@ -33,6 +33,7 @@ Module mlf_emgmm_b200
   ! .TRUE.: objects initialised from now on shard their points over every visible GPU inside this process (peer-memory
   ! all-reduce, mlf_b200_engine_create_multi); .FALSE.: the current CUDA device only.
   Logical, Public, Save :: mlf_b200_use_all_gpus = .FALSE.
+  Public :: mlf_b200_synth_gmm_f
 
   Type, Public, Extends(mlf_step_obj) :: mlf_algo_emgmm_b200
     real(c_double), pointer :: X(:,:), Mu(:,:), Cov(:,:,:), lambda(:)
@@ -243,5 +244,18 @@ Contains
     info = c_engine_expectation(top%engine, top%Mu, top%Cov, top%lambda, X, INT(nIn, c_int64_t), &
       C_LOC(Proba), C_NULL_PTR)
   End Function run_expectation
+
+  ! The data of the reference's own EM test program (tests/test_emgmm.f90:105-124: RandN centres, randOrthogonal(C12, weight),
+  ! RandN(X, X0 = XC(:,k), C12 = C12(:,:,k)), randPerm) generated by one CUDA kernel: X(ND, N), XC(ND, NC), C12(ND, ND, NC).
+  ! Seeded and counter-based (the reference's RANDOM_NUMBER stream is not): same seed, same data on any number of GPUs.
+  Integer Function mlf_b200_synth_gmm_f(X, XC, C12, sigmaC, sigmaX, seed) Result(info)
+    real(c_double), intent(out), contiguous :: X(:,:), XC(:,:), C12(:,:,:)
+    real(c_double), intent(in) :: sigmaC, sigmaX
+    integer(c_int64_t), intent(in) :: seed
+    integer(c_int64_t) :: nPts
+    nPts = INT(SIZE(X,2), c_int64_t)
+    info = c_synth_gmm(X, 0_c_int64_t, nPts, nPts, INT(SIZE(X,1), c_int), INT(SIZE(XC,2), c_int), sigmaC, sigmaX, seed, &
+      0_c_int, 0_c_int, XC, C12)
+  End Function mlf_b200_synth_gmm_f
 
 End Module mlf_emgmm_b200

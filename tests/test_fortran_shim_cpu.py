@@ -42,3 +42,16 @@ def test_shim_mirrors_the_reference_type_interface():
     # same slot names and restore rule as the reference init (:90-101)
     for token in ('C_CHAR_"Mu"', 'C_CHAR_"Cov"', 'C_CHAR_"lambda"', '"sumLL"', '"minProba"', "fixed_dims = [.TRUE., .FALSE.]"):
         assert token in f90, token
+
+
+def test_example_program_uses_only_what_the_shim_exports():
+    """fortran/example_emgmm_b200.f90 (the reference's testGMM switched to the library) calls only public names of the shim
+    module and type-bound procedures / components the shim type has."""
+    f90 = open(os.path.join(ROOT, "fortran", "mlf_emgmm_b200.f90")).read()
+    ex = open(os.path.join(ROOT, "fortran", "example_emgmm_b200.f90")).read()
+    assert "Use mlf_emgmm_b200" in ex and "type(mlf_algo_emgmm_b200) :: em" in ex
+    for name in ("mlf_b200_synth_gmm_f", "mlf_b200_use_all_gpus"):
+        assert name in ex and re.search(r"Public\s*(::)?[^\n]*\b" + name + r"\b", f90, flags=re.I), name
+    for member in re.findall(r"\bem%(\w+)", ex):
+        # own components / bindings, or inherited from the reference's mlf_step_obj (step) and mlf_obj (finalize)
+        assert re.search(r"\b" + member + r"\b", f90) or member in ("step",), member
