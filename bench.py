@@ -107,7 +107,7 @@ def bind_to_gpu_numa_node(gpu_index: int) -> str:
         return f"not bound ({type(exc).__name__})"
 
 
-def cpu_oracle_rate(d, K, n_cpu, min_proba, steps, warmup, threads=None):
+def cpu_oracle_rate(d, K, n_cpu, min_proba, steps, warmup, threads=None, sigma_c=SIGMA_C, sigma_x=SIGMA_X):
     """Times the CPU restatement of the reference algorithm (oracle/, kind "port") on a bounded sample."""
     from mlfortran_b200 import synth
     from oracle.emgmm_oracle import get
@@ -115,7 +115,7 @@ def cpu_oracle_rate(d, K, n_cpu, min_proba, steps, warmup, threads=None):
     orc = get()
     nthr = threads or min(K, os.cpu_count() or 1)
     orc.set_threads(nthr)
-    data = synth.make_mixture(d, K, max(n_cpu // K, 1), SIGMA_C, SIGMA_X, SEED)
+    data = synth.make_mixture(d, K, max(n_cpu // K, 1), sigma_c, sigma_x, SEED)
     X = data["X"]
     Mu, Cov, lam = synth.injected_init(data["centres"], SEED)
     if warmup > 0:
@@ -137,7 +137,7 @@ def run_reference(args, rank, world):
         return
     d, K = args.dims, args.comps
     n_cpu = args.cpu_points
-    r = cpu_oracle_rate(d, K, n_cpu, args.min_proba, args.steps, args.warmup)
+    r = cpu_oracle_rate(d, K, n_cpu, args.min_proba, args.steps, args.warmup, sigma_c=args.sigma_c, sigma_x=args.sigma_x)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["sec_per_step"] * 1e3 * (args.points / r["n"]), "higher_is_better": True,
@@ -165,6 +165,9 @@ def main():
     ap.add_argument("--comps", type=int, default=64)
     ap.add_argument("--min-proba", type=float, default=1.0, help="minProba as in tests/test_emgmm.f90:125")
     ap.add_argument("--cov-type", default="full", choices=["full", "diag"], help="diag = extension (BASELINE configs[4]); full = reference")
+    ap.add_argument("--sigma-c", type=float, default=SIGMA_C, help="spread of the cluster centres (tests/test_emgmm.f90 sigmaC); 8 = headline, "
+                    "<= 2 gives heavily overlapping clusters (worst case of the threshold protocol)")
+    ap.add_argument("--sigma-x", type=float, default=SIGMA_X, help="cluster width scale (tests/test_emgmm.f90 sigmaX)")
     ap.add_argument("--cpu-points", type=int, default=1000000, help="bounded CPU sample for cpu_baseline / --impl reference (SURVEY 8d: N_cpu = 1e6)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -215,7 +218,7 @@ def main():
     n_loc = hi - lo
     # the library's own device generator (mlf_b200_synth_gmm, recipe of tests/test_emgmm.f90:105-124): every point is a pure
     # function of (seed, global index), so the N-point data set is the same whatever the number of ranks
-    X, centres, _ = synth.make_mixture_device(d, K, n_loc, lo, N, SIGMA_C, SIGMA_X, SEED, dev)
+    X, centres, _ = synth.make_mixture_device(d, K, n_loc, lo, N, args.sigma_c, args.sigma_x, SEED, dev)
     Mu0, Cov0, lam0 = synth.injected_init(centres, SEED)
 
     em = mlf_algo_emgmm()
@@ -250,6 +253,7 @@ def main():
     clocks = sampler.stop(tw0, tw1) if sampler else None
     launches = em.launch_count() - l0
     times = em.times()
+    counters = em.counters()
     plan = em.kernel_plan()
     em.set_profile(False)
     sumll = em.sumLL
@@ -296,6 +300,7 @@ def main():
                           " (whitening DMMA + log-sum-exp + pass-A statistics + thresholded covariance scatter)" if fused
                           else " (roofline line = E-pass: whitening DMMA + log-sum-exp + pass-A statistics)"), "bound": "tensor",
         "sweeps_per_iteration": sweeps / it if fused else 1.0, "side_list_pairs": times.get("side_list_pairs", 0),
+        "kept_pairs_per_point": (counters["kept_pairs"] / it / max(n_loc * world, 1)) if fused else None,
         "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None, "traffic": traffic,
         "peak_source": ("fp64 DFMA on the CUDA cores (same fp64 datapath as DMMA; 'tensor' is kept as the bound label of the contract)"
                         if diag_cc else "fp64 DMMA (mma.sync m8n8k4.f64)") +
@@ -350,7 +355,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         os.sched_setaffinity(0, full_affinity)
-        r = cpu_oracle_rate(d, K, args.cpu_points, args.min_proba, 3, 1)
+        r = cpu_oracle_rate(d, K, args.cpu_points, args.min_proba, 3, 1, sigma_c=args.sigma_c, sigma_x=args.sigma_x)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
                "sample": f"oracle (C restatement of the reference, OpenMP over components) on N_cpu={r['n']} points of the same d={d}, K={K} mixture, "
                          f"3 EM iterations after 1 warm-up; {r['sec_per_step']:.2f} s/iteration"}
@@ -361,7 +366,7 @@ def main():
             "data": "synthetic", "em_iter_per_s": args.steps / (ms * 1e-3), "sumLL_last": sumll,
             "config": {"workload": f"synthetic GMM N={N:.0e} d={d} K={K} {'full' if args.cov_type == 'full' else 'diagonal'} covariance, points sharded over {world} GPU(s)"
                                    + (" (BASELINE configs[2])" if (d, K, args.cov_type) == (16, 64, "full") else ""),
-                       "N": N, "d": d, "K": K, "minProba": args.min_proba, "points_per_gpu": n_loc, "parallelism": f"points-sharded x{world}",
+                       "N": N, "d": d, "K": K, "minProba": args.min_proba, "sigmaC": args.sigma_c, "sigmaX": args.sigma_x, "points_per_gpu": n_loc, "parallelism": f"points-sharded x{world}",
                        "l2": "inputs larger than L2 (X is 12.8 GB per 1e8 points >> 126 MB); no explicit flush",
                        "timing": "CUDA events on the engine stream, max over ranks"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -126,6 +126,10 @@ const double *mlf_b200_resident_proba_device(MLF_OBJ *obj, int64_t *ld);
  * through the side list. */
 int mlf_b200_set_profile(MLF_OBJ *obj, int on);
 int mlf_b200_get_times(MLF_OBJ *obj, double out[8]);
+/* Integer counters since the last mlf_b200_set_profile / reset: out[0] = EM iterations counted (profiling on), out[1] = sweeps
+ * over X, out[2] = pairs settled through the side list, out[3] = (point, component) pairs whose covariance term was accumulated
+ * inside the sweep ("kept" by the reference's W >= minW test, src/mlf_matrix.f90:135; counted by the 16-warp sweep only). */
+int mlf_b200_get_counters(MLF_OBJ *obj, int64_t out[4]);
 int64_t mlf_b200_launch_count(MLF_OBJ *obj);
 void *mlf_b200_stream(MLF_OBJ *obj);
 int64_t mlf_b200_global_points(MLF_OBJ *obj);
@@ -171,12 +175,23 @@ int mlf_b200_engine_proba(MLF_B200_ENGINE *eng, double *ProbaC);
 int mlf_b200_engine_set_allreduce(MLF_B200_ENGINE *eng, mlf_b200_allreduce_fn fn, void *ctx, int rank, int world);
 const char *mlf_b200_engine_last_error(MLF_B200_ENGINE *eng);
 
-/* Generic dataset access on a checkpoint handle (root group; int64 / float64; dims in file (C) order, i.e. the
- * reverse of the Fortran shape).  mlf_b200_h5_get with data == NULL only reports type/rank/dims. */
+/* Generic dataset access on a checkpoint handle (file or group handle; int64 / float64; dims in file (C) order, i.e. the
+ * reverse of the Fortran shape; `name` may be a path "group/sub/name" below the handle).  mlf_b200_h5_get with
+ * data == NULL only reports type/rank/dims.  mlf_b200_h5_count / _name enumerate the datasets below the handle. */
 int mlf_b200_h5_put(MLF_OBJ *handler, const char *name, int dtype, int rank, const int64_t *dims, const void *data, int override_);
 int mlf_b200_h5_get(MLF_OBJ *handler, const char *name, int *dtype, int *rank, int64_t *dims, void *data, int64_t capacity_bytes);
 int mlf_b200_h5_count(MLF_OBJ *handler);
 const char *mlf_b200_h5_name(MLF_OBJ *handler, int idx);
+/* Objects / features of the opened file that lie outside the checkpoint layout (other types, chunked or compressed
+ * layouts, attributes, a user block): readable files that hold any are opened read-only; mlf_hdf5_openFile(.., rw=1)
+ * refuses them, because the built-in writer rewrites the file as a whole and would drop that content (the reference's
+ * H5Fopen_f(H5F_ACC_RDWR_F), src/mlf_hdf5.f90:204-207, keeps it). */
+int mlf_b200_h5_unsupported(MLF_OBJ *handler);
+/* Group handler below a file or group handler: mlf_hdf5_openGroup / getSubGroup (src/mlf_hdf5.f90:106-151).
+ * mode 0 = open an existing group, 1 = create (NULL if it exists), 2 = open, else create.  mlf_pushState on the returned
+ * handle writes the object's slots inside the group, as Hdf5PushSubObject does for sub-objects (:657-669), and
+ * mlf_emgmm_c(..., handler = group) restores from it.  Free with mlf_dealloc; the file is written when something was put. */
+MLF_OBJ *mlf_b200_h5_open_group(MLF_OBJ *handler, const char *name, int mode);
 
 #ifdef __cplusplus
 }

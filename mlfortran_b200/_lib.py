@@ -57,6 +57,7 @@ SYMBOLS = {
     "mlf_b200_resident_proba_device": (C.c_void_p, [C.c_void_p, c_int64_p]),
     "mlf_b200_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "mlf_b200_get_times": (C.c_int, [C.c_void_p, c_double_p]),
+    "mlf_b200_get_counters": (C.c_int, [C.c_void_p, c_int64_p]),
     "mlf_b200_launch_count": (C.c_int64, [C.c_void_p]),
     "mlf_b200_stream": (C.c_void_p, [C.c_void_p]),
     "mlf_b200_global_points": (C.c_int64, [C.c_void_p]),
@@ -78,6 +79,8 @@ SYMBOLS = {
     "mlf_b200_h5_get": (C.c_int, [C.c_void_p, C.c_char_p, c_int_p, c_int_p, c_int64_p, C.c_void_p, C.c_int64]),
     "mlf_b200_h5_count": (C.c_int, [C.c_void_p]),
     "mlf_b200_h5_name": (C.c_char_p, [C.c_void_p, C.c_int]),
+    "mlf_b200_h5_unsupported": (C.c_int, [C.c_void_p]),
+    "mlf_b200_h5_open_group": (C.c_void_p, [C.c_void_p, C.c_char_p, C.c_int]),
 }
 
 _lib = None

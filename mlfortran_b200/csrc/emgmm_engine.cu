@@ -39,6 +39,8 @@ EmgmmEngine::~EmgmmEngine() {
     if (b) cudaFree(b);
   if (dAmb_) cudaFree(dAmb_);
   if (dAmbCount_) cudaFree(dAmbCount_);
+  if (dAmbComp_) cudaFree(dAmbComp_);
+  if (dAmbPart_) cudaFree(dAmbPart_);
   if (dInfo_) cudaFree(dInfo_);
   if (dLabels_) cudaFree(dLabels_);
   for (auto& e : pev_)
@@ -79,6 +81,9 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
     legacy_estep_ = lg && lg[0] == '1';
     const char* bg = getenv("MLF_B200_BIG");
     big_ = bg && bg[0] == '1';
+    const char* dbg = getenv("MLF_B200_DEBUG");
+    debug_ = dbg && dbg[0] == '1';
+    if (const char* ac = getenv("MLF_B200_AMB_CAP")) amb_cap_ = std::max(8, std::min(atoi(ac), kAmbCapMax));   // tests: force overflows
   }
   // kernel generation for this shape: fused single sweep (pack + tile in shared memory, scatter accumulators in
   // registers) > resident-pack E-pass + stored responsibilities > large-shape kernels (pack streamed through L1)
@@ -137,9 +142,13 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   if (fused_) {
     // the 16-warp variant writes partials per (block, half) and keeps one side list per warp
     CKE(A(&dPartB2_, (size_t)2 * sms_ * KP * fgeom_.MSF), "cudaMalloc");
-    CKE(cudaMalloc((void**)&dAmb_, (size_t)sms_ * 16 * amb_cap_ * sizeof(AmbEntry)), "cudaMalloc side list");
-    CKE(cudaMalloc((void**)&dAmbCount_, (size_t)sms_ * 16 * sizeof(int)), "cudaMalloc");
-    CKE(cudaMemsetAsync(dAmbCount_, 0, (size_t)sms_ * 16 * sizeof(int), st_), "memset");
+    amb_lists_ = sms_ * 16;
+    // components a single list can hold: the warp that writes it owns one 8-component block (16-warp sweep), CBMAX blocks
+    // (8-warp sweep) or 32 lanes = 32 components (diagonal CUDA-core sweep)
+    amb_cmax_ = use16_ ? 8 : (used_ ? 32 : 8 * fgeom_.CBMAX);
+    CKE(cudaMalloc((void**)&dAmb_, (size_t)amb_lists_ * amb_cap_ * sizeof(AmbEntry)), "cudaMalloc side list");
+    CKE(cudaMalloc((void**)&dAmbCount_, (size_t)amb_lists_ * sizeof(int)), "cudaMalloc");
+    CKE(cudaMemsetAsync(dAmbCount_, 0, (size_t)amb_lists_ * sizeof(int), st_), "memset");
   }
   CKE(A(&dMu_, (size_t)K * d), "cudaMalloc");
   CKE(A(&dCov_, (size_t)K * d * d), "cudaMalloc");
@@ -186,6 +195,31 @@ int EmgmmEngine::ensure_gamma() {
   if (dGamma_) return 0;
   CKE(cudaMalloc((void**)&dGamma_, std::max<size_t>((size_t)geom_.K * ldg_, 1) * sizeof(double)), "cudaMalloc gamma (N*K responsibilities)");
   CKE(cudaMemsetAsync(dGamma_, 0, (size_t)geom_.K * ldg_ * sizeof(double), st_), "memset gamma");
+  return 0;
+}
+
+int EmgmmEngine::ensure_amb_scratch() {
+  if (dAmbPart_) return 0;
+  const int d = geom_.d;
+  CKE(cudaMalloc((void**)&dAmbComp_, (size_t)amb_lists_ * (amb_cmax_ + 1) * sizeof(int)), "cudaMalloc side-list scratch");
+  CKE(cudaMalloc((void**)&dAmbPart_, (size_t)amb_lists_ * amb_cmax_ * (d * d + d + 1) * sizeof(double)), "cudaMalloc side-list scratch");
+  return 0;
+}
+
+// A sweep overflowed a side list: four times the capacity for the sweeps to come (the current iteration is repeated with
+// the exact threshold, which lists nothing).
+int EmgmmEngine::grow_amb_lists() {
+  if (amb_cap_ >= kAmbCapMax) return 0;
+  const int cap = std::min(kAmbCapMax, amb_cap_ * 4);
+  AmbEntry* p = nullptr;
+  if (cudaMalloc((void**)&p, (size_t)amb_lists_ * cap * sizeof(AmbEntry)) != cudaSuccess) {
+    cudaGetLastError();   // not fatal: the protocol falls back to the repeated sweep
+    return 0;
+  }
+  CKE(cudaStreamSynchronize(st_), "sync");
+  cudaFree(dAmb_);
+  dAmb_ = p;
+  amb_cap_ = cap;
   return 0;
 }
 
@@ -285,6 +319,11 @@ int EmgmmEngine::ensure_moments() {
   CKE(launch_moments(g, dX_, n_, dShift_, dMomPart_, grid, 0, st_), "moments");
   ++launches_;
   return finish_moments(grid);
+}
+
+int EmgmmEngine::prepare() {
+  CKE(cudaSetDevice(device_), "cudaSetDevice");
+  return ensure_moments();
 }
 
 // M-pass dispatch: thresholded centred scatter of every component into dStatsB_ (fixed-order reduction over chunks).
@@ -500,7 +539,7 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
   const int64_t nA = (int64_t)KP * g.DS, nB = (int64_t)KP * f.MSF;
   const double minW = 1e-3 / (double)(float)nglob_;  // 1d-3/real(NX)  (src/unsupervised/mlf_gaussian.f90:50)
   double* dFlags = dAB_ + nA + nB;                    // [listed pairs, overflowing lists] ride in the same all-reduce
-  std::vector<double> hA((size_t)nA + 0), hflag(2), tlo((size_t)KP), thi((size_t)KP), sk((size_t)K);
+  std::vector<double> hA((size_t)nA + 0), hflag(3), tlo((size_t)KP), thi((size_t)KP), sk((size_t)K);
   gamma_current_ = false;
   for (int64_t it = 0; it < niter; ++it) {
     cudaEvent_t* ev_ = prof ? &pev_[(size_t)6 * it] : nullptr;
@@ -560,20 +599,27 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
       }
       CKE(launch_reduce_partials(dPartA_, nslots, nA, dAB_, st_), "reduce statsA");
       CKE(launch_reduce_partials(dPartB2_, nslots, nB, dAB_ + nA, st_), "reduce statsB");
-      CKE(launch_amb_summary(dAmbCount_, nlists, amb_cap_, dFlags, st_), "amb summary");
+      CKE(launch_amb_summary(dAmbCount_, nlists, amb_cap_, dFlags, st_, dAB_ + nA, KP, f.MSF, g.MB * 64 + 8 * g.DN + 1), "amb summary");
       launches_ += 3;
       times_.sweeps += 1;
-      if (int r = allreduce(dAB_, nA + nB + 2)) return r;
+      if (int r = allreduce(dAB_, nA + nB + 3)) return r;
       // verification needs s_k and the list flags on the host: one small D2H + sync per sweep
       CKE(cudaMemcpyAsync(hA.data(), dAB_, nA * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H statsA");
-      CKE(cudaMemcpyAsync(hflag.data(), dFlags, 2 * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H flags");
+      CKE(cudaMemcpyAsync(hflag.data(), dFlags, 3 * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H flags");
       CKE(cudaStreamSynchronize(st_), "sync");
-      bool ok = hflag[1] == 0.0 && hflag[0] <= 200000.0;
+      bool ok = hflag[1] == 0.0;
+      int missed = 0;
       for (int k = 0; k < K; ++k) {
         sk[(size_t)k] = hA[(size_t)k * g.DS];
         const double tau = minW * sk[(size_t)k];
-        if (!(tlo[(size_t)k] <= tau && tau <= thi[(size_t)k])) ok = false;  // also catches NaN
+        if (!(tlo[(size_t)k] <= tau && tau <= thi[(size_t)k])) { ok = false; ++missed; }  // also catches NaN
       }
+      if (debug_ && rank_ == 0)
+        fprintf(stderr, "mlfortran_b200[debug]: sweep %lld pass %d%s: listed pairs %.0f, overflowed lists %.0f (cap %d), kept pairs %.0f, "
+                "components outside the predicted band %d -> %s\n", (long long)it, pass, exact ? " (exact thresholds)" : "", hflag[0], hflag[1],
+                amb_cap_, hflag[2], missed, (ok || exact) ? "accepted" : "repeat with exact thresholds");
+      if (!ok && !exact && hflag[1] != 0.0)
+        if (int r = grow_amb_lists()) return r;
       if (ok || exact) break;
       exact = true;  // s_k is known now: repeat the sweep with tlo == thi == minW*s_k (the side list stays empty)
     }
@@ -581,8 +627,10 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
     if (prof) cudaEventRecord(ev_[3], st_);
     const double* statsC = nullptr;
     if (hflag[0] > 0.0) {
-      CKE(launch_amb_resolve(g, dX_, dAmb_, amb_cap_, dAmbCount_, nlists, dAB_, minW, dMuOld_, dStatsC_, st_), "amb resolve");
-      ++launches_;
+      if (int r = ensure_amb_scratch()) return r;
+      CKE(launch_amb_resolve(g, dX_, dAmb_, amb_cap_, dAmbCount_, nlists, dAB_, minW, dMuOld_, dStatsC_, st_, amb_cmax_, dAmbComp_, dAmbPart_),
+          "amb resolve");
+      launches_ += 2;
       if (int r = allreduce(dStatsC_, (int64_t)K * (d * d + d + 1))) return r;
       statsC = dStatsC_;
       times_.amb_pairs += (int64_t)hflag[0];
@@ -591,6 +639,7 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
     CKE(launch_finalize_fused(g, f, dAB_, dAB_ + nA, statsC, dMuOld_, minProba, dMu_, dCov_, dLambda_, st_, cov_diag_ ? 1 : 0), "finalize");
     ++launches_;
     if (prof) cudaEventRecord(ev_[5], st_);
+    times_.kept_pairs += (int64_t)hflag[2];
     s_prev2_ = s_prev_;
     s_prev_ = sk;
   }
@@ -645,8 +694,9 @@ int EmgmmEngine::materialize_gamma() {
   CKE(cudaSetDevice(device_), "cudaSetDevice");
   if (gamma_current_) return 0;
   if (int r = ensure_gamma()) return r;
-  if (!prev_valid_ || n_ == 0) return 0;  // no E-step yet: ProbaC = 0 (src/unsupervised/mlf_emgmm.f90:119)
-  if (int r = ensure_moments()) return r;
+  if (!prev_valid_) return 0;  // no E-step yet: ProbaC = 0 (src/unsupervised/mlf_emgmm.f90:119)
+  if (int r = ensure_moments()) return r;  // collective: empty shards join it before they leave
+  if (n_ == 0) return 0;
   CKE(launch_refresh(geom_, dPrevMu_, dPrevCov_, dPrevLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_,
                      dPack2_, dMuOld_, dShift_, 1, cov_diag_ ? 1 : 0, &fgeom_, 0), "refresh");
   refresh_count_ = 0;  // scratch now holds the eigenvectors of the previous parameters: next refresh starts cold
@@ -664,8 +714,8 @@ const double* EmgmmEngine::gamma_device() {
 
 int EmgmmEngine::resident_proba(double* P_host) {
   CKE(cudaSetDevice(device_), "cudaSetDevice");
-  if (n_ == 0) return 0;
   if (int r = materialize_gamma()) return r;
+  if (n_ == 0) return 0;
   CKE(cudaMemcpy2DAsync(P_host, (size_t)n_ * sizeof(double), dGamma_, (size_t)ldg_ * sizeof(double), (size_t)n_ * sizeof(double),
                         geom_.K, cudaMemcpyDeviceToHost, st_), "D2H ProbaC");
   CKE(cudaStreamSynchronize(st_), "sync");
@@ -674,8 +724,8 @@ int EmgmmEngine::resident_proba(double* P_host) {
 
 int EmgmmEngine::resident_labels(int32_t* labels_host) {
   CKE(cudaSetDevice(device_), "cudaSetDevice");
+  if (int r = ensure_moments()) return r;  // collective: empty shards join it before they leave
   if (n_ == 0) return 0;
-  if (int r = ensure_moments()) return r;
   if (!dLabels_) CKE(cudaMalloc((void**)&dLabels_, (size_t)n_ * sizeof(int32_t)), "cudaMalloc labels");
   if (int r = do_refresh()) return r;
   if (legacy_estep_) {

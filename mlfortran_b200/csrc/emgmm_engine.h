@@ -20,6 +20,7 @@ struct EngineTimes {  // CUDA-event milliseconds accumulated over iterate() call
   int64_t iters = 0;
   int64_t sweeps = 0;     // fused path: sweeps over X (1 per iteration when the threshold band held, 2 otherwise)
   int64_t amb_pairs = 0;  // fused path: pairs settled through the side list
+  int64_t kept_pairs = 0; // fused path (k_em16): (point, component) pairs whose scatter term was accumulated inside the sweep
 };
 
 class EmgmmEngine {
@@ -38,6 +39,11 @@ class EmgmmEngine {
   }
   void set_stream(cudaStream_t st);
   int refresh_x(const double* X, bool x_on_device);
+  // Global moments + shift of the resident data.  COLLECTIVE when an all-reduce is installed: every rank / shard must
+  // call it (empty shards too).  step / kmeans_init / expectation / resident_* call it themselves when the moments are
+  // stale (after init, refresh_x, set_allreduce), so the first of those calls is collective as well; callers that want
+  // to run inference on one rank only call prepare() on all ranks first.
+  int prepare();
 
   int upload_params(const double* Mu, const double* Cov, const double* lambda);
   int download_params(double* Mu, double* Cov, double* lambda);
@@ -141,7 +147,15 @@ class EmgmmEngine {
   bool gamma_current_ = false;  // dGamma_ holds the responsibilities of the last E-step
   AmbEntry* dAmb_ = nullptr;
   int* dAmbCount_ = nullptr;
-  int amb_cap_ = 1024;
+  int amb_cap_ = 2048;          // entries per list; grown (x4, up to kAmbCapMax) when a sweep overflows a list
+  static constexpr int kAmbCapMax = 32768;
+  int amb_lists_ = 0;           // lists allocated (16 per block for the 16-warp sweep, 8 otherwise)
+  int* dAmbComp_ = nullptr;     // k_amb_partial scratch: components present per list
+  double* dAmbPart_ = nullptr;  //                       and their partial [scatter | sum g z | sum g]
+  int amb_cmax_ = 8;
+  bool debug_ = false;          // MLF_B200_DEBUG=1: one stderr line per sweep (threshold band / side list / repeat decisions)
+  int ensure_amb_scratch();
+  int grow_amb_lists();
   std::vector<double> s_prev_, s_prev2_;
   int32_t* dLabels_ = nullptr;
   int egrid_ = 0, mgx_ = 0, mgy_ = 0;

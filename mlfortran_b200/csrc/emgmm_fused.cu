@@ -527,45 +527,120 @@ cudaError_t launch_em(const Geom& g, const FusedGeom& f, const EmArgs& a, bool s
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// side list of undecided pairs: settle against the exact threshold minW * s_k, accumulate their contribution
-// relative to the current mean.  One block per component, thread (a,b) owns one scatter entry; entries are visited
-// in list order, so the sums are deterministic.  outC[k] = [d*d scatter (column-major) | d sum g z | sum g].
+// side list of undecided pairs: settle against the exact threshold minW * s_k and accumulate their contribution
+// relative to the current mean.  outC[k] = [d*d scatter (column-major) | d sum g z | sum g].
+// Two kernels, both with a fixed summation order (entries in list order, lists in index order), so the result is
+// deterministic:
+//   k_amb_partial  one block per list: for every component that occurs in the list (<= cmax), thread e accumulates
+//                  entry e of that component's [scatter | sum g z | sum g] over the list's entries;
+//   k_amb_reduce   one block per component: sums the lists' partials in list order.
+// The first version walked every entry of every list serially in every thread of every component's block and capped
+// the protocol at 200 000 listed pairs; this one settles millions of pairs in well under a millisecond.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void k_amb_resolve(int d, int K, int DS, const double* __restrict__ X, const AmbEntry* __restrict__ amb, int cap,
-                              const int* __restrict__ counts, int nlists, const double* __restrict__ statsA, double minW,
-                              const double* __restrict__ muold, int ldmu, double* __restrict__ outC) {
-  const int k = blockIdx.x;
-  const int nt = blockDim.x;
-  const double thr = minW * statsA[(size_t)k * DS];
-  const double* mu = muold + (size_t)k * ldmu;
-  double* o = outC + (size_t)k * (d * d + d + 1);
-  for (int e = threadIdx.x; e < d * d + d + 1; e += nt) {
-    const int a = (e < d * d) ? e % d : (e - d * d);
-    const int b = (e < d * d) ? e / d : -1;
-    double acc = 0;
-    for (int l = 0; l < nlists; ++l) {
-      const int n = counts[l] < cap ? counts[l] : cap;
-      const AmbEntry* list = amb + (size_t)l * cap;
-      for (int j = 0; j < n; ++j) {
-        const AmbEntry en = list[j];
-        if ((int)(en.key & 1023) != k || en.g < thr) continue;
-        const long long p = en.key >> 10;
-        if (e == d * d + d) acc += en.g;
-        else if (b < 0) acc = fma(en.g, X[p * d + a] - mu[a], acc);
-        else acc = fma(en.g * (X[p * d + a] - mu[a]), X[p * d + b] - mu[b], acc);
+constexpr int kAmbStage = 1024;   // entries staged in shared memory at a time
+
+__global__ void __launch_bounds__(288) k_amb_partial(int d, int DS, const double* __restrict__ X, const AmbEntry* __restrict__ amb, int cap,
+                                                     const int* __restrict__ counts, const double* __restrict__ statsA, double minW,
+                                                     const double* __restrict__ muold, int ldmu, int cmax, int* __restrict__ pcomp,
+                                                     double* __restrict__ partial) {
+  __shared__ AmbEntry s_e[kAmbStage];
+  __shared__ unsigned s_mask[32];      // components 0..1023 present in the list
+  __shared__ int s_comp[64];
+  __shared__ int s_ncomp;
+  const int l = blockIdx.x;
+  const int n = counts[l] < cap ? counts[l] : cap;
+  const AmbEntry* list = amb + (size_t)l * cap;
+  const int ne = d * d + d + 1;
+  int* pc = pcomp + (size_t)l * (cmax + 1);
+  if (n <= 0) {
+    if (threadIdx.x == 0) pc[0] = 0;
+    return;
+  }
+  if (threadIdx.x < 32) s_mask[threadIdx.x] = 0;
+  __syncthreads();
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const int k = (int)(list[j].key & 1023);
+    atomicOr(&s_mask[k >> 5], 1u << (k & 31));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int c = 0;
+    for (int w = 0; w < 32; ++w)
+      for (unsigned m = s_mask[w]; m; m &= m - 1)
+        if (c < cmax && c < 64) s_comp[c++] = 32 * w + __ffs(m) - 1;
+    s_ncomp = c;
+    pc[0] = c;
+    for (int i = 0; i < c; ++i) pc[1 + i] = s_comp[i];
+  }
+  __syncthreads();
+  const int nc = s_ncomp;
+  for (int ci = 0; ci < nc; ++ci) {
+    const int k = s_comp[ci];
+    const double thr = minW * statsA[(size_t)k * DS];
+    const double* mu = muold + (size_t)k * ldmu;
+    for (int e0 = 0; e0 < ne; e0 += blockDim.x) {
+      const int e = e0 + threadIdx.x;
+      const int a = (e < d * d) ? e % d : (e - d * d);
+      const int b = (e < d * d) ? e / d : -1;
+      double acc = 0;
+      for (int j0 = 0; j0 < n; j0 += kAmbStage) {
+        const int m = min(kAmbStage, n - j0);
+        __syncthreads();
+        for (int j = threadIdx.x; j < m; j += blockDim.x) s_e[j] = list[j0 + j];
+        __syncthreads();
+        if (e < ne) {
+          for (int j = 0; j < m; ++j) {
+            const AmbEntry en = s_e[j];
+            if ((int)(en.key & 1023) != k || en.g < thr) continue;
+            const long long p = en.key >> 10;
+            if (e == d * d + d) acc += en.g;
+            else if (b < 0) acc = fma(en.g, X[p * d + a] - mu[a], acc);
+            else acc = fma(en.g * (X[p * d + a] - mu[a]), X[p * d + b] - mu[b], acc);
+          }
+        }
       }
+      if (e < ne) partial[((size_t)l * cmax + ci) * ne + e] = acc;
     }
-    o[e] = acc;
   }
 }
+
+__global__ void __launch_bounds__(288) k_amb_reduce(int d, int nlists, int cmax, const int* __restrict__ pcomp, const double* __restrict__ partial,
+                                                    double* __restrict__ outC) {
+  extern __shared__ short s_slot[];   // [nlists]: slot of component k inside list l's partials, or -1
+  const int k = blockIdx.x;
+  const int ne = d * d + d + 1;
+  for (int l = threadIdx.x; l < nlists; l += blockDim.x) {
+    const int* pc = pcomp + (size_t)l * (cmax + 1);
+    short slot = -1;
+    for (int i = 0; i < pc[0]; ++i)
+      if (pc[1 + i] == k) slot = (short)i;
+    s_slot[l] = slot;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+    double acc = 0;
+    for (int l = 0; l < nlists; ++l) {
+      const int sl = s_slot[l];
+      if (sl >= 0) acc += partial[((size_t)l * cmax + sl) * ne + e];
+    }
+    outC[(size_t)k * ne + e] = acc;
+  }
+}
+
 cudaError_t launch_amb_resolve(const Geom& g, const double* X, const AmbEntry* amb, int cap, const int* counts, int nlists,
-                               const double* statsA, double minW, const double* muold, double* outC, cudaStream_t st) {
-  k_amb_resolve<<<g.K, 256, 0, st>>>(g.d, g.K, g.DS, X, amb, cap, counts, nlists, statsA, minW, muold, 8 * g.DN, outC);
+                               const double* statsA, double minW, const double* muold, double* outC, cudaStream_t st, int cmax, int* pcomp,
+                               double* partial) {
+  k_amb_partial<<<nlists, 288, 0, st>>>(g.d, g.DS, X, amb, cap, counts, statsA, minW, muold, 8 * g.DN, cmax, pcomp, partial);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  k_amb_reduce<<<g.K, 288, (size_t)nlists * sizeof(short), st>>>(g.d, nlists, cmax, pcomp, partial, outC);
   return cudaGetLastError();
 }
 
-// flags[0] = listed pairs on this rank, flags[1] = lists that overflowed their capacity (both all-reduced as doubles)
-__global__ void __launch_bounds__(256) k_amb_summary(const int* __restrict__ counts, int nlists, int cap, double* __restrict__ flags) {
+// flags[0] = listed pairs on this rank, flags[1] = lists that overflowed their capacity, flags[2] = pairs that passed the
+// certainly-kept test in the sweep (pad slot of the pass-B statistics; profiling counter) -- all-reduced as doubles
+__global__ void __launch_bounds__(256) k_amb_summary(const int* __restrict__ counts, int nlists, int cap, double* __restrict__ flags,
+                                                     const double* __restrict__ statsB, int KP, int MSF, int off) {
   __shared__ long long s_tot[256];
   __shared__ int s_over[256];
   long long tot = 0;
@@ -584,10 +659,15 @@ __global__ void __launch_bounds__(256) k_amb_summary(const int* __restrict__ cou
   if (threadIdx.x == 0) {
     flags[0] = (double)s_tot[0];
     flags[1] = (double)s_over[0];
+    double kept = 0;
+    if (statsB)
+      for (int k = 0; k < KP; ++k) kept += statsB[(size_t)k * MSF + off];
+    flags[2] = kept;
   }
 }
-cudaError_t launch_amb_summary(const int* counts, int nlists, int cap, double* flags, cudaStream_t st) {
-  k_amb_summary<<<1, 256, 0, st>>>(counts, nlists, cap, flags);
+cudaError_t launch_amb_summary(const int* counts, int nlists, int cap, double* flags, cudaStream_t st, const double* statsB, int KP, int MSF,
+                               int off) {
+  k_amb_summary<<<1, 256, 0, st>>>(counts, nlists, cap, flags, statsB, KP, MSF, off);
   return cudaGetLastError();
 }
 

@@ -140,7 +140,8 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   const int slot = 2 * blockIdx.x + half;
   double* outA = A.partA + (size_t)slot * KP * DS;
   double* outB = A.partB + (size_t)slot * KP * MSF;
-  double accA[DN][2], accK[DN][2], sg, sg2, sk, thi_r, tlo_r;
+  double accA[DN][2], accK[DN][2], sg, sg2, sk, thi_r, tlo_r, nk0;
+  int nk = 0;   // pairs of this lane's component that passed the certainly-kept test (profiling counter, pad slot of MSF)
   {
     const bool ld = accu && own;
     const double* o = outA + (size_t)(8 * cb + g) * DS;
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
     sg = (ld && t == 0) ? o[0] : 0.0;
     sg2 = (ld && t == 0) ? o[1] : 0.0;
     sk = (ld && t == 0) ? ok[8 * DN] : 0.0;
+    nk0 = (ld && t == 0) ? ok[8 * DN + 1] : 0.0;
     // "not below the threshold and not zero" as one comparison: responsibilities are >= 0 (or NaN), so
     // !(a < t) && a != 0  <=>  !(a < max(t, smallest subnormal))
     thi_r = own ? fmax(A.thi[8 * cb + g], 4.9406564584124654e-324) : INFINITY;
@@ -337,6 +339,7 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
         const bool mid = !hi && !(a < tlo_r);
         const double ahi = hi ? a : 0.0;
         sk += ahi;
+        nk += hi ? 1 : 0;
         const unsigned mh = __ballot_sync(kFull, hi);
         const unsigned mm = __ballot_sync(kFull, mid);
         if (mh) {
@@ -410,12 +413,13 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   // ---- per-(block, half) partials -------------------------------------------------------------------------------------
   if (own) {
     double a = sg, b = sg2, c = sk;
+    nk += __shfl_xor_sync(kFull, nk, 1); nk += __shfl_xor_sync(kFull, nk, 2);
     a += shx(a, 1); a += shx(a, 2);
     b += shx(b, 1); b += shx(b, 2);
     c += shx(c, 1); c += shx(c, 2);
     double* o = outA + (size_t)(8 * cb + g) * DS;
     double* ok = outB + (size_t)(8 * cb + g) * MSF + MB * 64;
-    if (t == 0) { o[0] = a; o[1] = b; ok[8 * DN] = c; ok[8 * DN + 1] = 0.0; }
+    if (t == 0) { o[0] = a; o[1] = b; ok[8 * DN] = c; ok[8 * DN + 1] = nk0 + (double)nk; }
 #pragma unroll
     for (int db = 0; db < DN; ++db) {
       o[2 + 8 * db + 2 * t] = accA[db][0];

@@ -88,9 +88,13 @@ cudaError_t launch_em16(const Geom& g, const FusedGeom& f, const EmArgs& a, int 
 bool emd_ok(const Geom& g, const FusedGeom& f, size_t smem_limit);
 cudaError_t launch_selftest_exp(const double* in, double* out, int64_t n, int which, cudaStream_t st);   // exp_tab (which = 0) / exp_tab128 (1) on n device values
 cudaError_t launch_emd(const Geom& g, const FusedGeom& f, EmArgs a, int grid, size_t smem_limit, cudaStream_t st);
+// cmax: upper bound of distinct components per list (a warp's lists only hold the components that warp owns);
+// pcomp: [nlists][cmax+1] ints, partial: [nlists][cmax][d*d+d+1] doubles of scratch
 cudaError_t launch_amb_resolve(const Geom& g, const double* X, const AmbEntry* amb, int cap, const int* counts, int nlists,
-                               const double* statsA, double minW, const double* muold, double* outC, cudaStream_t st);
-cudaError_t launch_amb_summary(const int* counts, int nlists, int cap, double* flags, cudaStream_t st);
+                               const double* statsA, double minW, const double* muold, double* outC, cudaStream_t st, int cmax, int* pcomp,
+                               double* partial);
+cudaError_t launch_amb_summary(const int* counts, int nlists, int cap, double* flags, cudaStream_t st, const double* statsB = nullptr,
+                               int KP = 0, int MSF = 0, int off = 0);
 cudaError_t launch_finalize_fused(const Geom& g, const FusedGeom& f, const double* statsA, const double* statsB, const double* statsC,
                                   const double* muold, double minProba, double* Mu, double* Cov, double* lambda, cudaStream_t st,
                                   int cov_diag = 0);

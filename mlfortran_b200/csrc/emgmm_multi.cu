@@ -169,6 +169,9 @@ int MultiEngine::kmeans_init(int nkm, uint64_t seed) {
   return run_all([&](Worker& w) { return w.eng->kmeans_init(nkm, seed); });
 }
 int MultiEngine::expectation(const double* Xq, int64_t nq, double* P_host, int32_t* labels_host) {
+  // the moments / shift behind the parameter pack are all-reduced over the shards: every shard takes part in that step
+  // (right after init, a checkpoint restore, inject or refresh_x nothing has run yet), then shard 0 evaluates the query
+  if (int r0 = run_all([&](Worker& w) { return w.eng->prepare(); })) return r0;
   cudaSetDevice(w_[0].device);
   int r = w_[0].eng->expectation(Xq, false, nq, P_host, labels_host);
   if (r != 0) err_ = w_[0].eng->last_error();
@@ -178,16 +181,15 @@ int MultiEngine::resident_proba(double* P_host) {
   // each shard fills its column range of ProbaC(N,K): P[k*N + lo .. hi)
   return run_all([&](Worker& w) {
     const int64_t nl = w.hi - w.lo;
-    if (nl == 0) return 0;
-    std::vector<double> tmp((size_t)K_ * nl);
-    int r = w.eng->resident_proba(tmp.data());
-    if (r != 0) return r;
+    std::vector<double> tmp((size_t)K_ * std::max<int64_t>(nl, 1));
+    int r = w.eng->resident_proba(tmp.data());  // empty shards still join the collective moments step inside
+    if (r != 0 || nl == 0) return r;
     for (int k = 0; k < K_; ++k) std::memcpy(P_host + (size_t)k * n_ + w.lo, tmp.data() + (size_t)k * nl, (size_t)nl * sizeof(double));
     return 0;
   });
 }
 int MultiEngine::resident_labels(int32_t* labels_host) {
-  return run_all([&](Worker& w) { return (w.hi > w.lo) ? w.eng->resident_labels(labels_host + w.lo) : 0; });
+  return run_all([&](Worker& w) { return w.eng->resident_labels(labels_host + w.lo); });  // empty shards join the collectives
 }
 void MultiEngine::set_profile(bool on) {
   for (auto& w : w_) w.eng->set_profile(on);

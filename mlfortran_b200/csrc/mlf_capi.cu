@@ -42,17 +42,56 @@ struct Slot {
   bool has_fields = false;
 };
 
-struct Hdf5Handle : Handle {
+// One open checkpoint file, shared by the file handle and the group handles opened from it (mlf_hdf5_file /
+// mlf_hdf5_group, src/mlf_hdf5.f90:46-82).  The file is rewritten as a whole -- only when something was put since the
+// last write (dirty), never on a plain open/close, and never for a file that holds anything this module cannot
+// represent (mlf_hdf5_openFile refuses rw on such files: a rewrite would drop that content).
+struct H5File {
   std::string path;
   bool writable = true;
-  std::vector<mlfh5::Dataset> ds;
-  Hdf5Handle() : Handle(KIND_HDF5) {}
+  bool dirty = false;
+  mlfh5::Contents c;
   mlfh5::Dataset* find(const std::string& n) {
-    for (auto& d : ds)
+    for (auto& d : c.ds)
       if (d.name == n) return &d;
     return nullptr;
   }
-  int flush() { return writable ? mlfh5::write_file(path, ds) : 0; }
+  bool has_group(const std::string& g) const {
+    for (const auto& x : c.groups)
+      if (x == g) return true;
+    return false;
+  }
+  int flush() {
+    if (!writable || !dirty) return 0;
+    const int r = mlfh5::write_file(path, c);
+    if (r == 0) dirty = false;
+    return r;
+  }
+};
+
+struct Hdf5Handle : Handle {
+  std::shared_ptr<H5File> file;
+  std::string prefix;   // "" for the file handle, "group/sub/" for a group handle
+  Hdf5Handle() : Handle(KIND_HDF5) {}
+  bool writable() const { return file->writable; }
+  mlfh5::Dataset* find(const std::string& n) { return file->find(prefix + n); }
+  // false when the path collides with the file's structure: a group of that name, or a dataset where a group is needed
+  bool put(mlfh5::Dataset&& nd) {
+    nd.name = prefix + nd.name;
+    if (nd.name.empty() || nd.name.back() == '/' || file->has_group(nd.name)) return false;
+    for (size_t p = nd.name.find('/'); p != std::string::npos; p = nd.name.find('/', p + 1)) {
+      const std::string anc = nd.name.substr(0, p);
+      if (anc.empty() || file->find(anc)) return false;
+    }
+    for (size_t p = nd.name.find('/'); p != std::string::npos; p = nd.name.find('/', p + 1))
+      if (!file->has_group(nd.name.substr(0, p))) file->c.groups.push_back(nd.name.substr(0, p));
+    mlfh5::Dataset* dst = file->find(nd.name);
+    if (dst) *dst = std::move(nd);
+    else file->c.ds.push_back(std::move(nd));
+    file->dirty = true;
+    return true;
+  }
+  int flush() { return file->flush(); }
 };
 
 struct EmObject : Handle {
@@ -335,21 +374,27 @@ int mlf_pushState(MLF_OBJ* handler, MLF_OBJ* obj, int override_) {
   Hdf5Handle* h = as_h5(handler);
   EmObject* o = as_em(obj);
   if (!h || !o) return -1;
-  if (!h->writable) return mlf_FILEERROR;
-  // one dataset per allocated slot, named by r_name, dims reversed (src/mlf_hdf5.f90:696-736)
+  if (!h->writable()) return mlf_FILEERROR;
+  // one dataset per allocated slot, named by r_name, dims reversed (src/mlf_hdf5.f90:696-736); with override the
+  // datasets must exist already (H5Dopen_f) and are rewritten, without it they must not (H5Dcreate_f) -- :294-300
   for (const Slot& s : o->slots) {
     mlfh5::Dataset* dst = h->find(s.name);
     if (dst && !override_) {
-      fprintf(stderr, "mlf_pushState: dataset %s exists (override not set)\n", s.name.c_str());
+      fprintf(stderr, "Error creating dataset: %s\n", s.name.c_str());
       return mlf_FILEERROR;
     }
+    if (!dst && override_) {
+      fprintf(stderr, "Error opening resource %s\n", s.name.c_str());
+      return mlf_FILEERROR;
+    }
+  }
+  for (const Slot& s : o->slots) {
     mlfh5::Dataset nd;
     nd.name = s.name;
     nd.type = (s.dt == mlf_INT64) ? mlfh5::I64 : mlfh5::F64;
     for (int i = s.rank - 1; i >= 0; --i) nd.dims.push_back((uint64_t)s.dims[i]);
     nd.data.assign((const uint8_t*)s.ptr, (const uint8_t*)s.ptr + s.bytes);
-    if (dst) *dst = std::move(nd);
-    else h->ds.push_back(std::move(nd));
+    if (!h->put(std::move(nd))) return mlf_FILEERROR;
   }
   return h->flush();
 }
@@ -405,8 +450,10 @@ MLF_OBJ* mlf_hdf5_createFile(const char* fname, int trunk) {
     if (f) { fclose(f); fprintf(stderr, "Error while creating file: %s\n", fname); return nullptr; }
   }
   std::unique_ptr<Hdf5Handle> h(new Hdf5Handle());
-  h->path = fname;
-  h->writable = true;
+  h->file = std::make_shared<H5File>();
+  h->file->path = fname;
+  h->file->writable = true;
+  h->file->dirty = true;   // H5Fcreate_f leaves an (empty) file behind at once
   if (h->flush() < 0) { fprintf(stderr, "Error while creating file: %s\n", fname); return nullptr; }
   return h.release();
 }
@@ -414,9 +461,17 @@ MLF_OBJ* mlf_hdf5_createFile(const char* fname, int trunk) {
 MLF_OBJ* mlf_hdf5_openFile(const char* fname, int rw) {
   if (!fname) return nullptr;
   std::unique_ptr<Hdf5Handle> h(new Hdf5Handle());
-  h->path = fname;
-  h->writable = rw != 0;
-  if (mlfh5::read_file(h->path, h->ds) < 0) { fprintf(stderr, "Error while opening file: %s\n", fname); return nullptr; }
+  h->file = std::make_shared<H5File>();
+  h->file->path = fname;
+  h->file->writable = rw != 0;
+  if (mlfh5::read_file(h->file->path, h->file->c) < 0) { fprintf(stderr, "Error while opening file: %s\n", fname); return nullptr; }
+  if (rw != 0 && !h->file->c.lossy.empty()) {
+    // the built-in writer rewrites the whole file from what the reader understood: content it cannot represent would be
+    // lost (the reference's H5Fopen_f(H5F_ACC_RDWR_F) keeps it), so such files open read-only or not at all
+    fprintf(stderr, "Error while opening file: %s (read-write refused: %zu object(s) outside the checkpoint layout, first: %s)\n", fname,
+            h->file->c.lossy.size(), h->file->c.lossy[0].c_str());
+    return nullptr;
+  }
   return h.release();
 }
 
@@ -548,6 +603,13 @@ int mlf_b200_get_times(MLF_OBJ* obj, double out[8]) {
   out[6] = (double)t.sweeps; out[7] = (double)t.amb_pairs;
   return 0;
 }
+int mlf_b200_get_counters(MLF_OBJ* obj, int64_t out[4]) {
+  EmObject* o = as_em(obj);
+  if (!o || !out) return -1;
+  const mlfb200::EngineTimes t = o->multi ? o->multi->times() : o->eng.times();
+  out[0] = t.iters; out[1] = t.sweeps; out[2] = t.amb_pairs; out[3] = t.kept_pairs;
+  return 0;
+}
 int64_t mlf_b200_launch_count(MLF_OBJ* obj) {
   EmObject* o = as_em(obj);
   return o ? (o->multi ? o->multi->launches() : o->eng.launches()) : -1;
@@ -564,7 +626,7 @@ int64_t mlf_b200_global_points(MLF_OBJ* obj) {
 int mlf_b200_h5_put(MLF_OBJ* handler, const char* name, int dtype, int rank, const int64_t* dims, const void* data, int override_) {
   Hdf5Handle* h = as_h5(handler);
   if (!h || !name || rank < 1 || rank > MLF_MAXRANK || !dims || !data) return -1;
-  if (!h->writable) return mlf_FILEERROR;
+  if (!h->writable()) return mlf_FILEERROR;
   if (dtype != mlf_INT64 && dtype != mlf_DOUBLE) return mlf_WRONGTYPE;
   mlfh5::Dataset nd;
   nd.name = name;
@@ -576,8 +638,7 @@ int mlf_b200_h5_put(MLF_OBJ* handler, const char* name, int dtype, int rank, con
   nd.data.assign((const uint8_t*)data, (const uint8_t*)data + nd.count() * 8);
   mlfh5::Dataset* dst = h->find(nd.name);
   if (dst && !override_) return mlf_FILEERROR;
-  if (dst) *dst = std::move(nd);
-  else h->ds.push_back(std::move(nd));
+  if (!h->put(std::move(nd))) return mlf_FILEERROR;
   return h->flush();
 }
 
@@ -597,14 +658,48 @@ int mlf_b200_h5_get(MLF_OBJ* handler, const char* name, int* dtype, int* rank, i
   return 0;
 }
 
+// datasets below the handle (file: all of them; group handle: the ones inside the group), by path relative to it
 int mlf_b200_h5_count(MLF_OBJ* handler) {
   Hdf5Handle* h = as_h5(handler);
-  return h ? (int)h->ds.size() : -1;
+  if (!h) return -1;
+  int n = 0;
+  for (const auto& d : h->file->c.ds) n += d.name.compare(0, h->prefix.size(), h->prefix) == 0;
+  return n;
 }
 const char* mlf_b200_h5_name(MLF_OBJ* handler, int idx) {
   Hdf5Handle* h = as_h5(handler);
-  if (!h || idx < 0 || idx >= (int)h->ds.size()) return nullptr;
-  return h->ds[(size_t)idx].name.c_str();
+  if (!h || idx < 0) return nullptr;
+  for (const auto& d : h->file->c.ds)
+    if (d.name.compare(0, h->prefix.size(), h->prefix) == 0 && idx-- == 0) return d.name.c_str() + h->prefix.size();
+  return nullptr;
+}
+int mlf_b200_h5_unsupported(MLF_OBJ* handler) {
+  Hdf5Handle* h = as_h5(handler);
+  return h ? (int)h->file->c.lossy.size() : -1;
+}
+
+// mlf_hdf5_openGroup / getSubGroup (src/mlf_hdf5.f90:106-151): a handler for the group `name` below this handler.
+// mode 0 = open an existing group (H5Gopen_f), 1 = create it (H5Gcreate_f fails when it exists), 2 = open, else create
+// (getSubGroup).  The group handle shares the file with its parent; mlf_pushState(group, obj, ...) writes the object's
+// slots inside the group (Hdf5PushSubObject, :657-669); free it with mlf_dealloc.
+MLF_OBJ* mlf_b200_h5_open_group(MLF_OBJ* handler, const char* name, int mode) {
+  Hdf5Handle* h = as_h5(handler);
+  if (!h || !name || !*name || std::strchr(name, '/') || !std::strcmp(name, ".") || !std::strcmp(name, "..")) return nullptr;
+  const std::string path = h->prefix + name;
+  const bool exists = h->file->has_group(path);
+  if (h->file->find(path)) return nullptr;   // a dataset of that name
+  if (mode == 0 && !exists) return nullptr;
+  if (mode == 1 && exists) return nullptr;
+  if (!exists) {
+    if (!h->file->writable) return nullptr;
+    h->file->c.groups.push_back(path);
+    h->file->dirty = true;
+    if (h->file->flush() < 0) return nullptr;
+  }
+  std::unique_ptr<Hdf5Handle> g(new Hdf5Handle());
+  g->file = h->file;
+  g->prefix = path + "/";
+  return g.release();
 }
 
 // ---- engine-level entry points (bound by fortran/mlf_emgmm_b200.f90) ---------------------------------------------

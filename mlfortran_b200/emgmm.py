@@ -48,6 +48,25 @@ class mlf_hdf5_file:
         self._h = _lib.load().mlf_hdf5_openFile(fname.encode(), 1 if rw else 0)
         return 0 if self._h else -1
 
+    def open_group(self, groupName: str, create: bool = False) -> "mlf_hdf5_file | None":
+        """handler => this%open_group(groupName, create) (src/mlf_hdf5.f90:106-131); None on failure."""
+        return self._group(groupName, 1 if create else 0)
+
+    def getSubObject(self, obj_name: str) -> "mlf_hdf5_file | None":
+        """ptr => this%getSubObject(obj_name): open the group, else create it (src/mlf_hdf5.f90:133-151)."""
+        return self._group(obj_name, 2)
+
+    def _group(self, name: str, mode: int):
+        h = _lib.load().mlf_b200_h5_open_group(self._h, name.encode(), mode)
+        if not h:
+            return None
+        g = mlf_hdf5_file()
+        g._h = h
+        return g
+
+    def unsupported(self) -> int:
+        return _lib.load().mlf_b200_h5_unsupported(self._h)
+
     def pushState(self, obj: "mlf_algo_emgmm", override: bool = False) -> int:
         return _lib.load().mlf_pushState(self._h, obj._h, 1 if override else 0)
 
@@ -314,6 +333,11 @@ class mlf_algo_emgmm:
         out = (C.c_double * 8)()
         self._lib.mlf_b200_get_times(self._h, out)
         return dict(zip(["refresh_ms", "estep_ms", "mid_ms", "mstep_ms", "finalize_ms", "iters", "sweeps", "side_list_pairs"], list(out)))
+
+    def counters(self) -> dict:
+        out = (C.c_int64 * 4)()
+        self._lib.mlf_b200_get_counters(self._h, out)
+        return dict(zip(["iters", "sweeps", "side_list_pairs", "kept_pairs"], [int(v) for v in out]))
 
     def launch_count(self) -> int:
         return int(self._lib.mlf_b200_launch_count(self._h))

@@ -169,6 +169,36 @@ def test_config2_1e6_d2_k8(oracle):
         em.finalize()
 
 
+@pytest.mark.parametrize("sigma_c,mp", [(8.0, 1.0), (8.0, 0.0), (1.0, 1.0), (1.0, 0.0)],
+                         ids=["separated_mp1", "separated_mp0", "overlapping_mp1", "overlapping_mp0"])
+def test_config3_trajectory_1e6_d16_k64(sigma_c, mp, oracle):
+    """full-trajectory parity at N=1e6 with the headline's d=16, K=64 -- on the bench mixture
+    (sigmaC=8: clusters ~45 sigma apart) and on a heavily overlapping one (sigmaC=1: every point has many live components,
+    the kept set of the covariance threshold is large and the side list is exercised), both minProba regimes."""
+    d, K, iters = 16, 64, 5
+    data = synth.make_mixture(d, K, 15625, sigma_c, 1.0, 3)
+    X = data["X"]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 3)
+    oMu, oCov, olam, otr = oracle.em_iterations(X, Mu0, Cov0, lam0, mp, iters)
+    em = make_em(X, K, mp, Mu0, Cov0, lam0)
+    assert "k_em16" in em.kernel_plan()
+    info, _ = em.step(iters)
+    assert info == 0, em.last_error()
+    check_against(em, oMu, oCov, olam, otr)
+    cnt = em.counters()
+    assert cnt["sweeps"] >= iters
+    # E-step with the final parameters on a sample + labels except near-ties
+    ns = 50000
+    info, P = em.getProba(X[:ns])
+    _, oP, _ = oracle.exp_step(X[:ns], em.Mu, em.Cov, em.lambda_)
+    assert info == 0 and np.abs(P - oP).max() <= 1e-10
+    info, cl = em.getClass(X[:ns])
+    bad = cl != oracle.get_class(oP)
+    if bad.any():
+        assert near_tie_mask(oracle, X[:ns], em.Mu, em.Cov, em.lambda_)[bad].all()
+    em.finalize()
+
+
 # ---- known-answer cases on the CUDA path (same analytic expectations as tests/test_oracle_kat.py) -------------------
 def test_kat_single_component_ms_squared():
     rng = np.random.default_rng(1)
@@ -742,9 +772,32 @@ def test_checkpoint_restore_continues_identically(tmp_path, oracle):
     np.testing.assert_array_equal(b.Cov, ref.Cov)
     np.testing.assert_array_equal(b.lambda_, ref.lambda_)
     assert b.sumLL == ref.sumLL and b.niter == 6
-    for o in (ref, a, b):
-        o.finalize()
     g.finalize()
+    # override rewrites existing datasets (H5Dopen_f) and fails on a file that does not hold them; without override the
+    # datasets must not exist yet (H5Dcreate_f) -- src/mlf_hdf5.f90:294-300
+    f = mlf_hdf5_file()
+    assert f.openFile(path, rw=True) == 0
+    assert f.pushState(b) != 0
+    assert f.pushState(b, override=True) == 0
+    np.testing.assert_array_equal(f.get("Mu"), b.Mu)
+    # a second object checkpointed into a group of the same file, as a sub-object would be (Hdf5PushSubObject, :657-669)
+    grp = f.getSubObject("second")
+    assert grp is not None and grp.pushState(a, override=True) != 0 and grp.pushState(a) == 0
+    grp.finalize()
+    f.finalize()
+    g = mlf_hdf5_file()
+    assert g.openFile(path, rw=False) == 0 and g.unsupported() == 0
+    assert sorted(g.names()) == sorted(["iPar", "rPar", "iVar", "rVar", "Mu", "Cov", "lambda"] + ["second/" + n for n in ["iPar", "rPar", "iVar", "rVar", "Mu", "Cov", "lambda"]])
+    gg = g.open_group("second")
+    c = mlf_algo_emgmm()
+    assert c.init(X, 1, 1.0, data_handler=gg) == 0 and c.niter == 3
+    assert c.step(3)[0] == 0
+    np.testing.assert_array_equal(c.Mu, ref.Mu)
+    assert c.sumLL == ref.sumLL
+    gg.finalize()
+    g.finalize()
+    for o in (ref, a, b, c):
+        o.finalize()
 
 
 def test_run_to_run_determinism():
@@ -1008,6 +1061,14 @@ def test_single_process_multi_gpu_object(devices, oracle):
     if devices:
         assert f"{len(devices)} shards" in em.kernel_plan()
     em.inject(Mu0, Cov0, lam0)
+    # inference BEFORE any step (round-1 advisor finding: the all-reduced moments behind the parameter pack were only
+    # ever produced inside step(), so getProba / getClass / labels on a multi-shard object hung at the peer barrier)
+    _, P0, _ = oracle.exp_step(X[:300], Mu0, Cov0, lam0)
+    info, Pq = em.getProba(X[:300])
+    assert info == 0 and np.abs(Pq - P0).max() <= 1e-11
+    info, cl0 = em.getClass(X[:300])
+    assert info == 0 and (cl0 == oracle.get_class(P0)).all()
+    assert em.labels().shape == (X.shape[0],)
     assert em.step(5)[0] == 0, em.last_error()
     check_against(em, oMu, oCov, olam, otr)
     assert em.global_points() == X.shape[0]
@@ -1025,6 +1086,27 @@ def test_single_process_multi_gpu_object(devices, oracle):
     em.set_seed(5)
     assert em.step(3)[0] == 0, em.last_error()
     assert np.isfinite(em.Mu).all() and em.niter == 3
+    em.finalize()
+
+
+def test_multi_object_with_empty_shards_joins_the_collectives(oracle):
+    """More shards than points: the empty shards must still take part in the all-reduced moments step that labels(),
+    ProbaC and getProba trigger (they used to return early and leave their peers waiting at the barrier)."""
+    rng = np.random.default_rng(4)
+    X = np.ascontiguousarray(np.concatenate([rng.standard_normal((3, 3)), 6.0 + rng.standard_normal((3, 3))]))
+    Mu0 = np.ascontiguousarray(X[[0, 5]] + 0.1)
+    Cov0 = np.tile(np.eye(3), (2, 1, 1))
+    lam0 = np.full(2, 0.5)
+    em = mlf_algo_emgmm()
+    assert em.init(X, 2, 0.0, devices=[0] * 8) == 0       # 6 points over 8 shards: two are empty
+    em.inject(Mu0, Cov0, lam0)
+    _, P0, _ = oracle.exp_step(X, Mu0, Cov0, lam0)
+    np.testing.assert_array_equal(em.labels(), oracle.get_class(P0))
+    assert em.ProbaC.shape == (2, 6)          # no E-step yet: zeros (src/unsupervised/mlf_emgmm.f90:119)
+    info, Pq = em.getProba(X)
+    assert info == 0 and np.abs(Pq - P0).max() <= 1e-12
+    assert em.step(2)[0] == 0, em.last_error()
+    assert np.abs(em.ProbaC.sum(0) - 1.0).max() <= 1e-13
     em.finalize()
 
 
