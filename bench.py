@@ -154,6 +154,75 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_infer(args):
+    """`--mode infer`: getClass / getProba on caller-owned HOST data through the C-ABI, pinned and
+    pageable, in points/s, next to the PCIe bound measured in the same run with plain pinned cudaMemcpy probes."""
+    import ctypes as C
+
+    import torch
+
+    from mlfortran_b200 import _lib, mlf_algo_emgmm, synth
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    d, K = args.dims, args.comps
+    nq = int(args.infer_points)
+    ntrain = min(nq, 4_000_000)
+    X, centres, _ = synth.make_mixture_device(d, K, nq, 0, nq, args.sigma_c, args.sigma_x, SEED, dev)
+    Mu0, Cov0, lam0 = synth.injected_init(centres, SEED)
+    em = mlf_algo_emgmm()
+    if em.init(X[:ntrain].contiguous(), K, args.min_proba) != 0:
+        raise SystemExit("bench.py: init failed")
+    em.inject(Mu0, Cov0, lam0)
+    em.step(2)
+    lib = _lib.load()
+    Xpin = torch.empty((nq, d), dtype=torch.float64, pin_memory=True)
+    Xpin.copy_(X)
+    torch.cuda.synchronize(dev)
+    Xpage = Xpin.numpy().copy()
+    cl_pin = torch.zeros(nq, dtype=torch.int32, pin_memory=True)
+    cl_page = np.zeros(nq, dtype=np.int32)
+    npb = min(nq, int(args.infer_proba_points))
+    P_pin = torch.empty((K, npb), dtype=torch.float64, pin_memory=True)
+    P_page = np.empty((K, npb))
+
+    def timed(fn, reps=3):
+        fn()
+        best = 1e30
+        for _ in range(reps):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            rc = fn()
+            torch.cuda.synchronize(dev)
+            best = min(best, time.perf_counter() - t0)
+            if rc != 0:
+                raise SystemExit(f"bench.py: inference call failed: {em.last_error()}")
+        return best
+
+    # PCIe probes: one pinned cudaMemcpy each way, same bytes as the calls move
+    dbuf = torch.empty((nq, d), dtype=torch.float64, device=dev)
+    dP = torch.empty((K, npb), dtype=torch.float64, device=dev)
+    t_h2d = timed(lambda: (dbuf.copy_(Xpin, non_blocking=True), 0)[1])
+    t_d2h = timed(lambda: (P_pin.copy_(dP, non_blocking=True), 0)[1])
+    h2d_gbs, d2h_gbs = 8 * nq * d / t_h2d * 1e-9, 8 * K * npb / t_d2h * 1e-9
+    res = {}
+    res["getClass_pinned"] = nq / timed(lambda: lib.mlf_getClass(em._h, Xpin.data_ptr(), cl_pin.data_ptr(), d, nq))
+    res["getClass_pageable"] = nq / timed(lambda: lib.mlf_getClass(em._h, Xpage.ctypes.data, cl_page.ctypes.data, d, nq))
+    res["getProba_pinned"] = npb / timed(lambda: lib.mlf_getProba(em._h, Xpin.data_ptr(), P_pin.data_ptr(), d, npb, K))
+    res["getProba_pageable"] = npb / timed(lambda: lib.mlf_getProba(em._h, Xpage.ctypes.data, P_page.ctypes.data, d, npb, K))
+    assert np.array_equal(cl_pin.numpy(), cl_page)
+    bound_class = 1.0 / (8 * d / (h2d_gbs * 1e9))                       # H2D of X bounds getClass (labels are 4 B/point)
+    bound_proba = 1.0 / max(8 * d / (h2d_gbs * 1e9), 8 * K / (d2h_gbs * 1e9))   # full duplex: the larger direction bounds getProba
+    line = {"metric": "inference on host data (points/s)", "mode": "infer", "unit": "points/s", "n_gpus": 1, "dtype": "f64",
+            "config": {"workload": f"getClass on {nq:.0e} / getProba on {npb:.0e} caller-owned host points, d={d} K={K}", "d": d, "K": K},
+            "value": res["getClass_pinned"], "results": res,
+            "pcie": {"h2d_gbs": h2d_gbs, "d2h_gbs": d2h_gbs, "bound_getClass": bound_class, "bound_getProba": bound_proba},
+            "frac_of_pcie_bound": {"getClass_pinned": res["getClass_pinned"] / bound_class, "getClass_pageable": res["getClass_pageable"] / bound_class,
+                                   "getProba_pinned": res["getProba_pinned"] / bound_proba, "getProba_pageable": res["getProba_pageable"] / bound_proba}}
+    print(json.dumps(line), flush=True)
+    em.finalize()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -170,6 +239,9 @@ def main():
     ap.add_argument("--sigma-x", type=float, default=SIGMA_X, help="cluster width scale (tests/test_emgmm.f90 sigmaX)")
     ap.add_argument("--cpu-points", type=int, default=1000000, help="bounded CPU sample for cpu_baseline / --impl reference (SURVEY 8d: N_cpu = 1e6)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
+    ap.add_argument("--mode", default="train", choices=["train", "infer"], help="infer: getClass / getProba throughput on host data (not the contract line)")
+    ap.add_argument("--infer-points", type=float, default=2e7)
+    ap.add_argument("--infer-proba-points", type=float, default=5e6)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -179,6 +251,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.mode == "infer":
+        if rank == 0:
+            run_infer(args)
         return
     if args.warmup < 3:
         args.warmup = max(args.warmup, 1)  # the driver's default is >= 3; tiny dev runs may pass less

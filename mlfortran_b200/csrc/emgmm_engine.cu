@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <thread>
 
 namespace mlfb200 {
 
@@ -45,6 +46,13 @@ EmgmmEngine::~EmgmmEngine() {
   if (dLabels_) cudaFree(dLabels_);
   for (auto& e : pev_)
     if (e) cudaEventDestroy(e);
+  free_infer_buffers();
+  for (InferBuf& b : inf_) {
+    if (b.in) cudaEventDestroy(b.in);
+    if (b.comp) cudaEventDestroy(b.comp);
+    if (b.out) cudaEventDestroy(b.out);
+  }
+  if (dst_) cudaStreamDestroy(dst_);
   if (own_stream_ && st_) cudaStreamDestroy(st_);
 }
 
@@ -208,9 +216,17 @@ int EmgmmEngine::ensure_amb_scratch() {
 
 // A sweep overflowed a side list: four times the capacity for the sweeps to come (the current iteration is repeated with
 // the exact threshold, which lists nothing).
-int EmgmmEngine::grow_amb_lists() {
+int EmgmmEngine::grow_amb_lists(int64_t longest) {
   if (amb_cap_ >= kAmbCapMax) return 0;
-  const int cap = std::min(kAmbCapMax, amb_cap_ * 4);
+  // room for the longest list this rank just saw (+25 %), at least four times the old capacity; never more than a quarter
+  // of the free device memory or 8 GB
+  size_t fr = 0, tot = 0;
+  if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); fr = 0; }
+  const int64_t budget = (int64_t)std::min<size_t>(fr / 4, (size_t)8 << 30) / ((int64_t)amb_lists_ * (int64_t)sizeof(AmbEntry));
+  int64_t want = std::max<int64_t>((int64_t)amb_cap_ * 4, longest + longest / 4 + 64);
+  want = std::min<int64_t>(std::min<int64_t>(want, kAmbCapMax), budget);
+  if (want <= amb_cap_) return 0;
+  const int cap = (int)want;
   AmbEntry* p = nullptr;
   if (cudaMalloc((void**)&p, (size_t)amb_lists_ * cap * sizeof(AmbEntry)) != cudaSuccess) {
     cudaGetLastError();   // not fatal: the protocol falls back to the repeated sweep
@@ -539,7 +555,7 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
   const int64_t nA = (int64_t)KP * g.DS, nB = (int64_t)KP * f.MSF;
   const double minW = 1e-3 / (double)(float)nglob_;  // 1d-3/real(NX)  (src/unsupervised/mlf_gaussian.f90:50)
   double* dFlags = dAB_ + nA + nB;                    // [listed pairs, overflowing lists] ride in the same all-reduce
-  std::vector<double> hA((size_t)nA + 0), hflag(3), tlo((size_t)KP), thi((size_t)KP), sk((size_t)K);
+  std::vector<double> hA((size_t)nA + 0), hflag(4), tlo((size_t)KP), thi((size_t)KP), sk((size_t)K);
   gamma_current_ = false;
   for (int64_t it = 0; it < niter; ++it) {
     cudaEvent_t* ev_ = prof ? &pev_[(size_t)6 * it] : nullptr;
@@ -566,15 +582,32 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
         if (k >= K) { lo = hi = INFINITY; }
         else if (exact) { lo = hi = minW * sk[(size_t)k]; }
         else {
-          double sp, rho;
-          if (s_prev_.empty()) { sp = (double)nglob_ / K; rho = 0.5; }
+          // Predictor of s_k = sum_i gamma_ik for the iteration under way.  EM moves s_k smoothly, so the last step is
+          // extrapolated (centre s + ds) and the half-width follows the *change* of the step (second difference), not the
+          // step itself: the band has to hold the finished s_k, and every pair whose responsibility falls inside it costs a
+          // side-list entry.  (The first version centred the band on the last s_k with half-width 8|ds|: on overlapping
+          // mixtures that listed 1e7..3e8 pairs per sweep and still missed.)  A component that missed gets a wider band
+          // (x4 per miss) until it hits again.
+          double c, hw;
+          if (s_prev_.empty()) { c = (double)nglob_ / K; hw = 0.5 * c; }
           else {
-            sp = s_prev_[(size_t)k];
-            rho = s_prev2_.empty() ? 0.25 : 8.0 * std::fabs(sp - s_prev2_[(size_t)k]) / std::max(std::fabs(sp), 1e-300);
-            rho = std::min(0.5, std::max(rho, 1e-6));
+            const double s1 = s_prev_[(size_t)k];
+            if (s_prev2_.empty()) { c = s1; hw = 0.25 * std::fabs(s1); }
+            else {
+              const double ds = s1 - s_prev2_[(size_t)k];
+              c = s1 + ds;
+              if (s_prev3_.empty()) hw = 2.0 * std::fabs(ds);
+              else {
+                const double dds = ds - (s_prev2_[(size_t)k] - s_prev3_[(size_t)k]);
+                hw = std::max(3.0 * std::fabs(dds), 0.125 * std::fabs(ds));
+              }
+            }
+            hw = std::max(hw, 1e-7 * std::fabs(c));
+            if (!band_widen_.empty()) hw *= band_widen_[(size_t)k];
+            hw = std::min(hw, 0.6 * std::fabs(c));
           }
-          lo = minW * sp * (1.0 - rho);
-          hi = minW * sp * (1.0 + rho);
+          lo = minW * std::max(c - hw, 0.0);
+          hi = minW * (c + hw);
         }
         tlo[(size_t)k] = lo; thi[(size_t)k] = hi;
       }
@@ -605,21 +638,24 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
       if (int r = allreduce(dAB_, nA + nB + 3)) return r;
       // verification needs s_k and the list flags on the host: one small D2H + sync per sweep
       CKE(cudaMemcpyAsync(hA.data(), dAB_, nA * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H statsA");
-      CKE(cudaMemcpyAsync(hflag.data(), dFlags, 3 * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H flags");
+      CKE(cudaMemcpyAsync(hflag.data(), dFlags, 4 * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H flags");
       CKE(cudaStreamSynchronize(st_), "sync");
       bool ok = hflag[1] == 0.0;
       int missed = 0;
+      if (!exact && band_widen_.size() != (size_t)K) band_widen_.assign((size_t)K, 1.0);
       for (int k = 0; k < K; ++k) {
         sk[(size_t)k] = hA[(size_t)k * g.DS];
         const double tau = minW * sk[(size_t)k];
-        if (!(tlo[(size_t)k] <= tau && tau <= thi[(size_t)k])) { ok = false; ++missed; }  // also catches NaN
+        const bool hit = tlo[(size_t)k] <= tau && tau <= thi[(size_t)k];   // false for NaN as well
+        if (!hit) { ok = false; ++missed; }
+        if (!exact) band_widen_[(size_t)k] = hit ? std::max(1.0, 0.5 * band_widen_[(size_t)k]) : std::min(256.0, 4.0 * band_widen_[(size_t)k]);
       }
       if (debug_ && rank_ == 0)
         fprintf(stderr, "mlfortran_b200[debug]: sweep %lld pass %d%s: listed pairs %.0f, overflowed lists %.0f (cap %d), kept pairs %.0f, "
                 "components outside the predicted band %d -> %s\n", (long long)it, pass, exact ? " (exact thresholds)" : "", hflag[0], hflag[1],
                 amb_cap_, hflag[2], missed, (ok || exact) ? "accepted" : "repeat with exact thresholds");
       if (!ok && !exact && hflag[1] != 0.0)
-        if (int r = grow_amb_lists()) return r;
+        if (int r = grow_amb_lists((int64_t)hflag[3])) return r;
       if (ok || exact) break;
       exact = true;  // s_k is known now: repeat the sweep with tlo == thi == minW*s_k (the side list stays empty)
     }
@@ -640,12 +676,91 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
     ++launches_;
     if (prof) cudaEventRecord(ev_[5], st_);
     times_.kept_pairs += (int64_t)hflag[2];
+    s_prev3_ = s_prev2_;
     s_prev2_ = s_prev_;
     s_prev_ = sk;
   }
   return 0;
 }
 
+namespace {
+// host copy on a few threads: a single thread moves ~10 GB/s, the PCIe link behind it 55
+void parallel_rows_copy(char* dst, size_t dst_pitch, const char* src, size_t src_pitch, size_t width, size_t rows) {
+  const size_t total = width * rows;
+  const int nt = total < (8u << 20) ? 1 : 4;
+  auto work = [&](int t) {
+    if (rows == 1) {
+      const size_t lo = total * t / nt, hi = total * (t + 1) / nt;
+      std::memcpy(dst + lo, src + lo, hi - lo);
+      return;
+    }
+    for (size_t r = rows * t / nt; r < rows * (t + 1) / nt; ++r) std::memcpy(dst + r * dst_pitch, src + r * src_pitch, width);
+  };
+  if (nt == 1) { work(0); return; }
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+}
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+}  // namespace
+
+void EmgmmEngine::free_infer_buffers() {
+  for (InferBuf& b : inf_) {
+    if (b.dX) cudaFree(b.dX);
+    if (b.dP) cudaFree(b.dP);
+    if (b.dL) cudaFree(b.dL);
+    if (b.hX) cudaFreeHost(b.hX);
+    if (b.hP) cudaFreeHost(b.hP);
+    if (b.hL) cudaFreeHost(b.hL);
+    b.dX = b.dP = b.hX = b.hP = nullptr;
+    b.dL = b.hL = nullptr;
+  }
+  inf_chunk_ = 0;
+  inf_hasP_ = inf_hasL_ = inf_hasHX_ = false;
+}
+
+// Persistent buffers of the streamed inference path: allocated at first use, kept for the object's lifetime, regrown only
+// when a call needs something the previous ones did not (responsibilities after labels-only calls, a larger chunk).
+int EmgmmEngine::ensure_infer_buffers(int64_t chunk, bool wantP, bool wantL, bool stageX) {
+  const int d = geom_.d, K = geom_.K;
+  if (chunk <= inf_chunk_ && (!wantP || inf_hasP_) && (!wantL || inf_hasL_) && (!stageX || inf_hasHX_)) return 0;
+  wantP |= inf_hasP_; wantL |= inf_hasL_; stageX |= inf_hasHX_;
+  chunk = std::max(chunk, inf_chunk_);
+  CKE(cudaStreamSynchronize(st_), "sync");
+  free_infer_buffers();
+  if (!dst_) CKE(cudaStreamCreateWithFlags(&dst_, cudaStreamNonBlocking), "cudaStreamCreate");
+  const int64_t ldq = ((chunk + 31) / 32) * 32;
+  for (InferBuf& b : inf_) {
+    CKE(cudaMalloc((void**)&b.dX, (size_t)chunk * d * sizeof(double)), "cudaMalloc inference X chunk");
+    if (stageX) CKE(cudaMallocHost((void**)&b.hX, (size_t)chunk * d * sizeof(double)), "cudaMallocHost inference X staging");
+    if (wantP) {
+      CKE(cudaMalloc((void**)&b.dP, (size_t)K * ldq * sizeof(double)), "cudaMalloc inference P chunk");
+      CKE(cudaMallocHost((void**)&b.hP, (size_t)K * chunk * sizeof(double)), "cudaMallocHost inference P staging");
+    }
+    if (wantL) {
+      CKE(cudaMalloc((void**)&b.dL, (size_t)chunk * sizeof(int32_t)), "cudaMalloc inference labels chunk");
+      CKE(cudaMallocHost((void**)&b.hL, (size_t)chunk * sizeof(int32_t)), "cudaMallocHost inference labels staging");
+    }
+    if (!b.in) {
+      CKE(cudaEventCreateWithFlags(&b.in, cudaEventDisableTiming), "cudaEventCreate");
+      CKE(cudaEventCreateWithFlags(&b.comp, cudaEventDisableTiming), "cudaEventCreate");
+      CKE(cudaEventCreateWithFlags(&b.out, cudaEventDisableTiming), "cudaEventCreate");
+    }
+  }
+  inf_chunk_ = chunk; inf_hasP_ = wantP; inf_hasL_ = wantL; inf_hasHX_ = stageX;
+  return 0;
+}
+
+// ExpStep on caller data (getProba / getClass, src/mlf_models.f90:239-249,302-313; src/unsupervised/mlf_emgmm.f90:161-171).
+// The query is streamed through two persistent chunk buffers on three streams: while chunk c is evaluated, chunk c+1 is on
+// its way to the device and the results of chunk c-1 on their way back.  Pinned caller memory is copied directly; pageable
+// memory goes through the object's own pinned staging buffers (host copies on four threads), so the PCIe link, not a
+// synchronous pageable copy, bounds the call.
 int EmgmmEngine::expectation(const double* Xq, bool on_device, int64_t nq, double* P_host, int32_t* labels_host) {
   CKE(cudaSetDevice(device_), "cudaSetDevice");
   if (nq <= 0) return 0;
@@ -653,39 +768,73 @@ int EmgmmEngine::expectation(const double* Xq, bool on_device, int64_t nq, doubl
   const Geom& g = geom_;
   const int d = g.d, K = g.K;
   if (int r = do_refresh()) return r;
-  const int64_t chunk = std::min<int64_t>(nq, (int64_t)1 << 20);
-  const int64_t ldq = ((chunk + 31) / 32) * 32;
-  double *dxq = nullptr, *dpq = nullptr;
-  int32_t* dlq = nullptr;
-  if (!on_device) CKE(cudaMalloc((void**)&dxq, (size_t)chunk * d * sizeof(double)), "cudaMalloc Xq");
-  CKE(cudaMalloc((void**)&dpq, (size_t)K * ldq * sizeof(double)), "cudaMalloc Pq");
-  if (labels_host) CKE(cudaMalloc((void**)&dlq, (size_t)chunk * sizeof(int32_t)), "cudaMalloc labels");
+  // chunk: ~128 MB of whichever of input / output is larger per point, at most 2^20 points
+  const int64_t per_pt = 8 * (int64_t)std::max(d, P_host ? K : 1);
+  int64_t chunk = std::min<int64_t>((int64_t)1 << 20, std::max<int64_t>(4096, ((int64_t)1 << 27) / per_pt));
+  if (const char* ic = getenv("MLF_B200_INFER_CHUNK")) chunk = std::max<int64_t>(32, atoll(ic));   // tests: many small chunks
+  chunk = std::min<int64_t>(((nq + 31) / 32) * 32, (chunk / 32) * 32);
+  const bool x_direct = on_device || is_pinned(Xq);
+  const bool p_direct = P_host && is_pinned(P_host);
+  const bool l_direct = labels_host && is_pinned(labels_host);
+  if (int r = ensure_infer_buffers(chunk, P_host != nullptr, labels_host != nullptr, !x_direct)) return r;
+  chunk = std::min(chunk, inf_chunk_);
+  const int64_t ldq = ((inf_chunk_ + 31) / 32) * 32;
+  // hand the staged results of the chunk that used buffer b to the caller
+  auto drain = [&](InferBuf& b) -> int {
+    if (!b.pending) return 0;
+    CKE(cudaEventSynchronize(b.out), "sync inference D2H");
+    if (P_host && !p_direct)
+      parallel_rows_copy((char*)(P_host + b.s), (size_t)nq * sizeof(double), (const char*)b.hP, (size_t)b.n * sizeof(double), (size_t)b.n * sizeof(double), K);
+    if (labels_host && !l_direct) std::memcpy(labels_host + b.s, b.hL, (size_t)b.n * sizeof(int32_t));
+    b.pending = false;
+    return 0;
+  };
+  // everything queued on the compute stream so far (refresh) precedes the first chunk's kernel by stream order
   int rc = 0;
-  for (int64_t s = 0; s < nq && rc == 0; s += chunk) {
-    const int64_t n = std::min(chunk, nq - s);
-    const double* xs = Xq + (size_t)s * d;
+  int64_t c = 0;
+  for (int64_t s0 = 0; s0 < nq && rc == 0; s0 += chunk, ++c) {
+    InferBuf& b = inf_[c & 1];
+    const int64_t n = std::min(chunk, nq - s0);
+    if ((rc = drain(b))) break;   // also guarantees that the buffer's previous kernel and copies are complete
+    const double* xs = Xq + (size_t)s0 * d;
     if (!on_device) {
-      cudaError_t e = cudaMemcpyAsync(dxq, xs, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice, st_);
-      if (e != cudaSuccess) { rc = fail("H2D Xq", e); break; }
-      xs = dxq;
+      const double* src = xs;
+      if (!x_direct) {
+        parallel_rows_copy((char*)b.hX, 0, (const char*)xs, 0, (size_t)n * d * sizeof(double), 1);
+        src = b.hX;
+      }
+      CKE(cudaMemcpyAsync(b.dX, src, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice, cst_), "H2D Xq chunk");
+      CKE(cudaEventRecord(b.in, cst_), "event");
+      CKE(cudaStreamWaitEvent(st_, b.in, 0), "wait");
+      xs = b.dX;
     }
-    rc = run_estep(xs, n, dpq, ldq, dlq, false);
-    if (rc) break;
+    if ((rc = run_estep(xs, n, P_host ? b.dP : nullptr, ldq, labels_host ? b.dL : nullptr, false))) break;
+    CKE(cudaEventRecord(b.comp, st_), "event");
+    CKE(cudaStreamWaitEvent(dst_, b.comp, 0), "wait");
     if (P_host) {
-      cudaError_t e = cudaMemcpy2DAsync(P_host + s, (size_t)nq * sizeof(double), dpq, (size_t)ldq * sizeof(double),
-                                        (size_t)n * sizeof(double), K, cudaMemcpyDeviceToHost, st_);
-      if (e != cudaSuccess) { rc = fail("D2H P", e); break; }
+      if (p_direct)
+        CKE(cudaMemcpy2DAsync(P_host + s0, (size_t)nq * sizeof(double), b.dP, (size_t)ldq * sizeof(double), (size_t)n * sizeof(double), K,
+                              cudaMemcpyDeviceToHost, dst_), "D2H P chunk");
+      else
+        CKE(cudaMemcpy2DAsync(b.hP, (size_t)n * sizeof(double), b.dP, (size_t)ldq * sizeof(double), (size_t)n * sizeof(double), K,
+                              cudaMemcpyDeviceToHost, dst_), "D2H P chunk");
     }
-    if (labels_host) {
-      cudaError_t e = cudaMemcpyAsync(labels_host + s, dlq, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st_);
-      if (e != cudaSuccess) { rc = fail("D2H labels", e); break; }
-    }
-    cudaError_t e = cudaStreamSynchronize(st_);
-    if (e != cudaSuccess) { rc = fail("sync", e); break; }
+    if (labels_host)
+      CKE(cudaMemcpyAsync(l_direct ? labels_host + s0 : b.hL, b.dL, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, dst_), "D2H labels chunk");
+    CKE(cudaEventRecord(b.out, dst_), "event");
+    // the next use of this buffer's device memory (H2D of chunk c+2 on the copy stream) must follow this chunk's kernel and copies
+    CKE(cudaStreamWaitEvent(cst_, b.out, 0), "wait");
+    b.s = s0; b.n = n; b.pending = true;
   }
-  if (dxq) cudaFree(dxq);
-  cudaFree(dpq);
-  if (dlq) cudaFree(dlq);
+  for (InferBuf& b : inf_) {
+    const int r = drain(b);
+    if (rc == 0) rc = r;
+  }
+  if (rc != 0) {   // leave no copy in flight into buffers the caller owns
+    cudaStreamSynchronize(cst_); cudaStreamSynchronize(st_);
+    if (dst_) cudaStreamSynchronize(dst_);
+    for (InferBuf& b : inf_) b.pending = false;
+  }
   return rc;
 }
 

@@ -148,15 +148,16 @@ class EmgmmEngine {
   AmbEntry* dAmb_ = nullptr;
   int* dAmbCount_ = nullptr;
   int amb_cap_ = 2048;          // entries per list; grown (x4, up to kAmbCapMax) when a sweep overflows a list
-  static constexpr int kAmbCapMax = 32768;
+  static constexpr int kAmbCapMax = 262144;
   int amb_lists_ = 0;           // lists allocated (16 per block for the 16-warp sweep, 8 otherwise)
   int* dAmbComp_ = nullptr;     // k_amb_partial scratch: components present per list
   double* dAmbPart_ = nullptr;  //                       and their partial [scatter | sum g z | sum g]
   int amb_cmax_ = 8;
   bool debug_ = false;          // MLF_B200_DEBUG=1: one stderr line per sweep (threshold band / side list / repeat decisions)
   int ensure_amb_scratch();
-  int grow_amb_lists();
-  std::vector<double> s_prev_, s_prev2_;
+  int grow_amb_lists(int64_t longest);
+  std::vector<double> s_prev_, s_prev2_, s_prev3_;   // s_k of the last three iterations (threshold-band predictor)
+  std::vector<double> band_widen_;                  // per-component widening factor: x4 after a miss, halved after a hit
   int32_t* dLabels_ = nullptr;
   int egrid_ = 0, mgx_ = 0, mgy_ = 0;
   bool moments_ready_ = false;
@@ -169,6 +170,20 @@ class EmgmmEngine {
   bool cov_diag_ = false;
   int64_t launches_ = 0;
   std::vector<cudaEvent_t> pev_;  // 6 profiling events per iteration (only when set_profile(true))
+  // streamed inference on caller data (expectation): persistent double buffers, three streams (H2D copy, compute, D2H copy)
+  struct InferBuf {
+    double *dX = nullptr, *dP = nullptr, *hX = nullptr, *hP = nullptr;   // device chunk buffers; pinned staging (pageable callers)
+    int32_t *dL = nullptr, *hL = nullptr;
+    cudaEvent_t in = nullptr, comp = nullptr, out = nullptr;
+    int64_t s = 0, n = 0;   // chunk in flight whose staged output still has to be handed to the caller
+    bool pending = false;
+  };
+  InferBuf inf_[2];
+  int64_t inf_chunk_ = 0;
+  bool inf_hasP_ = false, inf_hasL_ = false, inf_hasHX_ = false;
+  cudaStream_t dst_ = nullptr;   // device -> host copies of inference results
+  int ensure_infer_buffers(int64_t chunk, bool wantP, bool wantL, bool stageX);
+  void free_infer_buffers();
 };
 
 }  // namespace mlfb200

@@ -642,18 +642,23 @@ cudaError_t launch_amb_resolve(const Geom& g, const double* X, const AmbEntry* a
 __global__ void __launch_bounds__(256) k_amb_summary(const int* __restrict__ counts, int nlists, int cap, double* __restrict__ flags,
                                                      const double* __restrict__ statsB, int KP, int MSF, int off) {
   __shared__ long long s_tot[256];
-  __shared__ int s_over[256];
+  __shared__ int s_over[256], s_max[256];
   long long tot = 0;
-  int over = 0;
+  int over = 0, mx = 0;
   for (int l = threadIdx.x; l < nlists; l += 256) {
     tot += counts[l];
     over += counts[l] > cap;
+    mx = max(mx, counts[l]);
   }
   s_tot[threadIdx.x] = tot;
   s_over[threadIdx.x] = over;
+  s_max[threadIdx.x] = mx;
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
-    if (threadIdx.x < s) { s_tot[threadIdx.x] += s_tot[threadIdx.x + s]; s_over[threadIdx.x] += s_over[threadIdx.x + s]; }
+    if (threadIdx.x < s) {
+      s_tot[threadIdx.x] += s_tot[threadIdx.x + s]; s_over[threadIdx.x] += s_over[threadIdx.x + s];
+      s_max[threadIdx.x] = max(s_max[threadIdx.x], s_max[threadIdx.x + s]);
+    }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
@@ -663,6 +668,7 @@ __global__ void __launch_bounds__(256) k_amb_summary(const int* __restrict__ cou
     if (statsB)
       for (int k = 0; k < KP; ++k) kept += statsB[(size_t)k * MSF + off];
     flags[2] = kept;
+    flags[3] = (double)s_max[0];   // longest list of THIS rank (outside the all-reduced range)
   }
 }
 cudaError_t launch_amb_summary(const int* counts, int nlists, int cap, double* flags, cudaStream_t st, const double* statsB, int KP, int MSF,

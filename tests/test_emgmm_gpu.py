@@ -707,6 +707,47 @@ def test_tiny_and_ragged_point_counts(n, oracle):
     em.finalize()
 
 
+@pytest.mark.parametrize("chunk", ["4096", "100000", None], ids=["chunk4096", "chunk100000", "default_chunk"])
+def test_streamed_inference_chunks_pinned_and_pageable(chunk, oracle, monkeypatch):
+    """getProba / getClass on caller data (src/mlf_models.f90:239-249,302-313): the query is streamed through two chunk
+    buffers on three streams; results must not depend on the chunking, on whether the caller's arrays are pinned or
+    pageable, on ragged tails, or on the order of proba / label calls (the buffers persist and regrow between calls)."""
+    import torch
+
+    if chunk:
+        monkeypatch.setenv("MLF_B200_INFER_CHUNK", chunk)
+    d, K = 5, 7
+    data = synth.make_mixture(d, K, 300, 3.0, 1.0, 77)
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 77)
+    em = make_em(data["X"], K, 0.0, Mu0, Cov0, lam0)
+    assert em.step(3)[0] == 0
+    rng = np.random.default_rng(3)
+    nq = 23457
+    Xq = np.ascontiguousarray(data["X"][rng.integers(0, data["X"].shape[0], nq)] + 0.3 * rng.standard_normal((nq, d)))
+    _, oP, _ = oracle.exp_step(Xq, em.Mu, em.Cov, em.lambda_)
+    ocl = oracle.get_class(oP)
+    tie = near_tie_mask(oracle, Xq, em.Mu, em.Cov, em.lambda_)
+    info, cl = em.getClass(Xq)                    # labels first: no responsibility buffers yet
+    assert info == 0 and ((cl == ocl) | tie).all()
+    info, P = em.getProba(Xq)                     # buffers regrow for the responsibilities
+    assert info == 0 and np.abs(P - oP).max() <= 1e-11
+    # pinned caller arrays take the direct-copy path
+    Xp = torch.empty((nq, d), dtype=torch.float64, pin_memory=True)
+    Xp.copy_(torch.from_numpy(Xq))
+    Pp = torch.empty((K, nq), dtype=torch.float64, pin_memory=True)
+    lib = _lib.load()
+    assert lib.mlf_getProba(em._h, Xp.data_ptr(), Pp.data_ptr(), d, nq, K) == 0
+    np.testing.assert_array_equal(Pp.numpy(), P)
+    clp = torch.zeros(nq, dtype=torch.int32, pin_memory=True)
+    assert lib.mlf_getClass(em._h, Xp.data_ptr(), clp.data_ptr(), d, nq) == 0
+    np.testing.assert_array_equal(clp.numpy(), cl)
+    for n in (1, 31, 4097):                        # ragged and tiny queries after a large one
+        info, Pn = em.getProba(Xq[:n])
+        assert info == 0 and np.array_equal(Pn, P[:, :n])
+    assert em.step(1)[0] == 0                      # the object keeps training afterwards
+    em.finalize()
+
+
 def test_empty_query_and_uninitialised_object():
     X = np.zeros((10, 2))
     em = mlf_algo_emgmm()
