@@ -300,8 +300,14 @@ def main():
     em = mlf_algo_emgmm()
     if em.init(X, K, args.min_proba, cov_type=args.cov_type) != 0:
         raise SystemExit("bench.py: init failed")
-    if world > 1:
-        em.set_allreduce(parallel.make_allreduce(None, dev), rank, world)
+    def attach(obj):
+        if world > 1:
+            if os.environ.get("MLF_BENCH_ALLREDUCE", "nccl") == "callback":   # A/B: Python callback over torch.distributed
+                obj.set_allreduce(parallel.make_allreduce(None, dev), rank, world)
+            else:                                                           # native: ncclAllReduce on the engine stream, no Python per iteration
+                parallel.attach_nccl(obj, rank, world, device=dev)
+
+    attach(em)
     em.inject(Mu0, Cov0, lam0)
     info, _ = em.step(args.warmup)
     if info < 0:
@@ -405,8 +411,7 @@ def main():
         em = mlf_algo_emgmm()
         if em.init(Xn, K, args.min_proba, device=local_rank, cov_type=args.cov_type) != 0:
             raise SystemExit("bench.py: e2e init failed")
-        if world > 1:
-            em.set_allreduce(parallel.make_allreduce(None, dev), rank, world)
+        attach(em)
         em.inject(Mu0, Cov0, lam0)
         em.step(1)  # warm-up
         barrier()

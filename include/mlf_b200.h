@@ -100,6 +100,16 @@ MLF_OBJ *mlf_b200_emgmm_create_multi(const double *X, int64_t nX, int nY, int nC
  * pointer buf, enqueued on CUDA stream `stream`.  The object then treats its X as one shard of the global data. */
 typedef int (*mlf_b200_allreduce_fn)(void *ctx, double *buf, int64_t count, void *stream);
 int mlf_b200_set_allreduce(MLF_OBJ *obj, mlf_b200_allreduce_fn fn, void *ctx, int rank, int world);
+/* Native NCCL instead of a callback (one process per GPU; libnccl.so.2 is dlopen'ed on first use, the library does not link
+ * it): the per-iteration statistics all-reduce becomes one ncclAllReduce(ncclDouble, ncclSum) on the object's stream.
+ *   mlf_b200_set_nccl_comm   borrow a communicator the caller built (ncclComm_t passed as void*); rank / world come from it;
+ *   mlf_b200_nccl_unique_id  rank 0 fills 128 bytes (ncclUniqueId) that the caller distributes (MPI_Bcast, a file, ...);
+ *   mlf_b200_nccl_init       every rank: ncclCommInitRank on the object's device with that id; the communicator belongs to the
+ *                            object and is destroyed by mlf_dealloc.
+ * All ranks must construct their objects with shards of one data set and call mlf_step the same number of times. */
+int mlf_b200_set_nccl_comm(MLF_OBJ *obj, void *nccl_comm);
+int mlf_b200_nccl_unique_id(void *id128);
+int mlf_b200_nccl_init(MLF_OBJ *obj, const void *id128, int rank, int world);
 
 int mlf_b200_set_initialized(MLF_OBJ *obj, int initialized); /* the Fortran API exposes %initialized directly */
 int mlf_b200_get_initialized(MLF_OBJ *obj);

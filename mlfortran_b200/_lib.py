@@ -44,6 +44,9 @@ SYMBOLS = {
     "mlf_b200_emgmm_create": (C.c_void_p, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_uint]),
     "mlf_b200_emgmm_create_multi": (C.c_void_p, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_void_p, c_int_p, C.c_int, C.c_uint]),
     "mlf_b200_set_allreduce": (C.c_int, [C.c_void_p, ALLREDUCE_FN, C.c_void_p, C.c_int, C.c_int]),
+    "mlf_b200_set_nccl_comm": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mlf_b200_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "mlf_b200_nccl_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "mlf_b200_set_initialized": (C.c_int, [C.c_void_p, C.c_int]),
     "mlf_b200_get_initialized": (C.c_int, [C.c_void_p]),
     "mlf_b200_set_seed": (C.c_int, [C.c_void_p, C.c_uint64]),

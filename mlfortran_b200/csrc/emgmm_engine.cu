@@ -555,7 +555,7 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
   const int64_t nA = (int64_t)KP * g.DS, nB = (int64_t)KP * f.MSF;
   const double minW = 1e-3 / (double)(float)nglob_;  // 1d-3/real(NX)  (src/unsupervised/mlf_gaussian.f90:50)
   double* dFlags = dAB_ + nA + nB;                    // [listed pairs, overflowing lists] ride in the same all-reduce
-  std::vector<double> hA((size_t)nA + 0), hflag(4), tlo((size_t)KP), thi((size_t)KP), sk((size_t)K);
+  std::vector<double> hA((size_t)nA + 0), hflag(4), tlo((size_t)KP), thi((size_t)KP), plo((size_t)KP), phi((size_t)KP), sk((size_t)K);
   gamma_current_ = false;
   for (int64_t it = 0; it < niter; ++it) {
     cudaEvent_t* ev_ = prof ? &pev_[(size_t)6 * it] : nullptr;
@@ -574,42 +574,50 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
       ++launches_;
     }
     if (prof) cudaEventRecord(ev_[1], st_);
-    // threshold band [tlo, thi] = minW * [s_lo, s_hi]; s_k predicted from the previous iterations
+    // ---- threshold band [plo, phi] = minW * (c -+ hw): s_k = sum_i gamma_ik predicted from the previous iterations ------
+    // In its smooth phase EM moves s_k steadily, so the last step is extrapolated (centre s + ds) and the half-width
+    // follows the CHANGE of the step (second difference): the band must hold the finished s_k, and every pair whose
+    // responsibility falls inside it costs a side-list entry.  In the violent phase (overlapping clusters under the
+    // reference's determinant sign, SURVEY fact 0.2: components halve or double per iteration) nothing predicts s_k; then
+    // the iteration is run as "statistics first": pass 0 with infinite thresholds (E-step + pass-A statistics only: no
+    // scatter, no list), pass 1 with the exact thresholds.  The prediction is still scored against the finished s_k, and
+    // the single-sweep mode returns after it would have held.
+    bool smooth = !s_prev2_.empty();
+    for (int k = 0; k < KP; ++k) {
+      double lo, hi;
+      if (k >= K) { lo = hi = INFINITY; }
+      else {
+        double c, hw;
+        if (s_prev_.empty()) { c = (double)nglob_ / K; hw = 0.5 * c; }
+        else {
+          const double s1 = s_prev_[(size_t)k];
+          if (s_prev2_.empty()) { c = s1; hw = 0.25 * std::fabs(s1); }
+          else {
+            const double ds = s1 - s_prev2_[(size_t)k];
+            if (!(std::fabs(ds) <= 0.05 * std::fabs(s1))) smooth = false;
+            c = s1 + ds;
+            if (s_prev3_.empty()) hw = 2.0 * std::fabs(ds);
+            else {
+              const double dds = ds - (s_prev2_[(size_t)k] - s_prev3_[(size_t)k]);
+              hw = std::max(3.0 * std::fabs(dds), 0.125 * std::fabs(ds));
+            }
+          }
+          hw = std::max(hw, 1e-7 * std::fabs(c));
+          if (band_widen_.size() == (size_t)K) hw *= band_widen_[(size_t)k];
+          hw = std::min(hw, 0.6 * std::fabs(c));
+        }
+        lo = minW * std::max(c - hw, 0.0);
+        hi = minW * (c + hw);
+      }
+      plo[(size_t)k] = lo; phi[(size_t)k] = hi;
+    }
+    const bool stats_first = !s_prev2_.empty() && (!smooth || band_misses_ > 0);
     bool exact = false;
     for (int pass = 0; pass < 2; ++pass) {
       for (int k = 0; k < KP; ++k) {
-        double lo, hi;
-        if (k >= K) { lo = hi = INFINITY; }
-        else if (exact) { lo = hi = minW * sk[(size_t)k]; }
-        else {
-          // Predictor of s_k = sum_i gamma_ik for the iteration under way.  EM moves s_k smoothly, so the last step is
-          // extrapolated (centre s + ds) and the half-width follows the *change* of the step (second difference), not the
-          // step itself: the band has to hold the finished s_k, and every pair whose responsibility falls inside it costs a
-          // side-list entry.  (The first version centred the band on the last s_k with half-width 8|ds|: on overlapping
-          // mixtures that listed 1e7..3e8 pairs per sweep and still missed.)  A component that missed gets a wider band
-          // (x4 per miss) until it hits again.
-          double c, hw;
-          if (s_prev_.empty()) { c = (double)nglob_ / K; hw = 0.5 * c; }
-          else {
-            const double s1 = s_prev_[(size_t)k];
-            if (s_prev2_.empty()) { c = s1; hw = 0.25 * std::fabs(s1); }
-            else {
-              const double ds = s1 - s_prev2_[(size_t)k];
-              c = s1 + ds;
-              if (s_prev3_.empty()) hw = 2.0 * std::fabs(ds);
-              else {
-                const double dds = ds - (s_prev2_[(size_t)k] - s_prev3_[(size_t)k]);
-                hw = std::max(3.0 * std::fabs(dds), 0.125 * std::fabs(ds));
-              }
-            }
-            hw = std::max(hw, 1e-7 * std::fabs(c));
-            if (!band_widen_.empty()) hw *= band_widen_[(size_t)k];
-            hw = std::min(hw, 0.6 * std::fabs(c));
-          }
-          lo = minW * std::max(c - hw, 0.0);
-          hi = minW * (c + hw);
-        }
-        tlo[(size_t)k] = lo; thi[(size_t)k] = hi;
+        if (k >= K || (pass == 0 && stats_first)) tlo[(size_t)k] = thi[(size_t)k] = INFINITY;
+        else if (exact) tlo[(size_t)k] = thi[(size_t)k] = minW * sk[(size_t)k];
+        else { tlo[(size_t)k] = plo[(size_t)k]; thi[(size_t)k] = phi[(size_t)k]; }
       }
       CKE(cudaMemcpyAsync(dTlo_, tlo.data(), KP * sizeof(double), cudaMemcpyHostToDevice, st_), "H2D tlo");
       CKE(cudaMemcpyAsync(dThi_, thi.data(), KP * sizeof(double), cudaMemcpyHostToDevice, st_), "H2D thi");
@@ -640,20 +648,24 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
       CKE(cudaMemcpyAsync(hA.data(), dAB_, nA * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H statsA");
       CKE(cudaMemcpyAsync(hflag.data(), dFlags, 4 * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H flags");
       CKE(cudaStreamSynchronize(st_), "sync");
-      bool ok = hflag[1] == 0.0;
+      bool ok = hflag[1] == 0.0 && !(pass == 0 && stats_first);
       int missed = 0;
       if (!exact && band_widen_.size() != (size_t)K) band_widen_.assign((size_t)K, 1.0);
       for (int k = 0; k < K; ++k) {
         sk[(size_t)k] = hA[(size_t)k * g.DS];
+        if (exact) continue;
+        // the prediction is scored in both modes (in statistics-first mode in hindsight)
         const double tau = minW * sk[(size_t)k];
-        const bool hit = tlo[(size_t)k] <= tau && tau <= thi[(size_t)k];   // false for NaN as well
+        const bool hit = plo[(size_t)k] <= tau && tau <= phi[(size_t)k];   // false for NaN as well
         if (!hit) { ok = false; ++missed; }
-        if (!exact) band_widen_[(size_t)k] = hit ? std::max(1.0, 0.5 * band_widen_[(size_t)k]) : std::min(256.0, 4.0 * band_widen_[(size_t)k]);
+        band_widen_[(size_t)k] = hit ? std::max(1.0, 0.5 * band_widen_[(size_t)k]) : std::min(256.0, 4.0 * band_widen_[(size_t)k]);
       }
+      if (!exact) band_misses_ = missed > 0 ? 2 : std::max(0, band_misses_ - 1);   // two clean iterations re-arm the single sweep
       if (debug_ && rank_ == 0)
-        fprintf(stderr, "mlfortran_b200[debug]: sweep %lld pass %d%s: listed pairs %.0f, overflowed lists %.0f (cap %d), kept pairs %.0f, "
-                "components outside the predicted band %d -> %s\n", (long long)it, pass, exact ? " (exact thresholds)" : "", hflag[0], hflag[1],
-                amb_cap_, hflag[2], missed, (ok || exact) ? "accepted" : "repeat with exact thresholds");
+        fprintf(stderr, "mlfortran_b200[debug]: iteration %lld pass %d (%s): listed pairs %.0f, overflowed lists %.0f (cap %d), kept pairs %.0f, "
+                "components outside the predicted band %d%s -> %s\n", (long long)it, pass,
+                exact ? "exact thresholds" : (stats_first ? "statistics only" : "predicted band"), hflag[0], hflag[1], amb_cap_, hflag[2], missed,
+                smooth ? "" : " (not smooth)", (ok || exact) ? "accepted" : "second pass with exact thresholds");
       if (!ok && !exact && hflag[1] != 0.0)
         if (int r = grow_amb_lists((int64_t)hflag[3])) return r;
       if (ok || exact) break;
@@ -687,7 +699,7 @@ namespace {
 // host copy on a few threads: a single thread moves ~10 GB/s, the PCIe link behind it 55
 void parallel_rows_copy(char* dst, size_t dst_pitch, const char* src, size_t src_pitch, size_t width, size_t rows) {
   const size_t total = width * rows;
-  const int nt = total < (8u << 20) ? 1 : 4;
+  const int nt = total < (8u << 20) ? 1 : (total < (64u << 20) ? 4 : 8);
   auto work = [&](int t) {
     if (rows == 1) {
       const size_t lo = total * t / nt, hi = total * (t + 1) / nt;
@@ -822,8 +834,8 @@ int EmgmmEngine::expectation(const double* Xq, bool on_device, int64_t nq, doubl
     if (labels_host)
       CKE(cudaMemcpyAsync(l_direct ? labels_host + s0 : b.hL, b.dL, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, dst_), "D2H labels chunk");
     CKE(cudaEventRecord(b.out, dst_), "event");
-    // the next use of this buffer's device memory (H2D of chunk c+2 on the copy stream) must follow this chunk's kernel and copies
-    CKE(cudaStreamWaitEvent(cst_, b.out, 0), "wait");
+    // (the next use of this buffer -- H2D of chunk c+2 -- is enqueued only after drain() has waited for b.out on the host, so
+    // no stream-side wait is needed; one on the copy stream would also hold back chunk c+1's upload into the OTHER buffer)
     b.s = s0; b.n = n; b.pending = true;
   }
   for (InferBuf& b : inf_) {

@@ -75,6 +75,7 @@ class EmgmmEngine {
   int K() const { return geom_.K; }
   const Geom& geom() const { return geom_; }
   cudaStream_t stream() const { return st_; }
+  int device() const { return device_; }
   const std::string& last_error() const { return err_; }
   // which kernel generation this (d, K) runs through (for bench output and logs)
   std::string plan() const;
@@ -157,6 +158,7 @@ class EmgmmEngine {
   int ensure_amb_scratch();
   int grow_amb_lists(int64_t longest);
   std::vector<double> s_prev_, s_prev2_, s_prev3_;   // s_k of the last three iterations (threshold-band predictor)
+  int band_misses_ = 0;                             // > 0: recent prediction miss -> statistics-first iterations
   std::vector<double> band_widen_;                  // per-component widening factor: x4 after a miss, halved after a hit
   int32_t* dLabels_ = nullptr;
   int egrid_ = 0, mgx_ = 0, mgy_ = 0;

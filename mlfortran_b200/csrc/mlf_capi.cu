@@ -16,6 +16,7 @@
 #include "emgmm_engine.h"
 #include "emgmm_multi.h"
 #include "mlf_hdf5_min.h"
+#include "mlf_nccl.h"
 
 using mlfb200::EmgmmEngine;
 using mlfb200::MultiEngine;
@@ -122,6 +123,12 @@ struct EmObject : Handle {
   std::vector<double> trace;
   std::string err, plan;
   int rank = 0, world = 1;
+  void* nccl_comm = nullptr;   // native NCCL all-reduce (mlf_b200_set_nccl_comm / mlf_b200_nccl_init)
+  bool nccl_owned = false;
+  ~EmObject() {
+    if (nccl_comm && nccl_owned)
+      if (const mlfb200::NcclApi* api = mlfb200::nccl_api()) api->CommDestroy(nccl_comm);
+  }
   uint64_t seed = 0x9E3779B97F4A7C15ull;
 
   int64_t& niter() { return iVar[0]; }
@@ -507,6 +514,56 @@ int mlf_b200_set_allreduce(MLF_OBJ* obj, mlf_b200_allreduce_fn fn, void* ctx, in
   o->eng.set_allreduce(fn, ctx, rank, world);
   o->rank = rank;
   o->world = world;
+  return 0;
+}
+
+// ---- native NCCL: the statistics all-reduce as a plain ncclAllReduce on the engine's stream -----------------------
+static int nccl_trampoline(void* ctx, double* buf, int64_t count, void* stream) {
+  EmObject* o = static_cast<EmObject*>(ctx);
+  const mlfb200::NcclApi* api = mlfb200::nccl_api();
+  if (!api || !o->nccl_comm) return -1;
+  const int r = api->AllReduce(buf, buf, (size_t)count, 8 /* ncclFloat64 */, 0 /* ncclSum */, o->nccl_comm, stream);
+  if (r != 0) fprintf(stderr, "mlfortran_b200: ncclAllReduce failed: %s\n", api->GetErrorString ? api->GetErrorString(r) : "?");
+  return r == 0 ? 0 : -1;
+}
+
+int mlf_b200_nccl_unique_id(void* id128) {
+  const mlfb200::NcclApi* api = mlfb200::nccl_api();
+  if (!api || !id128) return -1;
+  return api->GetUniqueId(id128) == 0 ? 0 : mlf_OTHERERROR;
+}
+
+int mlf_b200_set_nccl_comm(MLF_OBJ* obj, void* comm) {
+  EmObject* o = as_em(obj);
+  const mlfb200::NcclApi* api = mlfb200::nccl_api();
+  if (!o || o->multi || !api || !comm) return -1;
+  int rank = 0, world = 1;
+  if (api->CommUserRank(comm, &rank) != 0 || api->CommCount(comm, &world) != 0) return mlf_OTHERERROR;
+  if (o->nccl_comm && o->nccl_owned) api->CommDestroy(o->nccl_comm);
+  o->nccl_comm = comm;
+  o->nccl_owned = false;
+  o->eng.set_allreduce(&nccl_trampoline, o, rank, world);
+  o->rank = rank;
+  o->world = world;
+  return 0;
+}
+
+int mlf_b200_nccl_init(MLF_OBJ* obj, const void* id128, int rank, int world) {
+  EmObject* o = as_em(obj);
+  const mlfb200::NcclApi* api = mlfb200::nccl_api();
+  if (!o || o->multi || !api || !id128 || world < 1 || rank < 0 || rank >= world) return -1;
+  mlfb200::NcclApi::UniqueId id;
+  std::memcpy(id.b, id128, sizeof id.b);
+  if (cudaSetDevice(o->eng.device()) != cudaSuccess) return mlf_OTHERERROR;
+  void* comm = nullptr;
+  const int r = api->CommInitRank(&comm, world, id, rank);
+  if (r != 0) {
+    fprintf(stderr, "mlfortran_b200: ncclCommInitRank failed: %s\n", api->GetErrorString ? api->GetErrorString(r) : "?");
+    return mlf_OTHERERROR;
+  }
+  const int rc = mlf_b200_set_nccl_comm(obj, comm);
+  if (rc != 0) { api->CommDestroy(comm); return rc; }
+  o->nccl_owned = true;
   return 0;
 }
 

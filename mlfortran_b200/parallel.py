@@ -2,9 +2,16 @@
 
 The reference has no distributed layer (OpenMP over components only, src/unsupervised/mlf_emgmm.f90:179,199).
 Every E/M quantity is a sum over points, so points are partitioned into contiguous shards and the engine
-all-reduces two small fp64 buffers per iteration (pass-A statistics K*(2+d), pass-B scatter K*d*d) plus the
-global moments once.  This module only supplies the partition arithmetic and the all-reduce callback; the
-engine decides what to reduce.
+all-reduces ONE small fp64 buffer per iteration on the single-sweep path -- pass-A statistics, thresholded scatter and
+the side-list flags together, 144 KB at d=16, K=64 -- plus a second, tiny one only when pairs were listed (the two-pass
+shapes, d > 16, reduce pass-A statistics and scatter separately), and the global moments once per data set.
+
+Two ways to supply the collective, both leaving the decision of WHAT to reduce to the engine:
+  * attach_nccl(em, ...)   native: the library dlopens libnccl.so.2, builds its own communicator from a 128-byte id
+                           that torch.distributed only has to broadcast once, and every iteration's all-reduce is a
+                           plain ncclAllReduce on the engine's stream -- no Python in the iteration loop;
+  * make_allreduce(...)    a Python callback over torch.distributed (gloo for the CPU tests of the host logic, NCCL as
+                           a fallback).
 """
 from __future__ import annotations
 
@@ -54,3 +61,24 @@ def make_allreduce(group=None, device=None):
         return 0
 
     return fn
+
+
+def attach_nccl(em, rank: int, world: int, group=None, device=None) -> None:
+    """Native NCCL all-reduce for a one-process-per-GPU job: rank 0 draws an ncclUniqueId through the library
+    (mlf_b200_nccl_unique_id), torch.distributed broadcasts those 128 bytes once, and every rank joins with
+    mlf_b200_nccl_init.  A C or Fortran caller does the same with MPI_Bcast."""
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib
+
+    lib = _lib.load()
+    buf = (C.c_ubyte * 128)()
+    if rank == 0 and lib.mlf_b200_nccl_unique_id(buf) != 0:
+        raise RuntimeError("mlf_b200_nccl_unique_id failed (libnccl.so.2 not loadable?)")
+    t = torch.tensor(list(buf), dtype=torch.uint8, device=device if device is not None else "cpu")
+    dist.broadcast(t, src=0, group=group)
+    ident = (C.c_ubyte * 128)(*t.cpu().tolist())
+    rc = lib.mlf_b200_nccl_init(em._h, ident, rank, world)
+    if rc != 0:
+        raise RuntimeError(f"mlf_b200_nccl_init failed with {rc}")

@@ -737,13 +737,13 @@ def test_streamed_inference_chunks_pinned_and_pageable(chunk, oracle, monkeypatc
     Pp = torch.empty((K, nq), dtype=torch.float64, pin_memory=True)
     lib = _lib.load()
     assert lib.mlf_getProba(em._h, Xp.data_ptr(), Pp.data_ptr(), d, nq, K) == 0
-    np.testing.assert_array_equal(Pp.numpy(), P)
+    assert np.abs(Pp.numpy() - P).max() <= 1e-13   # (each call refreshes the parameter pack: warm-started Jacobi, last-bit differences)
     clp = torch.zeros(nq, dtype=torch.int32, pin_memory=True)
     assert lib.mlf_getClass(em._h, Xp.data_ptr(), clp.data_ptr(), d, nq) == 0
-    np.testing.assert_array_equal(clp.numpy(), cl)
+    assert ((clp.numpy() == cl) | tie).all()
     for n in (1, 31, 4097):                        # ragged and tiny queries after a large one
         info, Pn = em.getProba(Xq[:n])
-        assert info == 0 and np.array_equal(Pn, P[:, :n])
+        assert info == 0 and np.abs(Pn - P[:, :n]).max() <= 1e-13
     assert em.step(1)[0] == 0                      # the object keeps training afterwards
     em.finalize()
 
@@ -1084,6 +1084,25 @@ def test_two_shards_kmeans_initialiser(oracle):
     # every true centre is recovered (well-separated clusters, EM refines the k-means centres)
     dist = np.linalg.norm(Mu[:, None, :] - centres[None], axis=2)
     assert (dist.min(axis=0) < 0.5).all()
+
+
+def test_native_nccl_allreduce_world_of_one(oracle):
+    """mlf_b200_nccl_unique_id / mlf_b200_nccl_init: the library dlopens libnccl.so.2, builds its own communicator and the
+    statistics all-reduce of every iteration is a plain ncclAllReduce on the engine's stream (no callback).  One GPU here,
+    so the communicator has a single rank; bench.py runs the same path with 2..8 ranks."""
+    lib = _lib.load()
+    data = synth.make_mixture(4, 5, 400, 4.0, 1.0, 91)
+    X = data["X"]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 91)
+    oMu, oCov, olam, otr = oracle.em_iterations(X, Mu0, Cov0, lam0, 0.0, 4)
+    em = make_em(X, 5, 0.0, Mu0, Cov0, lam0)
+    ident = (C.c_ubyte * 128)()
+    assert lib.mlf_b200_nccl_unique_id(ident) == 0 and any(ident)
+    assert lib.mlf_b200_nccl_init(em._h, ident, 0, 1) == 0
+    assert lib.mlf_b200_nccl_init(em._h, ident, 1, 1) == -1        # rank outside the world
+    assert em.step(4)[0] == 0, em.last_error()
+    check_against(em, oMu, oCov, olam, otr)
+    em.finalize()                                                  # destroys the communicator the object owns
 
 
 # ---- single-process multi-GPU object (peer-memory all-reduce); on a one-GPU box the shards share the device ----------
