@@ -140,6 +140,12 @@ int mlf_b200_get_times(MLF_OBJ *obj, double out[8]);
  * over X, out[2] = pairs settled through the side list, out[3] = (point, component) pairs whose covariance term was accumulated
  * inside the sweep ("kept" by the reference's W >= minW test, src/mlf_matrix.f90:135; counted by the 16-warp sweep only). */
 int mlf_b200_get_counters(MLF_OBJ *obj, int64_t out[4]);
+/* The 16-warp sweep (d <= 16, K <= 64) evaluates the log-densities either by whitening the points or, when that is safe, as the
+ * expanded quadratic form c + b.x' - 1/2 x'^T invC x' about the data's mean (fewer tensor-core tiles, no squares / reduction).
+ * "Safe" is decided per refresh from a bound S_k on the magnitude of the form's terms over the data (rounding error ~ 4 u S_k,
+ * held against MLF_B200_QF_TOL = 5e-11 by default; MLF_B200_QF=0 always whitens, =2 never does).  *qf_sweeps = sweeps since the
+ * last counter reset that took the quadratic form, *bound = max_k S_k of the most recent sweep.  Either pointer may be NULL. */
+int mlf_b200_get_qf_stats(MLF_OBJ *obj, int64_t *qf_sweeps, double *bound);
 int64_t mlf_b200_launch_count(MLF_OBJ *obj);
 void *mlf_b200_stream(MLF_OBJ *obj);
 int64_t mlf_b200_global_points(MLF_OBJ *obj);

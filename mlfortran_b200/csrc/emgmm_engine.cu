@@ -32,7 +32,8 @@ EmgmmEngine::~EmgmmEngine() {
                     dStatsA_, dStatsB_, dPartA_, dPartB_, dSc_, dMean_, dNglob_};
   for (double* b : bufs)
     if (b) cudaFree(b);
-  double* fb[] = {dPack2_, dMuOld_, dTlo_, dThi_, dAB_, dPartB2_, dStatsC_, dPrevMu_, dPrevCov_, dPrevLambda_, dShift_, dMomPart_, dMomRaw_};
+  double* fb[] = {dPack2_, dMuOld_, dTlo_, dThi_, dAB_, dPartB2_, dStatsC_, dPrevMu_, dPrevCov_, dPrevLambda_, dShift_, dMomPart_, dMomRaw_,
+                  dPackQ_, dQfS_, dRad_, dRadPart_};
   for (auto& e : cev_)
     if (e) cudaEventDestroy(e);
   if (cst_) cudaStreamDestroy(cst_);
@@ -113,6 +114,13 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
     use16_ = fused_ && em16_ok(geom_, fgeom_, smem_limit_) && !(e16 && e16[0] == '0');
     const char* ed = getenv("MLF_B200_EMD");
     used_ = fused_ && cov_diag_ && emd_ok(geom_, fgeom_, smem_limit_) && !(ed && ed[0] == '0');
+    // quadratic-form logits inside the 16-warp sweep, guarded by the magnitude bounds of k_refresh
+    const char* q = getenv("MLF_B200_QF");
+    const int qmode = q ? atoi(q) : 1;
+    qf_ = use16_ && !used_ && !cov_diag_ && qmode != 0 && em16_qf_ok(geom_, fgeom_, smem_limit_);
+    double tol = 5e-11;
+    if (const char* qt = getenv("MLF_B200_QF_TOL")) tol = atof(qt);
+    qf_limit_ = qmode == 2 ? INFINITY : tol / (4.0 * 1.1102230246251565e-16);
   }
   n_ = n_local;
   nglob_ = n_local;
@@ -144,6 +152,11 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   CKE(A(&dMomPart_, (size_t)sms_ * std::max(g.MB * 64 + 8 * g.DN, d + 1)), "cudaMalloc");
   CKE(A(&dMomRaw_, (size_t)g.MB * 64 + 8 * g.DN), "cudaMalloc");
   CKE(cudaStreamCreateWithFlags(&cst_, cudaStreamNonBlocking), "cudaStreamCreate");
+  if (qf_) {
+    CKE(A(&dPackQ_, (size_t)g.K8 * qf_stride(g.DM)), "cudaMalloc");
+    CKE(A(&dQfS_, KP), "cudaMalloc");
+    CKE(A(&dRadPart_, (size_t)sms_ * 16), "cudaMalloc");
+  }
   CKE(A(&dPrevMu_, (size_t)K * d), "cudaMalloc");
   CKE(A(&dPrevCov_, (size_t)K * d * d), "cudaMalloc");
   CKE(A(&dPrevLambda_, K), "cudaMalloc");
@@ -241,8 +254,10 @@ int EmgmmEngine::grow_amb_lists(int64_t longest) {
 
 // InverseSymMatrix eigen branch + packing for both kernel generations (k_refresh).
 int EmgmmEngine::do_refresh(bool with_sumll) {
+  QfRefresh q{};
+  if (qf_) { q.packq = dPackQ_; q.qfS = dQfS_; q.rad = rad_ready_ ? dRad_ : nullptr; q.nrad = rad_world_; }
   CKE(launch_refresh(geom_, dMu_, dCov_, dLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_, dPack2_, dMuOld_,
-                     dShift_, with_sumll ? 1 : 0, cov_diag_ ? 1 : 0, &fgeom_, (refresh_count_ % 8 != 0) ? 1 : 0), "refresh");
+                     dShift_, with_sumll ? 1 : 0, cov_diag_ ? 1 : 0, &fgeom_, (refresh_count_ % 8 != 0) ? 1 : 0, qf_ ? &q : nullptr), "refresh");
   ++refresh_count_;  // every 8th refresh restarts the eigenvectors from the identity (bounds their orthogonality drift)
   ++launches_;
   return 0;
@@ -264,6 +279,7 @@ int EmgmmEngine::refresh_x(const double* X, bool x_on_device) {
     }
   }
   moments_ready_ = false;
+  rad_ready_ = false;
   if (!fused_) shift_ready_ = false;  // the shift is re-taken as the exact mean of the new data
   return 0;
 }
@@ -335,6 +351,26 @@ int EmgmmEngine::ensure_moments() {
   CKE(launch_moments(g, dX_, n_, dShift_, dMomPart_, grid, 0, st_), "moments");
   ++launches_;
   return finish_moments(grid);
+}
+
+// Radius of the resident data about the shift, per coordinate and rank (guard of the quadratic-form sweep).  COLLECTIVE like
+// ensure_moments: the per-rank maxima are gathered through the sum all-reduce (every rank fills its own slot of a zeroed
+// buffer), so that all ranks hold the same bounds and take the same decision.
+int EmgmmEngine::ensure_radius() {
+  if (!qf_ || rad_ready_) return 0;
+  if (rad_world_ < world_) {
+    if (dRad_) cudaFree(dRad_);
+    dRad_ = nullptr;
+    CKE(cudaMalloc((void**)&dRad_, (size_t)world_ * 16 * sizeof(double)), "cudaMalloc");
+    rad_world_ = world_;
+  }
+  CKE(cudaMemsetAsync(dRad_, 0, (size_t)rad_world_ * 16 * sizeof(double), st_), "memset");
+  const int grid = std::max(1, std::min<int>(sms_, (int)((n_ + 255) / 256)));
+  CKE(launch_absmax(dX_, n_, geom_.d, dShift_, dRadPart_, grid, dRad_ + (size_t)rank_ * 16, st_), "absmax");
+  launches_ += 2;
+  if (int r = allreduce(dRad_, (int64_t)rad_world_ * 16)) return r;
+  rad_ready_ = true;
+  return 0;
 }
 
 int EmgmmEngine::prepare() {
@@ -555,6 +591,7 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
   const int64_t nA = (int64_t)KP * g.DS, nB = (int64_t)KP * f.MSF;
   const double minW = 1e-3 / (double)(float)nglob_;  // 1d-3/real(NX)  (src/unsupervised/mlf_gaussian.f90:50)
   double* dFlags = dAB_ + nA + nB;                    // [listed pairs, overflowing lists] ride in the same all-reduce
+  std::vector<double> hQ((size_t)KP);
   std::vector<double> hA((size_t)nA + 0), hflag(4), tlo((size_t)KP), thi((size_t)KP), plo((size_t)KP), phi((size_t)KP), sk((size_t)K);
   gamma_current_ = false;
   for (int64_t it = 0; it < niter; ++it) {
@@ -568,6 +605,8 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
     // X was refreshed from host memory: its upload runs chunk by chunk underneath this iteration's first sweep, and the
     // global moments (hence sumLL) become final only after it
     const bool streamed = pending_host_ != nullptr;
+    if (!streamed)
+      if (int r = ensure_radius()) return r;
     if (int r = do_refresh(!streamed)) return r;
     if (!streamed) {
       CKE(launch_sum_k(dSumLLk_, K, dSumLL_ + it, st_), "sum_k");
@@ -627,6 +666,8 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
       a.gamma = nullptr; a.ldg = 0; a.labels = nullptr; a.raw = 0;
       a.partA = dPartA_; a.partB = dPartB2_; a.amb = dAmb_; a.amb_cap = amb_cap_; a.amb_count = dAmbCount_;
       a.accumulate = 0; a.p_offset = 0;
+      // quadratic-form logits when the bounds of this refresh allow (decided by the kernels); never while X is still arriving
+      a.packq = dPackQ_; a.qfS = dQfS_; a.qf_limit = (qf_ && rad_ready_ && !(streamed && pass == 0)) ? qf_limit_ : -1.0;
       if (streamed && pass == 0) {
         if (int r = streamed_sweep(a)) return r;
         CKE(launch_sumll(g, dMu_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, st_), "sumll");
@@ -647,7 +688,15 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
       // verification needs s_k and the list flags on the host: one small D2H + sync per sweep
       CKE(cudaMemcpyAsync(hA.data(), dAB_, nA * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H statsA");
       CKE(cudaMemcpyAsync(hflag.data(), dFlags, 4 * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H flags");
+      if (a.qf_limit >= 0.0) CKE(cudaMemcpyAsync(hQ.data(), dQfS_, KP * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H bounds");
       CKE(cudaStreamSynchronize(st_), "sync");
+      if (a.qf_limit >= 0.0) {   // the decision the blocks took (same rule), for the counters only
+        bool bad = false;
+        double mx = 0;
+        for (int k = 0; k < KP; ++k) { bad |= !(hQ[(size_t)k] <= a.qf_limit); mx = std::fmax(mx, hQ[(size_t)k]); if (hQ[(size_t)k] != hQ[(size_t)k]) mx = NAN; }
+        times_.qf_bound = mx;
+        if (!bad) times_.qf_sweeps += 1;
+      }
       bool ok = hflag[1] == 0.0 && !(pass == 0 && stats_first);
       int missed = 0;
       if (!exact && band_widen_.size() != (size_t)K) band_widen_.assign((size_t)K, 1.0);

@@ -21,6 +21,8 @@ struct EngineTimes {  // CUDA-event milliseconds accumulated over iterate() call
   int64_t sweeps = 0;     // fused path: sweeps over X (1 per iteration when the threshold band held, 2 otherwise)
   int64_t amb_pairs = 0;  // fused path: pairs settled through the side list
   int64_t kept_pairs = 0; // fused path (k_em16): (point, component) pairs whose scatter term was accumulated inside the sweep
+  int64_t qf_sweeps = 0;  // sweeps whose logits came from the expanded quadratic form (the others whitened the points)
+  double qf_bound = 0;    // max_k S_k of the last sweep (magnitude bound of the quadratic form's terms); inf: radius unknown
 };
 
 class EmgmmEngine {
@@ -35,7 +37,7 @@ class EmgmmEngine {
   // cov_diag: diagonal-covariance extension, fixed at construction so that the kernel plan can use the compressed pack
   int init(const double* X, bool x_on_device, int64_t n_local, int d, int K, int device, bool cov_diag = false);
   void set_allreduce(allreduce_fn fn, void* ctx, int rank, int world) {
-    ar_ = fn; ar_ctx_ = ctx; rank_ = rank; world_ = world < 1 ? 1 : world; moments_ready_ = false; shift_ready_ = false;
+    ar_ = fn; ar_ctx_ = ctx; rank_ = rank; world_ = world < 1 ? 1 : world; moments_ready_ = false; shift_ready_ = false; rad_ready_ = false;
   }
   void set_stream(cudaStream_t st);
   int refresh_x(const double* X, bool x_on_device);
@@ -160,6 +162,14 @@ class EmgmmEngine {
   std::vector<double> s_prev_, s_prev2_, s_prev3_;   // s_k of the last three iterations (threshold-band predictor)
   int band_misses_ = 0;                             // > 0: recent prediction miss -> statistics-first iterations
   std::vector<double> band_widen_;                  // per-component widening factor: x4 after a miss, halved after a hit
+  // quadratic-form variant of the 16-warp sweep (emgmm_kernels.cuh, qf_*): coefficient pack, per-component magnitude bounds,
+  // per-rank radius of the data about the shift (gathered), and the limit the bounds are held against
+  double *dPackQ_ = nullptr, *dQfS_ = nullptr, *dRad_ = nullptr, *dRadPart_ = nullptr;
+  int rad_world_ = 0;           // rank slots allocated in dRad_
+  bool qf_ = false;             // variant available for this shape (MLF_B200_QF=0 disables, =2 forces it whatever the bounds say)
+  bool rad_ready_ = false;
+  double qf_limit_ = 0;         // S_k <= qf_limit_  <=>  estimated logit error 4 u S_k <= MLF_B200_QF_TOL (default 5e-11)
+  int ensure_radius();
   int32_t* dLabels_ = nullptr;
   int egrid_ = 0, mgx_ = 0, mgy_ = 0;
   bool moments_ready_ = false;

@@ -59,8 +59,18 @@ constexpr int kTmemCols = 512;  // 4 warps per lane quarter x 8 components x 16 
 }  // namespace
 
 size_t em16_smem_bytes(const Geom& g, const FusedGeom& f) { return f.smem + (kExpTabN + 128) * sizeof(double) + 32; }
+// quadratic-form variant: the coefficient pack [K8][qf_stride] replaces the whitening pack; plus the feature table and the
+// shifted points of every warp ([16 warps x 8 points][4 DM + 4])
+size_t em16_qf_smem_bytes(const Geom& g, const FusedGeom& f) {
+  const size_t KP = (size_t)g.K8 * 8;
+  return em16_smem_bytes(g, f) - KP * f.PSF * sizeof(double) +
+         ((size_t)g.K8 * qf_stride(g.DM) + 2 * (size_t)qf_nsteps(g.DM) + 128 * (size_t)(4 * g.DM + 4)) * sizeof(double);
+}
 bool em16_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
   return f.GPW == 2 && !f.diag && g.DN <= 2 && g.K8 <= 8 && f.scatter_ok && em16_smem_bytes(g, f) <= smem_limit;
+}
+bool em16_qf_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
+  return em16_ok(g, f, smem_limit) && em16_qf_smem_bytes(g, f) <= smem_limit;
 }
 
 // VAR (MLF_B200_EM16_VAR, default 53; every variant produces the same bits):
@@ -83,9 +93,16 @@ bool em16_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
 // memory per tile instead of living in registers (+0.5 ms), eight instead of four exps in flight in P2 (+-0),
 // requesting the next component's scatter accumulators from tensor memory while the current one is updated (dynamic component
 // index instead of the unrolled loop: +1.4 ms).
-template <int DM, int VAR>
+// QF: logits by the expanded quadratic form (emgmm_kernels.cuh, qf_*) instead of whitening: the point's monomials are the
+// register-resident A operand (two passes of <= 19 k-steps at d = 16, half-way logits parked in the logit tile), the
+// coefficient fragments of 8 components the B operand, the accumulator is the logit.  Both variants are launched for a sweep;
+// each block decides from the bounds S_k left by k_refresh which of the two does the work (the other returns at once), so
+// the choice needs no host round trip.  Measured in isolation (bench/micro/p1_quadform.cu): 2.24 ms against 3.27 ms for the
+// whitening loop on the same points.
+template <int DM, int VAR, bool QF>
 __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   constexpr bool FOLD = (VAR & 1) != 0;
+  static_assert(!QF || FOLD, "the quadratic-form variant keeps 1/sum beside the tile");
   constexpr int PIPE = (VAR >> 1) & 3;
   constexpr int SPLIT = (VAR >> 3) & 3;   // trailing group barrier as a split mbarrier: 1 wait after the X loads are issued, 2 after the first DMMA group, 3 after the second
   constexpr bool PREF = (VAR & 32) != 0;  // the next tile's points are fetched into registers before the statistics phase
@@ -97,12 +114,21 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   constexpr int DS = 8 * DN + 2;
   constexpr int MSF = MB * 64 + 8 * DN + 2;
   constexpr int TP = 64;   // points per group tile
+  constexpr int D4 = 4 * DM, NF = qf_nsteps(DM), QS = qf_stride(DM), XQ = D4 + 4;
+  constexpr int NPASS = NF > 20 ? 2 : 1, NH = (NF + NPASS - 1) / NPASS;   // k-steps of the first pass (registers: 2 per k-step)
   extern __shared__ __align__(16) double smem[];
   const int K8 = A.K8, KP = K8 * 8, K4 = 2 * K8, S = A.S, d = A.d;
   const int64_t N = A.N;
-  double* sp = smem;                                  // [KP][PSF]
-  double* smu = sp + (size_t)KP * PSF;                // [KP][8 DN]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  {  // which variant sweeps: every S_k inside the limit -> quadratic form, otherwise (or NaN, or no limit) whitening
+    bool bad = !(A.qf_limit >= 0.0) || A.qfS == nullptr;
+    if (!bad)
+      for (int i = tid; i < KP; i += kThreads16) bad |= !(A.qfS[i] <= A.qf_limit);
+    const bool use_qf = __syncthreads_or(bad ? 1 : 0) == 0;
+    if (use_qf != QF) return;
+  }
+  double* sp = smem;                                  // [KP][PSF] whitening pack / [K8][QS] quadratic-form pack
+  double* smu = sp + (QF ? (size_t)K8 * QS : (size_t)KP * PSF);   // [KP][8 DN]
   const int cb = warp & 7, half = warp >> 3;   // half = group index
   const int wg = warp & 7;                      // warp index inside the group
   double* xs = smu + (size_t)KP * 8 * DN + (size_t)half * TP * XS;                    // [2][64][XS] raw points, per group
@@ -118,8 +144,20 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (tid < kExpTabN) etab[tid] = kExpTab[tid];
-
-  for (int i = tid; i < KP * PSF; i += kThreads16) sp[i] = A.pack2[i];
+  // QF: feature table (byte offsets of the two factors inside a staged point) and this warp's 8 staged points x' = x - shift
+  uint32_t* ftab = reinterpret_cast<uint32_t*>(etab + kExpTabN + 2 * TP + 4);                   // [4 NF]
+  double* xq = etab + kExpTabN + 2 * TP + 4 + 2 * NF + (size_t)(warp * 8 + g) * XQ;              // [16 x 8][XQ]
+  if (QF) {
+    for (int f = tid; f < 4 * NF; f += kThreads16) {
+      int i = 0, j = 0;
+      qf_feature(D4, f, i, j);
+      ftab[f] = (uint32_t)(8 * i) | ((uint32_t)(8 * j) << 16);
+    }
+    if (t == 0) { xq[D4] = 1.0; xq[D4 + 1] = 0.0; }
+    for (int i = tid; i < K8 * QS; i += kThreads16) sp[i] = A.packq[i];
+  } else {
+    for (int i = tid; i < KP * PSF; i += kThreads16) sp[i] = A.pack2[i];
+  }
   for (int i = tid; i < KP * 8 * DN; i += kThreads16) smu[i] = A.muold[i];
   double sh[DM];
 #pragma unroll
@@ -207,10 +245,40 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
       if (8 * DN > 4 * DM) xr[4 * DM + t] = 0.0;
     };
     if (SPLIT < 2) { wait_prev(); stage_x(); }
-#pragma unroll
-    for (int mb = 0; mb < DM; ++mb) xa[mb] = xraw[mb] - sh[mb];
     double* row = tile + (size_t)(wg * 8 + g) * S;
     double rmax = -INFINITY;
+    if constexpr (QF) {
+      // ---- P1 (quadratic form): monomials of the warp's 8 points x coefficient fragments of 8 components per DMMA ---------
+      __syncwarp();   // every lane is done with the previous tile's staged points
+#pragma unroll
+      for (int mb = 0; mb < DM; ++mb) xq[4 * mb + t] = xraw[mb] - sh[mb];
+      __syncwarp();
+      const char* xqb = reinterpret_cast<const char*>(xq);
+#pragma unroll
+      for (int pass = 0; pass < NPASS; ++pass) {
+        const int s0 = pass * NH, ns = pass == 0 ? NH : NF - NH;
+        double f[NH];
+#pragma unroll
+        for (int s = 0; s < NH; ++s)
+          if (s < ns) {
+            const uint32_t w = ftab[4 * (s0 + s) + t];
+            f[s] = *reinterpret_cast<const double*>(xqb + (w & 0xffffu)) * *reinterpret_cast<const double*>(xqb + (w >> 16));
+          }
+        for (int cq = 0; cq < K8; ++cq) {
+          const double* q = sp + (size_t)cq * QS;
+          const double2 v = pass == 0 ? *reinterpret_cast<const double2*>(q + NF * 32 + 2 * t) : *reinterpret_cast<const double2*>(row + 8 * cq + 2 * t);
+          double c[2] = {v.x, v.y};
+#pragma unroll
+          for (int s = 0; s < NH; ++s)
+            if (s < ns) dmma(c, f[s], q[(s0 + s) * 32 + lane]);
+          if (SPLIT >= 2 && pass == 0 && cq == 0) { wait_prev(); stage_x(); }
+          *reinterpret_cast<double2*>(row + 8 * cq + 2 * t) = make_double2(c[0], c[1]);
+          if (pass == NPASS - 1) rmax = fmax(rmax, fmax(c[0], c[1]));
+        }
+      }
+    } else {
+#pragma unroll
+    for (int mb = 0; mb < DM; ++mb) xa[mb] = xraw[mb] - sh[mb];
     // |u|^2 of the four components of group k4 for this thread's output columns
     auto comp4 = [&](int k4, double (&part)[4]) {
 #pragma unroll
@@ -290,15 +358,26 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
       }
       reduce4(K4 - 1, pb);
     }
+    }   // !QF
     // ---- P2: log-sum-exp over the components ---------------------------------------------------------------------
     rmax = fmax(rmax, shx(rmax, 1));
     rmax = fmax(rmax, shx(rmax, 2));
     double sum = 0;
+    if constexpr (QF) {   // each lane exponentiates the two logits per component block it wrote itself
+#pragma unroll 2
+      for (int cq = 0; cq < K8; ++cq) {
+        const double2 v = *reinterpret_cast<const double2*>(row + 8 * cq + 2 * t);
+        const double e0 = exp_tab(v.x - rmax, etab), e1 = exp_tab(v.y - rmax, etab);
+        *reinterpret_cast<double2*>(row + 8 * cq + 2 * t) = make_double2(e0, e1);
+        sum += e0; sum += e1;
+      }
+    } else {
 #pragma unroll 2
     for (int k4 = 0; k4 < K4; k4 += 2) {
       const double e0 = exp_tab(row[4 * k4 + t] - rmax, etab), e1 = exp_tab(row[4 * k4 + 4 + t] - rmax, etab);
       row[4 * k4 + t] = e0; row[4 * k4 + 4 + t] = e1;
       sum += e0; sum += e1;
+    }
     }
     sum += shx(sum, 1);
     sum += shx(sum, 2);
@@ -452,11 +531,22 @@ cudaError_t launch_em16(const Geom& g, const FusedGeom& f, const EmArgs& a, int 
   const size_t smem = em16_smem_bytes(g, f);
   const char* ev = getenv("MLF_B200_EM16_VAR");   // A/B switch, read per launch (tests flip it inside one process)
   const int var = ev ? atoi(ev) : 53;
+  // quadratic-form variant first (it returns at once unless every S_k is inside the limit), then the whitening variant
+  // (which returns at once in exactly that case)
+  const bool qf = a.qf_limit >= 0.0 && a.packq && a.qfS && em16_qf_ok(g, f, smem_limit);
+  const size_t smem_q = em16_qf_smem_bytes(g, f);
+  EmArgs aw = a;
+  if (!qf) { aw.qf_limit = -1.0; }
 #define MLF_E16V(DMv, V)                                                                                               \
   case 64 * DMv + V: {                                                                                                  \
-    cudaError_t e = cudaFuncSetAttribute(k_em16<DMv, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    if (qf) {                                                                                                           \
+      cudaError_t e = cudaFuncSetAttribute(k_em16<DMv, 53, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q); \
+      if (e != cudaSuccess) return e;                                                                                  \
+      k_em16<DMv, 53, true><<<grid, kThreads16, smem_q, st>>>(aw);                                                     \
+    }                                                                                                                   \
+    cudaError_t e = cudaFuncSetAttribute(k_em16<DMv, V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                                    \
-    k_em16<DMv, V><<<grid, kThreads16, smem, st>>>(a);                                                                 \
+    k_em16<DMv, V, false><<<grid, kThreads16, smem, st>>>(aw);                                                         \
   } break;
 #define MLF_E16(DMv) MLF_E16V(DMv, 0) MLF_E16V(DMv, 5) MLF_E16V(DMv, 21) MLF_E16V(DMv, 53)
   switch (64 * g.DM + (var & 63)) {

@@ -83,8 +83,11 @@ __global__ void __launch_bounds__(1024) k_refresh(Geom g, const double* __restri
                                                  double* __restrict__ pack, double* __restrict__ sumLLk,
                                                  int* __restrict__ info, double* __restrict__ pack2, double* __restrict__ muold,
                                                  int PSF, int OFFB2, int OFFC2, const double* __restrict__ shift, int do_sumll, int use_smem,
-                                                 int cov_diag, int diag_pack, int warm) {
+                                                 int cov_diag, int diag_pack, int warm, QfRefresh qf) {
   const int k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, d = g.d;
+  // quadratic-form pack (k_em16 QF variant): component k is column k % 8 of block k / 8, B-fragment order (lane = 4 column + k-index)
+  const int qNF = qf_nsteps(g.DM), qD4 = 4 * g.DM;
+  double* pq = qf.packq ? qf.packq + (size_t)(k >> 3) * qf_stride(g.DM) : nullptr;
   const int OFFMU = g.NB * 32, OFFC = OFFMU + 4 * g.DM;
   double* pk = pack + (size_t)k * g.PS;
   if (k >= g.K) {  // dummy component: contributes gamma = 0
@@ -95,6 +98,10 @@ __global__ void __launch_bounds__(1024) k_refresh(Geom g, const double* __restri
       double* p2 = pack2 + (size_t)k * PSF;
       for (int i = tid; i < PSF; i += nt) p2[i] = (i == OFFC2) ? -INFINITY : 0.0;
       for (int i = tid; i < 8 * g.DN; i += nt) muold[(size_t)k * 8 * g.DN + i] = 0.0;
+    }
+    if (pq) {
+      for (int f = tid; f < 4 * qNF; f += nt) pq[(f >> 2) * 32 + (k & 7) * 4 + (f & 3)] = 0.0;
+      if (tid == 0) { pq[qNF * 32 + (k & 7)] = -INFINITY; qf.qfS[k] = 0.0; }
     }
     return;
   }
@@ -229,6 +236,50 @@ __global__ void __launch_bounds__(1024) k_refresh(Geom g, const double* __restri
     W[i] = acc;
   }
   __syncthreads();
+  if (pq) {
+    // coefficients of the expanded quadratic form about the shift, straight from invC (both triangles, as the reference's
+    // z^T (invC z) reads them): linear invC mu', quadratic -1/2 invC_ii and -(invC_ij + invC_ji)/2, constant c_k - 1/2 mu'^T invC mu'
+    __shared__ double s_mp[16], s_b[16], s_r[16];
+    if (tid < 16) {
+      s_mp[tid] = (tid < d) ? Mu[(size_t)k * d + tid] - shift[tid] : 0.0;
+      double r = INFINITY;   // radius of the data about the shift, per coordinate; unknown => the guard rejects
+      if (qf.rad) {
+        r = 0.0;
+        for (int w = 0; w < qf.nrad; ++w) r = fmax(r, qf.rad[(size_t)w * 16 + tid]);
+      }
+      s_r[tid] = (tid < d) ? r : 0.0;
+    }
+    __syncthreads();
+    if (tid < 16) {
+      double acc = 0;
+      if (tid < d)
+        for (int e = 0; e < d; ++e) acc = fma(0.5 * (W[(size_t)e * d + tid] + W[(size_t)tid * d + e]), s_mp[e], acc);
+      s_b[tid] = acc;
+    }
+    __syncthreads();
+    double sabs = 0;
+    for (int f = tid; f < 4 * qNF; f += nt) {
+      int i, j;
+      qf_feature(qD4, f, i, j);
+      double th = 0.0, mag = 0.0;
+      if (i < d && j == qD4) { th = s_b[i]; mag = fabs(th) * s_r[i]; }
+      else if (i < d && j < d) {
+        th = (i == j) ? -0.5 * W[(size_t)i * d + i] : -0.5 * (W[(size_t)j * d + i] + W[(size_t)i * d + j]);
+        mag = fabs(th) * s_r[i] * s_r[j];
+      }
+      pq[(f >> 2) * 32 + (k & 7) * 4 + (f & 3)] = th;
+      sabs += mag;
+    }
+    sabs = block_sum(sabs, s_red);
+    if (tid == 0) {
+      double c2 = 0;
+      for (int a = 0; a < d; ++a) c2 = fma(s_b[a], s_mp[a], c2);
+      const double ckq = log(lambda[k]) - lnDet;
+      pq[qNF * 32 + (k & 7)] = ckq - 0.5 * c2;
+      qf.qfS[k] = sabs + fabs(0.5 * c2) + fabs(ckq);
+    }
+    __syncthreads();
+  }
   // in-place Cholesky W = L L^T (lower), right-looking
   for (int j = 0; j < d; ++j) {
     if (tid == 0) W[(size_t)j * d + j] = sqrt(W[(size_t)j * d + j]);
@@ -296,8 +347,10 @@ __global__ void __launch_bounds__(1024) k_refresh(Geom g, const double* __restri
 cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, const double* lambda, const double* Sc,
                            const double* mean, double Nglob, double* scratch, double* pack, double* sumLLk, int* info,
                            cudaStream_t st, double* pack2, double* muold, const double* shift, int do_sumll, int cov_diag,
-                           const FusedGeom* fg, int warm) {
+                           const FusedGeom* fg, int warm, const QfRefresh* qf) {
   const FusedGeom f = fg ? *fg : make_fused_geom(g);
+  QfRefresh q{};
+  if (qf && g.DM <= 4) q = *qf;
   const bool large = g.d > 32;
   const size_t dyn = large ? (size_t)g.d * g.d * sizeof(double) : 0;
   if (large) {
@@ -308,7 +361,7 @@ cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, c
   // loads in flight, so the block is as large as the register file allows
   k_refresh<<<g.K8 * 8, g.d > 64 ? 1024 : (large ? 256 : 128), dyn, st>>>(g, Mu, Cov, lambda, Sc, mean, Nglob, scratch, pack, sumLLk, info, pack2, muold,
                                                      f.PSF, f.OFFB, f.OFFC, shift ? shift : mean, do_sumll, large ? 1 : 0, cov_diag, f.diag ? 1 : 0,
-                                                     warm ? 1 : 0);
+                                                     warm ? 1 : 0, q);
   return cudaGetLastError();
 }
 
@@ -340,6 +393,50 @@ __global__ void __launch_bounds__(128) k_sumll(Geom g, const double* __restrict_
 cudaError_t launch_sumll(const Geom& g, const double* Mu, const double* Sc, const double* mean, double Nglob, const double* scratch,
                          const double* pack, double* sumLLk, cudaStream_t st) {
   k_sumll<<<g.K, 128, 0, st>>>(g, Mu, Sc, mean, Nglob, scratch, pack, sumLLk);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-coordinate radius of the data about the shift: max_i |x_ia - shift_a| (d <= 16).  Bounds the magnitude of the terms
+// of the expanded quadratic form (guard of the k_em16 QF variant).  One HBM pass, once per resident data set.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_absmax(const double* __restrict__ X, int64_t N, int d, const double* __restrict__ shift,
+                                                double* __restrict__ partial) {
+  __shared__ double red[8][16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ppw = 32 / d;                        // points per warp and load
+  const int pl = lane / d, a = lane - pl * d;    // lanes >= ppw*d idle
+  const bool on = pl < ppw;
+  const double sh = on ? shift[a] : 0.0;
+  double m = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * 8 * ppw;
+  for (int64_t p = ((int64_t)blockIdx.x * 8 + warp) * ppw + pl; p < N; p += stride)
+    if (on) m = fmax(m, fabs(X[p * d + a] - sh));   // fmax drops NaN: a NaN coordinate poisons the sweep either way
+  if (lane < 16) red[warp][lane] = 0.0;
+  __syncwarp();
+  // lanes of the same coordinate: combine through shared memory (ppw <= 32 values per coordinate and warp)
+  for (int q = 0; q < ppw; ++q) {
+    if (on && pl == q) red[warp][a] = fmax(red[warp][a], m);
+    __syncwarp();
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v = fmax(v, red[w][threadIdx.x]);
+    partial[(size_t)blockIdx.x * 16 + threadIdx.x] = v;
+  }
+}
+__global__ void k_absmax_finish(const double* __restrict__ partial, int grid, double* __restrict__ out) {
+  const int a = threadIdx.x;
+  if (a >= 16) return;
+  double v = 0.0;
+  for (int b = 0; b < grid; ++b) v = fmax(v, partial[(size_t)b * 16 + a]);
+  out[a] = v;
+}
+cudaError_t launch_absmax(const double* X, int64_t N, int d, const double* shift, double* partial, int grid, double* out, cudaStream_t st) {
+  if (d > 16) return cudaErrorInvalidConfiguration;
+  k_absmax<<<grid, 256, 0, st>>>(X, N, d, shift, partial);
+  k_absmax_finish<<<1, 32, 0, st>>>(partial, grid, out);
   return cudaGetLastError();
 }
 

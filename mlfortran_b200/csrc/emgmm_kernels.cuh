@@ -57,6 +57,39 @@ struct EmArgs {
   int accumulate;        // start from the partials / list counts already stored (chunked sweep of a streamed X)
   long long p_offset;    // index of X[0] inside the rank's shard (side-list keys)
   int hard;              // k-means assignment: one-hot responsibilities of the largest logit (E-pass variants only)
+  // expanded-quadratic-form logits of the 16-warp sweep (see qf_* below); qf_limit < 0: whitening only
+  const double* packq;   // [K8][qf_stride(DM)] coefficient fragments + the 8 constants of each component block
+  const double* qfS;     // [K8*8] magnitude bound S_k of the terms of component k's quadratic form over the data
+  double qf_limit;       // the sweep uses the quadratic form iff every S_k <= qf_limit (decided on the device, no host sync)
+};
+
+// ---- expanded quadratic form of the log-density (k_em16<.., QF = true>) ------------------------------------------------------------
+// logit_k(x) = c_k - 1/2 (x'-mu')^T invC_k (x'-mu')  with x' = x - shift, mu' = mu_k - shift
+//            = [c_k - 1/2 mu'^T invC mu'] + (invC mu') . x' - 1/2 x'^T invC x'
+// is ONE dot product of the component's coefficient vector with the point's monomials: D4 linear ones (x'_i) and the
+// D4 (D4+1)/2 products x'_i x'_j (i <= j), D4 = 4 DM padded coordinates.  At d = 16 that is 152 features = 38 DMMA k-steps
+// for 8 points x 8 components (4.75 DMMA per component instead of the 6 of the triangular whitening, and no squares or
+// quad reduction afterwards: the accumulator is the logit).  Its rounding error is u * S_k, S_k = sum of the magnitudes of
+// the terms (it grows with (distance from the shift / cluster width)^2, where whitening grows linearly), so the engine
+// bounds S_k per component at every refresh and the sweep falls back to whitening when the bound exceeds qf_limit.
+__host__ __device__ constexpr int qf_nfeat(int DM) { return 4 * DM + (4 * DM) * (4 * DM + 1) / 2; }
+__host__ __device__ constexpr int qf_nsteps(int DM) { return (qf_nfeat(DM) + 3) / 4; }
+__host__ __device__ constexpr int qf_stride(int DM) { return qf_nsteps(DM) * 32 + 8; }
+// feature f -> factors (i, j): coordinate indices into the padded point [x'_0 .. x'_{D4-1}, 1, 0]; f >= qf_nfeat: (D4+1, D4+1) = 0
+__host__ __device__ constexpr void qf_feature(int D4, int f, int& i, int& j) {
+  if (f < D4) { i = f; j = D4; return; }
+  int q = f - D4;
+  for (int r = 0; r < D4; ++r) {
+    if (q < D4 - r) { i = r; j = r + q; return; }
+    q -= D4 - r;
+  }
+  i = D4 + 1; j = D4 + 1;
+}
+struct QfRefresh {       // extra outputs of k_refresh for the quadratic-form sweep
+  double* packq;         // [K8][qf_stride(DM)]
+  double* qfS;           // [K8*8]
+  const double* rad;     // [nrad][16]: per-rank maxima of |x_a - shift_a| (gathered through the sum all-reduce); nullptr: unknown
+  int nrad;
 };
 
 constexpr int kEstepThreads = 256;      // 8 warps per persistent block
@@ -69,7 +102,9 @@ constexpr int kMstepTilePts = 2048;     // points per block tile of the M-pass s
 cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, const double* lambda, const double* Sc,
                            const double* mean, double Nglob, double* scratch, double* pack, double* sumLLk, int* info,
                            cudaStream_t st, double* pack2 = nullptr, double* muold = nullptr, const double* shift = nullptr,
-                           int do_sumll = 1, int cov_diag = 0, const FusedGeom* fg = nullptr, int warm = 0);
+                           int do_sumll = 1, int cov_diag = 0, const FusedGeom* fg = nullptr, int warm = 0, const QfRefresh* qf = nullptr);
+// max_i |x_ia - shift_a| per coordinate (d <= 16): partial[grid][16], then out[a] = max over blocks (16 values)
+cudaError_t launch_absmax(const double* X, int64_t N, int d, const double* shift, double* partial, int grid, double* out, cudaStream_t st);
 cudaError_t launch_sumll(const Geom& g, const double* Mu, const double* Sc, const double* mean, double Nglob, const double* scratch,
                          const double* pack, double* sumLLk, cudaStream_t st);
 // Global moments about `shift`: partial[grid][MB*64 + 8*DN]; finish turns the all-reduced sums into mean and centred scatter.
@@ -83,6 +118,7 @@ cudaError_t launch_em(const Geom& g, const FusedGeom& f, const EmArgs& a, bool s
 // 16-warp variant with the scatter accumulators in tensor memory (emgmm_fused16.cu): partials per (block, half) -> 2*grid slots,
 // side lists per warp -> 16*grid lists.
 bool em16_ok(const Geom& g, const FusedGeom& f, size_t smem_limit);
+bool em16_qf_ok(const Geom& g, const FusedGeom& f, size_t smem_limit);   // the quadratic-form variant fits shared memory
 cudaError_t launch_em16(const Geom& g, const FusedGeom& f, const EmArgs& a, int grid, size_t smem_limit, cudaStream_t st);
 // Diagonal-covariance extension at small d / large K on the fp64 CUDA cores (emgmm_diag.cu): lane = component.
 bool emd_ok(const Geom& g, const FusedGeom& f, size_t smem_limit);

@@ -667,6 +667,14 @@ int mlf_b200_get_counters(MLF_OBJ* obj, int64_t out[4]) {
   out[0] = t.iters; out[1] = t.sweeps; out[2] = t.amb_pairs; out[3] = t.kept_pairs;
   return 0;
 }
+int mlf_b200_get_qf_stats(MLF_OBJ* obj, int64_t* qf_sweeps, double* bound) {
+  EmObject* o = as_em(obj);
+  if (!o) return -1;
+  const mlfb200::EngineTimes t = o->multi ? o->multi->times() : o->eng.times();
+  if (qf_sweeps) *qf_sweeps = t.qf_sweeps;
+  if (bound) *bound = t.qf_bound;
+  return 0;
+}
 int64_t mlf_b200_launch_count(MLF_OBJ* obj) {
   EmObject* o = as_em(obj);
   return o ? (o->multi ? o->multi->launches() : o->eng.launches()) : -1;

@@ -419,6 +419,7 @@ def test_em16_scheduling_variants_are_bit_identical(oracle, monkeypatch):
     X = data["X"][: 29_003]
     Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 173)
     ref = None
+    monkeypatch.setenv("MLF_B200_QF", "0")   # the variants are whitening schedules; the quadratic-form sweep has its own tests
     for var in ("0", "5", "21", "53"):
         monkeypatch.setenv("MLF_B200_EM16_VAR", var)
         em = make_em(X, K, 1.0, Mu0, Cov0, lam0)
@@ -434,6 +435,89 @@ def test_em16_scheduling_variants_are_bit_identical(oracle, monkeypatch):
         else:
             for a, b in zip(got, ref):
                 assert np.array_equal(a, b), f"variant {var} differs from variant 0"
+
+
+# ---- expanded-quadratic-form logits of the 16-warp sweep ---------------------------------------------------------------------
+QF_CASES = [
+    # d, K, n_per_comp, sigma_c, minProba, iters
+    (16, 64, 500, 8.0, 1.0, 4),
+    (16, 24, 1237, 5.0, 0.0, 4),
+    (16, 64, 300, 1.0, 1.0, 4),
+    (13, 9, 301, 5.0, 0.5, 4),
+    (9, 17, 400, 4.0, 1.0, 3),
+    (8, 40, 250, 6.0, 0.0, 3),
+    (5, 3, 700, 3.0, 1.0, 5),
+    (2, 8, 5000, 6.0, 0.0, 5),
+    (1, 2, 77, 5.0, 0.0, 4),
+]
+
+
+@pytest.mark.parametrize("mode", ["2", "0"], ids=["quadratic_form_forced", "whitening_only"])
+@pytest.mark.parametrize("case", QF_CASES, ids=[f"d{c[0]}_K{c[1]}_sc{c[3]}_mp{c[4]}" for c in QF_CASES])
+def test_quadratic_form_and_whitening_sweeps_match_oracle(case, mode, oracle, monkeypatch):
+    """The 16-warp sweep has two ways to the log-densities: whitening (u = L^T(x-m) + bias, |u|^2) and the expanded quadratic
+    form c + b.x' - 1/2 x'^T invC x' (one dot product of coefficients with the point's monomials).  Both must give the oracle's
+    trajectory; MLF_B200_QF=2 / 0 force one or the other, and the counters say which one swept."""
+    d, K, npc, sc, mp, iters = case
+    monkeypatch.setenv("MLF_B200_QF", mode)
+    data = synth.make_mixture(d, K, npc, sc, 1.0, 1000 + d * K)
+    X = data["X"][: K * npc - 3]   # ragged tail tile
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 1000 + d)
+    oMu, oCov, olam, otr = oracle.em_iterations(X, Mu0, Cov0, lam0, mp, iters)
+    em = make_em(X, K, mp, Mu0, Cov0, lam0)
+    assert "k_em16" in em.kernel_plan()
+    em.set_profile(True)
+    info, _ = em.step(iters)
+    assert info == 0, em.last_error()
+    check_against(em, oMu, oCov, olam, otr)
+    q, c = em.qf_stats(), em.counters()
+    assert c["sweeps"] >= iters
+    assert q["qf_sweeps"] == (c["sweeps"] if mode == "2" else 0), (q, c)
+    em.finalize()
+
+
+def test_quadratic_form_guard(oracle, monkeypatch):
+    """Default mode: the sweep takes the quadratic form only while the magnitude bound of its terms keeps the estimated rounding
+    error of a logit under 5e-11.  The bench mixture (clusters ~45 sigma from the mean) passes; clusters 2e4 widths from the mean
+    (terms ~1e9, error ~1e-7 if expanded) must be whitened -- and both runs must still match the oracle."""
+    monkeypatch.delenv("MLF_B200_QF", raising=False)
+    d, K, iters = 16, 16, 3
+    for sc, expect_qf in ((8.0, True), (5000.0, False)):
+        data = synth.make_mixture(d, K, 400, sc, 1.0, 77)
+        X = data["X"]
+        Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 77)
+        oMu, oCov, olam, otr = oracle.em_iterations(X, Mu0, Cov0, lam0, 1.0, iters)
+        em = make_em(X, K, 1.0, Mu0, Cov0, lam0)
+        em.set_profile(True)
+        assert em.step(iters)[0] == 0, em.last_error()
+        check_against(em, oMu, oCov, olam, otr)
+        q, c = em.qf_stats(), em.counters()
+        assert (q["qf_sweeps"] == c["sweeps"]) if expect_qf else (q["qf_sweeps"] == 0), (sc, q, c)
+        assert np.isfinite(q["bound"]) and (q["bound"] <= 5e-11 / 4.5e-16) == expect_qf
+        em.finalize()
+
+
+def test_quadratic_form_accuracy_against_50_digit_arithmetic(monkeypatch):
+    """The quadratic-form sweep against the reference's formulas in 50-digit arithmetic at the guard's edge: d = 16, clusters ~100
+    widths from the data's mean (bound ~1e5), one iteration.  The parameters stay two orders inside the 1e-9 budget."""
+    from oracle import emgmm_mp
+
+    monkeypatch.setenv("MLF_B200_QF", "2")
+    d, K = 16, 3
+    data = synth.make_mixture(d, K, 40, 25.0, 1.0, 5)
+    X = data["X"]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 5)
+    mMu, mCov, mLam, mLL, _ = emgmm_mp.em_iteration(X, Mu0, Cov0, lam0, 1.0)
+    em = make_em(X, K, 1.0, Mu0, Cov0, lam0)
+    em.set_profile(True)
+    assert em.step(1)[0] == 0, em.last_error()
+    assert em.qf_stats()["qf_sweeps"] >= 1
+    eMu = np.array([[float(v) for v in r] for r in mMu])
+    eCov = np.array([[[float(v) for v in r] for r in Cm] for Cm in mCov])
+    eLam = np.array([float(v) for v in mLam])
+    assert abs(em.sumLL - float(mLL)) <= 1e-11 * abs(float(mLL))
+    assert rel(em.Mu, eMu) <= 1e-11 and rel(em.Cov, eCov) <= 1e-11 and np.abs(em.lambda_ - eLam).max() <= 1e-11
+    em.finalize()
 
 
 @pytest.mark.parametrize("env", [{"MLF_B200_EM16": "0"}, {"MLF_B200_LEGACY": "1"}], ids=["k_em_8warps", "first_generation"])
