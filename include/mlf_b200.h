@@ -146,6 +146,11 @@ int mlf_b200_get_counters(MLF_OBJ *obj, int64_t out[4]);
  * held against MLF_B200_QF_TOL = 5e-11 by default; MLF_B200_QF=0 always whitens, =2 never does).  *qf_sweeps = sweeps since the
  * last counter reset that took the quadratic form, *bound = max_k S_k of the most recent sweep.  Either pointer may be NULL. */
 int mlf_b200_get_qf_stats(MLF_OBJ *obj, int64_t *qf_sweeps, double *bound);
+/* Iterations (since the last counter reset) whose covariance thresholds could not be predicted and that therefore ran
+ * "statistics first": one sweep for the E-step and the pass-A statistics with the responsibilities kept in HBM (8 N K bytes,
+ * allocated at first need; MLF_B200_GSTORE=0 forbids it), then a scatter pass over the stored responsibilities with the exact
+ * thresholds -- instead of a second full sweep. */
+int64_t mlf_b200_scatter_passes(MLF_OBJ *obj);
 int64_t mlf_b200_launch_count(MLF_OBJ *obj);
 void *mlf_b200_stream(MLF_OBJ *obj);
 int64_t mlf_b200_global_points(MLF_OBJ *obj);

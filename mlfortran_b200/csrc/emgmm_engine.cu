@@ -33,7 +33,7 @@ EmgmmEngine::~EmgmmEngine() {
   for (double* b : bufs)
     if (b) cudaFree(b);
   double* fb[] = {dPack2_, dMuOld_, dTlo_, dThi_, dAB_, dPartB2_, dStatsC_, dPrevMu_, dPrevCov_, dPrevLambda_, dShift_, dMomPart_, dMomRaw_,
-                  dPackQ_, dQfS_, dRad_, dRadPart_};
+                  dPackQ_, dQfS_, dRad_, dRadPart_, dGTiles_};
   for (auto& e : cev_)
     if (e) cudaEventDestroy(e);
   if (cst_) cudaStreamDestroy(cst_);
@@ -353,6 +353,26 @@ int EmgmmEngine::ensure_moments() {
   return finish_moments(grid);
 }
 
+// HBM home of the responsibilities in statistics-first iterations ([tile][64][KP]); false (and the protocol keeps its second
+// full sweep) when disabled (MLF_B200_GSTORE=0) or when the allocation does not fit.
+bool EmgmmEngine::ensure_gtiles() {
+  if (dGTiles_) return true;
+  if (gtiles_failed_) return false;
+  const char* e = getenv("MLF_B200_GSTORE");
+  if (e && e[0] == '0') { gtiles_failed_ = true; return false; }
+  const size_t ntiles = (size_t)((n_ + 63) / 64);
+  const size_t bytes = std::max<size_t>(ntiles, 1) * 64 * (size_t)geom_.K8 * 8 * sizeof(double);
+  size_t fr = 0, tot = 0;
+  if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); fr = 0; }
+  if (bytes + ((size_t)2 << 30) > fr || cudaMalloc((void**)&dGTiles_, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    dGTiles_ = nullptr;
+    gtiles_failed_ = true;   // keep at least 2 GB of head room for the caller; fall back to the repeated sweep
+    return false;
+  }
+  return true;
+}
+
 // Radius of the resident data about the shift, per coordinate and rank (guard of the quadratic-form sweep).  COLLECTIVE like
 // ensure_moments: the per-rank maxima are gathered through the sum all-reduce (every rank fills its own slot of a zeroed
 // buffer), so that all ranks hold the same bounds and take the same decision.
@@ -651,8 +671,30 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
       plo[(size_t)k] = lo; phi[(size_t)k] = hi;
     }
     const bool stats_first = !s_prev2_.empty() && (!smooth || band_misses_ > 0);
+    // statistics-first iterations of the 16-warp sweep keep the responsibilities of pass 0 in HBM (8 N KP bytes, allocated at
+    // first need; 51 GB at N=1e8, K=64) so that pass 1 is a scatter from stored tiles instead of a second full sweep
+    const bool gstore = stats_first && !streamed && use16_ && ensure_gtiles();
     bool exact = false;
     for (int pass = 0; pass < 2; ++pass) {
+      if (gstore && pass == 1) {
+        for (int k = 0; k < KP; ++k) thi[(size_t)k] = k < K ? minW * sk[(size_t)k] : INFINITY;
+        CKE(cudaMemcpyAsync(dThi_, thi.data(), KP * sizeof(double), cudaMemcpyHostToDevice, st_), "H2D thi");
+        EmArgs a{};
+        a.X = dX_; a.N = n_; a.d = d; a.K = K; a.K8 = g.K8; a.S = g.S;
+        a.muold = dMuOld_; a.thi = dThi_; a.partB = dPartB2_; a.gtiles = dGTiles_; a.qf_limit = -1.0;
+        CKE(launch_scatter16(g, f, a, egrid_, smem_limit_, st_), "scatter pass (stored responsibilities)");
+        CKE(launch_reduce_partials(dPartB2_, nslots, nB, dAB_ + nA, st_), "reduce statsB");
+        CKE(launch_amb_summary(dAmbCount_, nlists, amb_cap_, dFlags, st_, dAB_ + nA, KP, f.MSF, g.MB * 64 + 8 * g.DN + 1), "amb summary");
+        launches_ += 3;
+        times_.scatter_passes += 1;
+        if (int r = allreduce(dAB_ + nA, nB + 3)) return r;
+        CKE(cudaMemcpyAsync(hflag.data(), dFlags, 4 * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H flags");
+        CKE(cudaStreamSynchronize(st_), "sync");
+        if (debug_ && rank_ == 0)
+          fprintf(stderr, "mlfortran_b200[debug]: iteration %lld pass 1 (scatter from stored responsibilities, exact thresholds): kept pairs %.0f -> accepted\n",
+                  (long long)it, hflag[2]);
+        break;
+      }
       for (int k = 0; k < KP; ++k) {
         if (k >= K || (pass == 0 && stats_first)) tlo[(size_t)k] = thi[(size_t)k] = INFINITY;
         else if (exact) tlo[(size_t)k] = thi[(size_t)k] = minW * sk[(size_t)k];
@@ -674,7 +716,8 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
         CKE(launch_sum_k(dSumLLk_, K, dSumLL_ + it, st_), "sum_k");
         launches_ += 2;
       } else {
-        if (use16_) CKE(launch_em16(g, f, a, egrid_, smem_limit_, st_), "em sweep (fused, 16 warps)");
+        a.gtiles = dGTiles_;
+        if (use16_) CKE(launch_em16(g, f, a, egrid_, smem_limit_, st_, gstore && pass == 0), "em sweep (fused, 16 warps)");
         else if (used_) CKE(launch_emd(g, f, a, egrid_, smem_limit_, st_), "em sweep (fused, diagonal)");
         else CKE(launch_em(g, f, a, true, egrid_, smem_limit_, st_), "em sweep (fused)");
         ++launches_;

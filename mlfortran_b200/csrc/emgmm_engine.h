@@ -21,6 +21,7 @@ struct EngineTimes {  // CUDA-event milliseconds accumulated over iterate() call
   int64_t sweeps = 0;     // fused path: sweeps over X (1 per iteration when the threshold band held, 2 otherwise)
   int64_t amb_pairs = 0;  // fused path: pairs settled through the side list
   int64_t kept_pairs = 0; // fused path (k_em16): (point, component) pairs whose scatter term was accumulated inside the sweep
+  int64_t scatter_passes = 0;  // statistics-first iterations whose second pass scattered from stored responsibilities
   int64_t qf_sweeps = 0;  // sweeps whose logits came from the expanded quadratic form (the others whitened the points)
   double qf_bound = 0;    // max_k S_k of the last sweep (magnitude bound of the quadratic form's terms); inf: radius unknown
 };
@@ -170,6 +171,9 @@ class EmgmmEngine {
   bool rad_ready_ = false;
   double qf_limit_ = 0;         // S_k <= qf_limit_  <=>  estimated logit error 4 u S_k <= MLF_B200_QF_TOL (default 5e-11)
   int ensure_radius();
+  double* dGTiles_ = nullptr;   // responsibilities of statistics-first iterations, [tile][64][K8*8]
+  bool gtiles_failed_ = false;
+  bool ensure_gtiles();
   int32_t* dLabels_ = nullptr;
   int egrid_ = 0, mgx_ = 0, mgy_ = 0;
   bool moments_ready_ = false;

@@ -98,9 +98,15 @@ bool em16_qf_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
 // coefficient fragments of 8 components the B operand, the accumulator is the logit.  Both variants are launched for a sweep;
 // each block decides from the bounds S_k left by k_refresh which of the two does the work (the other returns at once), so
 // the choice needs no host round trip.  Measured in isolation (bench/micro/p1_quadform.cu): 2.24 ms against 3.27 ms for the
-// whitening loop on the same points.
-template <int DM, int VAR, bool QF>
+// whitening loop on the same points; in the sweep at N=1e8, d=16, K=64: 95.2 ms against 116.9.  (QFM = 2 interleaves the
+// accumulator chains of two component blocks: 96.5 ms, not instantiated.)
+template <int DM, int VAR, int QFM, bool STORE>
 __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
+  // STORE: "statistics first" pass of an iteration whose covariance thresholds cannot be predicted: E-step + pass-A statistics
+  // only (no classification, no scatter), and the tile of finished responsibilities goes to HBM ([tile][64][KP], A.gtiles) for
+  // the scatter pass k_scatter16, which then knows the exact thresholds.
+  constexpr bool QF = QFM != 0;       // QFM: 0 whitening, 1 quadratic form, 2 quadratic form with the chains of two component blocks interleaved
+  constexpr int CH = QFM == 2 ? 2 : 1;
   constexpr bool FOLD = (VAR & 1) != 0;
   static_assert(!QF || FOLD, "the quadratic-form variant keeps 1/sum beside the tile");
   constexpr int PIPE = (VAR >> 1) & 3;
@@ -264,16 +270,31 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
             const uint32_t w = ftab[4 * (s0 + s) + t];
             f[s] = *reinterpret_cast<const double*>(xqb + (w & 0xffffu)) * *reinterpret_cast<const double*>(xqb + (w >> 16));
           }
-        for (int cq = 0; cq < K8; ++cq) {
-          const double* q = sp + (size_t)cq * QS;
-          const double2 v = pass == 0 ? *reinterpret_cast<const double2*>(q + NF * 32 + 2 * t) : *reinterpret_cast<const double2*>(row + 8 * cq + 2 * t);
-          double c[2] = {v.x, v.y};
+        for (int cq = 0; cq < K8; cq += CH) {
+          const double* q[CH];
+          double c[CH][2];
+          bool live[CH];
+#pragma unroll
+          for (int u = 0; u < CH; ++u) {
+            live[u] = cq + u < K8;   // odd K8: the last pair's second chain recomputes the last block and is not stored
+            const int cu = live[u] ? cq + u : K8 - 1;
+            q[u] = sp + (size_t)cu * QS;
+            const double2 v = pass == 0 ? *reinterpret_cast<const double2*>(q[u] + NF * 32 + 2 * t) : *reinterpret_cast<const double2*>(row + 8 * cu + 2 * t);
+            c[u][0] = v.x; c[u][1] = v.y;
+          }
 #pragma unroll
           for (int s = 0; s < NH; ++s)
-            if (s < ns) dmma(c, f[s], q[(s0 + s) * 32 + lane]);
+            if (s < ns) {
+#pragma unroll
+              for (int u = 0; u < CH; ++u) dmma(c[u], f[s], q[u][(s0 + s) * 32 + lane]);
+            }
           if (SPLIT >= 2 && pass == 0 && cq == 0) { wait_prev(); stage_x(); }
-          *reinterpret_cast<double2*>(row + 8 * cq + 2 * t) = make_double2(c[0], c[1]);
-          if (pass == NPASS - 1) rmax = fmax(rmax, fmax(c[0], c[1]));
+#pragma unroll
+          for (int u = 0; u < CH; ++u)
+            if (live[u]) {
+              *reinterpret_cast<double2*>(row + 8 * (cq + u) + 2 * t) = make_double2(c[u][0], c[u][1]);
+              if (pass == NPASS - 1) rmax = fmax(rmax, fmax(c[u][0], c[u][1]));
+            }
         }
       }
     } else {
@@ -387,6 +408,18 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
     } else {
       for (int k4 = 0; k4 < K4; ++k4) row[4 * k4 + t] *= inv;
     }
+    if constexpr (STORE) {   // this warp's 8 rows, normalised, as one coalesced 16-byte store per lane and row
+      __syncwarp();
+      double* go = A.gtiles + ((size_t)bt * TP + wg * 8) * KP;
+      if (2 * lane < KP) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const double2 v = *reinterpret_cast<const double2*>(tile + (size_t)(wg * 8 + r) * S + 2 * lane);
+          const double iv = invs[wg * 8 + r];
+          *reinterpret_cast<double2*>(go + (size_t)r * KP + 2 * lane) = make_double2(v.x * iv, v.y * iv);
+        }
+      }
+    }
     // the group's responsibilities and points are complete: 256-thread named barrier of this group only
     asm volatile("bar.sync %0, 256;\n" ::"r"(1 + half) : "memory");
     if (PREF) {
@@ -413,6 +446,7 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
         sg2 = fma(a, a, sg2);
 #pragma unroll
         for (int db = 0; db < DN; ++db) dmma(accA[db], a, b[db]);
+        if constexpr (STORE) continue;
         // "If(W(i) < minW0) CYCLE" (src/mlf_matrix.f90:135); g == 0 adds nothing and is never listed
         const bool hi = !(a < thi_r);
         const bool mid = !hi && !(a < tlo_r);
@@ -445,7 +479,7 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
       }
     }
     // ---- P3b: covariance scatter of this block's 8 components over the kept groups of the tile ----------------------
-    if (own) {
+    if (own && !STORE) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         unsigned pm = __ballot_sync(kFull, (act >> q) & 1u);
@@ -526,8 +560,202 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   }
 }
 
-cudaError_t launch_em16(const Geom& g, const FusedGeom& f, const EmArgs& a, int grid, size_t smem_limit, cudaStream_t st) {
+// Scatter pass of a "statistics first" iteration (see STORE above): the responsibilities of the sweep's tiles come back from HBM
+// (cp.async, two tile buffers per group: tile i+1 lands while tile i is scattered), the thresholds are exact, nothing is listed.
+// Same tile -> (block, group) assignment, warp -> component block assignment and instruction order of the accumulations as
+// P3 of k_em16, so the partials equal those of a repeated full sweep bit for bit.  HBM-bound when few pairs are kept
+// (8 (KP + d) bytes per point), DMMA-bound when most are (the dense d x d scatter of the reference's dsyrk).
+template <int DM>
+__global__ void __launch_bounds__(kThreads16, 1) k_scatter16(EmArgs A) {
+  constexpr int DN = (DM + 1) / 2;
+  constexpr int XS = 8 * DN + 4;
+  constexpr int MB = DN * (DN + 1) / 2;
+  constexpr int MSF = MB * 64 + 8 * DN + 2;
+  constexpr int TP = 64;
+  extern __shared__ __align__(16) double smem[];
+  const int K8 = A.K8, KP = K8 * 8, S = A.S, d = A.d;
+  const int64_t N = A.N;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int cb = warp & 7, half = warp >> 3, wg = warp & 7;
+  double* smu = smem;                                                     // [KP][8 DN]
+  double* xsb = smu + (size_t)KP * 8 * DN + (size_t)half * 2 * TP * XS;   // [2 groups][2 buffers][64][XS]
+  double* tlb = smu + (size_t)KP * 8 * DN + (size_t)4 * TP * XS + (size_t)half * 2 * TP * S;   // [2 groups][2 buffers][64][S]
+  uint32_t* s_taddr = reinterpret_cast<uint32_t*>(smu + (size_t)KP * 8 * DN + (size_t)4 * TP * XS + (size_t)4 * TP * S);
+  const bool own = cb < K8;
+  for (int i = tid; i < KP * 8 * DN; i += kThreads16) smu[i] = A.muold[i];
+  // padding of the point tiles (coordinates d .. 8 DN - 1) is never written by the copies: zero it once
+  for (int i = tid; i < 4 * TP * XS; i += kThreads16) smu[(size_t)KP * 8 * DN + i] = 0.0;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(s_taddr)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tbase = *s_taddr + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(128 * (warp >> 2));
+  const int slot = 2 * blockIdx.x + half;
+  double* outB = A.partB + (size_t)slot * KP * MSF;
+  double accK[DN][2], sk = 0.0;
+  int nk = 0;
+  const double thi_r = own ? fmax(A.thi[8 * cb + g], 4.9406564584124654e-324) : INFINITY;
+#pragma unroll
+  for (int b = 0; b < DN; ++b) { accK[b][0] = 0.0; accK[b][1] = 0.0; }
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+#pragma unroll
+    for (int b = 0; b < MB; ++b) tmem_st2(tbase + 16 * q + 4 * b, 0.0, 0.0);
+  tmem_wait_st();
+
+  const int64_t ntiles = (N + TP - 1) / TP;
+  const int64_t bt0 = 2 * (int64_t)blockIdx.x + half, btstep = 2 * (int64_t)gridDim.x;
+  // this warp copies its own 8 rows of the tile: responsibilities (KP doubles, 16-byte pieces) and points (d doubles, 8-byte pieces;
+  // rows past N are zero-filled by a zero source size)
+  auto fetch = [&](int64_t bt, int buf) {
+    const double* gsrc = A.gtiles + ((size_t)bt * TP + wg * 8) * KP;
+    double* tdst = tlb + (size_t)buf * TP * S + (size_t)(wg * 8) * S;
+    for (int i = lane; i < 8 * (KP / 2); i += 32) {
+      const int r = i / (KP / 2), c = i - r * (KP / 2);
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tdst + (size_t)r * S + 2 * c);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gsrc + (size_t)r * KP + 2 * c) : "memory");
+    }
+    double* xdst = xsb + (size_t)buf * TP * XS + (size_t)(wg * 8) * XS;
+    const int64_t p0 = bt * TP + wg * 8;
+    for (int i = lane; i < 8 * d; i += 32) {
+      const int r = i / d, a = i - r * d;
+      const bool in = p0 + r < N;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(xdst + (size_t)r * XS + a);
+      const double* src = A.X + (in ? (p0 + r) * d + a : 0);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(src), "r"(in ? 8 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  if (bt0 < ntiles) fetch(bt0, 0);
+  int buf = 0;
+  for (int64_t bt = bt0; bt < ntiles; bt += btstep, buf ^= 1) {
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    // tile bt is complete for every warp of the group, and every warp is done with the other buffer (tile bt - step)
+    asm volatile("bar.sync %0, 256;\n" ::"r"(1 + half) : "memory");
+    if (bt + btstep < ntiles) fetch(bt + btstep, buf ^ 1);
+    const double* tile = tlb + (size_t)buf * TP * S;
+    const double* xs = xsb + (size_t)buf * TP * XS;
+    unsigned act = 0;
+    if (own) {
+      const double* tcol = tile + 8 * cb + g;
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int pb = i;
+        const double a = tcol[(size_t)(4 * pb + t) * S];
+        const bool hi = !(a < thi_r);
+        const double ahi = hi ? a : 0.0;
+        sk += ahi;
+        nk += hi ? 1 : 0;
+        const unsigned mh = __ballot_sync(kFull, hi);
+        if (mh) {
+          double b[DN];
+#pragma unroll
+          for (int db = 0; db < DN; ++db) b[db] = xs[(size_t)(4 * pb + t) * XS + 8 * db + g];
+#pragma unroll
+          for (int db = 0; db < DN; ++db) dmma(accK[db], ahi, b[db]);
+          unsigned cm = mh | (mh >> 1);
+          cm |= cm >> 2;
+          cm &= 0x11111111u;
+          cm = (cm | (cm >> 3)) & 0x03030303u;
+          cm = (cm | (cm >> 6)) & 0x000f000fu;
+          cm = (cm | (cm >> 12)) & 0xffu;
+          if (lane == i) act = cm;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        unsigned pm = __ballot_sync(kFull, (act >> q) & 1u);
+        if (pm == 0) continue;
+        const double thq = __shfl_sync(kFull, thi_r, 4 * q);
+        const double* mq = smu + (size_t)(8 * cb + q) * 8 * DN;
+        double mu_q[DN];
+#pragma unroll
+        for (int ab = 0; ab < DN; ++ab) mu_q[ab] = mq[8 * ab + g];
+        const double* tq = tile + 8 * cb + q;
+        double acc[MB][2];
+#pragma unroll
+        for (int b = 0; b < MB; ++b) tmem_ld2(tbase + 16 * q + 4 * b, acc[b][0], acc[b][1]);
+        while (pm) {
+          const int pb = __ffs(pm) - 1;
+          pm &= pm - 1;
+          const double aq = tq[(size_t)(4 * pb + t) * S];
+          const double w = !(aq < thq) ? aq : 0.0;
+          double z[DN], wz[DN];
+#pragma unroll
+          for (int ab = 0; ab < DN; ++ab) {
+            z[ab] = xs[(size_t)(4 * pb + t) * XS + 8 * ab + g] - mu_q[ab];
+            wz[ab] = w * z[ab];
+          }
+#pragma unroll
+          for (int ab = 0; ab < DN; ++ab)
+#pragma unroll
+            for (int bb = 0; bb <= ab; ++bb) dmma(acc[ab * (ab + 1) / 2 + bb], wz[ab], z[bb]);
+        }
+#pragma unroll
+        for (int b = 0; b < MB; ++b) tmem_st2(tbase + 16 * q + 4 * b, acc[b][0], acc[b][1]);
+      }
+      tmem_wait_st();
+    }
+  }
+  if (own) {
+    double c = sk;
+    nk += __shfl_xor_sync(kFull, nk, 1); nk += __shfl_xor_sync(kFull, nk, 2);
+    c += shx(c, 1); c += shx(c, 2);
+    double* ok = outB + (size_t)(8 * cb + g) * MSF + MB * 64;
+    if (t == 0) { ok[8 * DN] = c; ok[8 * DN + 1] = (double)nk; }
+#pragma unroll
+    for (int db = 0; db < DN; ++db) {
+      ok[8 * db + 2 * t] = accK[db][0];
+      ok[8 * db + 2 * t + 1] = accK[db][1];
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      double* oq = outB + (size_t)(8 * cb + q) * MSF;
+#pragma unroll
+      for (int bq = 0; bq < MB; ++bq) {
+        double v0, v1;
+        tmem_ld2(tbase + 16 * q + 4 * bq, v0, v1);
+        oq[bq * 64 + g * 8 + 2 * t] = v0;
+        oq[bq * 64 + g * 8 + 2 * t + 1] = v1;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(*s_taddr), "n"(kTmemCols) : "memory");
+  }
+}
+
+size_t scatter16_smem_bytes(const Geom& g, const FusedGeom& f) {
+  return ((size_t)g.K8 * 8 * 8 * g.DN + 4 * 64 * (size_t)f.XS + 4 * 64 * (size_t)g.S + 2) * sizeof(double);
+}
+cudaError_t launch_scatter16(const Geom& g, const FusedGeom& f, const EmArgs& a, int grid, size_t smem_limit, cudaStream_t st) {
+  if (!em16_ok(g, f, smem_limit) || !a.gtiles) return cudaErrorInvalidConfiguration;
+  const size_t smem = scatter16_smem_bytes(g, f);
+  if (smem > smem_limit) return cudaErrorInvalidConfiguration;
+#define MLF_S16(DMv)                                                                                              \
+  case DMv: {                                                                                                     \
+    cudaError_t e = cudaFuncSetAttribute(k_scatter16<DMv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                               \
+    k_scatter16<DMv><<<grid, kThreads16, smem, st>>>(a);                                                          \
+  } break;
+  switch (g.DM) {
+    MLF_S16(1) MLF_S16(2) MLF_S16(3) MLF_S16(4)
+    default: return cudaErrorInvalidConfiguration;
+  }
+#undef MLF_S16
+  return cudaGetLastError();
+}
+
+cudaError_t launch_em16(const Geom& g, const FusedGeom& f, const EmArgs& a, int grid, size_t smem_limit, cudaStream_t st, bool store) {
   if (!em16_ok(g, f, smem_limit)) return cudaErrorInvalidConfiguration;
+  if (store && !a.gtiles) return cudaErrorInvalidConfiguration;
   const size_t smem = em16_smem_bytes(g, f);
   const char* ev = getenv("MLF_B200_EM16_VAR");   // A/B switch, read per launch (tests flip it inside one process)
   const int var = ev ? atoi(ev) : 53;
@@ -537,22 +765,29 @@ cudaError_t launch_em16(const Geom& g, const FusedGeom& f, const EmArgs& a, int 
   const size_t smem_q = em16_qf_smem_bytes(g, f);
   EmArgs aw = a;
   if (!qf) { aw.qf_limit = -1.0; }
-#define MLF_E16V(DMv, V)                                                                                               \
-  case 64 * DMv + V: {                                                                                                  \
-    if (qf) {                                                                                                           \
-      cudaError_t e = cudaFuncSetAttribute(k_em16<DMv, 53, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q); \
-      if (e != cudaSuccess) return e;                                                                                  \
-      k_em16<DMv, 53, true><<<grid, kThreads16, smem_q, st>>>(aw);                                                     \
-    }                                                                                                                   \
-    cudaError_t e = cudaFuncSetAttribute(k_em16<DMv, V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return e;                                                                                    \
-    k_em16<DMv, V, false><<<grid, kThreads16, smem, st>>>(aw);                                                         \
-  } break;
+  auto go = [&](auto kern, size_t sm) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kThreads16, sm, st>>>(aw);
+    return cudaSuccess;
+  };
+  cudaError_t e = cudaSuccess;
+#define MLF_E16V(DMv, V)                                                              \
+  case 64 * DMv + V:                                                                   \
+    if (store) {                                                                       \
+      if (qf) e = go(k_em16<DMv, 53, 1, true>, smem_q);                                \
+      if (e == cudaSuccess) e = go(k_em16<DMv, 53, 0, true>, smem);                    \
+    } else {                                                                           \
+      if (qf) e = go(k_em16<DMv, 53, 1, false>, smem_q);                               \
+      if (e == cudaSuccess) e = go(k_em16<DMv, V, 0, false>, smem);                    \
+    }                                                                                  \
+    break;
 #define MLF_E16(DMv) MLF_E16V(DMv, 0) MLF_E16V(DMv, 5) MLF_E16V(DMv, 21) MLF_E16V(DMv, 53)
   switch (64 * g.DM + (var & 63)) {
     MLF_E16(1) MLF_E16(2) MLF_E16(3) MLF_E16(4)
     default: return cudaErrorInvalidConfiguration;
   }
+  if (e != cudaSuccess) return e;
 #undef MLF_E16V
 #undef MLF_E16
   return cudaGetLastError();

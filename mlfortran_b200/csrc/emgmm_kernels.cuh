@@ -61,6 +61,9 @@ struct EmArgs {
   const double* packq;   // [K8][qf_stride(DM)] coefficient fragments + the 8 constants of each component block
   const double* qfS;     // [K8*8] magnitude bound S_k of the terms of component k's quadratic form over the data
   double qf_limit;       // the sweep uses the quadratic form iff every S_k <= qf_limit (decided on the device, no host sync)
+  // "statistics first" iterations: responsibilities of the sweep's 64-point tiles, [tile][64][K8*8], written by the statistics
+  // pass (launch_em16 with store = true) and read back by the scatter pass (launch_scatter16)
+  double* gtiles;
 };
 
 // ---- expanded quadratic form of the log-density (k_em16<.., QF = true>) ------------------------------------------------------------
@@ -119,7 +122,11 @@ cudaError_t launch_em(const Geom& g, const FusedGeom& f, const EmArgs& a, bool s
 // side lists per warp -> 16*grid lists.
 bool em16_ok(const Geom& g, const FusedGeom& f, size_t smem_limit);
 bool em16_qf_ok(const Geom& g, const FusedGeom& f, size_t smem_limit);   // the quadratic-form variant fits shared memory
-cudaError_t launch_em16(const Geom& g, const FusedGeom& f, const EmArgs& a, int grid, size_t smem_limit, cudaStream_t st);
+cudaError_t launch_em16(const Geom& g, const FusedGeom& f, const EmArgs& a, int grid, size_t smem_limit, cudaStream_t st, bool store = false);
+// Scatter pass of a "statistics first" iteration: thresholded covariance scatter + kept sums from the stored responsibilities
+// (a.gtiles) with the exact thresholds a.thi; same tile -> (block, group) assignment and the same arithmetic as the fused sweep,
+// so the pass-B partials are bit-identical to a repeated full sweep.  Writes a.partB only.
+cudaError_t launch_scatter16(const Geom& g, const FusedGeom& f, const EmArgs& a, int grid, size_t smem_limit, cudaStream_t st);
 // Diagonal-covariance extension at small d / large K on the fp64 CUDA cores (emgmm_diag.cu): lane = component.
 bool emd_ok(const Geom& g, const FusedGeom& f, size_t smem_limit);
 cudaError_t launch_selftest_exp(const double* in, double* out, int64_t n, int which, cudaStream_t st);   // exp_tab (which = 0) / exp_tab128 (1) on n device values

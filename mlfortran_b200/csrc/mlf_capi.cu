@@ -675,6 +675,11 @@ int mlf_b200_get_qf_stats(MLF_OBJ* obj, int64_t* qf_sweeps, double* bound) {
   if (bound) *bound = t.qf_bound;
   return 0;
 }
+int64_t mlf_b200_scatter_passes(MLF_OBJ* obj) {
+  EmObject* o = as_em(obj);
+  if (!o) return -1;
+  return (o->multi ? o->multi->times() : o->eng.times()).scatter_passes;
+}
 int64_t mlf_b200_launch_count(MLF_OBJ* obj) {
   EmObject* o = as_em(obj);
   return o ? (o->multi ? o->multi->launches() : o->eng.launches()) : -1;

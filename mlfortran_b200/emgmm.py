@@ -343,7 +343,7 @@ class mlf_algo_emgmm:
         """Sweeps that evaluated the log-densities as the expanded quadratic form, and the magnitude bound of the last sweep."""
         n, b = C.c_int64(0), C.c_double(0.0)
         self._lib.mlf_b200_get_qf_stats(self._h, C.byref(n), C.byref(b))
-        return {"qf_sweeps": int(n.value), "bound": float(b.value)}
+        return {"qf_sweeps": int(n.value), "bound": float(b.value), "scatter_passes": int(self._lib.mlf_b200_scatter_passes(self._h))}
 
     def launch_count(self) -> int:
         return int(self._lib.mlf_b200_launch_count(self._h))

@@ -320,6 +320,36 @@ def test_fused_sweep_band_and_side_list(oracle):
     em.finalize()
 
 
+@pytest.mark.parametrize("shape", [(16, 64, 700, 1.0, 1.0), (16, 20, 1500, 1.0, 0.0), (5, 6, 3000, 1.0, 0.0), (12, 33, 900, 0.7, 1.0)],
+                         ids=["d16_K64", "d16_K20", "d5_K6", "d12_K33"])
+def test_statistics_first_scatter_from_stored_responsibilities(shape, oracle, monkeypatch):
+    """Overlapping clusters in the violent phase of the reference's dynamics: s_k cannot be predicted, so the iteration runs
+    "statistics first".  With the responsibilities of pass 0 kept in HBM (default) pass 1 is a scatter from the stored tiles
+    (k_scatter16); with MLF_B200_GSTORE=0 it is a second full sweep.  Same arithmetic in the same order: both give the same
+    bits, and the oracle's trajectory."""
+    d, K, npc, sc, mp = shape
+    iters = 6   # later iterations of these mixtures are in the collapse regime, which amplifies rounding differences a thousandfold per step
+    data = synth.make_mixture(d, K, npc, sc, 1.0, 31 + d)
+    X = data["X"][: K * npc - 37]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 31 + d)
+    oMu, oCov, olam, otr = oracle.em_iterations(X, Mu0, Cov0, lam0, mp, iters)
+    got = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MLF_B200_GSTORE", mode)
+        em = make_em(X, K, mp, Mu0, Cov0, lam0)
+        assert "k_em16" in em.kernel_plan()
+        em.set_profile(True)
+        assert em.step(iters)[0] == 0, em.last_error()
+        check_against(em, oMu, oCov, olam, otr)
+        q, c = em.qf_stats(), em.counters()
+        got[mode] = (em.Mu.copy(), em.Cov.copy(), em.lambda_.copy(), em.sumLL_trace().copy(), q["scatter_passes"], c["sweeps"])
+        em.finalize()
+    assert got["1"][4] >= 2, got["1"][4:]          # the scatter pass ran ...
+    assert got["0"][4] == 0 and got["0"][5] == got["1"][5] + got["1"][4]   # ... in place of that many full sweeps
+    for a, b in zip(got["1"][:4], got["0"][:4]):
+        assert np.array_equal(a, b)
+
+
 def test_streamed_refresh_of_x(oracle):
     """refresh_x(host X) + step: the upload is chunked underneath the first sweep and the global moments (sumLL) are
     re-accumulated about the old shift; results must equal a fresh run on the new data."""
