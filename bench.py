@@ -223,6 +223,41 @@ def run_infer(args):
     em.finalize()
 
 
+def parity_spot_check(X, d, K, Mu0, Cov0, lam0, min_proba, n_check=1_000_000, iters=2):
+    """the first n_check points of the bench's own data set copied back to the host and run through the oracle
+    from the bench's initial parameters; the CUDA path (through the C-ABI, a second small object) does the same iterations on the
+    same points.  Outside every timed region; part of the cpu_baseline leg (the one place bench.py may execute oracle/ as checker)."""
+    import numpy as np
+
+    from mlfortran_b200 import mlf_algo_emgmm
+    from oracle.emgmm_oracle import get
+
+    ns = int(min(n_check, X.shape[0]))
+    Xs = np.ascontiguousarray(X[:ns].cpu().numpy())
+    o = get()
+    oMu, oCov, olam, otr = o.em_iterations(Xs, Mu0, Cov0, lam0, min_proba, iters)
+    em = mlf_algo_emgmm()
+    if em.init(Xs, K, min_proba) != 0:
+        return {"error": "init failed"}
+    em.inject(Mu0, Cov0, lam0)
+    info, _ = em.step(iters)
+    if info < 0:
+        return {"error": em.last_error()}
+    tr = em.sumLL_trace()
+    nq = min(20000, ns)
+    _, P = em.getProba(Xs[:nq])
+    _, oP, _ = o.exp_step(Xs[:nq], em.Mu, em.Cov, em.lambda_)
+    rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+    out = {"sample": f"first {ns} points of rank 0's shard, {iters} EM iterations from the bench's initial parameters: CUDA path through the C-ABI vs the oracle; "
+                     f"E-step (getProba) on the first {nq} of them with the final parameters",
+           "sumLL_rel": float(np.abs((tr - otr) / otr).max()), "Mu_rel": rel(em.Mu, oMu), "Cov_rel": rel(em.Cov, oCov),
+           "lambda_abs": float(np.abs(em.lambda_ - olam).max()), "proba_abs": float(np.abs(P - oP).max()),
+           "logits": em.qf_stats(), "tolerances": {"sumLL_rel": 1e-10, "Mu_rel": 1e-9, "Cov_rel": 1e-9, "lambda_abs": 1e-9, "proba_abs": 1e-9}}
+    out["pass"] = bool(out["sumLL_rel"] <= 1e-10 and out["Mu_rel"] <= 1e-9 and out["Cov_rel"] <= 1e-9 and out["lambda_abs"] <= 1e-9 and out["proba_abs"] <= 1e-9)
+    em.finalize()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -438,8 +473,11 @@ def main():
     em.finalize()
 
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
         os.sched_setaffinity(0, full_affinity)
+        if args.cov_type == "full":
+            parity = parity_spot_check(X, d, K, Mu0, Cov0, lam0, args.min_proba)
         r = cpu_oracle_rate(d, K, args.cpu_points, args.min_proba, 3, 1, sigma_c=args.sigma_c, sigma_x=args.sigma_x)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
                "sample": f"oracle (C restatement of the reference, OpenMP over components) on N_cpu={r['n']} points of the same d={d}, K={K} mixture, "
@@ -454,7 +492,7 @@ def main():
                        "N": N, "d": d, "K": K, "minProba": args.min_proba, "sigmaC": args.sigma_c, "sigmaX": args.sigma_x, "points_per_gpu": n_loc, "parallelism": f"points-sharded x{world}",
                        "l2": "inputs larger than L2 (X is 12.8 GB per 1e8 points >> 126 MB); no explicit flush",
                        "timing": "CUDA events on the engine stream, max over ranks"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

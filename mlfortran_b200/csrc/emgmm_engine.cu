@@ -1105,11 +1105,23 @@ int EmgmmEngine::kmeans_init(int nkm, uint64_t seed) {
   uint64_t rng = seed;
   const int grid = sms_;
   const int64_t chunk = std::max<int64_t>(1, (n_ + grid - 1) / grid);
-  double *dMinDist = nullptr, *dPart = nullptr, *dOut = nullptr, *dCnt = nullptr;
+  // second-generation kernels (emgmm_kmeans.cu; MLF_B200_KMEANS_V1=1 keeps the first generation for A/B runs)
+  const char* v1 = getenv("MLF_B200_KMEANS_V1");
+  const bool gen2 = !(v1 && v1[0] == '1');
+  const bool fast_seed = gen2 && d <= 64;
+  const bool fast_lloyd = gen2 && !legacy_estep_ && !big_ && lloyd16_ok(g);
+  const int sgrid = (int)std::max<int64_t>(1, std::min<int64_t>(4 * (int64_t)sms_, (n_ + 255) / 256));
+  const int64_t schunk = std::max<int64_t>(256, (((n_ + sgrid - 1) / sgrid + 255) / 256) * 256);
+  double *dMinDist = nullptr, *dPart = nullptr, *dOut = nullptr, *dCnt = nullptr, *dGather = nullptr;
   CKE(cudaMalloc((void**)&dMinDist, std::max<int64_t>(n_, 1) * sizeof(double)), "cudaMalloc minDist");
-  CKE(cudaMalloc((void**)&dPart, grid * sizeof(double)), "cudaMalloc");
+  CKE(cudaMalloc((void**)&dPart, (size_t)std::max(grid, sgrid) * sizeof(double)), "cudaMalloc");
   CKE(cudaMalloc((void**)&dOut, (size_t)std::max(d, world_) * sizeof(double)), "cudaMalloc");
   CKE(cudaMalloc((void**)&dCnt, K * sizeof(double)), "cudaMalloc");
+  CKE(cudaMalloc((void**)&dGather, (size_t)world_ * sizeof(double)), "cudaMalloc");
+  cudaEvent_t tev[3] = {nullptr, nullptr, nullptr};
+  if (debug_)
+    for (auto& e : tev) cudaEventCreate(&e);
+  if (debug_) cudaEventRecord(tev[0], st_);
   int rc = 0;
   auto seed_pass = [&](const double* centre, int first) -> int {
     CKE(launch_seed_update(dX_, n_, d, centre, dMinDist, first, chunk, grid, dPart, st_), "seed_update");
@@ -1119,10 +1131,23 @@ int EmgmmEngine::kmeans_init(int nkm, uint64_t seed) {
   // Mu(:,1) = mean(X,2); Mu(:,1) = GetFarPoint(X, Mu(:,1:1)); Mu(:,i) = GetFarPoint(X, Mu(:,1:i-1))
   for (int i = 0; i < K && rc == 0; ++i) {
     const double* centre = (i == 0) ? dMean_ : dMu_ + (size_t)(i - 1) * d;
-    rc = seed_pass(centre, i <= 1 ? 1 : 0);
-    if (rc == 0) rc = draw_far_point(next_uniform(rng), grid, chunk, dMinDist, dPart, dOut);
+    if (fast_seed) {   // everything stays on the stream: no host round trip per centre
+      const double u = next_uniform(rng);
+      if (launch_seed_update2(dX_, n_, d, centre, dMinDist, i <= 1 ? 1 : 0, schunk, sgrid, dPart, st_) != cudaSuccess ||
+          launch_seed_total(dPart, sgrid, dGather, world_, rank_, st_) != cudaSuccess) { rc = -7; break; }
+      if (world_ > 1 && (rc = allreduce(dGather, world_))) break;
+      if (launch_seed_draw(dX_, d, n_, dMinDist, dPart, sgrid, schunk, dGather, world_, rank_, u, dOut, st_) != cudaSuccess) { rc = -7; break; }
+      if (world_ > 1 && (rc = allreduce(dOut, d))) break;
+      launches_ += 3;
+    } else {
+      rc = seed_pass(centre, i <= 1 ? 1 : 0);
+      if (rc == 0) rc = draw_far_point(next_uniform(rng), grid, chunk, dMinDist, dPart, dOut);
+    }
     if (rc == 0 && cudaMemcpyAsync(dMu_ + (size_t)i * d, dOut, d * sizeof(double), cudaMemcpyDeviceToDevice, st_) != cudaSuccess) rc = -7;
   }
+  if (debug_) cudaEventRecord(tev[1], st_);
+  const int64_t ltiles = (n_ + 63) / 64;
+  const int lgrid = (int)std::max<int64_t>(1, std::min<int64_t>(sms_, (ltiles + 1) / 2));
   std::vector<double> cnt((size_t)K);
   for (int it = 1; it < nkm && rc == 0; ++it) {
     // mlf_EvaluateClass + EvaluateCentres
@@ -1132,6 +1157,14 @@ int EmgmmEngine::kmeans_init(int nkm, uint64_t seed) {
       launches_ += 2;
       if ((rc = allreduce(dStatsA_, (int64_t)K * (d + 1)))) break;
       if (launch_kmeans_centres(dStatsA_, K, d, dMu_, dCnt, st_) != cudaSuccess) { rc = -7; break; }
+    } else if (fast_lloyd) {
+      // one sweep: scores from the linear monomials only (DM DMMA k-steps per 8 points x 8 centres), first maximum, one-hot
+      // DMMA statistics in the layout of EM's pass A
+      if (launch_lloyd16(g, dX_, n_, dMu_, dShift_, dPartA_, lgrid, st_) != cudaSuccess) { rc = -7; break; }
+      if (launch_reduce_partials(dPartA_, 2 * lgrid, (int64_t)g.K8 * 8 * g.DS, dStatsA_, st_) != cudaSuccess) { rc = -7; break; }
+      launches_ += 2;
+      if ((rc = allreduce(dStatsA_, (int64_t)g.K8 * 8 * g.DS))) break;
+      if (launch_kmeans_centres_a(g, dStatsA_, dMu_, dCnt, st_) != cudaSuccess) { rc = -7; break; }
     } else {
       // assignment through the E-pass kernel in hard mode: distances as DMMA tiles, one-hot labels, and the cluster
       // counts / coordinate sums from the same fixed-order pass-A statistics as EM (deterministic, no atomics)
@@ -1164,8 +1197,18 @@ int EmgmmEngine::kmeans_init(int nkm, uint64_t seed) {
   }
   if (rc == 0 && launch_identity_cov(K, d, dCov_, dLambda_, st_) != cudaSuccess) rc = -7;
   ++launches_;
+  if (debug_) cudaEventRecord(tev[2], st_);
   cudaStreamSynchronize(st_);
-  cudaFree(dMinDist); cudaFree(dPart); cudaFree(dOut); cudaFree(dCnt);
+  if (debug_) {
+    float ms_seed = 0, ms_lloyd = 0;
+    cudaEventElapsedTime(&ms_seed, tev[0], tev[1]);
+    cudaEventElapsedTime(&ms_lloyd, tev[1], tev[2]);
+    if (rank_ == 0)
+      fprintf(stderr, "mlfortran_b200[debug]: k-means initialiser: seeding of %d centres %.1f ms (%s), %d Lloyd steps %.1f ms (%s)\n", K, ms_seed,
+              fast_seed ? "device-side draw" : "host-side draw", nkm - 1, ms_lloyd, fast_lloyd ? "k_lloyd16" : "E-pass kernel in hard mode");
+    for (auto& e : tev) cudaEventDestroy(e);
+  }
+  cudaFree(dMinDist); cudaFree(dPart); cudaFree(dOut); cudaFree(dCnt); cudaFree(dGather);
   if (rc != 0 && err_.empty()) err_ = "k-means initialiser failed";
   return rc;
 }

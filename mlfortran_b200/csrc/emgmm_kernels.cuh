@@ -201,6 +201,15 @@ cudaError_t launch_seed_update(const double* X, int64_t N, int d, const double* 
 cudaError_t launch_seed_pick(const double* X, int d, const double* minDist, int64_t lo, int64_t hi, double target,
                              double* out, cudaStream_t st);
 cudaError_t launch_kmeans_centres(const double* sums, int K, int d, double* Mu, double* counts, cudaStream_t st);
+// Second-generation initialiser kernels (emgmm_kmeans.cu): seeding without host round trips, Lloyd step in one sweep.
+cudaError_t launch_seed_update2(const double* X, int64_t N, int d, const double* centre, double* minDist, int first, int64_t chunk, int grid,
+                                double* partial, cudaStream_t st);   // d <= 64
+cudaError_t launch_seed_total(const double* partial, int grid, double* gather, int world, int rank, cudaStream_t st);
+cudaError_t launch_seed_draw(const double* X, int d, int64_t n, const double* minDist, const double* partial, int grid, int64_t chunk,
+                             const double* gather, int world, int rank, double u, double* out, cudaStream_t st);
+bool lloyd16_ok(const Geom& g);
+cudaError_t launch_lloyd16(const Geom& g, const double* X, int64_t N, const double* Mu, const double* shift, double* partA, int grid,
+                           cudaStream_t st);   // partA[2 grid][K8*8][DS]
 cudaError_t launch_kmeans_centres_a(const Geom& g, const double* statsA, double* Mu, double* counts, cudaStream_t st);
 cudaError_t launch_identity_cov(int K, int d, double* Cov, double* lambda, cudaStream_t st);
 // Pack for the k-means assignment through the E-pass kernels: L = I, bias = -(centre - shift), constant 0.

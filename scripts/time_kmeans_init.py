@@ -5,7 +5,7 @@ import numpy as np, torch
 from mlfortran_b200 import mlf_algo_emgmm, synth
 N = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000_000
 dev = torch.device("cuda", 0)
-X, centres, _ = synth.make_mixture_torch(16, 64, N, 8.0, 1.0, 3, dev)
+X, centres, _ = synth.make_mixture_device(16, 64, N, 0, N, 8.0, 1.0, 3, dev)
 em = mlf_algo_emgmm()
 assert em.init(X, 64, 1.0) == 0
 em.set_seed(7)
