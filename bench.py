@@ -233,7 +233,7 @@ def parity_spot_check(X, d, K, Mu0, Cov0, lam0, min_proba, n_check=1_000_000, it
     from oracle.emgmm_oracle import get
 
     ns = int(min(n_check, X.shape[0]))
-    Xs = np.ascontiguousarray(X[:ns].cpu().numpy())
+    Xs = np.ascontiguousarray(X[:ns] if isinstance(X, np.ndarray) else X[:ns].cpu().numpy())
     o = get()
     oMu, oCov, olam, otr = o.em_iterations(Xs, Mu0, Cov0, lam0, min_proba, iters)
     em = mlf_algo_emgmm()
@@ -277,6 +277,8 @@ def main():
     ap.add_argument("--mode", default="train", choices=["train", "infer"], help="infer: getClass / getProba throughput on host data (not the contract line)")
     ap.add_argument("--infer-points", type=float, default=2e7)
     ap.add_argument("--infer-proba-points", type=float, default=5e6)
+    ap.add_argument("--host-buffer", default=os.environ.get("MLF_BENCH_HOST_BUFFER", "pinned"), choices=["pinned", "wc"],
+                    help="e2e leg: the caller's host array is page-locked (torch pin_memory) or page-locked write-combined (mlf_b200_host_alloc)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -440,13 +442,33 @@ def main():
     e2e = None
     if not args.no_e2e:
         e_steps = args.e2e_steps or min(args.steps, 5)
-        Xh = torch.empty((n_loc, d), dtype=torch.float64, pin_memory=True)
+        wc_ptr = None
+        if args.host_buffer == "wc":
+            import ctypes
+            wc_ptr = em._lib.mlf_b200_host_alloc(max(8 * n_loc * d, 8), 1)
+            if not wc_ptr:
+                raise SystemExit("bench.py: mlf_b200_host_alloc failed")
+            Xn = np.ctypeslib.as_array((ctypes.c_double * (n_loc * d)).from_address(wc_ptr)).reshape(n_loc, d)
+            Xh = torch.from_numpy(Xn)
+        else:
+            Xh = torch.empty((n_loc, d), dtype=torch.float64, pin_memory=True)
+            Xn = Xh.numpy()
         Xh.copy_(X)
         torch.cuda.synchronize(dev)
+        # ceiling of the upload: the rank's whole shard as ONE plain cudaMemcpyAsync from the same host buffer, all ranks at once
+        probe_ms = []
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            barrier()
+            pe0.record()
+            X.copy_(Xh, non_blocking=True)
+            pe1.record()
+            torch.cuda.synchronize(dev)
+            probe_ms.append(max_over_ranks(pe0.elapsed_time(pe1)))
+        probe_gbs = 8.0 * n_loc * d / (min(probe_ms) * 1e-3) * 1e-9 if n_loc else 0.0
         em.finalize()
         del X
         torch.cuda.empty_cache()
-        Xn = Xh.numpy()
         em = mlf_algo_emgmm()
         if em.init(Xn, K, args.min_proba, device=local_rank, cov_type=args.cov_type) != 0:
             raise SystemExit("bench.py: e2e init failed")
@@ -469,15 +491,23 @@ def main():
                "steps": e_steps, "ms_per_step": el / e_steps * 1e3, "em_iter_per_s": e_steps / el, "host_affinity": numa_note,
                "note": "per rank and step: mlf_b200_refresh_x(pinned host X) + mlf_step(1) + parameters/sumLL back; the X upload is "
                        "chunked underneath the step's sweep, so the step is PCIe-bound (h2d_bytes / ms_per_step = achieved H2D GB/s)",
-               "h2d_gbs": (8 * n_loc * d + pbytes) / (el / e_steps) * 1e-9}
+               "h2d_gbs": (8 * n_loc * d + pbytes) / (el / e_steps) * 1e-9,
+               "host_buffer": "page-locked" + (", write-combined" if args.host_buffer == "wc" else ""),
+               "h2d_probe_gbs": probe_gbs, "h2d_probe_note": "per rank: the shard as one plain cudaMemcpyAsync from the same host buffer with every rank "
+                                                              "copying at once (slowest rank, best of 3) -- the ceiling the streamed step is held against"}
     em.finalize()
+    if e2e is not None and args.host_buffer == "wc":
+        del Xh
+        if not (rank == 0 and world == 1 and not args.no_cpu):
+            del Xn
+            em._lib.mlf_b200_host_free(wc_ptr)
 
     cpu = None
     parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
         os.sched_setaffinity(0, full_affinity)
         if args.cov_type == "full":
-            parity = parity_spot_check(X, d, K, Mu0, Cov0, lam0, args.min_proba)
+            parity = parity_spot_check(X if args.no_e2e else Xn, d, K, Mu0, Cov0, lam0, args.min_proba)   # the device copy was released for the e2e leg
         r = cpu_oracle_rate(d, K, args.cpu_points, args.min_proba, 3, 1, sigma_c=args.sigma_c, sigma_x=args.sigma_x)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
                "sample": f"oracle (C restatement of the reference, OpenMP over components) on N_cpu={r['n']} points of the same d={d}, K={K} mixture, "

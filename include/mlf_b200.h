@@ -13,6 +13,7 @@
 #ifndef MLF_B200_H
 #define MLF_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -120,7 +121,17 @@ int mlf_b200_set_seed(MLF_OBJ *obj, uint64_t seed);
  * Returns -7 (mlf_OTHERERROR) when asked for full covariances on an object constructed with MLF_B200_COV_DIAG whose
  * kernels were planned around the diagonal-compressed parameter pack (d <= 8 with K >= 128): construct a new object. */
 int mlf_b200_set_cov_type(MLF_OBJ *obj, int cov_type);
-int mlf_b200_refresh_x(MLF_OBJ *obj, const double *X);        /* re-copy X after the caller changed it */
+/* Re-copy X after the caller changed it.  For a host array on the fused path (d <= 16) the upload is DEFERRED: it runs chunk
+ * by chunk underneath the sweep of the next mlf_step, so X must stay valid and unchanged until that step has returned (the
+ * reference's own contract is stronger: `this%X => X` borrows the array for the object's lifetime,
+ * src/unsupervised/mlf_emgmm.f90:86).  Other paths copy before returning. */
+int mlf_b200_refresh_x(MLF_OBJ *obj, const double *X);
+/* Page-locked host memory for arrays that are handed to mlf_emgmm_c / mlf_b200_refresh_x / mlf_getClass / mlf_getProba
+ * (pageable arrays work too, through a staging copy at roughly half the PCIe rate).  write_combined != 0 asks for
+ * write-combined memory: not snooped by the CPU caches during the GPU's reads, for upload-only buffers that the host
+ * fills once and never reads back.  NULL on failure. */
+void *mlf_b200_host_alloc(size_t bytes, int write_combined);
+void mlf_b200_host_free(void *p);
 const char *mlf_b200_last_error(MLF_OBJ *obj);
 /* Which kernel generation this object's (d, K) runs through (object-owned string). */
 const char *mlf_b200_kernel_plan(MLF_OBJ *obj);

@@ -63,6 +63,8 @@ SYMBOLS = {
     "mlf_b200_get_counters": (C.c_int, [C.c_void_p, c_int64_p]),
     "mlf_b200_get_qf_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "mlf_b200_scatter_passes": (C.c_int64, [C.c_void_p]),
+    "mlf_b200_host_alloc": (C.c_void_p, [C.c_size_t, C.c_int]),
+    "mlf_b200_host_free": (None, [C.c_void_p]),
     "mlf_b200_launch_count": (C.c_int64, [C.c_void_p]),
     "mlf_b200_stream": (C.c_void_p, [C.c_void_p]),
     "mlf_b200_global_points": (C.c_int64, [C.c_void_p]),

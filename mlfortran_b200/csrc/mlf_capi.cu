@@ -599,6 +599,16 @@ int mlf_b200_refresh_x(MLF_OBJ* obj, const double* X) {
   return o->multi ? o->multi->refresh_x(X) : o->eng.refresh_x(X, o->x_on_device);
 }
 
+void* mlf_b200_host_alloc(size_t bytes, int write_combined) {
+  void* p = nullptr;
+  const unsigned flags = cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0u);
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, flags) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void mlf_b200_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 const char* mlf_b200_kernel_plan(MLF_OBJ* obj) {
   EmObject* o = as_em(obj);
   if (!o) return "invalid handle";
