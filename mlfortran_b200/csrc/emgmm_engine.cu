@@ -44,6 +44,7 @@ EmgmmEngine::~EmgmmEngine() {
   if (dAmbComp_) cudaFree(dAmbComp_);
   if (dAmbPart_) cudaFree(dAmbPart_);
   if (dInfo_) cudaFree(dInfo_);
+  if (dVValid_) cudaFree(dVValid_);
   if (dLabels_) cudaFree(dLabels_);
   for (auto& e : pev_)
     if (e) cudaEventDestroy(e);
@@ -189,6 +190,8 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   CKE(A(&dMean_, (size_t)8 * g.DN + 8), "cudaMalloc");
   CKE(A(&dNglob_, 8), "cudaMalloc");
   CKE(cudaMalloc((void**)&dInfo_, sizeof(int) * KP), "cudaMalloc");
+  CKE(cudaMalloc((void**)&dVValid_, sizeof(int) * KP), "cudaMalloc");
+  CKE(cudaMemsetAsync(dVValid_, 0, sizeof(int) * KP, st_), "memset");
   return refresh_x(X, x_on_device);
 }
 
@@ -257,7 +260,7 @@ int EmgmmEngine::do_refresh(bool with_sumll) {
   QfRefresh q{};
   if (qf_) { q.packq = dPackQ_; q.qfS = dQfS_; q.rad = rad_ready_ ? dRad_ : nullptr; q.nrad = rad_world_; }
   CKE(launch_refresh(geom_, dMu_, dCov_, dLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_, dPack2_, dMuOld_,
-                     dShift_, with_sumll ? 1 : 0, cov_diag_ ? 1 : 0, &fgeom_, (refresh_count_ % 8 != 0) ? 1 : 0, qf_ ? &q : nullptr), "refresh");
+                     dShift_, with_sumll ? 1 : 0, cov_diag_ ? 1 : 0, &fgeom_, (refresh_count_ % 8 != 0) ? 1 : 0, qf_ ? &q : nullptr, dVValid_), "refresh");
   ++refresh_count_;  // every 8th refresh restarts the eigenvectors from the identity (bounds their orthogonality drift)
   ++launches_;
   return 0;

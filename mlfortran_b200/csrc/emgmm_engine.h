@@ -137,6 +137,7 @@ class EmgmmEngine {
   double *dStatsA_ = nullptr, *dStatsB_ = nullptr, *dPartA_ = nullptr, *dPartB_ = nullptr;
   double *dSc_ = nullptr, *dMean_ = nullptr, *dNglob_ = nullptr;
   int* dInfo_ = nullptr;
+  int* dVValid_ = nullptr;   // per component: the eigenvectors in scratch are valid (the eigen branch of k_refresh ran)
   // fused path
   double *dPack2_ = nullptr, *dMuOld_ = nullptr, *dTlo_ = nullptr, *dThi_ = nullptr, *dAB_ = nullptr, *dPartB2_ = nullptr, *dStatsC_ = nullptr;
   double *dPrevMu_ = nullptr, *dPrevCov_ = nullptr, *dPrevLambda_ = nullptr;  // parameters at the start of the last iteration (ProbaC)

@@ -13,6 +13,8 @@
 //              skipping 4-point groups in which no point passes the reference's W >= minW test.
 #include "emgmm_kernels.cuh"
 
+#include <cstdlib>
+
 #include <cmath>
 #include <cstdio>
 
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(1024) k_refresh(Geom g, const double* __restri
                                                  double* __restrict__ pack, double* __restrict__ sumLLk,
                                                  int* __restrict__ info, double* __restrict__ pack2, double* __restrict__ muold,
                                                  int PSF, int OFFB2, int OFFC2, const double* __restrict__ shift, int do_sumll, int use_smem,
-                                                 int cov_diag, int diag_pack, int warm, QfRefresh qf) {
+                                                 int cov_diag, int diag_pack, int warm, QfRefresh qf, int fastpath, int* __restrict__ vvalid) {
   const int k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, d = g.d;
   // quadratic-form pack (k_em16 QF variant): component k is column k % 8 of block k / 8, B-fragment order (lane = 4 column + k-index)
   const int qNF = qf_nsteps(g.DM), qD4 = 4 * g.DM;
@@ -120,6 +122,89 @@ __global__ void __launch_bounds__(1024) k_refresh(Geom g, const double* __restri
     const int lo = a < b ? a : b, hi = a < b ? b : a;
     return (cov_diag && a != b) ? 0.0 : Ck[(size_t)hi * d + lo];  // cov_diag: extension, diagonal of C only
   };
+  // ---- fast path for well-conditioned covariances ---------------------------------------------------------------------------
+  // InverseSymMatrix floors the spectrum at valM = 1e-8 max(lambda): when every eigenvalue is above that (cond(C) < 1e8) its
+  // result IS the plain inverse and lnDet = (d log 2pi - log det C)/2.  Both come out of one Cholesky factorisation -- d^3
+  // flops in ~4d block steps instead of Jacobi sweeps of d rounds each -- and a bound on the condition number comes with them:
+  // cond_2(C) <= |C|_F |C^-1|_F.  Taken only when that bound is below 1e6 (two decades inside the floor); otherwise, or when a
+  // pivot is not positive, the eigen branch below runs as before.  (Rounding: both routes carry cond(C) u.)
+  __shared__ int s_fast;
+  double lnDet = 0.0;
+  bool fast = false;
+  if (fastpath) {
+    double cn = 0;
+    for (int i = tid; i < d * d; i += nt) {
+      const int a = i % d, b = i / d;
+      const double v = csym(a, b);
+      A[i] = v;
+      cn = fma(v, v, cn);
+    }
+    cn = block_sum(cn, s_red);   // |C|_F^2 (also the barrier after the copy)
+    if (tid == 0) s_fast = 1;
+    __syncthreads();
+    for (int j = 0; j < d; ++j) {   // in-place Cholesky A = L L^T (lower), right-looking
+      const double pj = A[(size_t)j * d + j];
+      if (!(pj > 0.0) || !(pj < INFINITY)) {   // uniform: every thread reads the same pivot
+        if (tid == 0) s_fast = 0;
+        break;
+      }
+      const double ljj = sqrt(pj);
+      __syncthreads();
+      for (int i = j + tid; i < d; i += nt) A[(size_t)j * d + i] = (i == j) ? ljj : A[(size_t)j * d + i] / ljj;
+      __syncthreads();
+      const int rem = d - j - 1;
+      for (int i = tid; i < rem * rem; i += nt) {
+        const int a = j + 1 + i % rem, b = j + 1 + i / rem;
+        if (a >= b) A[(size_t)b * d + a] -= A[(size_t)j * d + a] * A[(size_t)j * d + b];
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+    if (s_fast) {
+      // W = L^-1 (lower, column-major): thread j solves L x = e_j by forward substitution
+      for (int j = tid; j < d; j += nt) {
+        double* x = W + (size_t)j * d;
+        for (int i = 0; i < j; ++i) x[i] = 0.0;
+        x[j] = 1.0 / A[(size_t)j * d + j];
+        for (int i = j + 1; i < d; ++i) {
+          double acc = 0;
+          for (int e = j; e < i; ++e) acc = fma(A[(size_t)e * d + i], x[e], acc);
+          x[i] = -acc / A[(size_t)i * d + i];
+        }
+      }
+      double ld = 0;
+      for (int a = 0; a < d; ++a) ld += log(A[(size_t)a * d + a]);   // every thread, same order
+      __syncthreads();
+      // invC = L^-T L^-1 -> A (the factor is not needed any more), then its norm
+      double cin = 0;
+      for (int i = tid; i < d * d; i += nt) {
+        const int a = i % d, b = i / d;
+        if (a < b) continue;
+        double acc = 0;
+        const double* wa = W + (size_t)a * d;
+        const double* wb = W + (size_t)b * d;
+        for (int e = a; e < d; ++e) acc = fma(wa[e], wb[e], acc);
+        cin += (a == b ? 1.0 : 2.0) * acc * acc;
+        // the strict upper part of A still holds nothing we need: write both triangles after the barrier below
+        A[(size_t)b * d + a] = acc;   // lower (a >= b)
+      }
+      cin = block_sum(cin, s_red);
+      for (int i = tid; i < d * d; i += nt) {
+        const int a = i % d, b = i / d;
+        if (a < b) A[(size_t)b * d + a] = A[(size_t)a * d + b];
+      }
+      __syncthreads();
+      fast = cn * cin < 1e12;   // (|C|_F |C^-1|_F)^2 < (1e6)^2; false for NaN
+      if (fast) {
+        for (int i = tid; i < d * d; i += nt) W[i] = A[i];
+        lnDet = 0.5 * d * log(2.0 * acos(-1.0)) - ld;
+        if (tid == 0 && info) info[k] = 0;
+      }
+      __syncthreads();
+    }
+  }
+  if (!fast) {
+  if (warm && vvalid && !vvalid[k]) warm = 0;   // the eigenvectors in scratch are only there if the eigen branch ran before
   if (warm) {
     // warm start: the eigenvectors V of the previous EM iteration are still in scratch and nearly diagonalise the
     // new covariance, so the sweeps start from A = V^T C V (two d^3 products) and converge in 2-3 sweeps instead of ~9
@@ -222,7 +307,6 @@ __global__ void __launch_bounds__(1024) k_refresh(Geom g, const double* __restri
     s_f[a] = (ld <= valM) ? penality : 1.0 / ld;
   }
   __syncthreads();
-  double lnDet;
   {
     double s = 0;
     for (int a = 0; a < d; ++a) s += log(s_f[a]);  // every thread, same order: deterministic
@@ -235,7 +319,9 @@ __global__ void __launch_bounds__(1024) k_refresh(Geom g, const double* __restri
     for (int e = 0; e < d; ++e) acc += V[(size_t)e * d + a] * s_f[e] * V[(size_t)e * d + b];
     W[i] = acc;
   }
+  if (tid == 0 && vvalid) vvalid[k] = 1;
   __syncthreads();
+  }   // !fast
   if (pq) {
     // coefficients of the expanded quadratic form about the shift, straight from invC (both triangles, as the reference's
     // z^T (invC z) reads them): linear invC mu', quadratic -1/2 invC_ii and -(invC_ij + invC_ji)/2, constant c_k - 1/2 mu'^T invC mu'
@@ -347,21 +433,24 @@ __global__ void __launch_bounds__(1024) k_refresh(Geom g, const double* __restri
 cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, const double* lambda, const double* Sc,
                            const double* mean, double Nglob, double* scratch, double* pack, double* sumLLk, int* info,
                            cudaStream_t st, double* pack2, double* muold, const double* shift, int do_sumll, int cov_diag,
-                           const FusedGeom* fg, int warm, const QfRefresh* qf) {
+                           const FusedGeom* fg, int warm, const QfRefresh* qf, int* vvalid) {
   const FusedGeom f = fg ? *fg : make_fused_geom(g);
   QfRefresh q{};
   if (qf && g.DM <= 4) q = *qf;
   const bool large = g.d > 32;
-  const size_t dyn = large ? (size_t)g.d * g.d * sizeof(double) : 0;
-  if (large) {
+  // the working matrix (Jacobi's A, the Cholesky factor of the fast path) lives in shared memory for every d
+  const size_t dyn = (size_t)g.d * g.d * sizeof(double);
+  if (dyn > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_refresh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
   }
+  const char* fe = getenv("MLF_B200_REFRESH_FAST");   // A/B switch, read per launch
+  const bool fastpath = !(fe && fe[0] == '0');
   // d > 64: the eigenvector updates go to global scratch (A and V do not both fit shared memory at d = 128) and are bound by
   // loads in flight, so the block is as large as the register file allows
   k_refresh<<<g.K8 * 8, g.d > 64 ? 1024 : (large ? 256 : 128), dyn, st>>>(g, Mu, Cov, lambda, Sc, mean, Nglob, scratch, pack, sumLLk, info, pack2, muold,
-                                                     f.PSF, f.OFFB, f.OFFC, shift ? shift : mean, do_sumll, large ? 1 : 0, cov_diag, f.diag ? 1 : 0,
-                                                     warm ? 1 : 0, q);
+                                                     f.PSF, f.OFFB, f.OFFC, shift ? shift : mean, do_sumll, 1, cov_diag, f.diag ? 1 : 0,
+                                                     warm ? 1 : 0, q, (fastpath && vvalid) ? 1 : 0, vvalid);
   return cudaGetLastError();
 }
 

@@ -105,7 +105,8 @@ constexpr int kMstepTilePts = 2048;     // points per block tile of the M-pass s
 cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, const double* lambda, const double* Sc,
                            const double* mean, double Nglob, double* scratch, double* pack, double* sumLLk, int* info,
                            cudaStream_t st, double* pack2 = nullptr, double* muold = nullptr, const double* shift = nullptr,
-                           int do_sumll = 1, int cov_diag = 0, const FusedGeom* fg = nullptr, int warm = 0, const QfRefresh* qf = nullptr);
+                           int do_sumll = 1, int cov_diag = 0, const FusedGeom* fg = nullptr, int warm = 0, const QfRefresh* qf = nullptr,
+                           int* vvalid = nullptr);   // vvalid: [K8*8] ints, zeroed by the caller once: enables the Cholesky fast path
 // max_i |x_ia - shift_a| per coordinate (d <= 16): partial[grid][16], then out[a] = max over blocks (16 values)
 cudaError_t launch_absmax(const double* X, int64_t N, int d, const double* shift, double* partial, int grid, double* out, cudaStream_t st);
 cudaError_t launch_sumll(const Geom& g, const double* Mu, const double* Sc, const double* mean, double Nglob, const double* scratch,

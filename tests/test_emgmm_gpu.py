@@ -350,6 +350,29 @@ def test_statistics_first_scatter_from_stored_responsibilities(shape, oracle, mo
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("shape", [(16, 8, 600, 6.0), (2, 3, 900, 4.0), (40, 5, 400, 4.0), (128, 3, 300, 3.0)], ids=["d16", "d2", "d40", "d128"])
+def test_refresh_cholesky_fast_path_and_eigen_branch_agree(shape, oracle, monkeypatch):
+    """k_refresh takes InverseSymMatrix's eigen branch (Jacobi, spectrum floor) only when it has to: for a covariance whose
+    condition number is provably below 1e6 the floor is inactive and the inverse / lnDet come from one Cholesky factorisation.
+    Both routes (MLF_B200_REFRESH_FAST=1 / 0) must give the oracle's trajectory and agree with each other far inside the budget."""
+    d, K, npc, sc = shape
+    data = synth.make_mixture(d, K, npc, sc, 1.0, 400 + d)
+    X = data["X"]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 400 + d)
+    iters = 3
+    oMu, oCov, olam, otr = oracle.em_iterations(X, Mu0, Cov0, lam0, 1.0, iters)
+    got = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MLF_B200_REFRESH_FAST", mode)
+        em = make_em(X, K, 1.0, Mu0, Cov0, lam0)
+        assert em.step(iters)[0] == 0, em.last_error()
+        check_against(em, oMu, oCov, olam, otr)
+        got[mode] = (em.Mu.copy(), em.Cov.copy(), em.sumLL_trace().copy())
+        em.finalize()
+    assert rel(got["1"][0], got["0"][0]) <= 1e-12 and rel(got["1"][1], got["0"][1]) <= 1e-11
+    assert np.abs((got["1"][2] - got["0"][2]) / got["0"][2]).max() <= 1e-13
+
+
 def test_streamed_refresh_of_x(oracle):
     """refresh_x(host X) + step: the upload is chunked underneath the first sweep and the global moments (sumLL) are
     re-accumulated about the old shift; results must equal a fresh run on the new data."""
