@@ -423,7 +423,7 @@ def main():
         "kept_pairs_per_point": (counters["kept_pairs"] / it / max(n_loc * world, 1)) if fused else None,
         # how the sweep formed the log-densities: expanded quadratic form (guarded by the magnitude bound of its terms) or whitening
         "logits": {"quadratic_form_sweeps": qf["qf_sweeps"], "whitening_sweeps": int(sweeps) - qf["qf_sweeps"] if fused else None,
-                   "scatter_passes_from_stored_responsibilities": qf["scatter_passes"], "term_magnitude_bound": qf["bound"], "guard": "4 u S_k <= 5e-11 (MLF_B200_QF_TOL)"} if "k_em16" in plan else None,
+                   "scatter_passes_from_stored_responsibilities": qf["scatter_passes"], "term_magnitude_bound": qf["bound"], "guard": "4 u S_k <= 5e-11 (MLF_B200_QF_TOL)"} if ("k_em16" in plan or "k_emd" in plan) else None,
         "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None, "traffic": traffic,
         "peak_source": ("fp64 DFMA on the CUDA cores (same fp64 datapath as DMMA; 'tensor' is kept as the bound label of the contract)"
                         if diag_cc else "fp64 DMMA (mma.sync m8n8k4.f64)") +

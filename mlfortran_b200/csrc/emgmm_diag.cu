@@ -34,7 +34,7 @@ constexpr int kXS = 12;   // row stride of the staged points: 8 coordinates, 1/s
 // row stride of the logit tile: the P2 access (TP/8 rows per warp, 32/(TP/8) lanes of 8 bytes each) must spread over the banks
 int emd_stride(int KP, int tp) { return ((KP + 15) / 16) * 16 + (tp == 64 ? 4 : 8); }
 size_t emd_smem(int KP, int tp) {
-  return ((size_t)tp * kXS + (size_t)tp * emd_stride(KP, tp) + 128 + 8 * (size_t)KP) * sizeof(double) + 8 * (size_t)tp * sizeof(int);
+  return ((size_t)tp * kXS + (size_t)tp * emd_stride(KP, tp) + 128 + 8 * (size_t)KP + (size_t)KP) * sizeof(double) + 8 * (size_t)tp * sizeof(int);
 }
 
 }  // namespace
@@ -52,7 +52,18 @@ bool emd_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
 // comparison and strength-reduced addressing took 185 -> 174 ms, sum g x' as DMMA tiles 174 -> 166, the whole main path of P3 in
 // the DMMA fragment layout 166 -> 160 (MLF_B200_EMD_XMMA=0 keeps the lane = component form).  No gain: driving the kept /
 // listed branches from one warp-wide OR of per-point flags, computed in the main path (177 ms) or inside the rare path (161 ms).
-template <int TP, bool XMMA>
+// QP1 (round 2): P1 on the tensor datapath after all -- not as tiles of the diagonal factor (7/8 zeros) but as the expanded form
+// logit = [c - 1/2 sum b_a^2] - sum_a (l_a b_a) x'_a - 1/2 sum_a l_a^2 x'_a^2: a dense dot product of 16 coefficients with the 16
+// monomials (x'_a, x'_a^2) of the point = 4 DMMA k-steps for 8 points x 8 components, with the warp's coefficient fragments
+// (4 blocks x 4 k-steps) in registers for the whole sweep.  Same datapath time as the 2 DFMA per dimension of the lane = component
+// form, but 16 DMMA + 2 loads per 8 points x 32 components instead of 128 DFMA + 32 broadcast loads: P1 was bound by instruction
+// issue, not by the fp64 pipe.  The expanded form cancels (terms ~ (distance from the shift / width)^2), so it is taken only
+// when the bound S_k that k_refresh leaves for every component keeps the estimated logit error under the engine's limit
+// (A.qfS, A.qf_limit; decided by every block, as in k_em16); the other variant returns at once.
+// Measured on the config-5 shard (N=1.25e8, d=8, K=256): 145.4 -> 143.0 ms per sweep only -- the lane = component P1 already ran
+// near the datapath rate (136 DFMA against 16 DMMA per 8 points x 32 components hold the fp64 pipe for the same 270 clocks);
+// what keeps this kernel at ~45 % of the pipe are the latency-bound softmax and statistics phases at two warps per scheduler.
+template <int TP, bool XMMA, bool QP1>
 __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
   constexpr int PSF = 20, XS = kXS, DS = 10, MSF = 74;
   constexpr int GP = TP / 8;       // points per warp in P2
@@ -65,7 +76,15 @@ __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
   double* etab = tile + (size_t)TP * S;    // [128] 2^(j/128)
   double* mus = etab + 128;                // [8][KP] scatter centres mu_old - shift, dimension-major
   int* wmax = reinterpret_cast<int*>(mus + 8 * (size_t)KP);   // [8 warps][TP] ordered key of the warp's largest logit, per point
+  double* cst = reinterpret_cast<double*>(wmax + 8 * TP);     // [KP] QP1: constant of the expanded logit
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane / TT, t = lane % TT;
+  {  // which P1 runs: every S_k inside the limit -> expanded form on the tensor datapath, otherwise (or NaN, or no limit) lane = component
+    bool bad = !(A.qf_limit >= 0.0) || A.qfS == nullptr;
+    if (!bad)
+      for (int i = tid; i < KP; i += 256) bad |= !(A.qfS[i] <= A.qf_limit);
+    const bool use_q = __syncthreads_or(bad ? 1 : 0) == 0;
+    if (use_q != QP1) return;
+  }
   const int comp = 32 * warp + lane;       // the component this lane owns in P1 / P3
   const bool own = comp < KP;
   const bool wact = 32 * warp < KP;        // warp-uniform: this warp owns at least one component
@@ -79,6 +98,23 @@ __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
     if (own) mus[a * KP + comp] = A.muold[(size_t)comp * 8 + a] - A.shift[a];
   }
   if (own) { ck = A.pack2[(size_t)comp * PSF + 16]; thi = A.thi[comp]; tlo = A.tlo[comp]; }
+  const int gq = lane >> 2, tq = lane & 3;
+  double thq[4][4];   // QP1: coefficient fragments (B operand): block b, k-step s -> coefficient of monomial 4 s + tq for component 32 warp + 8 b + gq
+  if (QP1) {
+    double bb = 0;
+#pragma unroll
+    for (int a = 0; a < kD; ++a) bb = fma(b[a], b[a], bb);
+    if (own) cst[comp] = ck - 0.5 * bb;   // -inf for dummy components
+#pragma unroll
+    for (int bq = 0; bq < 4; ++bq) {
+      const int c = 32 * warp + 8 * bq + gq;
+      const bool ok = c < KP;
+      const double l0 = ok ? A.pack2[(size_t)c * PSF + tq] : 0.0, l1 = ok ? A.pack2[(size_t)c * PSF + 4 + tq] : 0.0;
+      const double b0 = ok ? A.pack2[(size_t)c * PSF + 8 + tq] : 0.0, b1 = ok ? A.pack2[(size_t)c * PSF + 12 + tq] : 0.0;
+      thq[bq][0] = -l0 * b0; thq[bq][1] = -l1 * b1;               // x'_tq, x'_{4+tq}
+      thq[bq][2] = -0.5 * l0 * l0; thq[bq][3] = -0.5 * l1 * l1;   // x'_tq^2, x'_{4+tq}^2
+    }
+  }
   // "not below the threshold and not zero" as one comparison: responsibilities are >= 0 (or NaN), so
   // !(a < t) && a != 0  <=>  !(a < max(t, smallest subnormal)); NaN stays a candidate as before
   const double tlo_e = fmax(tlo, 4.9406564584124654e-324), thi_e = fmax(thi, 4.9406564584124654e-324);
@@ -89,7 +125,6 @@ __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
   // XMMA: sum g x' as DMMA tiles [8 components x 4 points].[4 points x 8 dims], one per 8-component block of the warp; lane
   // (gq, tq) holds dims 2 tq, 2 tq + 1 of component 32 warp + 8 b + gq.  One shared-memory load per block instead of the four
   // broadcast LDS.128 per point of the lane = component form (the P3 loop is bound by shared-memory instruction issue).
-  const int gq = lane >> 2, tq = lane & 3;
   double accX[4][2], sgq[4], sg2q[4], tloq[4];   // sum g and sum g^2 ride along in the same layout (per lane: its point column)
 #pragma unroll
   for (int a = 0; a < kD; ++a) {
@@ -144,7 +179,41 @@ __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
     }
     __syncthreads();
     // ---- P1: lane = component; logits of PB points at a time (PB independent chains), and the warp's maximum per point ----
-    if (wact) {
+    if (wact && QP1) {
+#pragma unroll 1
+      for (int pt0 = 0; pt0 < TP; pt0 += 8) {
+        const double xlo = xs[(pt0 + gq) * XS + tq], xhi = xs[(pt0 + gq) * XS + 4 + tq];
+        const double x2lo = xlo * xlo, x2hi = xhi * xhi;
+        double c[4][2];
+#pragma unroll
+        for (int bq = 0; bq < 4; ++bq) {
+          const int cc = (32 * warp + 8 * bq < KP) ? 32 * warp + 8 * bq + 2 * tq : 0;
+          const double2 v = *reinterpret_cast<const double2*>(cst + cc);
+          c[bq][0] = v.x; c[bq][1] = v.y;
+        }
+#pragma unroll
+        for (int bq = 0; bq < 4; ++bq) dmma(c[bq], xlo, thq[bq][0]);
+#pragma unroll
+        for (int bq = 0; bq < 4; ++bq) dmma(c[bq], xhi, thq[bq][1]);
+#pragma unroll
+        for (int bq = 0; bq < 4; ++bq) dmma(c[bq], x2lo, thq[bq][2]);
+#pragma unroll
+        for (int bq = 0; bq < 4; ++bq) dmma(c[bq], x2hi, thq[bq][3]);
+        double mx = -INFINITY;
+#pragma unroll
+        for (int bq = 0; bq < 4; ++bq)
+          if (32 * warp + 8 * bq < KP) {   // warp-uniform
+            *reinterpret_cast<double2*>(tile + (size_t)(pt0 + gq) * S + 32 * warp + 8 * bq + 2 * tq) = make_double2(c[bq][0], c[bq][1]);
+            mx = fmax(mx, fmax(c[bq][0], c[bq][1]));
+          }
+        const int hi = __double2hiint(mx);
+        int mk = hi ^ ((hi >> 31) & 0x7fffffff);
+        mk = max(mk, __shfl_xor_sync(kFull, mk, 1));
+        mk = max(mk, __shfl_xor_sync(kFull, mk, 2));
+        if (tq == 0) wmax[warp * TP + pt0 + gq] = mk;
+      }
+    }
+    if (wact && !QP1) {
       constexpr int PB = (TP == 64) ? 8 : 4;
 #pragma unroll 1
       for (int pt0 = 0; pt0 < TP; pt0 += PB) {
@@ -358,11 +427,20 @@ static cudaError_t launch_emd_t(const Geom& g, EmArgs a, int grid, cudaStream_t 
   const size_t smem = emd_smem(KP, TP);
   const char* ev = getenv("MLF_B200_EMD_XMMA");   // A/B switch: 0 = sum g x on the CUDA cores (lane = component)
   const bool xmma = !(ev && ev[0] == '0');
-  cudaError_t e = cudaFuncSetAttribute(xmma ? k_emd<TP, true> : k_emd<TP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
   a.S = emd_stride(KP, TP);
-  if (xmma) k_emd<TP, true><<<grid, 256, smem, st>>>(a);
-  else k_emd<TP, false><<<grid, 256, smem, st>>>(a);
+  auto go = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, 256, smem, st>>>(a);
+    return cudaSuccess;
+  };
+  // expanded-form P1 first (returns at once unless every bound S_k is inside the limit), then the lane = component P1
+  const bool qp1 = xmma && a.qf_limit >= 0.0 && a.qfS;
+  if (!qp1) a.qf_limit = -1.0;
+  cudaError_t e = cudaSuccess;
+  if (qp1) e = go(k_emd<TP, true, true>);
+  if (e == cudaSuccess) e = xmma ? go(k_emd<TP, true, false>) : go(k_emd<TP, false, false>);
+  if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }
 
@@ -386,6 +464,8 @@ cudaError_t launch_selftest_exp(const double* in, double* out, int64_t n, int wh
 
 cudaError_t launch_emd(const Geom& g, const FusedGeom& f, EmArgs a, int grid, size_t smem_limit, cudaStream_t st) {
   if (!emd_ok(g, f, smem_limit)) return cudaErrorInvalidConfiguration;
+  // (32-point tiles with two blocks per SM -- 128 registers -- were measured again with the expanded-form P1: 184 bytes of
+  // spills, 261 ms per iteration against 200; only the 64-point instantiation is built)
   return launch_emd_t<64>(g, a, grid, st);
 }
 

@@ -118,7 +118,9 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
     // quadratic-form logits inside the 16-warp sweep, guarded by the magnitude bounds of k_refresh
     const char* q = getenv("MLF_B200_QF");
     const int qmode = q ? atoi(q) : 1;
-    qf_ = use16_ && !used_ && !cov_diag_ && qmode != 0 && em16_qf_ok(geom_, fgeom_, smem_limit_);
+    qf16_ = use16_ && !used_ && !cov_diag_ && qmode != 0 && em16_qf_ok(geom_, fgeom_, smem_limit_);
+    qfd_ = used_ && qmode != 0;   // expanded-form P1 of the diagonal sweep (k_emd QP1), same guard
+    qf_ = qf16_ || qfd_;
     double tol = 5e-11;
     if (const char* qt = getenv("MLF_B200_QF_TOL")) tol = atof(qt);
     qf_limit_ = qmode == 2 ? INFINITY : tol / (4.0 * 1.1102230246251565e-16);
@@ -154,7 +156,7 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   CKE(A(&dMomRaw_, (size_t)g.MB * 64 + 8 * g.DN), "cudaMalloc");
   CKE(cudaStreamCreateWithFlags(&cst_, cudaStreamNonBlocking), "cudaStreamCreate");
   if (qf_) {
-    CKE(A(&dPackQ_, (size_t)g.K8 * qf_stride(g.DM)), "cudaMalloc");
+    if (qf16_) CKE(A(&dPackQ_, (size_t)g.K8 * qf_stride(g.DM)), "cudaMalloc");
     CKE(A(&dQfS_, KP), "cudaMalloc");
     CKE(A(&dRadPart_, (size_t)sms_ * 16), "cudaMalloc");
   }

@@ -168,6 +168,7 @@ class EmgmmEngine {
   // per-rank radius of the data about the shift (gathered), and the limit the bounds are held against
   double *dPackQ_ = nullptr, *dQfS_ = nullptr, *dRad_ = nullptr, *dRadPart_ = nullptr;
   int rad_world_ = 0;           // rank slots allocated in dRad_
+  bool qf16_ = false, qfd_ = false;   // which sweep has an expanded-form variant: k_em16 (full covariances), k_emd (diagonal)
   bool qf_ = false;             // variant available for this shape (MLF_B200_QF=0 disables, =2 forces it whatever the bounds say)
   bool rad_ready_ = false;
   double qf_limit_ = 0;         // S_k <= qf_limit_  <=>  estimated logit error 4 u S_k <= MLF_B200_QF_TOL (default 5e-11)

@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(1024) k_refresh(Geom g, const double* __restri
     if (pq) {
       for (int f = tid; f < 4 * qNF; f += nt) pq[(f >> 2) * 32 + (k & 7) * 4 + (f & 3)] = 0.0;
       if (tid == 0) { pq[qNF * 32 + (k & 7)] = -INFINITY; qf.qfS[k] = 0.0; }
+    } else if (qf.qfS && tid == 0) {
+      qf.qfS[k] = 0.0;
     }
     return;
   }
@@ -409,6 +411,22 @@ __global__ void __launch_bounds__(1024) k_refresh(Geom g, const double* __restri
       muold[(size_t)k * 8 * g.DN + n] = (n < d) ? muk[n] : 0.0;
     }
     if (tid == 0) { p2[OFFC2] = ck; p2[OFFC2 + 1] = 0; p2[OFFC2 + 2] = 0; p2[OFFC2 + 3] = 0; }
+    if (diag_pack && qf.qfS && !pq) {
+      // magnitude bound of the expanded diagonal logit (k_emd QP1): sum_a (l_a^2 R_a^2 / 2 + |l_a b_a| R_a + b_a^2 / 2) + |c|,
+      // R_a = radius of the data about the shift in coordinate a (unknown: +inf, the guard rejects)
+      double part = 0;
+      for (int n = tid; n < d; n += nt) {
+        double r = INFINITY;
+        if (qf.rad) {
+          r = 0.0;
+          for (int w = 0; w < qf.nrad; ++w) r = fmax(r, qf.rad[(size_t)w * 16 + n]);
+        }
+        const double l = W[(size_t)n * d + n], bb = l * (muk[n] - shift[n]);
+        part += 0.5 * l * l * r * r + fabs(l * bb) * r + 0.5 * bb * bb;
+      }
+      part = block_sum(part, s_red);
+      if (tid == 0) qf.qfS[k] = part + fabs(ck);
+    }
   }
 
   if (!do_sumll) return;   // streamed refresh of X: the moments are not final yet, k_sumll runs after the sweep

@@ -689,10 +689,14 @@ EMD_CASES = [
 ]
 
 
+@pytest.mark.parametrize("qmode", ["2", "0"], ids=["expanded_form_dmma", "lane_per_component_dfma"])
 @pytest.mark.parametrize("case", EMD_CASES, ids=[f"d{c[0]}_K{c[1]}" for c in EMD_CASES])
-def test_diagonal_cuda_core_kernel_matches_oracle(case, oracle):
-    """k_emd (lane = component, fp64 FMA on the CUDA cores; the plan for diagonal covariances at d <= 8, K >= 128)."""
+def test_diagonal_cuda_core_kernel_matches_oracle(case, qmode, oracle, monkeypatch):
+    """k_emd, the plan for diagonal covariances at d <= 8, K >= 128 (statistics: lane = component on the CUDA cores), with both forms
+    of its logits phase: the expanded form as DMMA tiles (16 monomials x'_a, x'_a^2; MLF_B200_QF=2 forces it) and the lane =
+    component DFMA form (MLF_B200_QF=0)."""
     d, K, npc, sc, seed, mp, iters = case
+    monkeypatch.setenv("MLF_B200_QF", qmode)
     data = synth.make_mixture(d, K, npc, sc, 1.0, seed)
     X = data["X"]
     Mu0, Cov0, lam0 = synth.injected_init(data["centres"], seed)
@@ -713,6 +717,7 @@ def test_diagonal_cuda_core_kernel_matches_oracle(case, oracle):
         top2 = np.sort(Pn, axis=0)[-2:]
         assert ((top2[1] - top2[0]) <= 1e-9 * top2[1])[bad].all()
     assert em.times()["sweeps"] >= iters
+    assert em.qf_stats()["qf_sweeps"] == (em.counters()["sweeps"] if qmode == "2" else 0)
     em.finalize()
 
 
