@@ -98,15 +98,19 @@ bool em16_qf_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
 // coefficient fragments of 8 components the B operand, the accumulator is the logit.  Both variants are launched for a sweep;
 // each block decides from the bounds S_k left by k_refresh which of the two does the work (the other returns at once), so
 // the choice needs no host round trip.  Measured in isolation (bench/micro/p1_quadform.cu): 2.24 ms against 3.27 ms for the
-// whitening loop on the same points; in the sweep at N=1e8, d=16, K=64: 95.2 ms against 116.9.  (QFM = 2 interleaves the
-// accumulator chains of two component blocks: 96.5 ms, not instantiated.)
+// whitening loop on the same points; in the sweep at N=1e8, d=16, K=64: 95.2 ms against 116.9.  Scheduling experiments on this
+// variant, all measured at the headline shape and none kept (QFM >> 1 selects them, not instantiated): accumulator chains of two
+// component blocks interleaved 96.5 ms; eight exps in flight in P2 95.1; P3a unrolled 8 times 95.4; the barrier between softmax and
+// statistics replaced by one mbarrier per producer warp, consumers starting with their own points' groups, 97.1.  The sweep sits
+// at ~95 ms whatever is moved: the datapath is saturated while warps are in P1 and idles when both groups are in P2 / P3.
 template <int DM, int VAR, int QFM, bool STORE>
 __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   // STORE: "statistics first" pass of an iteration whose covariance thresholds cannot be predicted: E-step + pass-A statistics
   // only (no classification, no scatter), and the tile of finished responsibilities goes to HBM ([tile][64][KP], A.gtiles) for
   // the scatter pass k_scatter16, which then knows the exact thresholds.
-  constexpr bool QF = QFM != 0;       // QFM: 0 whitening, 1 quadratic form, 2 quadratic form with the chains of two component blocks interleaved
-  constexpr int CH = QFM == 2 ? 2 : 1;
+  constexpr bool QF = (QFM & 1) != 0;   // QFM: 0 whitening, odd: quadratic form; QFM >> 1 = experiment (MLF_B200_QF_EXP, A/B runs)
+  constexpr int EXPV = QFM >> 1;       // 1: eight exps in flight in P2; 2: P3a unrolled 8 times (neither instantiated, see above)
+  constexpr int CH = 1;
   constexpr bool FOLD = (VAR & 1) != 0;
   static_assert(!QF || FOLD, "the quadratic-form variant keeps 1/sum beside the tile");
   constexpr int PIPE = (VAR >> 1) & 3;
@@ -385,7 +389,7 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
     rmax = fmax(rmax, shx(rmax, 2));
     double sum = 0;
     if constexpr (QF) {   // each lane exponentiates the two logits per component block it wrote itself
-#pragma unroll 2
+#pragma unroll (EXPV == 1 ? 4 : 2)
       for (int cq = 0; cq < K8; ++cq) {
         const double2 v = *reinterpret_cast<const double2*>(row + 8 * cq + 2 * t);
         const double e0 = exp_tab(v.x - rmax, etab), e1 = exp_tab(v.y - rmax, etab);
@@ -435,7 +439,7 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
     if (own) {
       const int64_t q0 = bt * TP;
       const double* tcol = tile + 8 * cb + g;
-#pragma unroll 4
+#pragma unroll (EXPV == 2 ? 8 : 4)
       for (int i = 0; i < 16; ++i) {
         const int pb = i;
         const double a = FOLD ? tcol[(size_t)(4 * pb + t) * S] * invs[4 * pb + t] : tcol[(size_t)(4 * pb + t) * S];
@@ -464,7 +468,7 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
           cm = (cm | (cm >> 3)) & 0x03030303u;
           cm = (cm | (cm >> 6)) & 0x000f000fu;
           cm = (cm | (cm >> 12)) & 0xffu;
-          if (lane == i) act = cm;
+          if (lane == pb) act = cm;
         }
         if (mm) {
           const int sl = nAmb + __popc(mm & ((1u << lane) - 1u));
