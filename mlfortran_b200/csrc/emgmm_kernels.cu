@@ -458,7 +458,7 @@ cudaError_t launch_refresh(const Geom& g, const double* Mu, const double* Cov, c
   const bool large = g.d > 32;
   // the working matrix (Jacobi's A, the Cholesky factor of the fast path) lives in shared memory for every d
   const size_t dyn = (size_t)g.d * g.d * sizeof(double);
-  if (dyn > 48 * 1024) {
+  if (dyn > 32 * 1024) {   // static shared memory (reduction scratch, rotation parameters) comes on top of the 48 KB default limit
     cudaError_t e = cudaFuncSetAttribute(k_refresh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
   }
@@ -760,7 +760,7 @@ k_estep(const double* __restrict__ X, int64_t N, int d, int K, int K8, int S, co
         const int k = 4 * k4 + t;
         const double gk = row[grp][k] * inv;
         row[grp][k] = gk;
-        if (valid && k < K) gamma[(size_t)k * ldg + p] = gk;
+        if (gamma != nullptr && valid && k < K) gamma[(size_t)k * ldg + p] = gk;   // labels-only calls (getClass) pass no buffer
       }
       if (labels != nullptr && valid && t == 0) labels[p] = am + 1;  // MAXLOC: first maximum, 1-based
     }

@@ -27,6 +27,8 @@ for i in range(n_cases):
         global bad
         bad += 1
         print("FAIL", what, tag, kw, flush=True)
+        if os.environ.get("MLF_FUZZ_STOP") == "1":
+            os._exit(1)
     # (a) fresh object: initialiser, then one EM iteration from whatever it produced
     em = mlf_algo_emgmm()
     if em.init(X, K, mp) != 0:

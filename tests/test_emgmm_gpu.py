@@ -373,6 +373,51 @@ def test_refresh_cholesky_fast_path_and_eigen_branch_agree(shape, oracle, monkey
     assert np.abs((got["1"][2] - got["0"][2]) / got["0"][2]).max() <= 1e-13
 
 
+def test_labels_only_inference_on_first_generation_plan(oracle):
+    """getClass passes no responsibility buffer to the E-pass; the first-generation kernel (still the plan where the fused pack
+    does not fit shared memory, e.g. d = 24, K = 46) must not write one.  Found by scripts/fuzz_api.py in round 2."""
+    d, K = 24, 46
+    data = synth.make_mixture(d, K, 74, 3.0, 1.0, 9063)
+    X = data["X"]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 9063)
+    em = make_em(X, K, 1.0, Mu0, Cov0, lam0)
+    assert "k_estep<" in em.kernel_plan(), em.kernel_plan()
+    assert em.step(2)[0] == 0, em.last_error()
+    Q = np.ascontiguousarray(X[:257] + 0.1)
+    info, cl = em.getClass(Q)          # labels only, before any getProba on this object
+    assert info == 0, em.last_error()
+    _, Po, _ = oracle.exp_step(Q, em.Mu, em.Cov, em.lambda_)
+    top2 = np.sort(Po, axis=0)[-2:]
+    assert ((cl == oracle.get_class(Po)) | ((top2[1] - top2[0]) <= 1e-9 * top2[1])).all()
+    info, P = em.getProba(Q)
+    assert info == 0 and np.abs(P - Po).max() <= 1e-9
+    em.finalize()
+
+
+def test_refresh_shared_memory_opt_in_in_a_fresh_process():
+    """k_refresh at 64 < d < 78 needs more than the default 48 KB of shared memory once its static scratch is counted; the opt-in
+    is per process, so a d = 128 test earlier in the same process hides a missing one.  Fresh process, d = 70 first.  Found by
+    scripts/fuzz_parity.py in round 2."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from mlfortran_b200 import mlf_algo_emgmm, synth\n"
+        "from oracle.emgmm_oracle import get\n"
+        "d, K = 70, 5\n"
+        "data = synth.make_mixture(d, K, 200, 3.0, 1.0, 5040)\n"
+        "Mu0, Cov0, lam0 = synth.injected_init(data['centres'], 5040)\n"
+        "em = mlf_algo_emgmm(); assert em.init(data['X'], K, 1.0) == 0\n"
+        "em.inject(Mu0, Cov0, lam0)\n"
+        "info, _ = em.step(2); assert info == 0, em.last_error()\n"
+        "oMu, oCov, olam, otr = get().em_iterations(data['X'], Mu0, Cov0, lam0, 1.0, 2)\n"
+        "assert np.abs((em.sumLL_trace() - otr) / otr).max() <= 1e-10 and np.abs(em.Cov - oCov).max() <= 1e-9 * np.abs(oCov).max()\n"
+        "print('ok')\n" % root)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
 def test_streamed_refresh_of_x(oracle):
     """refresh_x(host X) + step: the upload is chunked underneath the first sweep and the global moments (sumLL) are
     re-accumulated about the old shift; results must equal a fresh run on the new data."""
