@@ -33,7 +33,7 @@ Module mlf_emgmm_b200
   ! .TRUE.: objects initialised from now on shard their points over every visible GPU inside this process (peer-memory
   ! all-reduce, mlf_b200_engine_create_multi); .FALSE.: the current CUDA device only.
   Logical, Public, Save :: mlf_b200_use_all_gpus = .FALSE.
-  Public :: mlf_b200_synth_gmm_f
+  Public :: mlf_b200_synth_gmm_f, mlf_b200_nccl_unique_id_f
 
   Type, Public, Extends(mlf_step_obj) :: mlf_algo_emgmm_b200
     real(c_double), pointer :: X(:,:), Mu(:,:), Cov(:,:,:), lambda(:)
@@ -47,6 +47,7 @@ Module mlf_emgmm_b200
     procedure :: reinit => emgmm_b200_reinit
     procedure :: stepF => emgmm_b200_stepF
     procedure :: getProbaC => emgmm_b200_getProbaC
+    procedure :: joinNccl => emgmm_b200_joinNccl
     procedure :: finalize => emgmm_b200_finalize
   End Type mlf_algo_emgmm_b200
 
@@ -104,6 +105,18 @@ Module mlf_emgmm_b200
       type(c_ptr), value :: eng
       real(c_double), intent(out) :: ProbaC(*)
     End Function c_engine_proba
+    ! One process per GPU (MPI): rank 0 draws the 128-byte ncclUniqueId, the caller broadcasts it (MPI_Bcast), every rank joins
+    ! before its first step.  The statistics all-reduce of every iteration is then an ncclAllReduce issued by the library.
+    Integer(c_int) Function c_nccl_unique_id(id) bind(C, name="mlf_b200_nccl_unique_id")
+      Import :: c_int, c_signed_char
+      integer(c_signed_char), intent(out) :: id(128)
+    End Function c_nccl_unique_id
+    Integer(c_int) Function c_engine_nccl_init(eng, id, rank, world) bind(C, name="mlf_b200_engine_nccl_init")
+      Import :: c_ptr, c_int, c_signed_char
+      type(c_ptr), value :: eng
+      integer(c_signed_char), intent(in) :: id(128)
+      integer(c_int), value :: rank, world
+    End Function c_engine_nccl_init
     ! Workload generator of tests/test_emgmm.f90:105-124 (RandN centres, randOrthogonal(C12, weight), RandN(X, X0, C12), randPerm)
     ! on the device: points n0+1 .. n0+nX of an nTotal-point job into X(nY, nX) (host array with flags = 0); XC(nY, nC) and
     ! C12(nY, nY, nC) come back as the test program's own arrays would.  Replaces the generation loop of testGMM at scale.
@@ -210,6 +223,20 @@ Contains
     real(c_double), intent(out) :: ProbaC(:,:)
     info = c_engine_proba(this%engine, ProbaC)
   End Function emgmm_b200_getProbaC
+
+  ! Sharded use, one MPI rank per GPU: X passed to init is this rank's contiguous shard of the points.
+  !   If(rank == 0) info = mlf_b200_nccl_unique_id_f(id);  CALL MPI_Bcast(id, 128, MPI_BYTE, 0, comm, ierr);  info = em%joinNccl(id, rank, world)
+  Integer Function mlf_b200_nccl_unique_id_f(id) Result(info)
+    integer(c_signed_char), intent(out) :: id(128)
+    info = c_nccl_unique_id(id)
+  End Function mlf_b200_nccl_unique_id_f
+
+  Integer Function emgmm_b200_joinNccl(this, id, rank, world) Result(info)
+    class(mlf_algo_emgmm_b200), intent(inout), target :: this
+    integer(c_signed_char), intent(in) :: id(128)
+    integer, intent(in) :: rank, world
+    info = c_engine_nccl_init(this%engine, id, INT(rank, c_int), INT(world, c_int))
+  End Function emgmm_b200_joinNccl
 
   Subroutine emgmm_b200_finalize(this)
     class(mlf_algo_emgmm_b200), intent(inout) :: this

@@ -205,6 +205,9 @@ int mlf_b200_engine_expectation(MLF_B200_ENGINE *eng, const double *Mu, const do
 /* ProbaC(nX,nC) of the resident points as of the last ExpStep (the Fortran type's public ProbaC component). */
 int mlf_b200_engine_proba(MLF_B200_ENGINE *eng, double *ProbaC);
 int mlf_b200_engine_set_allreduce(MLF_B200_ENGINE *eng, mlf_b200_allreduce_fn fn, void *ctx, int rank, int world);
+/* One process per GPU from Fortran (MPI): rank 0 calls mlf_b200_nccl_unique_id, the 128 bytes are broadcast (MPI_Bcast), every
+ * rank joins with this call before its first step; the communicator is destroyed with the engine. */
+int mlf_b200_engine_nccl_init(MLF_B200_ENGINE *eng, const void *id128, int rank, int world);
 const char *mlf_b200_engine_last_error(MLF_B200_ENGINE *eng);
 
 /* Generic dataset access on a checkpoint handle (file or group handle; int64 / float64; dims in file (C) order, i.e. the

@@ -81,6 +81,7 @@ SYMBOLS = {
     "mlf_b200_engine_expectation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "mlf_b200_engine_proba": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mlf_b200_engine_set_allreduce": (C.c_int, [C.c_void_p, ALLREDUCE_FN, C.c_void_p, C.c_int, C.c_int]),
+    "mlf_b200_engine_nccl_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "mlf_b200_engine_last_error": (C.c_char_p, [C.c_void_p]),
     "mlf_b200_h5_put": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, c_int64_p, C.c_void_p, C.c_int]),
     "mlf_b200_h5_get": (C.c_int, [C.c_void_p, C.c_char_p, c_int_p, c_int_p, c_int64_p, C.c_void_p, C.c_int64]),

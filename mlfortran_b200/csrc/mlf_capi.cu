@@ -788,7 +788,19 @@ struct EngHandle {  // one device, or every listed device of the box inside this
   std::unique_ptr<EmgmmEngine> single;
   std::unique_ptr<MultiEngine> multi;
   std::string err;
+  void* nccl_comm = nullptr;   // mlf_b200_engine_nccl_init: owned
+  ~EngHandle() {
+    single.reset();            // the engine's stream is drained before the communicator goes
+    if (nccl_comm)
+      if (const mlfb200::NcclApi* api = mlfb200::nccl_api()) api->CommDestroy(nccl_comm);
+  }
 };
+int eng_nccl_trampoline(void* ctx, double* buf, int64_t count, void* stream) {
+  EngHandle* h = static_cast<EngHandle*>(ctx);
+  const mlfb200::NcclApi* api = mlfb200::nccl_api();
+  if (!api || !h->nccl_comm) return -1;
+  return api->AllReduce(buf, buf, (size_t)count, 8 /* ncclFloat64 */, 0 /* ncclSum */, h->nccl_comm, stream) == 0 ? 0 : -1;
+}
 EngHandle* as_eng(MLF_B200_ENGINE* p) { return static_cast<EngHandle*>(p); }
 }  // namespace
 
@@ -855,6 +867,19 @@ int mlf_b200_engine_set_allreduce(MLF_B200_ENGINE* eng, mlf_b200_allreduce_fn fn
   EngHandle* e = as_eng(eng);
   if (!e || e->multi) return -1;
   e->single->set_allreduce(fn, ctx, rank, world);
+  return 0;
+}
+int mlf_b200_engine_nccl_init(MLF_B200_ENGINE* eng, const void* id128, int rank, int world) {
+  EngHandle* e = as_eng(eng);
+  const mlfb200::NcclApi* api = mlfb200::nccl_api();
+  if (!e || e->multi || !api || !id128 || world < 1 || rank < 0 || rank >= world || e->nccl_comm) return -1;
+  mlfb200::NcclApi::UniqueId id;
+  std::memcpy(id.b, id128, sizeof id.b);
+  if (cudaSetDevice(e->single->device()) != cudaSuccess) return mlf_OTHERERROR;
+  void* comm = nullptr;
+  if (api->CommInitRank(&comm, world, id, rank) != 0) return mlf_OTHERERROR;
+  e->nccl_comm = comm;
+  e->single->set_allreduce(&eng_nccl_trampoline, e, rank, world);
   return 0;
 }
 const char* mlf_b200_engine_last_error(MLF_B200_ENGINE* eng) {
