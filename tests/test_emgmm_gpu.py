@@ -1293,8 +1293,10 @@ def test_native_nccl_allreduce_world_of_one(oracle):
     # the same bring-up at the engine level (what the Fortran shim's joinNccl binds)
     n, d, K = X.shape[0], 4, 5
     eng = lib.mlf_b200_engine_create(X.ctypes.data, n, d, K, 0, 0)
-    assert eng and lib.mlf_b200_engine_nccl_init(eng, ident, 0, 1) == 0
-    assert lib.mlf_b200_engine_nccl_init(eng, ident, 0, 1) == -1   # one communicator per engine
+    ident2 = (C.c_ubyte * 128)()                                   # a unique id serves one communicator
+    assert lib.mlf_b200_nccl_unique_id(ident2) == 0
+    assert eng and lib.mlf_b200_engine_nccl_init(eng, ident2, 0, 1) == 0
+    assert lib.mlf_b200_engine_nccl_init(eng, ident2, 0, 1) == -1  # one communicator per engine
     Mu, Cov, lam, ll = Mu0.copy(), Cov0.copy(), lam0.copy(), C.c_double()
     assert lib.mlf_b200_engine_step(eng, 4, 0.0, Mu.ctypes.data, Cov.ctypes.data, lam.ctypes.data, C.byref(ll)) == 0
     assert abs(ll.value - otr[-1]) <= LL_RTOL * abs(otr[-1]) and rel(Mu, oMu) <= PAR_RTOL and rel(Cov, oCov) <= PAR_RTOL
