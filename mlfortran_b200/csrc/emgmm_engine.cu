@@ -115,6 +115,9 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
     use16_ = fused_ && em16_ok(geom_, fgeom_, smem_limit_) && !(e16 && e16[0] == '0');
     const char* ed = getenv("MLF_B200_EMD");
     used_ = fused_ && cov_diag_ && emd_ok(geom_, fgeom_, smem_limit_) && !(ed && ed[0] == '0');
+    // fewer than 8 component blocks: the statistics of a block are shared by several warps of a group (MLF_B200_EM16_SPLIT=0: one warp)
+    const char* es = getenv("MLF_B200_EM16_SPLIT");
+    spl_ = (use16_ && !(es && es[0] == '0')) ? em16_split(geom_.K8) : 1;
     // quadratic-form logits inside the 16-warp sweep, guarded by the magnitude bounds of k_refresh
     const char* q = getenv("MLF_B200_QF");
     const int qmode = q ? atoi(q) : 1;
@@ -165,7 +168,7 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   CKE(A(&dPrevLambda_, K), "cudaMalloc");
   if (fused_) {
     // the 16-warp variant writes partials per (block, half) and keeps one side list per warp
-    CKE(A(&dPartB2_, (size_t)2 * sms_ * KP * fgeom_.MSF), "cudaMalloc");
+    CKE(A(&dPartB2_, (size_t)2 * sms_ * spl_ * KP * fgeom_.MSF), "cudaMalloc");
     amb_lists_ = sms_ * 16;
     // components a single list can hold: the warp that writes it owns one 8-component block (16-warp sweep), CBMAX blocks
     // (8-warp sweep) or 32 lanes = 32 components (diagonal CUDA-core sweep)
@@ -184,7 +187,7 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
   CKE(A(&dSumLLk_, KP), "cudaMalloc");
   CKE(A(&dStatsA_, (size_t)KP * g.DS), "cudaMalloc");
   CKE(A(&dStatsB_, (size_t)K * g.MS), "cudaMalloc");
-  CKE(A(&dPartA_, (size_t)2 * sms_ * KP * g.DS), "cudaMalloc");
+  CKE(A(&dPartA_, (size_t)2 * sms_ * spl_ * KP * g.DS), "cudaMalloc");
   // pass-B partials: [mgx_][K][MS] (two-pass kernels, mgx_ <= sms_; large-shape kernels, mgx_*K <= 2*sms_+K), and the
   // unit-weight moments run of the large-shape M-pass ([<= 2*sms_][1][MS])
   CKE(A(&dPartB_, (size_t)std::max<int64_t>((int64_t)mgx_ * K, 2 * (int64_t)sms_ + K + 2) * g.MS), "cudaMalloc");
@@ -571,8 +574,8 @@ int EmgmmEngine::streamed_sweep(const EmArgs& base) {
     CKE(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
     cev_.push_back(e);
   }
-  CKE(cudaMemsetAsync(dPartA_, 0, (size_t)2 * sms_ * KP * g.DS * sizeof(double), st_), "memset");
-  CKE(cudaMemsetAsync(dPartB2_, 0, (size_t)2 * sms_ * KP * f.MSF * sizeof(double), st_), "memset");
+  CKE(cudaMemsetAsync(dPartA_, 0, (size_t)2 * sms_ * spl_ * KP * g.DS * sizeof(double), st_), "memset");
+  CKE(cudaMemsetAsync(dPartB2_, 0, (size_t)2 * sms_ * spl_ * KP * f.MSF * sizeof(double), st_), "memset");
   CKE(cudaMemsetAsync(dAmbCount_, 0, (size_t)nlists * sizeof(int), st_), "memset");
   CKE(cudaMemsetAsync(dMomPart_, 0, (size_t)sms_ * PM * sizeof(double), st_), "memset");
   // the copy may not overwrite X before everything queued so far (earlier sweeps) has read it
@@ -612,7 +615,7 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
   const FusedGeom& f = fgeom_;
   const int K = g.K, KP = g.K8 * 8, d = g.d;
   const int nlists = egrid_ * (use16_ ? 16 : kEstepThreads / 32);
-  const int nslots = use16_ ? 2 * egrid_ : egrid_;
+  const int nslots = use16_ ? 2 * egrid_ * spl_ : egrid_;
   const int64_t nA = (int64_t)KP * g.DS, nB = (int64_t)KP * f.MSF;
   const double minW = 1e-3 / (double)(float)nglob_;  // 1d-3/real(NX)  (src/unsupervised/mlf_gaussian.f90:50)
   double* dFlags = dAB_ + nA + nB;                    // [listed pairs, overflowing lists] ride in the same all-reduce
@@ -686,7 +689,7 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
         CKE(cudaMemcpyAsync(dThi_, thi.data(), KP * sizeof(double), cudaMemcpyHostToDevice, st_), "H2D thi");
         EmArgs a{};
         a.X = dX_; a.N = n_; a.d = d; a.K = K; a.K8 = g.K8; a.S = g.S;
-        a.muold = dMuOld_; a.thi = dThi_; a.partB = dPartB2_; a.gtiles = dGTiles_; a.qf_limit = -1.0;
+        a.muold = dMuOld_; a.thi = dThi_; a.partB = dPartB2_; a.gtiles = dGTiles_; a.qf_limit = -1.0; a.spl = spl_;
         CKE(launch_scatter16(g, f, a, egrid_, smem_limit_, st_), "scatter pass (stored responsibilities)");
         CKE(launch_reduce_partials(dPartB2_, nslots, nB, dAB_ + nA, st_), "reduce statsB");
         CKE(launch_amb_summary(dAmbCount_, nlists, amb_cap_, dFlags, st_, dAB_ + nA, KP, f.MSF, g.MB * 64 + 8 * g.DN + 1), "amb summary");
@@ -721,7 +724,7 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
         CKE(launch_sum_k(dSumLLk_, K, dSumLL_ + it, st_), "sum_k");
         launches_ += 2;
       } else {
-        a.gtiles = dGTiles_;
+        a.gtiles = dGTiles_; a.spl = spl_;
         if (use16_) CKE(launch_em16(g, f, a, egrid_, smem_limit_, st_, gstore && pass == 0), "em sweep (fused, 16 warps)");
         else if (used_) CKE(launch_emd(g, f, a, egrid_, smem_limit_, st_), "em sweep (fused, diagonal)");
         else CKE(launch_em(g, f, a, true, egrid_, smem_limit_, st_), "em sweep (fused)");

@@ -117,6 +117,7 @@ class EmgmmEngine {
   FusedGeom fgeom_{};
   bool fused_ = false;        // single-sweep path available for this (d, K)
   bool used_ = false;         // diagonal fused sweep on the CUDA cores (emgmm_diag.cu; MLF_B200_EMD=0 disables)
+  int spl_ = 1;               // k_em16: warps that share one component block's statistics (em16_split; 1 at K > 32)
   bool use16_ = false;        // 16-warp fused sweep with the scatter accumulators in tensor memory (MLF_B200_EM16=0 disables)
   bool legacy_estep_ = false; // MLF_B200_LEGACY=1: first-generation kernels (A/B comparisons)
   bool big_ = false;          // large-shape kernels (d > 32 or pack too large for shared memory; MLF_B200_BIG=1 forces them)

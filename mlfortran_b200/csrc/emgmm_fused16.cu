@@ -139,7 +139,9 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   }
   double* sp = smem;                                  // [KP][PSF] whitening pack / [K8][QS] quadratic-form pack
   double* smu = sp + (QF ? (size_t)K8 * QS : (size_t)KP * PSF);   // [KP][8 DN]
-  const int cb = warp & 7, half = warp >> 3;   // half = group index
+  const int half = warp >> 3;                   // group index
+  const int SPL = A.spl > 1 ? A.spl : 1;        // warps per component block in the statistics phases (small K)
+  const int cb = (warp & 7) % (8 / SPL), spw = (warp & 7) / (8 / SPL);   // component block and share of the tile's 4-point groups
   const int wg = warp & 7;                      // warp index inside the group
   double* xs = smu + (size_t)KP * 8 * DN + (size_t)half * TP * XS;                    // [2][64][XS] raw points, per group
   double* tile = smu + (size_t)KP * 8 * DN + (size_t)2 * TP * XS + (size_t)half * TP * S;  // [2][64][S] logits -> responsibilities
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   const uint32_t tbase = *s_taddr + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(128 * (warp >> 2));
 
   const bool accu = A.accumulate != 0;
-  const int slot = 2 * blockIdx.x + half;
+  const int slot = (2 * blockIdx.x + half) * SPL + spw;
   double* outA = A.partA + (size_t)slot * KP * DS;
   double* outB = A.partB + (size_t)slot * KP * MSF;
   double accA[DN][2], accK[DN][2], sg, sg2, sk, thi_r, tlo_r, nk0;
@@ -439,8 +441,9 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
     if (own) {
       const int64_t q0 = bt * TP;
       const double* tcol = tile + 8 * cb + g;
+      const int i0 = spw * (16 / SPL), i1 = i0 + 16 / SPL;
 #pragma unroll (EXPV == 2 ? 8 : 4)
-      for (int i = 0; i < 16; ++i) {
+      for (int i = i0; i < i1; ++i) {
         const int pb = i;
         const double a = FOLD ? tcol[(size_t)(4 * pb + t) * S] * invs[4 * pb + t] : tcol[(size_t)(4 * pb + t) * S];
         double b[DN];
@@ -580,7 +583,9 @@ __global__ void __launch_bounds__(kThreads16, 1) k_scatter16(EmArgs A) {
   const int K8 = A.K8, KP = K8 * 8, S = A.S, d = A.d;
   const int64_t N = A.N;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  const int cb = warp & 7, half = warp >> 3, wg = warp & 7;
+  const int half = warp >> 3, wg = warp & 7;
+  const int SPL = A.spl > 1 ? A.spl : 1;
+  const int cb = wg % (8 / SPL), spw = wg / (8 / SPL);
   double* smu = smem;                                                     // [KP][8 DN]
   double* xsb = smu + (size_t)KP * 8 * DN + (size_t)half * 2 * TP * XS;   // [2 groups][2 buffers][64][XS]
   double* tlb = smu + (size_t)KP * 8 * DN + (size_t)4 * TP * XS + (size_t)half * 2 * TP * S;   // [2 groups][2 buffers][64][S]
@@ -599,7 +604,7 @@ __global__ void __launch_bounds__(kThreads16, 1) k_scatter16(EmArgs A) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tbase = *s_taddr + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(128 * (warp >> 2));
-  const int slot = 2 * blockIdx.x + half;
+  const int slot = (2 * blockIdx.x + half) * SPL + spw;
   double* outB = A.partB + (size_t)slot * KP * MSF;
   double accK[DN][2], sk = 0.0;
   int nk = 0;
@@ -647,8 +652,9 @@ __global__ void __launch_bounds__(kThreads16, 1) k_scatter16(EmArgs A) {
     unsigned act = 0;
     if (own) {
       const double* tcol = tile + 8 * cb + g;
+      const int i0 = spw * (16 / SPL), i1 = i0 + 16 / SPL;
 #pragma unroll 4
-      for (int i = 0; i < 16; ++i) {
+      for (int i = i0; i < i1; ++i) {
         const int pb = i;
         const double a = tcol[(size_t)(4 * pb + t) * S];
         const bool hi = !(a < thi_r);

@@ -368,20 +368,25 @@ __global__ void __launch_bounds__(1024) k_refresh(Geom g, const double* __restri
     }
     __syncthreads();
   }
-  // in-place Cholesky W = L L^T (lower), right-looking
+  // Cholesky invC = L L^T (lower), right-looking, in the shared-memory working matrix (3 d barriers with global-memory round
+  // trips in between were most of the refresh at small d); L goes back to W for the packing below and for k_sumll
+  for (int i = tid; i < d * d; i += nt) A[i] = W[i];
+  __syncthreads();
   for (int j = 0; j < d; ++j) {
-    if (tid == 0) W[(size_t)j * d + j] = sqrt(W[(size_t)j * d + j]);
+    if (tid == 0) A[(size_t)j * d + j] = sqrt(A[(size_t)j * d + j]);
     __syncthreads();
-    const double ljj = W[(size_t)j * d + j];
-    for (int i = j + 1 + tid; i < d; i += nt) W[(size_t)j * d + i] /= ljj;
+    const double ljj = A[(size_t)j * d + j];
+    for (int i = j + 1 + tid; i < d; i += nt) A[(size_t)j * d + i] /= ljj;
     __syncthreads();
     const int rem = d - j - 1;
     for (int i = tid; i < rem * rem; i += nt) {
       const int a = j + 1 + i % rem, b = j + 1 + i / rem;
-      if (a >= b) W[(size_t)b * d + a] -= W[(size_t)j * d + a] * W[(size_t)j * d + b];
+      if (a >= b) A[(size_t)b * d + a] -= A[(size_t)j * d + a] * A[(size_t)j * d + b];
     }
     __syncthreads();
   }
+  for (int i = tid; i < d * d; i += nt) W[i] = A[i];
+  __syncthreads();
   // pack: B fragments of u = L^T z, block (mb, nb): lane l holds L[4mb + l%4][8nb + l/4]
   for (int i = tid; i < g.NB * 32; i += nt) {
     const int blk = i >> 5, l = i & 31;
@@ -853,15 +858,23 @@ cudaError_t launch_estep(const Geom& g, const double* X, int64_t N, const double
 // ---------------------------------------------------------------------------------------------------------------
 // reductions / small per-component kernels
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void k_reduce_partials(const double* __restrict__ partial, int nblocks, int64_t n, double* __restrict__ out) {
-  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (j >= n) return;
+// Four lanes per element: lane q sums the q-th quarter of the slots in slot order, then the four partial sums are combined in
+// a fixed tree -- a fixed association (run-to-run deterministic), with a dependent chain a quarter as long as one thread per
+// element (these reductions sit on the critical path of every iteration: 296 slots at the headline shape).
+__global__ void __launch_bounds__(128) k_reduce_partials(const double* __restrict__ partial, int nblocks, int64_t n, double* __restrict__ out) {
+  const int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 2;
+  const int q = threadIdx.x & 3;
+  const int per = (nblocks + 3) >> 2;
+  const int b0 = q * per, b1 = min(nblocks, b0 + per);
   double s = 0;
-  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * n + j];  // fixed order: run-to-run deterministic
-  out[j] = s;
+  if (j < n)
+    for (int b = b0; b < b1; ++b) s += partial[(size_t)b * n + j];
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  if (j < n && q == 0) out[j] = s;
 }
 cudaError_t launch_reduce_partials(const double* partial, int nblocks, int64_t n, double* out, cudaStream_t st) {
-  k_reduce_partials<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(partial, nblocks, n, out);
+  k_reduce_partials<<<(unsigned)((4 * n + 127) / 128), 128, 0, st>>>(partial, nblocks, n, out);
   return cudaGetLastError();
 }
 

@@ -64,7 +64,12 @@ struct EmArgs {
   // "statistics first" iterations: responsibilities of the sweep's 64-point tiles, [tile][64][K8*8], written by the statistics
   // pass (launch_em16 with store = true) and read back by the scatter pass (launch_scatter16)
   double* gtiles;
+  // k_em16 / k_scatter16 with fewer than 8 component blocks: the statistics of a component block are split over spl = 8 / K8'
+  // warps (K8' = K8 rounded up to a power of two), each taking 16 / spl of the tile's 4-point groups and writing its own slot of
+  // partials -- so that small K does not leave 7 of a group's 8 warps waiting for the one that owns the only block
+  int spl;               // 0 or 1: no split
 };
+inline int em16_split(int K8) { return K8 <= 1 ? 8 : (K8 <= 2 ? 4 : (K8 <= 4 ? 2 : 1)); }
 
 // ---- expanded quadratic form of the log-density (k_em16<.., QF = true>) ------------------------------------------------------------
 // logit_k(x) = c_k - 1/2 (x'-mu')^T invC_k (x'-mu')  with x' = x - shift, mu' = mu_k - shift
