@@ -620,7 +620,7 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
   const double minW = 1e-3 / (double)(float)nglob_;  // 1d-3/real(NX)  (src/unsupervised/mlf_gaussian.f90:50)
   double* dFlags = dAB_ + nA + nB;                    // [listed pairs, overflowing lists] ride in the same all-reduce
   std::vector<double> hQ((size_t)KP);
-  std::vector<double> hA((size_t)nA + 0), hflag(4), tlo((size_t)KP), thi((size_t)KP), plo((size_t)KP), phi((size_t)KP), sk((size_t)K);
+  std::vector<double> hA((size_t)nA + 0), hflag(5), tlo((size_t)KP), thi((size_t)KP), plo((size_t)KP), phi((size_t)KP), sk((size_t)K);
   gamma_current_ = false;
   for (int64_t it = 0; it < niter; ++it) {
     cudaEvent_t* ev_ = prof ? &pev_[(size_t)6 * it] : nullptr;
@@ -682,9 +682,10 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
     // statistics-first iterations of the 16-warp sweep keep the responsibilities of pass 0 in HBM (8 N KP bytes, allocated at
     // first need; 51 GB at N=1e8, K=64) so that pass 1 is a scatter from stored tiles instead of a second full sweep
     const bool gstore = stats_first && !streamed && use16_ && ensure_gtiles();
+    bool gvote = false;   // every rank of the job stored its responsibilities in pass 0 (all-reduced vote)
     bool exact = false;
     for (int pass = 0; pass < 2; ++pass) {
-      if (gstore && pass == 1) {
+      if (gstore && pass == 1 && gvote) {
         for (int k = 0; k < KP; ++k) thi[(size_t)k] = k < K ? minW * sk[(size_t)k] : INFINITY;
         CKE(cudaMemcpyAsync(dThi_, thi.data(), KP * sizeof(double), cudaMemcpyHostToDevice, st_), "H2D thi");
         EmArgs a{};
@@ -695,8 +696,8 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
         CKE(launch_amb_summary(dAmbCount_, nlists, amb_cap_, dFlags, st_, dAB_ + nA, KP, f.MSF, g.MB * 64 + 8 * g.DN + 1), "amb summary");
         launches_ += 3;
         times_.scatter_passes += 1;
-        if (int r = allreduce(dAB_ + nA, nB + 3)) return r;
-        CKE(cudaMemcpyAsync(hflag.data(), dFlags, 4 * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H flags");
+        if (int r = allreduce(dAB_ + nA, nB + 4)) return r;
+        CKE(cudaMemcpyAsync(hflag.data(), dFlags, 5 * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H flags");
         CKE(cudaStreamSynchronize(st_), "sync");
         if (debug_ && rank_ == 0)
           fprintf(stderr, "mlfortran_b200[debug]: iteration %lld pass 1 (scatter from stored responsibilities, exact thresholds): kept pairs %.0f -> accepted\n",
@@ -732,13 +733,15 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
       }
       CKE(launch_reduce_partials(dPartA_, nslots, nA, dAB_, st_), "reduce statsA");
       CKE(launch_reduce_partials(dPartB2_, nslots, nB, dAB_ + nA, st_), "reduce statsB");
-      CKE(launch_amb_summary(dAmbCount_, nlists, amb_cap_, dFlags, st_, dAB_ + nA, KP, f.MSF, g.MB * 64 + 8 * g.DN + 1), "amb summary");
+      // the vote rides in the all-reduce: the scatter pass replaces the second sweep only if EVERY rank stored its responsibilities
+      CKE(launch_amb_summary(dAmbCount_, nlists, amb_cap_, dFlags, st_, dAB_ + nA, KP, f.MSF, g.MB * 64 + 8 * g.DN + 1, (gstore && pass == 0) ? 1.0 : 0.0),
+          "amb summary");
       launches_ += 3;
       times_.sweeps += 1;
-      if (int r = allreduce(dAB_, nA + nB + 3)) return r;
+      if (int r = allreduce(dAB_, nA + nB + 4)) return r;
       // verification needs s_k and the list flags on the host: one small D2H + sync per sweep
       CKE(cudaMemcpyAsync(hA.data(), dAB_, nA * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H statsA");
-      CKE(cudaMemcpyAsync(hflag.data(), dFlags, 4 * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H flags");
+      CKE(cudaMemcpyAsync(hflag.data(), dFlags, 5 * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H flags");
       if (a.qf_limit >= 0.0) CKE(cudaMemcpyAsync(hQ.data(), dQfS_, KP * sizeof(double), cudaMemcpyDeviceToHost, st_), "D2H bounds");
       CKE(cudaStreamSynchronize(st_), "sync");
       if (a.qf_limit >= 0.0) {   // the decision the blocks took (same rule), for the counters only
@@ -748,6 +751,7 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
         times_.qf_bound = mx;
         if (!bad) times_.qf_sweeps += 1;
       }
+      if (pass == 0) gvote = hflag[3] == (double)world_;
       bool ok = hflag[1] == 0.0 && !(pass == 0 && stats_first);
       int missed = 0;
       if (!exact && band_widen_.size() != (size_t)K) band_widen_.assign((size_t)K, 1.0);
@@ -767,7 +771,7 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
                 exact ? "exact thresholds" : (stats_first ? "statistics only" : "predicted band"), hflag[0], hflag[1], amb_cap_, hflag[2], missed,
                 smooth ? "" : " (not smooth)", (ok || exact) ? "accepted" : "second pass with exact thresholds");
       if (!ok && !exact && hflag[1] != 0.0)
-        if (int r = grow_amb_lists((int64_t)hflag[3])) return r;
+        if (int r = grow_amb_lists((int64_t)hflag[4])) return r;
       if (ok || exact) break;
       exact = true;  // s_k is known now: repeat the sweep with tlo == thi == minW*s_k (the side list stays empty)
     }

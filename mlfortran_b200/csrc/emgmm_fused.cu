@@ -640,7 +640,7 @@ cudaError_t launch_amb_resolve(const Geom& g, const double* X, const AmbEntry* a
 // flags[0] = listed pairs on this rank, flags[1] = lists that overflowed their capacity, flags[2] = pairs that passed the
 // certainly-kept test in the sweep (pad slot of the pass-B statistics; profiling counter) -- all-reduced as doubles
 __global__ void __launch_bounds__(256) k_amb_summary(const int* __restrict__ counts, int nlists, int cap, double* __restrict__ flags,
-                                                     const double* __restrict__ statsB, int KP, int MSF, int off) {
+                                                     const double* __restrict__ statsB, int KP, int MSF, int off, double vote) {
   __shared__ long long s_tot[256];
   __shared__ int s_over[256], s_max[256];
   long long tot = 0;
@@ -668,12 +668,13 @@ __global__ void __launch_bounds__(256) k_amb_summary(const int* __restrict__ cou
     if (statsB)
       for (int k = 0; k < KP; ++k) kept += statsB[(size_t)k * MSF + off];
     flags[2] = kept;
-    flags[3] = (double)s_max[0];   // longest list of THIS rank (outside the all-reduced range)
+    flags[3] = vote;               // all-reduced: ranks that can run the scatter pass from stored responsibilities
+    flags[4] = (double)s_max[0];   // longest list of THIS rank (outside the all-reduced range)
   }
 }
 cudaError_t launch_amb_summary(const int* counts, int nlists, int cap, double* flags, cudaStream_t st, const double* statsB, int KP, int MSF,
-                               int off) {
-  k_amb_summary<<<1, 256, 0, st>>>(counts, nlists, cap, flags, statsB, KP, MSF, off);
+                               int off, double vote) {
+  k_amb_summary<<<1, 256, 0, st>>>(counts, nlists, cap, flags, statsB, KP, MSF, off, vote);
   return cudaGetLastError();
 }
 

@@ -143,7 +143,7 @@ cudaError_t launch_amb_resolve(const Geom& g, const double* X, const AmbEntry* a
                                const double* statsA, double minW, const double* muold, double* outC, cudaStream_t st, int cmax, int* pcomp,
                                double* partial);
 cudaError_t launch_amb_summary(const int* counts, int nlists, int cap, double* flags, cudaStream_t st, const double* statsB = nullptr,
-                               int KP = 0, int MSF = 0, int off = 0);
+                               int KP = 0, int MSF = 0, int off = 0, double vote = 0.0);   // flags[0..3] are all-reduced, flags[4] is local
 cudaError_t launch_finalize_fused(const Geom& g, const FusedGeom& f, const double* statsA, const double* statsB, const double* statsC,
                                   const double* muold, double minProba, double* Mu, double* Cov, double* lambda, cudaStream_t st,
                                   int cov_diag = 0);

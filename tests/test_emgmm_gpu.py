@@ -1347,6 +1347,25 @@ def test_single_process_multi_gpu_object(devices, oracle):
     em.finalize()
 
 
+def test_sharded_object_statistics_first_iterations(oracle):
+    """Overlapping clusters on a sharded object (three shards inside one process, peer-memory all-reduce): the statistics-first
+    protocol all-reduces the pass-A statistics after the sweep and only the scatter statistics after the scatter pass from the
+    stored responsibilities; every shard must take the same decisions and the result must be the oracle's."""
+    d, K, iters = 16, 20, 6
+    data = synth.make_mixture(d, K, 1500, 1.0, 1.0, 47)
+    X = data["X"][: K * 1500 - 11]
+    Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 47)
+    oMu, oCov, olam, otr = oracle.em_iterations(X, Mu0, Cov0, lam0, 1.0, iters)
+    em = mlf_algo_emgmm()
+    assert em.init(X, K, 1.0, devices=[0, 0, 0]) == 0
+    em.inject(Mu0, Cov0, lam0)
+    em.set_profile(True)
+    assert em.step(iters)[0] == 0, em.last_error()
+    check_against(em, oMu, oCov, olam, otr)
+    assert em.qf_stats()["scatter_passes"] >= 2
+    em.finalize()
+
+
 def test_multi_object_with_empty_shards_joins_the_collectives(oracle):
     """More shards than points: the empty shards must still take part in the all-reduced moments step that labels(),
     ProbaC and getProba trigger (they used to return early and leave their peers waiting at the barrier)."""
