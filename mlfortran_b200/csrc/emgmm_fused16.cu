@@ -103,7 +103,7 @@ bool em16_qf_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
 // component blocks interleaved 96.5 ms; eight exps in flight in P2 95.1; P3a unrolled 8 times 95.4; the barrier between softmax and
 // statistics replaced by one mbarrier per producer warp, consumers starting with their own points' groups, 97.1.  The sweep sits
 // at ~95 ms whatever is moved: the datapath is saturated while warps are in P1 and idles when both groups are in P2 / P3.
-template <int DM, int VAR, int QFM, bool STORE>
+template <int DM, int VAR, int QFM, bool STORE, bool SPLT>
 __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   // STORE: "statistics first" pass of an iteration whose covariance thresholds cannot be predicted: E-step + pass-A statistics
   // only (no classification, no scatter), and the tile of finished responsibilities goes to HBM ([tile][64][KP], A.gtiles) for
@@ -140,7 +140,9 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   double* sp = smem;                                  // [KP][PSF] whitening pack / [K8][QS] quadratic-form pack
   double* smu = sp + (QF ? (size_t)K8 * QS : (size_t)KP * PSF);   // [KP][8 DN]
   const int half = warp >> 3;                   // group index
-  const int SPL = A.spl > 1 ? A.spl : 1;        // warps per component block in the statistics phases (small K)
+  // SPLT: fewer than 8 component blocks, the statistics of a block are shared by A.spl = 2, 4 or 8 warps of the group (a template
+  // flag, not a run-time value: the headline shape has no register to spare for it)
+  const int SPL = SPLT ? A.spl : 1;
   const int cb = (warp & 7) % (8 / SPL), spw = (warp & 7) / (8 / SPL);   // component block and share of the tile's 4-point groups
   const int wg = warp & 7;                      // warp index inside the group
   double* xs = smu + (size_t)KP * 8 * DN + (size_t)half * TP * XS;                    // [2][64][XS] raw points, per group
@@ -441,7 +443,8 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
     if (own) {
       const int64_t q0 = bt * TP;
       const double* tcol = tile + 8 * cb + g;
-      const int i0 = spw * (16 / SPL), i1 = i0 + 16 / SPL;
+      // this warp's share of the tile's sixteen 4-point groups (all of them without the split: compile-time bounds)
+      const int i0 = SPLT ? spw * (16 / SPL) : 0, i1 = SPLT ? i0 + 16 / SPL : 16;
 #pragma unroll (EXPV == 2 ? 8 : 4)
       for (int i = i0; i < i1; ++i) {
         const int pb = i;
@@ -775,6 +778,7 @@ cudaError_t launch_em16(const Geom& g, const FusedGeom& f, const EmArgs& a, int 
   const size_t smem_q = em16_qf_smem_bytes(g, f);
   EmArgs aw = a;
   if (!qf) { aw.qf_limit = -1.0; }
+  const bool split = a.spl > 1;   // (the whitening scheduling variants MLF_B200_EM16_VAR != 53 exist without the split only)
   auto go = [&](auto kern, size_t sm) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return e;
@@ -784,12 +788,18 @@ cudaError_t launch_em16(const Geom& g, const FusedGeom& f, const EmArgs& a, int 
   cudaError_t e = cudaSuccess;
 #define MLF_E16V(DMv, V)                                                              \
   case 64 * DMv + V:                                                                   \
-    if (store) {                                                                       \
-      if (qf) e = go(k_em16<DMv, 53, 1, true>, smem_q);                                \
-      if (e == cudaSuccess) e = go(k_em16<DMv, 53, 0, true>, smem);                    \
+    if (store && split) {                                                              \
+      if (qf) e = go(k_em16<DMv, 53, 1, true, true>, smem_q);                          \
+      if (e == cudaSuccess) e = go(k_em16<DMv, 53, 0, true, true>, smem);              \
+    } else if (store) {                                                                \
+      if (qf) e = go(k_em16<DMv, 53, 1, true, false>, smem_q);                         \
+      if (e == cudaSuccess) e = go(k_em16<DMv, 53, 0, true, false>, smem);             \
+    } else if (split) {                                                                \
+      if (qf) e = go(k_em16<DMv, 53, 1, false, true>, smem_q);                         \
+      if (e == cudaSuccess) e = go(k_em16<DMv, 53, 0, false, true>, smem);             \
     } else {                                                                           \
-      if (qf) e = go(k_em16<DMv, 53, 1, false>, smem_q);                               \
-      if (e == cudaSuccess) e = go(k_em16<DMv, V, 0, false>, smem);                    \
+      if (qf) e = go(k_em16<DMv, 53, 1, false, false>, smem_q);                        \
+      if (e == cudaSuccess) e = go(k_em16<DMv, V, 0, false, false>, smem);             \
     }                                                                                  \
     break;
 #define MLF_E16(DMv) MLF_E16V(DMv, 0) MLF_E16V(DMv, 5) MLF_E16V(DMv, 21) MLF_E16V(DMv, 53)

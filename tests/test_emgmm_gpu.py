@@ -512,8 +512,8 @@ def test_em16_scheduling_variants_are_bit_identical(oracle, monkeypatch):
     """k_em16's scheduling variants (MLF_B200_EM16_VAR: pipelined quad reduction, 1/sum applied at the consumer, split
     tile-reuse barrier, register prefetch) only move instructions: parameters, sumLL and labels must agree to the last bit with
     the unpipelined kernel, on a ragged N that exercises the tail tile and several tiles per group."""
-    d, K = 16, 24
-    data = synth.make_mixture(d, K, 1237, 5.0, 1.0, 173)
+    d, K = 16, 40   # five component blocks: the variants exist for shapes without the small-K statistics split (K > 32)
+    data = synth.make_mixture(d, K, 743, 5.0, 1.0, 173)
     X = data["X"][: 29_003]
     Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 173)
     ref = None
