@@ -54,6 +54,17 @@ __device__ __forceinline__ void tmem_ld2(uint32_t taddr, double& v0, double& v1)
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
 constexpr int kThreads16 = 512;
+
+#ifdef MLF_TRACE
+// Debug builds only (make EXTRA=-DMLF_TRACE=1; scripts/trace_phases.py): phase timeline of block 0's sixteen warps over 64 tiles
+__device__ long long g_trace[64 * 16 * 8];
+#define MLF_STAMP(ph)                                                                                         \
+  do {                                                                                                        \
+    if (blockIdx.x == 0 && lane == 0 && tcount >= 8 && tcount < 72) g_trace[((tcount - 8) * 16 + warp) * 8 + (ph)] = clock64(); \
+  } while (0)
+#else
+#define MLF_STAMP(ph) do { } while (0)
+#endif
 constexpr int kTmemCols = 512;  // 4 warps per lane quarter x 8 components x 16 columns (MB <= 3 blocks x 4 columns, padded)
 
 }  // namespace
@@ -101,16 +112,22 @@ bool em16_qf_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
 // whitening loop on the same points; in the sweep at N=1e8, d=16, K=64: 95.2 ms against 116.9.  Scheduling experiments on this
 // variant, all measured at the headline shape and none kept (QFM >> 1 selects them, not instantiated): accumulator chains of two
 // component blocks interleaved 96.5 ms; eight exps in flight in P2 95.1; P3a unrolled 8 times 95.4; the barrier between softmax and
-// statistics replaced by one mbarrier per producer warp, consumers starting with their own points' groups, 97.1.  The sweep sits
-// at ~95 ms whatever is moved: the datapath is saturated while warps are in P1 and idles when both groups are in P2 / P3.
+// statistics replaced by one mbarrier per producer warp, consumers starting with their own points' groups, 97.1; the two groups
+// forced to take turns in P1 (P1 of one under P2 / P3 of the other, two mbarriers) 97.3, with two chains 98.6.
+// Why it sits at ~95 ms whatever is moved (phase timeline of a block, scripts/trace_phases.py on a -DMLF_TRACE=1 build, and
+// bench/micro/p1_quadform_occ.cu): a warp issues one DMMA per ~32 clocks at best, so the datapath (one DMMA per 16 clocks per
+// scheduler) needs >= 3 warps of a scheduler in P1 to saturate -- 0.88 of the peak with 4, 0.86 with 3, 0.75-0.80 with 2, 0.44-0.50 with
+// 1, prefetching or interleaving chains notwithstanding.  The two groups drift into near-synchrony: all four warps of a scheduler
+// are in P1 35 % of the time, two 29 %, none 22 %.  Taking turns removes the "none" state but leaves two warps in P1 all the time
+// (0.75) and doubles P3a's duration under the contention.  A third group would fix it; tensor memory (2 x 98 KB of scatter
+// accumulators) and shared memory (200 KB) are both full with two.
 template <int DM, int VAR, int QFM, bool STORE, bool SPLT>
 __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   // STORE: "statistics first" pass of an iteration whose covariance thresholds cannot be predicted: E-step + pass-A statistics
   // only (no classification, no scatter), and the tile of finished responsibilities goes to HBM ([tile][64][KP], A.gtiles) for
   // the scatter pass k_scatter16, which then knows the exact thresholds.
   constexpr bool QF = (QFM & 1) != 0;   // QFM: 0 whitening, odd: quadratic form; QFM >> 1 = experiment (MLF_B200_QF_EXP, A/B runs)
-  constexpr int EXPV = QFM >> 1;       // 1: eight exps in flight in P2; 2: P3a unrolled 8 times (neither instantiated, see above)
-  constexpr int CH = 1;
+  constexpr int CH = 1;                // interleaved accumulator chains per warp in P1 (2 was measured: see above)
   constexpr bool FOLD = (VAR & 1) != 0;
   static_assert(!QF || FOLD, "the quadratic-form variant keeps 1/sum beside the tile");
   constexpr int PIPE = (VAR >> 1) & 3;
@@ -230,8 +247,11 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   bool first = true;
   uint32_t phase = 0;
   double xraw[DM];
+  int tcount = -1;
   for (int64_t bt = 2 * (int64_t)blockIdx.x + half; bt < ntiles; bt += 2 * (int64_t)gridDim.x) {
     const int64_t p = bt * TP + wg * 8 + g;
+    ++tcount;
+    MLF_STAMP(0);
     // ---- P1: logits of this warp's 8 points against every component ---------------------------------------------
     double xa[DM];
     double* xr = xs + (size_t)(wg * 8 + g) * XS;
@@ -388,12 +408,13 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
       reduce4(K4 - 1, pb);
     }
     }   // !QF
+    MLF_STAMP(1);
     // ---- P2: log-sum-exp over the components ---------------------------------------------------------------------
     rmax = fmax(rmax, shx(rmax, 1));
     rmax = fmax(rmax, shx(rmax, 2));
     double sum = 0;
     if constexpr (QF) {   // each lane exponentiates the two logits per component block it wrote itself
-#pragma unroll (EXPV == 1 ? 4 : 2)
+#pragma unroll 2
       for (int cq = 0; cq < K8; ++cq) {
         const double2 v = *reinterpret_cast<const double2*>(row + 8 * cq + 2 * t);
         const double e0 = exp_tab(v.x - rmax, etab), e1 = exp_tab(v.y - rmax, etab);
@@ -428,8 +449,10 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
         }
       }
     }
+    MLF_STAMP(2);
     // the group's responsibilities and points are complete: 256-thread named barrier of this group only
     asm volatile("bar.sync %0, 256;\n" ::"r"(1 + half) : "memory");
+    MLF_STAMP(3);
     if (PREF) {
       const int64_t pn = p + 2 * (int64_t)gridDim.x * TP;
 #pragma unroll
@@ -445,7 +468,7 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
       const double* tcol = tile + 8 * cb + g;
       // this warp's share of the tile's sixteen 4-point groups (all of them without the split: compile-time bounds)
       const int i0 = SPLT ? spw * (16 / SPL) : 0, i1 = SPLT ? i0 + 16 / SPL : 16;
-#pragma unroll (EXPV == 2 ? 8 : 4)
+#pragma unroll 4
       for (int i = i0; i < i1; ++i) {
         const int pb = i;
         const double a = FOLD ? tcol[(size_t)(4 * pb + t) * S] * invs[4 * pb + t] : tcol[(size_t)(4 * pb + t) * S];
@@ -488,6 +511,7 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
         }
       }
     }
+    MLF_STAMP(4);
     // ---- P3b: covariance scatter of this block's 8 components over the kept groups of the tile ----------------------
     if (own && !STORE) {
 #pragma unroll
@@ -524,6 +548,7 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
       }
       tmem_wait_st();
     }
+    MLF_STAMP(5);
     // the group's tiles may be overwritten only after every warp of the group is done with them
     if (SPLIT) {
       __syncwarp();
@@ -814,3 +839,9 @@ cudaError_t launch_em16(const Geom& g, const FusedGeom& f, const EmArgs& a, int 
 }
 
 }  // namespace mlfb200
+
+#ifdef MLF_TRACE
+extern "C" int mlf_b200_trace_read(long long* out, int n) {
+  return cudaMemcpyFromSymbol(out, mlfb200::g_trace, sizeof(long long) * (size_t)(n < 64 * 16 * 8 ? n : 64 * 16 * 8)) == cudaSuccess ? 0 : -1;
+}
+#endif
