@@ -417,7 +417,7 @@ def main():
         pass
     roofline = {
         "kernel": plan + (" (diagonal whitening DFMA + log-sum-exp + pass-A statistics + thresholded variance scatter)" if diag_cc else
-                          " (whitening DMMA + log-sum-exp + pass-A statistics + thresholded covariance scatter)" if fused
+                          " (logits DMMA + log-sum-exp + pass-A statistics + thresholded covariance scatter)" if fused
                           else " (roofline line = E-pass: whitening DMMA + log-sum-exp + pass-A statistics)"), "bound": "tensor",
         "sweeps_per_iteration": sweeps / it if fused else 1.0, "side_list_pairs": times.get("side_list_pairs", 0),
         "kept_pairs_per_point": (counters["kept_pairs"] / it / max(n_loc * world, 1)) if fused else None,

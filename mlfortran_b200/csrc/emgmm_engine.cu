@@ -201,10 +201,12 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
 }
 
 std::string EmgmmEngine::plan() const {
-  char buf[256];
+  char buf[384];
   const Geom& g = geom_;
   if (use16_)
-    snprintf(buf, sizeof buf, "k_em16<%d>: fused single sweep, 16 warps/SM, software-pipelined whitening reduction, split tile barrier, covariance-scatter accumulators in tensor memory", g.DM);
+    snprintf(buf, sizeof buf, "k_em16<%d>: fused single sweep, 16 warps/SM, log-densities as the expanded quadratic form (%s) or by whitening, split tile barrier, "
+             "covariance-scatter accumulators in tensor memory%s", g.DM, qf16_ ? "guarded by the magnitude bound of its terms" : "disabled",
+             spl_ > 1 ? ", statistics of a component block shared by several warps" : "");
   else if (used_)
     snprintf(buf, sizeof buf, "k_emd: fused single sweep for diagonal covariances on the fp64 CUDA cores (lane = component)");
   else if (fused_)
