@@ -93,6 +93,7 @@ int EmgmmEngine::init(const double* X, bool x_on_device, int64_t n_local, int d,
     big_ = bg && bg[0] == '1';
     const char* dbg = getenv("MLF_B200_DEBUG");
     debug_ = dbg && dbg[0] == '1';
+    if (const char* sc = getenv("MLF_B200_STREAM_CHUNKS")) kStreamChunks = std::max(1, std::min(atoi(sc), 256));
     if (const char* ac = getenv("MLF_B200_AMB_CAP")) amb_cap_ = std::max(8, std::min(atoi(ac), kAmbCapMax));   // tests: force overflows
   }
   // kernel generation for this shape: fused single sweep (pack + tile in shared memory, scatter accumulators in

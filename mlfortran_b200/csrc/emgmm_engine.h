@@ -144,7 +144,7 @@ class EmgmmEngine {
   double *dPrevMu_ = nullptr, *dPrevCov_ = nullptr, *dPrevLambda_ = nullptr;  // parameters at the start of the last iteration (ProbaC)
   bool prev_valid_ = false;
   // streamed refresh of X: host pointer waiting to be uploaded underneath the next sweep
-  static constexpr int kStreamChunks = 16;
+  int kStreamChunks = 16;     // pieces of a streamed upload (MLF_B200_STREAM_CHUNKS)
   const double* pending_host_ = nullptr;
   double *dShift_ = nullptr, *dMomPart_ = nullptr, *dMomRaw_ = nullptr;
   bool shift_ready_ = false;
