@@ -60,7 +60,7 @@ bool emd_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
 // issue, not by the fp64 pipe.  The expanded form cancels (terms ~ (distance from the shift / width)^2), so it is taken only
 // when the bound S_k that k_refresh leaves for every component keeps the estimated logit error under the engine's limit
 // (A.qfS, A.qf_limit; decided by every block, as in k_em16); the other variant returns at once.
-// Measured on the config-5 shard (N=1.25e8, d=8, K=256): 145.4 -> 143.0 ms per sweep only -- the lane = component P1 already ran
+// Measured on the config-5 shard (N=1.25e8, d=8, K=256): 203.6 -> 200.2 ms per 1.4-sweep iteration only -- the lane = component P1 already ran
 // near the datapath rate (136 DFMA against 16 DMMA per 8 points x 32 components hold the fp64 pipe for the same 270 clocks);
 // what keeps this kernel at ~45 % of the pipe are the latency-bound softmax and statistics phases at two warps per scheduler.
 template <int TP, bool XMMA, bool QP1>
