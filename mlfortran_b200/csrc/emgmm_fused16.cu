@@ -192,8 +192,12 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
   }
   for (int i = tid; i < KP * 8 * DN; i += kThreads16) smu[i] = A.muold[i];
   double sh[DM];
+  // VEC (quadratic-form variant at d = 16): lane t of a point's quad loads coordinates 4t .. 4t+3 as two 16-byte loads instead of
+  // 4t', 4t'+4, ... as four 8-byte ones -- the monomials are formed from shared memory, so any register layout will do; the
+  // whitening variant needs x[4 mb + t] as its A fragments and keeps the scalar loads
+  const bool vec = QF && DM == 4 && d == 16 && (reinterpret_cast<uintptr_t>(A.X) & 15) == 0;
 #pragma unroll
-  for (int mb = 0; mb < DM; ++mb) sh[mb] = A.shift[4 * mb + t];
+  for (int mb = 0; mb < DM; ++mb) sh[mb] = vec ? A.shift[4 * t + mb] : A.shift[4 * mb + t];
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(s_taddr)),
                  "n"(kTmemCols)
@@ -256,13 +260,25 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
     // ---- P1: logits of this warp's 8 points against every component ---------------------------------------------
     double xa[DM];
     double* xr = xs + (size_t)(wg * 8 + g) * XS;
-    if (!PREF || first) {
+    auto load_x = [&](const int64_t pp) {
+      if (vec) {
+        if constexpr (DM == 4) {
+          double2 v0 = make_double2(0.0, 0.0), v1 = v0;
+          if (pp < N) {
+            const double2* src = reinterpret_cast<const double2*>(A.X + pp * 16 + 4 * t);
+            v0 = src[0]; v1 = src[1];
+          }
+          xraw[0] = v0.x; xraw[1] = v0.y; xraw[2] = v1.x; xraw[3] = v1.y;
+        }
+      } else {
 #pragma unroll
-      for (int mb = 0; mb < DM; ++mb) {
-        const int a = 4 * mb + t;
-        xraw[mb] = (p < N && a < d) ? A.X[p * d + a] : 0.0;
+        for (int mb = 0; mb < DM; ++mb) {
+          const int a = 4 * mb + t;
+          xraw[mb] = (pp < N && a < d) ? A.X[pp * d + a] : 0.0;
+        }
       }
-    }
+    };
+    if (!PREF || first) load_x(p);
     // the previous tile's buffers may be overwritten only after every warp of the group is done with them
     auto wait_prev = [&]() {
       if (SPLIT && !first) {
@@ -275,8 +291,15 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
       }
     };
     auto stage_x = [&]() {
+      if (vec) {
+        if constexpr (DM == 4) {
+          *reinterpret_cast<double2*>(xr + 4 * t) = make_double2(xraw[0], xraw[1]);
+          *reinterpret_cast<double2*>(xr + 4 * t + 2) = make_double2(xraw[2], xraw[3]);
+        }
+      } else {
 #pragma unroll
-      for (int mb = 0; mb < DM; ++mb) xr[4 * mb + t] = xraw[mb];
+        for (int mb = 0; mb < DM; ++mb) xr[4 * mb + t] = xraw[mb];
+      }
       if (8 * DN > 4 * DM) xr[4 * DM + t] = 0.0;
     };
     if (SPLIT < 2) { wait_prev(); stage_x(); }
@@ -285,8 +308,15 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
     if constexpr (QF) {
       // ---- P1 (quadratic form): monomials of the warp's 8 points x coefficient fragments of 8 components per DMMA ---------
       __syncwarp();   // every lane is done with the previous tile's staged points
+      if (vec) {
+        if constexpr (DM == 4) {
+          *reinterpret_cast<double2*>(xq + 4 * t) = make_double2(xraw[0] - sh[0], xraw[1] - sh[1]);
+          *reinterpret_cast<double2*>(xq + 4 * t + 2) = make_double2(xraw[2] - sh[2], xraw[3] - sh[3]);
+        }
+      } else {
 #pragma unroll
-      for (int mb = 0; mb < DM; ++mb) xq[4 * mb + t] = xraw[mb] - sh[mb];
+        for (int mb = 0; mb < DM; ++mb) xq[4 * mb + t] = xraw[mb] - sh[mb];
+      }
       __syncwarp();
       const char* xqb = reinterpret_cast<const char*>(xq);
 #pragma unroll
@@ -454,14 +484,7 @@ __global__ void __launch_bounds__(kThreads16, 1) k_em16(EmArgs A) {
     // the group's responsibilities and points are complete: 256-thread named barrier of this group only
     asm volatile("bar.sync %0, 256;\n" ::"r"(1 + half) : "memory");
     MLF_STAMP(3);
-    if (PREF) {
-      const int64_t pn = p + 2 * (int64_t)gridDim.x * TP;
-#pragma unroll
-      for (int mb = 0; mb < DM; ++mb) {
-        const int a = 4 * mb + t;
-        xraw[mb] = (pn < N && a < d) ? A.X[pn * d + a] : 0.0;
-      }
-    }
+    if (PREF) load_x(p + 2 * (int64_t)gridDim.x * TP);
     unsigned act = 0;   // lane pb: bit q set <=> component 8*cb+q keeps some point of 4-point group pb
     // ---- P3a: pass-A statistics of component block cb over the tile's 4-point groups; kept-group flags ---------------
     if (own) {
