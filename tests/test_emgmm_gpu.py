@@ -443,6 +443,42 @@ def test_streamed_refresh_of_x(oracle):
     em.finalize()
 
 
+@pytest.mark.parametrize("chunks,wc", [("16", 0), ("3", 1), ("1", 0), ("64", 1)], ids=["16_pieces_pinned", "3_pieces_write_combined", "1_piece_pinned", "64_pieces_write_combined"])
+def test_streamed_refresh_from_library_allocated_host_memory(chunks, wc, oracle, monkeypatch):
+    """mlf_b200_host_alloc (page-locked, optionally write-combined) as the caller's array for construction and for
+    mlf_b200_refresh_x, with the streamed upload cut into different numbers of pieces (MLF_B200_STREAM_CHUNKS; ragged last piece):
+    same numbers as the oracle on the new data every time, and -- the refreshed first step whitens, the later ones take the
+    quadratic form -- the counters show both logit paths on one object."""
+    monkeypatch.setenv("MLF_B200_STREAM_CHUNKS", chunks)
+    lib = _lib.load()
+    d, K = 16, 12
+    data = synth.make_mixture(d, K, 22000, 6.0, 1.0, 311)
+    X1 = data["X"][:263001]   # above the streaming threshold (4096 points per piece) for every piece count tried
+    n = X1.shape[0]
+    ptr = lib.mlf_b200_host_alloc(8 * n * d, wc)
+    assert ptr
+    try:
+        Xh = np.ctypeslib.as_array((C.c_double * (n * d)).from_address(ptr)).reshape(n, d)
+        Xh[...] = X1
+        Mu0, Cov0, lam0 = synth.injected_init(data["centres"], 311)
+        em = make_em(Xh, K, 1.0, Mu0, Cov0, lam0)
+        em.set_profile(True)
+        assert em.step(2)[0] == 0, em.last_error()
+        Mu1, Cov1, lam1 = em.Mu.copy(), em.Cov.copy(), em.lambda_.copy()
+        rng = np.random.default_rng(312)
+        X2 = np.ascontiguousarray(X1 + 0.05 * rng.standard_normal(X1.shape) - 0.2)
+        Xh[...] = X2                                   # the caller changes its array in place ...
+        assert em.refresh_x(Xh) == 0                   # ... and says so
+        assert em.step(3)[0] == 0, em.last_error()
+        oMu, oCov, olam, otr = oracle.em_iterations(X2, Mu1, Cov1, lam1, 1.0, 3)
+        check_against(em, oMu, oCov, olam, otr)
+        q, c = em.qf_stats(), em.counters()
+        assert 0 < q["qf_sweeps"] < c["sweeps"], (q, c)   # streamed sweep: whitening; resident sweeps: quadratic form
+        em.finalize()
+    finally:
+        lib.mlf_b200_host_free(ptr)
+
+
 # ---- randomized sweep over small shapes (every kernel plan that serves d <= 32) ----------------------------------------
 def _random_cases(n_cases, seed):
     rng = np.random.default_rng(seed)
