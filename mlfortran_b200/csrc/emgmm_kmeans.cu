@@ -28,6 +28,7 @@ constexpr int kSeedPts = 256;   // points per tile of k_seed_update2 (= threads 
 // of minDist^2.  The tile of 256 points is loaded with fully coalesced 8-byte loads and transposed through shared memory
 // (row stride d + 1 (d even) keeps the thread-per-point reads conflict-free).
 // ---------------------------------------------------------------------------------------------------------------
+template <int DC>   // DC = d when d is one of the instantiated sizes (the tile's loads are then held in registers one tile ahead), else 0
 __global__ void __launch_bounds__(kSeedPts) k_seed_update2(const double* __restrict__ X, int64_t N, int d, const double* __restrict__ centre,
                                                            double* __restrict__ minDist, int first, int64_t chunk, double* __restrict__ partial) {
   extern __shared__ double sm[];
@@ -40,24 +41,66 @@ __global__ void __launch_bounds__(kSeedPts) k_seed_update2(const double* __restr
   const int64_t lo = (int64_t)blockIdx.x * chunk;
   const int64_t hi = (lo + chunk < N) ? lo + chunk : N;
   double s = 0;
-  for (int64_t p0 = lo; p0 < hi; p0 += kSeedPts) {
-    const int np = (int)((hi - p0 < kSeedPts) ? hi - p0 : kSeedPts);
-    __syncthreads();   // previous tile consumed (and sc visible)
-    const double* src = X + p0 * d;
-    const int ne = np * d;
-    for (int e = tid; e < ne; e += kSeedPts) {
-      const int r = e / d, a = e - r * d;
-      tile[r * RS + a] = src[e];
+  if constexpr (DC > 0) {
+    // software pipeline: the next tile's coordinates (DC coalesced 8-byte loads per thread) and its old minDist are in flight
+    // while the current tile is transposed through shared memory and reduced -- one exposed memory latency per tile instead of two
+    double nx[DC], nm = 0.0;
+    auto fetch = [&](int64_t p0) {
+      const int np = (int)((hi - p0 < kSeedPts) ? hi - p0 : kSeedPts);
+      const double* src = X + p0 * DC;
+#pragma unroll
+      for (int i = 0; i < DC; ++i) nx[i] = (i * kSeedPts + tid < np * DC) ? src[i * kSeedPts + tid] : 0.0;
+      nm = (!first && tid < np) ? minDist[p0 + tid] : 0.0;
+    };
+    if (lo < hi) fetch(lo);
+    // element e = i * 256 + tid of a tile belongs to point e / DC, coordinate e % DC: advanced incrementally (no division per element)
+    const int r0 = tid / DC, a0 = tid - r0 * DC, dr = kSeedPts / DC, da = kSeedPts - dr * DC;
+    for (int64_t p0 = lo; p0 < hi; p0 += kSeedPts) {
+      const int np = (int)((hi - p0 < kSeedPts) ? hi - p0 : kSeedPts);
+      __syncthreads();   // previous tile consumed (and sc visible)
+      {
+        int r = r0, a = a0;
+#pragma unroll
+        for (int i = 0; i < DC; ++i) {
+          tile[r * RS + a] = nx[i];
+          r += dr; a += da;
+          if (a >= DC) { a -= DC; ++r; }
+        }
+      }
+      const double mold = nm;
+      if (p0 + kSeedPts < hi) fetch(p0 + kSeedPts);
+      __syncthreads();
+      if (tid < np) {
+        const double* x = tile + tid * RS;
+        double q = 0;
+#pragma unroll
+        for (int a = 0; a < DC; ++a) { const double t = x[a] - sc[a]; q = fma(t, t, q); }
+        double m = sqrt(q);  // norm2 (src/unsupervised/mlf_kmeans.f90:160)
+        if (!first) m = fmin(mold, m);
+        minDist[p0 + tid] = m;
+        s = fma(m, m, s);
+      }
     }
-    __syncthreads();
-    if (tid < np) {
-      const double* x = tile + tid * RS;
-      double q = 0;
-      for (int a = 0; a < d; ++a) { const double t = x[a] - sc[a]; q = fma(t, t, q); }
-      double m = sqrt(q);  // norm2 (src/unsupervised/mlf_kmeans.f90:160)
-      if (!first) m = fmin(minDist[p0 + tid], m);
-      minDist[p0 + tid] = m;
-      s = fma(m, m, s);
+  } else {
+    for (int64_t p0 = lo; p0 < hi; p0 += kSeedPts) {
+      const int np = (int)((hi - p0 < kSeedPts) ? hi - p0 : kSeedPts);
+      __syncthreads();   // previous tile consumed (and sc visible)
+      const double* src = X + p0 * d;
+      const int ne = np * d;
+      for (int e = tid; e < ne; e += kSeedPts) {
+        const int r = e / d, a = e - r * d;
+        tile[r * RS + a] = src[e];
+      }
+      __syncthreads();
+      if (tid < np) {
+        const double* x = tile + tid * RS;
+        double q = 0;
+        for (int a = 0; a < d; ++a) { const double t = x[a] - sc[a]; q = fma(t, t, q); }
+        double m = sqrt(q);  // norm2 (src/unsupervised/mlf_kmeans.f90:160)
+        if (!first) m = fmin(minDist[p0 + tid], m);
+        minDist[p0 + tid] = m;
+        s = fma(m, m, s);
+      }
     }
   }
   red[tid] = s;
@@ -71,12 +114,21 @@ __global__ void __launch_bounds__(kSeedPts) k_seed_update2(const double* __restr
 cudaError_t launch_seed_update2(const double* X, int64_t N, int d, const double* centre, double* minDist, int first, int64_t chunk, int grid,
                                 double* partial, cudaStream_t st) {
   const size_t smem = ((size_t)((d + 1) & ~1) + (size_t)kSeedPts * (d | 1)) * sizeof(double);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k_seed_update2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+  auto go = [&](auto kern) -> cudaError_t {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    kern<<<grid, kSeedPts, smem, st>>>(X, N, d, centre, minDist, first, chunk, partial);
+    return cudaGetLastError();
+  };
+  switch (d) {
+    case 2: return go(k_seed_update2<2>);
+    case 4: return go(k_seed_update2<4>);
+    case 8: return go(k_seed_update2<8>);
+    case 16: return go(k_seed_update2<16>);
+    default: return go(k_seed_update2<0>);
   }
-  k_seed_update2<<<grid, kSeedPts, smem, st>>>(X, N, d, centre, minDist, first, chunk, partial);
-  return cudaGetLastError();
 }
 
 // gather[r] = (r == rank) ? sum_b partial[b] : 0   (fixed order; all-reduced by the caller when world > 1)
