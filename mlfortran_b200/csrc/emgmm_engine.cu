@@ -732,7 +732,8 @@ int EmgmmEngine::iterate_fused(int64_t niter, double minProba, bool prof) {
         if (use16_) CKE(launch_em16(g, f, a, egrid_, smem_limit_, st_, gstore && pass == 0), "em sweep (fused, 16 warps)");
         else if (used_) CKE(launch_emd(g, f, a, egrid_, smem_limit_, st_), "em sweep (fused, diagonal)");
         else CKE(launch_em(g, f, a, true, egrid_, smem_limit_, st_), "em sweep (fused)");
-        ++launches_;
+        // with an expanded-form variant both variants of the sweep are launched and one of them returns at once
+        launches_ += ((use16_ || used_) && a.qf_limit >= 0.0) ? 2 : 1;
       }
       CKE(launch_reduce_partials(dPartA_, nslots, nA, dAB_, st_), "reduce statsA");
       CKE(launch_reduce_partials(dPartB2_, nslots, nB, dAB_ + nA, st_), "reduce statsB");
