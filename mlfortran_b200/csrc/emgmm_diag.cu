@@ -63,6 +63,10 @@ bool emd_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
 // Measured on the config-5 shard (N=1.25e8, d=8, K=256): 203.6 -> 200.2 ms per 1.4-sweep iteration only -- the lane = component P1 already ran
 // near the datapath rate (136 DFMA against 16 DMMA per 8 points x 32 components hold the fp64 pipe for the same 270 clocks);
 // what keeps this kernel at ~45 % of the pipe are the latency-bound softmax and statistics phases at two warps per scheduler.
+// Also measured with QP1 and not kept: the kept-set sums in the fragment layout as raw moments about the shift (sum_kept g x',
+// sum_kept g x'^2 as two DMMA per block and candidate group, re-centred at mu_old in the epilogue) in place of the lane = component
+// path: 233 ms per iteration against 200 -- four votes, two comparisons and a ballot per 4-point group and block cost more issue
+// slots than the one vote per group of the existing path saves.
 template <int TP, bool XMMA, bool QP1>
 __global__ void __launch_bounds__(256, 64 / TP) k_emd(EmArgs A) {
   constexpr int PSF = 20, XS = kXS, DS = 10, MSF = 74;
