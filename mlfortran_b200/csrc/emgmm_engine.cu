@@ -268,8 +268,11 @@ int EmgmmEngine::do_refresh(bool with_sumll) {
   QfRefresh q{};
   if (qf_) { q.packq = dPackQ_; q.qfS = dQfS_; q.rad = rad_ready_ ? dRad_ : nullptr; q.nrad = rad_world_; }
   CKE(launch_refresh(geom_, dMu_, dCov_, dLambda_, dSc_, dMean_, (double)nglob_, dScratch_, dPack_, dSumLLk_, dInfo_, st_, dPack2_, dMuOld_,
-                     dShift_, with_sumll ? 1 : 0, cov_diag_ ? 1 : 0, &fgeom_, (refresh_count_ % 8 != 0) ? 1 : 0, qf_ ? &q : nullptr, dVValid_), "refresh");
-  ++refresh_count_;  // every 8th refresh restarts the eigenvectors from the identity (bounds their orthogonality drift)
+                     dShift_, with_sumll ? 1 : 0, cov_diag_ ? 1 : 0, &fgeom_, (geom_.d > 32 && refresh_count_ % 8 != 0) ? 1 : 0, qf_ ? &q : nullptr, dVValid_), "refresh");
+  // eigen branch at d > 32: warm-started from the previous eigenvectors, every 8th refresh restarts them from the identity (bounds
+  // their orthogonality drift).  At d <= 32 the sweeps are cheap and always start cold, so that a restored object continues bit for
+  // bit like the uninterrupted one whichever branch its covariances take.
+  ++refresh_count_;
   ++launches_;
   return 0;
 }

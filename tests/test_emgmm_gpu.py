@@ -450,6 +450,7 @@ def test_streamed_refresh_from_library_allocated_host_memory(chunks, wc, oracle,
     same numbers as the oracle on the new data every time, and -- the refreshed first step whitens, the later ones take the
     quadratic form -- the counters show both logit paths on one object."""
     monkeypatch.setenv("MLF_B200_STREAM_CHUNKS", chunks)
+    monkeypatch.delenv("MLF_B200_QF", raising=False)   # the counters below describe the default (guarded) mode
     lib = _lib.load()
     d, K = 16, 12
     data = synth.make_mixture(d, K, 22000, 6.0, 1.0, 311)
@@ -1383,10 +1384,11 @@ def test_single_process_multi_gpu_object(devices, oracle):
     em.finalize()
 
 
-def test_sharded_object_statistics_first_iterations(oracle):
+def test_sharded_object_statistics_first_iterations(oracle, monkeypatch):
     """Overlapping clusters on a sharded object (three shards inside one process, peer-memory all-reduce): the statistics-first
     protocol all-reduces the pass-A statistics after the sweep and only the scatter statistics after the scatter pass from the
     stored responsibilities; every shard must take the same decisions and the result must be the oracle's."""
+    monkeypatch.delenv("MLF_B200_GSTORE", raising=False)   # the scatter-pass counter below describes the default mode
     d, K, iters = 16, 20, 6
     data = synth.make_mixture(d, K, 1500, 1.0, 1.0, 47)
     X = data["X"][: K * 1500 - 11]
