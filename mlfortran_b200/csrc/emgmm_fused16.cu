@@ -114,7 +114,8 @@ bool em16_qf_ok(const Geom& g, const FusedGeom& f, size_t smem_limit) {
 // component blocks interleaved 96.5 ms; eight exps in flight in P2 95.1; P3a unrolled 8 times 95.4; the barrier between softmax and
 // statistics replaced by one mbarrier per producer warp, consumers starting with their own points' groups, 97.1; the two groups
 // forced to take turns in P1 (P1 of one under P2 / P3 of the other, two mbarriers) 97.3, with two chains 98.6; the two groups
-// forced to start every tile together (block-wide barrier) 102.8.
+// forced to start every tile together (block-wide barrier) 102.8; the exps of a component block skipped when all of its 64 pairs
+// flush to zero (a third of the blocks on the bench mixture; bit-identical) 96.1 against 96.0 with the test compiled in and unused.
 // Why it sits at ~95 ms whatever is moved (phase timeline of a block, scripts/trace_phases.py on a -DMLF_TRACE=1 build, and
 // bench/micro/p1_quadform_occ.cu): a warp issues one DMMA per ~32 clocks at best, so the datapath (one DMMA per 16 clocks per
 // scheduler) needs >= 3 warps of a scheduler in P1 to saturate -- 0.88 of the peak with 4, 0.86 with 3, 0.75-0.80 with 2, 0.44-0.50 with
